@@ -1,0 +1,12 @@
+"""B200-native batched convex-MPC ground-reaction-force engine.
+
+Drop-in for ONE hot path of zerenluo123/Go1-QP-MPC-Controller:
+A1RobotControl::compute_grf -> ConvexMpc -> OSQP.  The product is
+csrc/ (hand-written sm_100a kernels behind the C ABI of include/mpc_b200.h);
+this package is the host-side mirror of the reference interface.
+"""
+from . import abi  # noqa: F401
+from .engine import (MpcEngine, MpcError, balance_config_default, config_default,  # noqa: F401
+                     config_hardware, generate_balance_states, generate_states, load_library,
+                     settings_osqp_default)
+from .convex_mpc import A1CtrlStates, A1RobotControl, ConvexMpc  # noqa: F401

@@ -1,0 +1,371 @@
+// Stance-balance GRF QP (A1RobotControl.cpp:11-48, :321-332, :377-444): 12
+// variables, 20 constraints.  ONE WARP PER PROBLEM: lane j < 12 owns variable j
+// and row j of P and of -K^-1 (registers), lane i < 20 owns constraint row i.
+// All exchanges are warp shuffles; no shared memory, no block barriers.  Same
+// OSQP-equivalent ADMM as the MPC path (Ruiz, per-row rho, sweep inverse,
+// residual termination, rho adaptation), computed in f64.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mpc_b200.h"
+
+namespace mpcb200 {
+
+constexpr int kBalanceThreads = 256;
+
+struct BalanceParams {
+  double Q[6];
+  double R, mu, F_min, F_max, mass;
+  double kp_lin[3], kd_lin[3], kp_ang[3], kd_ang[3];
+  double rho, sigma, alpha, eps_abs, eps_rel, adaptive_rho_tolerance;
+  int max_iter, check_termination, scaling, adaptive_rho, adaptive_rho_interval;
+};
+
+inline BalanceParams make_balance_params(const BalanceConfig& c) {
+  BalanceParams p{};
+  for (int i = 0; i < 6; ++i) p.Q[i] = c.Q[i];
+  p.R = c.R; p.mu = c.mu; p.F_min = c.F_min; p.F_max = c.F_max; p.mass = c.mass;
+  for (int i = 0; i < 3; ++i) {
+    p.kp_lin[i] = c.kp_linear[i]; p.kd_lin[i] = c.kd_linear[i];
+    p.kp_ang[i] = c.kp_angular[i]; p.kd_ang[i] = c.kd_angular[i];
+  }
+  p.rho = c.osqp.rho; p.sigma = c.osqp.sigma; p.alpha = c.osqp.alpha;
+  p.eps_abs = c.osqp.eps_abs; p.eps_rel = c.osqp.eps_rel;
+  p.adaptive_rho_tolerance = c.osqp.adaptive_rho_tolerance;
+  p.max_iter = c.osqp.max_iter; p.check_termination = c.osqp.check_termination;
+  p.scaling = c.osqp.scaling; p.adaptive_rho = c.osqp.adaptive_rho;
+  p.adaptive_rho_interval = c.osqp.adaptive_rho_interval;
+  return p;
+}
+
+__device__ __forceinline__ double bshfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double bwarp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double bwarp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double blimit(double v) {
+  v = v < 1e-4 ? 1.0 : v;
+  return v > 1e4 ? 1e4 : v;
+}
+
+// offsets (floats) inside BalanceStateIn
+constexpr int kBEuler = 0, kBPos = 3, kBAngVel = 6, kBLinVel = 9, kBEulerD = 12, kBPosD = 15,
+              kBLinVelD = 18, kBAngVelD = 21, kBRot = 24, kBRotZ = 33, kBFoot = 42, kBContacts = 54;
+
+__global__ void __launch_bounds__(kBalanceThreads)
+balance_qp_kernel(const BalanceStateIn* __restrict__ states, int num, float* __restrict__ P_out,
+                  float* __restrict__ q_out, float* __restrict__ l_out, float* __restrict__ u_out,
+                  MpcResult* __restrict__ results, const __grid_constant__ BalanceParams bp) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (kBalanceThreads / 32) + (threadIdx.x >> 5);
+  if (p >= num) return;  // warp-uniform
+  const float* st = reinterpret_cast<const float*>(states + p);
+
+  // ---- lane roles ----
+  const int j = lane < 12 ? lane : 11;   // variable (clamped for idle lanes)
+  const int lv = j / 3, cj = j % 3;
+  const int i = lane < 20 ? lane : 19;   // constraint row (clamped)
+  const bool is_var = lane < 12, is_row = lane < 20;
+  const int li = (i < 4) ? i : (i - 4) / 4;        // leg of row i
+  const int ki = (i < 4) ? 0 : (i - 4) % 4;
+  const int lat = (i < 4) ? -1 : (ki < 2 ? 0 : 1);  // lateral component of the row
+  const int ja = 3 * li + (lat < 0 ? 0 : lat);
+  const int jz = 3 * li + 2;
+  const double ca0 = (i < 4) ? 0.0 : ((ki & 1) ? -1.0 : 1.0);  // rows :33-47
+  const double cz0 = (i < 4) ? 1.0 : -bp.mu;
+  // rows touching variable j, with unscaled coefficients
+  int ridx[5];
+  double rco[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) { ridx[t] = 0; rco[t] = 0.0; }
+  if (cj == 0) { ridx[0] = 4 + 4 * lv; rco[0] = 1.0; ridx[1] = 5 + 4 * lv; rco[1] = -1.0; }
+  else if (cj == 1) { ridx[0] = 6 + 4 * lv; rco[0] = 1.0; ridx[1] = 7 + 4 * lv; rco[1] = -1.0; }
+  else {
+    ridx[0] = lv; rco[0] = 1.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { ridx[1 + t] = 4 + 4 * lv + t; rco[1 + t] = -bp.mu; }
+  }
+
+  // ---- build: root_acc, M = inertia_inv (6x12), P, q (A1RobotControl.cpp:379-406) ----
+  double R[9], Rz[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { R[k] = (double)st[kBRot + k]; Rz[k] = (double)st[kBRotZ + k]; }
+  double ee[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) ee[k] = (double)st[kBEulerD + k] - (double)st[kBEuler + k];
+  if (ee[2] > 3.1415926 * 1.5) ee[2] = (double)st[kBEulerD + 2] - 3.1415926 * 2 - (double)st[kBEuler + 2];
+  else if (ee[2] < -3.1415926 * 1.5) ee[2] = (double)st[kBEulerD + 2] + 3.1415926 * 2 - (double)st[kBEuler + 2];
+  double acc[6];
+  {
+    double Rtv[3], Rtw[3], tmp[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      Rtv[k] = R[k] * (double)st[kBLinVel] + R[3 + k] * (double)st[kBLinVel + 1] + R[6 + k] * (double)st[kBLinVel + 2];
+      Rtw[k] = R[k] * (double)st[kBAngVel] + R[3 + k] * (double)st[kBAngVel + 1] + R[6 + k] * (double)st[kBAngVel + 2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tmp[k] = bp.kd_lin[k] * ((double)st[kBLinVelD + k] - Rtv[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      acc[k] = bp.kp_lin[k] * ((double)st[kBPosD + k] - (double)st[kBPos + k]) +
+               (R[3 * k] * tmp[0] + R[3 * k + 1] * tmp[1] + R[3 * k + 2] * tmp[2]);
+      acc[3 + k] = bp.kp_ang[k] * ee[k] + bp.kd_ang[k] * ((double)st[kBAngVelD + k] - Rtw[k]);
+    }
+    acc[2] += bp.mass * 9.8;
+  }
+  // column j of M: top = e_cj, bottom = column cj of Rz' * skew(foot_lv)
+  double mj[6];
+  {
+    const double fx = st[kBFoot + 3 * lv], fy = st[kBFoot + 3 * lv + 1], fz = st[kBFoot + 3 * lv + 2];
+    const double sk[9] = {0.0, -fz, fy, fz, 0.0, -fx, -fy, fx, 0.0};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      mj[k] = (k == cj) ? 1.0 : 0.0;
+      double s = 0.0;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) s += Rz[3 * t + k] * sk[3 * t + cj];  // (Rz')[k][t] = Rz[t][k]
+      mj[3 + k] = s;
+    }
+  }
+  double Prow[12];  // row j of P
+  {
+    double qm[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) qm[k] = mj[k] * bp.Q[k];
+#pragma unroll
+    for (int b = 0; b < 12; ++b) {
+      double s = (b == j) ? bp.R : 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s += qm[k] * bshfl(mj[k], b);
+      Prow[b] = s;
+    }
+  }
+  double q0;
+  {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s += mj[k] * bp.Q[k] * acc[k];
+    q0 = -s;
+  }
+  // bounds (:409-413, :33-47)
+  double lb, ub;
+  if (i < 4) {
+    const double cf = (st[kBContacts + i] != 0.0f) ? 1.0 : 0.0;
+    lb = cf * bp.F_min;
+    ub = cf * bp.F_max;
+  } else {
+    lb = -MPC_INFTY;
+    ub = 0.0;
+  }
+  if (P_out != nullptr && is_var) {
+#pragma unroll
+    for (int b = 0; b < 12; ++b) P_out[size_t(p) * 144 + j * 12 + b] = (float)Prow[b];
+  }
+  if (q_out != nullptr && is_var) q_out[size_t(p) * 12 + j] = (float)q0;
+  if (l_out != nullptr && is_row) {
+    l_out[size_t(p) * 20 + i] = (float)lb;
+    u_out[size_t(p) * 20 + i] = (float)ub;
+  }
+  // (the QP never leaves registers here, so unlike the MPC path it is NOT
+  // rounded to fp32 before the solve; the fp32 copies above are parity output)
+
+  // ---- Ruiz equilibration (lane j: D_j, lane i: E_i) ----
+  double D = 1.0, E = 1.0, c = 1.0;
+  auto p_row_norm = [&](double Dj) {
+    double m = 0.0;
+#pragma unroll
+    for (int b = 0; b < 12; ++b) m = fmax(m, fabs(Prow[b]) * bshfl(Dj, b));
+    return m;
+  };
+  if (bp.scaling > 0) {
+    double nP = p_row_norm(D);
+    for (int it = 0; it < bp.scaling; ++it) {
+      // column norm of A for variable j
+      double nA = 0.0;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) nA = fmax(nA, fabs(rco[t]) * bshfl(E, ridx[t]));
+      nA *= D;
+      const double Dt = is_var ? rsqrt(blimit(fmax(nP, nA))) : 1.0;
+      // row norm of A for constraint i
+      const double da = bshfl(D, ja), dz = bshfl(D, jz);
+      const double nrow = E * fmax(fabs(ca0) * da, fabs(cz0) * dz);
+      const double Et = is_row ? rsqrt(blimit(nrow)) : 1.0;
+      D *= Dt;
+      E *= Et;
+      const double nP2 = c * D * p_row_norm(D);
+      const double mean = bwarp_sum(is_var ? nP2 : 0.0) / 12.0;
+      const double qn = bwarp_max(is_var ? fabs(c * D * q0) : 0.0);
+      const double ct = 1.0 / blimit(fmax(mean, blimit(qn)));
+      c *= ct;
+      nP = nP2 * ct;
+    }
+  }
+  const double cinv = 1.0 / c, Dinv = 1.0 / D, Einv = 1.0 / E;
+  const double qb = c * D * q0;
+  lb *= E;
+  ub *= E;
+  const int ctype = (lb < -MPC_INFTY * 1e-4 && ub > MPC_INFTY * 1e-4) ? -1 : ((ub - lb < 1e-4) ? 1 : 0);
+  double rho = bp.rho;
+  auto rho_of = [&](double rh) { return (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * rh : rh; };
+  double rv = rho_of(rho), rinv = 1.0 / rv;
+  // scaled constraint coefficients of row i
+  const double ca = E * ca0 * bshfl(D, ja);
+  const double cz = E * cz0 * bshfl(D, jz);
+  // scaled coefficients of the rows touching variable j
+  double rcs[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) rcs[t] = bshfl(E, ridx[t]) * rco[t] * D;
+
+  double a[12];  // row j of -K^-1
+  auto factor = [&]() {
+    // K = c D P D + sigma I + A' diag(rho) A
+#pragma unroll
+    for (int b = 0; b < 12; ++b) {
+      double v = c * D * Prow[b] * bshfl(D, b);
+      if (b == j) v += bp.sigma;
+      a[b] = v;
+    }
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+      const int ri = ridx[t];
+      const double rr = bshfl(rv, ri);
+      const double ca_i = bshfl(ca, ri), cz_i = bshfl(cz, ri);
+      const int lat_i = (ri < 4) ? -1 : (((ri - 4) % 4) < 2 ? 0 : 1);
+      const double wgt = rr * rcs[t];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const double aib = (cc == 2) ? cz_i : ((cc == lat_i) ? ca_i : 0.0);
+        const int b = 3 * lv + cc;
+#pragma unroll
+        for (int bb = 0; bb < 12; ++bb)
+          if (bb == b) a[bb] += wgt * aib;
+      }
+    }
+    // symmetric sweep, 12 pivots
+#pragma unroll 1
+    for (int k = 0; k < 12; ++k) {
+      double v[12];
+#pragma unroll
+      for (int b = 0; b < 12; ++b) v[b] = bshfl(a[b], k);
+      double d = 0.0;
+#pragma unroll
+      for (int b = 0; b < 12; ++b)
+        if (b == k) d = v[b];
+      const double dinv = 1.0 / d;
+      double vr = 0.0;
+#pragma unroll
+      for (int b = 0; b < 12; ++b)
+        if (b == j) vr = v[b];
+      if (j != k) {
+        const double w = -vr * dinv;
+#pragma unroll
+        for (int b = 0; b < 12; ++b) {
+          const double vb = (b == k) ? (d - 1.0) : v[b];
+          a[b] = fma(w, vb, a[b]);
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < 12; ++b) a[b] = (b == k) ? -dinv : a[b] * dinv;
+      }
+    }
+  };
+  factor();
+
+  // ---- ADMM ----
+  double x = 0.0, z = 0.0, y = 0.0;
+  int iter = 0, status = MPC_STATUS_UNSOLVED, rho_updates = 0;
+  double pri_out = 0.0;
+  for (iter = 1; iter <= bp.max_iter; ++iter) {
+    // rhs_j = sigma x - q + A'(rho z - y)
+    const double w = rv * z - y;
+    double rhs = bp.sigma * x - qb;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) rhs = fma(rcs[t], bshfl(w, ridx[t]), rhs);
+    double xt = 0.0;
+#pragma unroll
+    for (int b = 0; b < 12; ++b) xt = fma(a[b], bshfl(rhs, b), xt);
+    xt = -xt;
+    x = bp.alpha * xt + (1.0 - bp.alpha) * x;
+    const double zt = ca * bshfl(xt, ja) + cz * bshfl(xt, jz);
+    const double zr = bp.alpha * zt + (1.0 - bp.alpha) * z;
+    double zn = fmin(fmax(zr + rinv * y, lb), ub);
+    y += rv * (zr - zn);
+    z = zn;
+    const bool can_check = bp.check_termination > 0 && (iter % bp.check_termination == 0);
+    const bool can_adapt = bp.adaptive_rho && bp.adaptive_rho_interval > 0 &&
+                           (iter % bp.adaptive_rho_interval == 0);
+    const bool last = iter == bp.max_iter;
+    if (!(can_check || can_adapt || last)) continue;
+    // residuals
+    const double Ax = ca * bshfl(x, ja) + cz * bshfl(x, jz);
+    const double rp = is_row ? (Ax - z) : 0.0;
+    double Px = 0.0;
+    {
+      const double xD = D * x;
+#pragma unroll
+      for (int b = 0; b < 12; ++b) Px = fma(Prow[b], bshfl(xD, b), Px);
+      Px *= c * D;
+    }
+    double Aty = 0.0;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) Aty = fma(rcs[t], bshfl(y, ridx[t]), Aty);
+    const double rd = is_var ? (Px + qb + Aty) : 0.0;
+    const double m0 = bwarp_max(fabs(rp));
+    const double m1 = bwarp_max(fabs(Einv * rp));
+    const double m2 = bwarp_max(is_row ? fmax(fabs(Einv * z), fabs(Einv * Ax)) : 0.0);
+    const double m4 = bwarp_max(is_row ? fmax(fabs(z), fabs(Ax)) : 0.0);
+    const double m6 = bwarp_max(fabs(rd));
+    const double m7 = bwarp_max(fabs(Dinv * rd));
+    const double m8 = bwarp_max(is_var ? fmax(fmax(fabs(Dinv * qb), fabs(Dinv * Aty)), fabs(Dinv * Px)) : 0.0);
+    const double m9 = bwarp_max(is_var ? fmax(fmax(fabs(qb), fabs(Aty)), fabs(Px)) : 0.0);
+    const double pri = m1, dua = cinv * m7;
+    const double eps_pri = bp.eps_abs + bp.eps_rel * m2;
+    const double eps_dua = bp.eps_abs + bp.eps_rel * cinv * m8;
+    pri_out = pri;
+    if ((can_check || last) && pri < eps_pri && dua < eps_dua) { status = MPC_STATUS_SOLVED; break; }
+    if (last) {
+      status = (pri < 10.0 * eps_pri && dua < 10.0 * eps_dua) ? 2 : MPC_STATUS_MAX_ITER_REACHED;
+      break;
+    }
+    if (can_adapt) {
+      const double pn = m0 / (m4 + 1e-10);
+      const double dn = m6 / (m9 + 1e-10);
+      double rho_new = rho * sqrt(pn / (dn + 1e-10));
+      rho_new = fmin(fmax(rho_new, 1e-6), 1e6);
+      if (rho_new > rho * bp.adaptive_rho_tolerance || rho_new < rho / bp.adaptive_rho_tolerance) {
+        rho = rho_new;
+        rv = rho_of(rho);
+        rinv = 1.0 / rv;
+        ++rho_updates;
+        factor();
+      }
+    }
+  }
+  if (iter > bp.max_iter) iter = bp.max_iter;
+
+  // ---- unscale and rotate every leg to the body frame (:439-444) ----
+  const double xo = D * x;
+  const int leg = lane / 3 < 4 ? lane / 3 : 3;
+  const double f0 = bshfl(xo, 3 * leg), f1 = bshfl(xo, 3 * leg + 1), f2 = bshfl(xo, 3 * leg + 2);
+  if (is_var) {
+    const double g = R[cj] * f0 + R[3 + cj] * f1 + R[6 + cj] * f2;
+    const bool bad = isnan(f0) || isnan(f1) || isnan(f2);
+    results[p].grf[j] = bad ? 0.0f : (float)g;
+  }
+  if (lane == 12) {
+    results[p].status = status;
+    results[p].iters = iter;
+    results[p].rho_updates = rho_updates;
+    results[p].pri_res = (float)pri_out;
+  }
+}
+
+}  // namespace mpcb200

@@ -1,0 +1,243 @@
+// Host-side defaults and the synthetic state generator (no device code).
+//
+// Defaults restate the reference's configuration sources:
+//   config/gazebo_a1_mpc.yaml:6-13,40-72   (mass, inertia, q/r weights; primary)
+//   config/hardware_a1_mpc.yaml            (well-conditioned weights; secondary)
+//   ConvexMpc.cpp:8,223-224                (mu = 0.3, fz in [0,180])
+//   A1RobotControl.cpp:11-15,462           (stance-QP constants, mpc_dt)
+//   config/gazebo_a1_qp.yaml:54-68         (stance-QP PD gains)
+// Solver settings: OSQP 0.6.x library defaults (the reference only switches
+// verbosity and warm start, A1RobotControl.cpp:523-524); the benchmark set
+// tightens eps to 1e-5 and pins the adaptive-rho interval.
+#include <cmath>
+#include <cstring>
+
+#include "../../include/mpc_b200.h"
+
+extern "C" {
+
+int mpc_settings_osqp_default(MpcSolverSettings* s) {
+  if (!s) return MPC_ERR_INVALID;
+  s->rho = 0.1;
+  s->sigma = 1e-6;
+  s->alpha = 1.6;
+  s->eps_abs = 1e-3;
+  s->eps_rel = 1e-3;
+  s->eps_prim_inf = 1e-4;
+  s->eps_dual_inf = 1e-4;
+  s->max_iter = 4000;
+  s->check_termination = 25;
+  s->scaling = 10;
+  s->adaptive_rho = 1;
+  // Library default 0 = "choose from setup wall-clock time": not reproducible.
+  s->adaptive_rho_interval = 50;
+  s->adaptive_rho_tolerance = 5.0;
+  return MPC_OK;
+}
+
+int mpc_settings_benchmark(MpcSolverSettings* s) {
+  int rc = mpc_settings_osqp_default(s);
+  if (rc) return rc;
+  s->eps_abs = 1e-5;
+  s->eps_rel = 1e-5;
+  return MPC_OK;
+}
+
+static void fill_common(MpcConfig* cfg) {
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->horizon = MPC_HORIZON_DEFAULT;
+  cfg->dt = 0.0025;
+  cfg->mu = 0.3;
+  cfg->fz_min = 0.0;
+  cfg->fz_max = 180.0;
+  cfg->inertia[0] = 0.0168352186;
+  cfg->inertia[4] = 0.0656071082;
+  cfg->inertia[8] = 0.0742720659;
+  mpc_settings_benchmark(&cfg->osqp);
+}
+
+int mpc_config_default(MpcConfig* cfg) {
+  if (!cfg) return MPC_ERR_INVALID;
+  fill_common(cfg);
+  cfg->mass = 12.0;
+  const double q[13] = {20.0, 10.0, 1.0, 0.0, 0.0, 420.0, 0.05, 0.05, 0.05, 30.0, 30.0, 10.0, 0.0};
+  for (int i = 0; i < 13; ++i) cfg->q_weights[i] = q[i];
+  for (int i = 0; i < 12; ++i) cfg->r_weights[i] = 1e-7;
+  return MPC_OK;
+}
+
+int mpc_config_hardware(MpcConfig* cfg) {
+  if (!cfg) return MPC_ERR_INVALID;
+  fill_common(cfg);
+  cfg->mass = 13.5;
+  const double q[13] = {150.0, 150.0, 50.0, 0.0, 0.0, 80.0, 0.2, 0.2, 0.2, 0.3, 0.3, 0.3, 0.0};
+  for (int i = 0; i < 13; ++i) cfg->q_weights[i] = q[i];
+  for (int i = 0; i < 12; ++i) cfg->r_weights[i] = (i % 3 == 2) ? 0.001 : 0.01;
+  return MPC_OK;
+}
+
+int balance_config_default(BalanceConfig* cfg) {
+  if (!cfg) return MPC_ERR_INVALID;
+  std::memset(cfg, 0, sizeof(*cfg));
+  const double Q[6] = {1.0, 1.0, 1.0, 400.0, 400.0, 100.0};
+  for (int i = 0; i < 6; ++i) cfg->Q[i] = Q[i];
+  cfg->R = 1e-3;
+  cfg->mu = 0.7;
+  cfg->F_min = 0.0;
+  cfg->F_max = 180.0;
+  cfg->mass = 12.0;
+  const double kpl[3] = {100.0, 100.0, 300.0}, kdl[3] = {70.0, 70.0, 120.0};
+  const double kpa[3] = {150.0, 150.0, 1.0}, kda[3] = {4.5, 4.5, 30.0};
+  for (int i = 0; i < 3; ++i) {
+    cfg->kp_linear[i] = kpl[i];
+    cfg->kd_linear[i] = kdl[i];
+    cfg->kp_angular[i] = kpa[i];
+    cfg->kd_angular[i] = kda[i];
+  }
+  mpc_settings_benchmark(&cfg->osqp);
+  return MPC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Synthetic robot states.  Counter-based: state i of stream
+// `seed` depends only on (seed, i), so any shard of any batch can be produced
+// independently on any rank.  splitmix64; u = (x >> 11) * 2^-53.
+// ---------------------------------------------------------------------------
+namespace {
+
+struct SplitMix {
+  uint64_t s;
+  explicit SplitMix(uint64_t seed, uint64_t index)
+      : s(seed ^ ((index + 1) * 0x9E3779B97F4A7C15ULL)) {}
+  uint64_t next() {
+    s += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+  }
+  double u01() { return double(next() >> 11) * (1.0 / 9007199254740992.0); }
+  double uni(double lo, double hi) { return lo + (hi - lo) * u01(); }
+};
+
+// R = Rz(yaw) * Ry(pitch) * Rx(roll): the ZYX convention of Utils::quat_to_euler
+// (utils/Utils.cpp:7-33).
+void euler_to_rot(double roll, double pitch, double yaw, double* R) {
+  const double cr = std::cos(roll), sr = std::sin(roll);
+  const double cp = std::cos(pitch), sp = std::sin(pitch);
+  const double cy = std::cos(yaw), sy = std::sin(yaw);
+  R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
+  R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
+  R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
+}
+
+// default footholds, config/gazebo_a1_mpc.yaml:17-31 (FL, FR, RL, RR)
+const double kDefaultFoot[12] = {0.17, 0.15, -0.35, 0.17, -0.15, -0.35,
+                                 -0.17, 0.15, -0.35, -0.17, -0.15, -0.35};
+
+struct CommonDraw {
+  double euler[3], pos[3], w[3], v[3], R[9], foot_abs[12];
+};
+
+void draw_common(SplitMix& g, CommonDraw& d) {
+  d.euler[0] = g.uni(-0.2, 0.2);
+  d.euler[1] = g.uni(-0.2, 0.2);
+  d.euler[2] = g.uni(-3.14159265358979323846, 3.14159265358979323846);
+  d.pos[0] = g.uni(-1.0, 1.0);
+  d.pos[1] = g.uni(-1.0, 1.0);
+  d.pos[2] = g.uni(0.22, 0.32);
+  for (int i = 0; i < 3; ++i) d.w[i] = g.uni(-1.0, 1.0);
+  d.v[0] = g.uni(-0.6, 0.6);
+  d.v[1] = g.uni(-0.3, 0.3);
+  d.v[2] = g.uni(-0.2, 0.2);
+  euler_to_rot(d.euler[0], d.euler[1], d.euler[2], d.R);
+  double rel[12];
+  for (int i = 0; i < 12; ++i) rel[i] = kDefaultFoot[i] + g.uni(-0.05, 0.05);
+  // foot_pos_abs = R * foot_pos_rel (GazeboA1ROS.cpp:283)
+  for (int leg = 0; leg < 4; ++leg)
+    for (int r = 0; r < 3; ++r)
+      d.foot_abs[3 * leg + r] = d.R[3 * r] * rel[3 * leg] + d.R[3 * r + 1] * rel[3 * leg + 1] +
+                                d.R[3 * r + 2] * rel[3 * leg + 2];
+}
+
+}  // namespace
+
+int mpc_generate_states(uint64_t seed, uint64_t first_index, int32_t n, MpcStateIn* out) {
+  if (!out || n < 0) return MPC_ERR_INVALID;
+  for (int32_t k = 0; k < n; ++k) {
+    SplitMix g(seed, first_index + uint64_t(k));
+    CommonDraw d;
+    draw_common(g, d);
+    MpcStateIn& s = out[k];
+    std::memset(&s, 0, sizeof(s));
+    for (int i = 0; i < 3; ++i) {
+      s.euler[i] = float(d.euler[i]);
+      s.pos[i] = float(d.pos[i]);
+      s.ang_vel[i] = float(d.w[i]);
+      s.lin_vel[i] = float(d.v[i]);
+    }
+    s.euler_d[0] = 0.0f;
+    s.euler_d[1] = float(g.uni(-0.1, 0.1));
+    s.euler_d[2] = 0.0f;
+    s.pos_d_z = float(g.uni(0.25, 0.32));        // JOY_CMD_BODY_HEIGHT_MAX, A1Params.h:16
+    s.lin_vel_d[0] = float(g.uni(-0.6, 0.6));    // JOY_CMD_VELX_MAX, A1Params.h:19
+    s.lin_vel_d[1] = float(g.uni(-0.3, 0.3));    // JOY_CMD_VELY_MAX, A1Params.h:20
+    s.lin_vel_d[2] = 0.0f;
+    s.ang_vel_d[0] = 0.0f;
+    s.ang_vel_d[1] = 0.0f;
+    s.ang_vel_d[2] = float(g.uni(-0.8, 0.8));    // JOY_CMD_YAW_MAX, A1Params.h:21
+    for (int i = 0; i < 9; ++i) s.rot_mat[i] = float(d.R[i]);
+    for (int i = 0; i < 12; ++i) s.foot_pos_abs[i] = float(d.foot_abs[i]);
+    // trot pairs {FL,RR} / {FR,RL} 45 % each, four-stance 10 %
+    const double c = g.u01();
+    const bool a = c < 0.45, b = c >= 0.45 && c < 0.90;
+    s.contacts[0] = (a || (!a && !b)) ? 1.0f : 0.0f;
+    s.contacts[3] = s.contacts[0];
+    s.contacts[1] = (b || (!a && !b)) ? 1.0f : 0.0f;
+    s.contacts[2] = s.contacts[1];
+  }
+  return MPC_OK;
+}
+
+int balance_generate_states(uint64_t seed, uint64_t first_index, int32_t n, BalanceStateIn* out) {
+  if (!out || n < 0) return MPC_ERR_INVALID;
+  for (int32_t k = 0; k < n; ++k) {
+    SplitMix g(seed, first_index + uint64_t(k));
+    CommonDraw d;
+    draw_common(g, d);
+    BalanceStateIn& s = out[k];
+    std::memset(&s, 0, sizeof(s));
+    for (int i = 0; i < 3; ++i) {
+      s.euler[i] = float(d.euler[i]);
+      s.pos[i] = float(d.pos[i]);
+      s.ang_vel[i] = float(d.w[i]);
+      s.lin_vel[i] = float(d.v[i]);
+    }
+    s.euler_d[0] = 0.0f;
+    s.euler_d[1] = float(g.uni(-0.1, 0.1));
+    // desired yaw follows the current yaw plus a small command offset
+    s.euler_d[2] = float(d.euler[2] + g.uni(-0.2, 0.2));
+    s.pos_d[0] = float(d.pos[0]);
+    s.pos_d[1] = float(d.pos[1]);
+    s.pos_d[2] = float(g.uni(0.25, 0.32));
+    s.lin_vel_d[0] = float(g.uni(-0.6, 0.6));
+    s.lin_vel_d[1] = float(g.uni(-0.3, 0.3));
+    s.lin_vel_d[2] = 0.0f;
+    s.ang_vel_d[2] = float(g.uni(-0.8, 0.8));
+    for (int i = 0; i < 9; ++i) s.rot_mat[i] = float(d.R[i]);
+    double Rz[9];
+    euler_to_rot(0.0, 0.0, d.euler[2], Rz);
+    for (int i = 0; i < 9; ++i) s.rot_mat_z[i] = float(Rz[i]);
+    for (int i = 0; i < 12; ++i) s.foot_pos_abs[i] = float(d.foot_abs[i]);
+    // four-stance 80 %, trot pairs 10 % each
+    const double c = g.u01();
+    const bool all4 = c < 0.80, a = c >= 0.80 && c < 0.90;
+    s.contacts[0] = (all4 || a) ? 1.0f : 0.0f;
+    s.contacts[3] = s.contacts[0];
+    s.contacts[1] = (all4 || !a) ? 1.0f : 0.0f;
+    s.contacts[2] = s.contacts[1];
+  }
+  return MPC_OK;
+}
+
+}  // extern "C"

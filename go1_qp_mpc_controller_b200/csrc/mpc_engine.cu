@@ -1,0 +1,549 @@
+// C-ABI implementation of include/mpc_b200.h: engine life cycle, device memory,
+// kernel launches.  No PyTorch, no CPU fallback: without a CUDA device every
+// compute entry point fails with MPC_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mpc_b200.h"
+#include "balance_kernels.cuh"
+#include "mpc_kernels.cuh"
+
+using namespace mpcb200;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct MpcEngine {
+  int kind = 0;  // 0: MPC branch, 1: stance-balance QP branch
+  MpcConfig cfg{};
+  BalanceConfig bcfg{};
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int capacity = 0;
+  int n = 0;
+  MpcStateIn* d_states_own = nullptr;
+  const MpcStateIn* d_states = nullptr;
+  BalanceStateIn* d_bstates = nullptr;
+  float* d_P = nullptr;
+  float* d_q = nullptr;
+  float* d_l = nullptr;
+  float* d_u = nullptr;
+  float* d_x = nullptr;
+  MpcResult* d_results = nullptr;
+  int* d_counter = nullptr;
+  bool built = false, solved = false;
+  int64_t launches = 0;
+  BuildParams bp{};
+  SolveParams sp{};
+  BalanceParams bal{};
+  std::string err;
+};
+
+namespace {
+
+int fail(MpcEngine* e, int code, const std::string& msg) {
+  if (e) e->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(e, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _rc = (expr);                                                          \
+    if (_rc != cudaSuccess)                                                            \
+      return fail((e), MPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_rc)); \
+  } while (0)
+
+SolveParams make_solve_params(const MpcSolverSettings& s, double mu) {
+  SolveParams sp{};
+  sp.rho = s.rho;
+  sp.sigma = s.sigma;
+  sp.alpha = s.alpha;
+  sp.eps_abs = s.eps_abs;
+  sp.eps_rel = s.eps_rel;
+  sp.adaptive_rho_tolerance = s.adaptive_rho_tolerance;
+  sp.mu = mu;
+  sp.max_iter = s.max_iter;
+  sp.check_termination = s.check_termination;
+  sp.scaling = s.scaling;
+  sp.adaptive_rho = s.adaptive_rho;
+  sp.adaptive_rho_interval = s.adaptive_rho_interval;
+  return sp;
+}
+
+int validate_settings(const MpcSolverSettings& s, std::string* why) {
+  if (!(s.rho > 0) || !(s.sigma > 0) || !(s.alpha > 0 && s.alpha < 2)) { *why = "rho/sigma/alpha out of range"; return -1; }
+  if (s.max_iter <= 0 || s.check_termination < 0 || s.scaling < 0) { *why = "max_iter/check_termination/scaling out of range"; return -1; }
+  if (s.adaptive_rho && s.adaptive_rho_interval <= 0) { *why = "adaptive_rho needs a pinned adaptive_rho_interval > 0"; return -1; }
+  if (!(s.eps_abs >= 0) || !(s.eps_rel >= 0) || (s.eps_abs == 0 && s.eps_rel == 0)) { *why = "eps_abs/eps_rel out of range"; return -1; }
+  return 0;
+}
+
+int open_device(int device, int* num_sms, std::string* why) {
+  int count = 0;
+  cudaError_t rc = cudaGetDeviceCount(&count);
+  if (rc != cudaSuccess || count == 0) {
+    *why = std::string("no CUDA device (") + (rc == cudaSuccess ? "count 0" : cudaGetErrorString(rc)) +
+           "); this engine has no CPU fallback";
+    (void)cudaGetLastError();
+    return MPC_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) { *why = "device ordinal out of range"; return MPC_ERR_INVALID; }
+  rc = cudaSetDevice(device);
+  if (rc != cudaSuccess) { *why = cudaGetErrorString(rc); return MPC_ERR_CUDA; }
+  cudaDeviceProp prop;
+  rc = cudaGetDeviceProperties(&prop, device);
+  if (rc != cudaSuccess) { *why = cudaGetErrorString(rc); return MPC_ERR_CUDA; }
+  if (prop.major < 10) {
+    *why = "device is not sm_100 class; kernels are built for sm_100a only";
+    return MPC_ERR_UNSUPPORTED;
+  }
+  *num_sms = prop.multiProcessorCount;
+  return MPC_OK;
+}
+
+void free_buffers(MpcEngine* e) {
+  cudaFree(e->d_states_own);
+  cudaFree(e->d_bstates);
+  cudaFree(e->d_P);
+  cudaFree(e->d_q);
+  cudaFree(e->d_l);
+  cudaFree(e->d_u);
+  cudaFree(e->d_x);
+  cudaFree(e->d_results);
+  e->d_states_own = nullptr;
+  e->d_bstates = nullptr;
+  e->d_P = e->d_q = e->d_l = e->d_u = e->d_x = nullptr;
+  e->d_results = nullptr;
+  e->capacity = 0;
+}
+
+int reserve(MpcEngine* e, int n) {
+  if (n <= e->capacity) return MPC_OK;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  free_buffers(e);
+  int cap = 1;
+  while (cap < n) cap <<= 1;
+  if (cap < 64) cap = 64;
+  if (e->kind == 0) {
+    CUDA_TRY(e, cudaMalloc(&e->d_states_own, size_t(cap) * sizeof(MpcStateIn)));
+    CUDA_TRY(e, cudaMalloc(&e->d_P, size_t(cap) * kN * kN * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_q, size_t(cap) * kN * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_l, size_t(cap) * kM * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_u, size_t(cap) * kM * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_x, size_t(cap) * kN * sizeof(float)));
+  } else {
+    CUDA_TRY(e, cudaMalloc(&e->d_bstates, size_t(cap) * sizeof(BalanceStateIn)));
+    CUDA_TRY(e, cudaMalloc(&e->d_P, size_t(cap) * 144 * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_q, size_t(cap) * 12 * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_l, size_t(cap) * 20 * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_u, size_t(cap) * 20 * sizeof(float)));
+  }
+  CUDA_TRY(e, cudaMalloc(&e->d_results, size_t(cap) * sizeof(MpcResult)));
+  e->capacity = cap;
+  return MPC_OK;
+}
+
+int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n, float* P, float* q,
+                 float* l, float* u) {
+  const int grid = n < e->num_sms * 8 ? n : e->num_sms * 8;
+  qp_build_kernel<<<grid, kThreads, sizeof(BuildSmem), e->stream>>>(d_states, model, n, P, q, l, u, e->bp);
+  ++e->launches;
+  CUDA_TRY(e, cudaGetLastError());
+  return MPC_OK;
+}
+
+int launch_solve(MpcEngine* e, const float* P, const float* q, const float* l, const float* u,
+                 const MpcStateIn* d_states, MpcResult* res, float* x, int n) {
+  CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
+  const int grid = n < e->num_sms ? n : e->num_sms;
+  admm_solve_kernel<<<grid, kThreads, sizeof(SolveSmem), e->stream>>>(P, q, l, u, d_states, res, x, n,
+                                                                      e->d_counter, e->sp);
+  ++e->launches;
+  CUDA_TRY(e, cudaGetLastError());
+  return MPC_OK;
+}
+
+int create_common(int kind, int device, MpcEngine** out) {
+  if (!out) return fail(nullptr, MPC_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  std::string why;
+  int num_sms = 0;
+  int rc = open_device(device, &num_sms, &why);
+  if (rc != MPC_OK) return fail(nullptr, rc, why);
+  MpcEngine* e = new (std::nothrow) MpcEngine();
+  if (!e) return fail(nullptr, MPC_ERR_INVALID, "out of host memory");
+  e->kind = kind;
+  e->device = device;
+  e->num_sms = num_sms;
+  cudaError_t crc = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+  if (crc == cudaSuccess) crc = cudaMalloc(&e->d_counter, sizeof(int));
+  if (crc == cudaSuccess)
+    crc = cudaFuncSetAttribute(qp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(BuildSmem));
+  if (crc == cudaSuccess)
+    crc = cudaFuncSetAttribute(admm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(SolveSmem));
+  if (crc != cudaSuccess) {
+    std::string msg = std::string("engine setup: ") + cudaGetErrorString(crc);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    cudaFree(e->d_counter);
+    delete e;
+    return fail(nullptr, MPC_ERR_CUDA, msg);
+  }
+  e->stream = e->own_stream;
+  *out = e;
+  return MPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
+  if (!cfg) return fail(nullptr, MPC_ERR_INVALID, "cfg is NULL");
+  if (cfg->horizon != kH)
+    return fail(nullptr, MPC_ERR_UNSUPPORTED,
+                "horizon " + std::to_string(cfg->horizon) + " not built; this build has H = 10 kernels");
+  std::string why;
+  if (validate_settings(cfg->osqp, &why)) return fail(nullptr, MPC_ERR_INVALID, why);
+  if (!(cfg->dt > 0) || !(cfg->mass > 0) || !(cfg->mu > 0))
+    return fail(nullptr, MPC_ERR_INVALID, "dt/mass/mu must be positive");
+  MpcEngine* e = nullptr;
+  int rc = create_common(0, device, &e);
+  if (rc != MPC_OK) return rc;
+  e->cfg = *cfg;
+  e->bp.dt = cfg->dt;
+  e->bp.mu = cfg->mu;
+  e->bp.fz_min = cfg->fz_min;
+  e->bp.fz_max = cfg->fz_max;
+  e->bp.mass = cfg->mass;
+  for (int i = 0; i < 9; ++i) e->bp.inertia[i] = cfg->inertia[i];
+  for (int i = 0; i < 13; ++i) e->bp.Qd[i] = 2.0 * cfg->q_weights[i];
+  for (int i = 0; i < 12; ++i) e->bp.Rd[i] = 2.0 * cfg->r_weights[i];
+  e->sp = make_solve_params(cfg->osqp, cfg->mu);
+  *out = e;
+  return MPC_OK;
+}
+
+int balance_engine_create(const BalanceConfig* cfg, int32_t device, MpcEngine** out) {
+  if (!cfg) return fail(nullptr, MPC_ERR_INVALID, "cfg is NULL");
+  std::string why;
+  if (validate_settings(cfg->osqp, &why)) return fail(nullptr, MPC_ERR_INVALID, why);
+  MpcEngine* e = nullptr;
+  int rc = create_common(1, device, &e);
+  if (rc != MPC_OK) return rc;
+  e->bcfg = *cfg;
+  e->bal = make_balance_params(*cfg);
+  *out = e;
+  return MPC_OK;
+}
+
+void mpc_engine_destroy(MpcEngine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  free_buffers(e);
+  cudaFree(e->d_counter);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+const char* mpc_last_error(const MpcEngine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int mpc_set_stream(MpcEngine* e, void* cuda_stream) {
+  if (!e) return MPC_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+  return MPC_OK;
+}
+
+int mpc_synchronize(MpcEngine* e) {
+  if (!e) return MPC_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  return MPC_OK;
+}
+
+int64_t mpc_kernel_launches(const MpcEngine* e) { return e ? e->launches : 0; }
+
+int mpc_load_states(MpcEngine* e, const MpcStateIn* host, int32_t n) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (n < 0 || (n > 0 && !host)) return fail(e, MPC_ERR_INVALID, "bad state buffer");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  int rc = reserve(e, n);
+  if (rc) return rc;
+  if (n > 0)
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_states_own, host, size_t(n) * sizeof(MpcStateIn),
+                                cudaMemcpyHostToDevice, e->stream));
+  e->d_states = e->d_states_own;
+  e->n = n;
+  e->built = e->solved = false;
+  return MPC_OK;
+}
+
+int mpc_set_states_device(MpcEngine* e, const MpcStateIn* dev, int32_t n) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (n < 0 || (n > 0 && !dev)) return fail(e, MPC_ERR_INVALID, "bad device state buffer");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  int rc = reserve(e, n);
+  if (rc) return rc;
+  e->d_states = dev;
+  e->n = n;
+  e->built = e->solved = false;
+  return MPC_OK;
+}
+
+int mpc_build_qp_async(MpcEngine* e) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (!e->d_states && e->n > 0) return fail(e, MPC_ERR_STATE, "mpc_build_qp before mpc_load_states");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (e->n > 0) {
+    ModelIn none{};
+    int rc = launch_build(e, e->d_states, none, e->n, e->d_P, e->d_q, e->d_l, e->d_u);
+    if (rc) return rc;
+  }
+  e->built = true;
+  e->solved = false;
+  return MPC_OK;
+}
+
+int mpc_build_qp(MpcEngine* e) {
+  int rc = mpc_build_qp_async(e);
+  if (rc) return rc;
+  return mpc_synchronize(e);
+}
+
+int mpc_get_qp(MpcEngine* e, int32_t idx, float* P, float* q, float* l, float* u) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (!e->built) return fail(e, MPC_ERR_STATE, "mpc_get_qp before mpc_build_qp");
+  if (idx < 0 || idx >= e->n) return fail(e, MPC_ERR_INVALID, "problem index out of range");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (P) CUDA_TRY(e, cudaMemcpy(P, e->d_P + size_t(idx) * kN * kN, kN * kN * sizeof(float), cudaMemcpyDeviceToHost));
+  if (q) CUDA_TRY(e, cudaMemcpy(q, e->d_q + size_t(idx) * kN, kN * sizeof(float), cudaMemcpyDeviceToHost));
+  if (l) CUDA_TRY(e, cudaMemcpy(l, e->d_l + size_t(idx) * kM, kM * sizeof(float), cudaMemcpyDeviceToHost));
+  if (u) CUDA_TRY(e, cudaMemcpy(u, e->d_u + size_t(idx) * kM, kM * sizeof(float), cudaMemcpyDeviceToHost));
+  return MPC_OK;
+}
+
+int mpc_solve_async(MpcEngine* e) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (!e->built) return fail(e, MPC_ERR_STATE, "mpc_solve before mpc_build_qp");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (e->n > 0) {
+    int rc = launch_solve(e, e->d_P, e->d_q, e->d_l, e->d_u, e->d_states, e->d_results, e->d_x, e->n);
+    if (rc) return rc;
+  }
+  e->solved = true;
+  return MPC_OK;
+}
+
+int mpc_solve(MpcEngine* e) {
+  int rc = mpc_solve_async(e);
+  if (rc) return rc;
+  return mpc_synchronize(e);
+}
+
+int mpc_get_results(MpcEngine* e, MpcResult* host) {
+  if (!e) return MPC_ERR_INVALID;
+  if (!e->solved) return fail(e, MPC_ERR_STATE, "mpc_get_results before mpc_solve");
+  if (e->n > 0 && !host) return fail(e, MPC_ERR_INVALID, "host buffer is NULL");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (e->n > 0)
+    CUDA_TRY(e, cudaMemcpyAsync(host, e->d_results, size_t(e->n) * sizeof(MpcResult),
+                                cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  return MPC_OK;
+}
+
+int mpc_results_device(MpcEngine* e, const MpcResult** dev) {
+  if (!e || !dev) return MPC_ERR_INVALID;
+  if (!e->solved) return fail(e, MPC_ERR_STATE, "mpc_results_device before mpc_solve");
+  *dev = e->d_results;
+  return MPC_OK;
+}
+
+int mpc_get_solution(MpcEngine* e, int32_t idx, float* x) {
+  if (!e || e->kind != 0 || !x) return MPC_ERR_INVALID;
+  if (!e->solved) return fail(e, MPC_ERR_STATE, "mpc_get_solution before mpc_solve");
+  if (idx < 0 || idx >= e->n) return fail(e, MPC_ERR_INVALID, "problem index out of range");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaMemcpy(x, e->d_x + size_t(idx) * kN, kN * sizeof(float), cudaMemcpyDeviceToHost));
+  return MPC_OK;
+}
+
+int mpc_compute_grf_batch(MpcEngine* e, const MpcStateIn* host_in, MpcResult* host_out, int32_t n) {
+  int rc = mpc_load_states(e, host_in, n);
+  if (rc) return rc;
+  rc = mpc_build_qp_async(e);
+  if (rc) return rc;
+  rc = mpc_solve_async(e);
+  if (rc) return rc;
+  return mpc_get_results(e, host_out);
+}
+
+// ---- ConvexMpc surface, one problem -----------------------------------------
+
+int mpc_qp_mats_from_model(MpcEngine* e, const double* A_mat_d, const double* B_mat_d_list,
+                           const double* mpc_states, const double* mpc_states_d,
+                           const int32_t* contacts, double* hessian, double* gradient, double* lb,
+                           double* ub) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (!A_mat_d || !B_mat_d_list || !mpc_states || !mpc_states_d || !contacts)
+    return fail(e, MPC_ERR_INVALID, "NULL model input");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const size_t nd = 169 + size_t(kH) * 156 + 13 + kS;
+  double* d_model = nullptr;
+  int* d_contacts = nullptr;
+  float* d_out = nullptr;  // P | q | l | u
+  const size_t nout = size_t(kN) * kN + kN + 2 * kM;
+  CUDA_TRY(e, cudaMalloc(&d_model, nd * sizeof(double)));
+  cudaError_t crc = cudaMalloc(&d_contacts, 4 * sizeof(int));
+  if (crc == cudaSuccess) crc = cudaMalloc(&d_out, nout * sizeof(float));
+  std::vector<double> hm(nd);
+  std::memcpy(hm.data(), A_mat_d, 169 * sizeof(double));
+  std::memcpy(hm.data() + 169, B_mat_d_list, size_t(kH) * 156 * sizeof(double));
+  std::memcpy(hm.data() + 169 + kH * 156, mpc_states, 13 * sizeof(double));
+  std::memcpy(hm.data() + 169 + kH * 156 + 13, mpc_states_d, kS * sizeof(double));
+  if (crc == cudaSuccess)
+    crc = cudaMemcpyAsync(d_model, hm.data(), nd * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+  if (crc == cudaSuccess)
+    crc = cudaMemcpyAsync(d_contacts, contacts, 4 * sizeof(int), cudaMemcpyHostToDevice, e->stream);
+  int rc = MPC_OK;
+  std::vector<float> ho(nout);
+  if (crc == cudaSuccess) {
+    ModelIn m{};
+    m.A_d = d_model;
+    m.B_d_list = d_model + 169;
+    m.x0 = d_model + 169 + kH * 156;
+    m.x_ref = d_model + 169 + kH * 156 + 13;
+    m.contacts = d_contacts;
+    rc = launch_build(e, nullptr, m, 1, d_out, d_out + kN * kN, d_out + kN * kN + kN,
+                      d_out + kN * kN + kN + kM);
+    if (rc == MPC_OK) {
+      crc = cudaMemcpyAsync(ho.data(), d_out, nout * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+      if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
+    }
+  }
+  cudaFree(d_model);
+  cudaFree(d_contacts);
+  cudaFree(d_out);
+  if (rc) return rc;
+  if (crc != cudaSuccess) return fail(e, MPC_ERR_CUDA, cudaGetErrorString(crc));
+  if (hessian) for (size_t i = 0; i < size_t(kN) * kN; ++i) hessian[i] = ho[i];
+  if (gradient) for (int i = 0; i < kN; ++i) gradient[i] = ho[size_t(kN) * kN + i];
+  if (lb) for (int i = 0; i < kM; ++i) lb[i] = ho[size_t(kN) * kN + kN + i];
+  if (ub) for (int i = 0; i < kM; ++i) ub[i] = ho[size_t(kN) * kN + kN + kM + i];
+  return MPC_OK;
+}
+
+int mpc_solve_qp(MpcEngine* e, const double* hessian, const double* gradient, const double* lb,
+                 const double* ub, double* solution, int32_t* status, int32_t* iters) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (!hessian || !gradient || !lb || !ub || !solution) return fail(e, MPC_ERR_INVALID, "NULL QP input");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const size_t nin = size_t(kN) * kN + kN + 2 * kM;
+  std::vector<float> hi(nin);
+  for (size_t i = 0; i < size_t(kN) * kN; ++i) hi[i] = (float)hessian[i];
+  for (int i = 0; i < kN; ++i) hi[size_t(kN) * kN + i] = (float)gradient[i];
+  for (int i = 0; i < kM; ++i) hi[size_t(kN) * kN + kN + i] = (float)lb[i];
+  for (int i = 0; i < kM; ++i) hi[size_t(kN) * kN + kN + kM + i] = (float)ub[i];
+  float* d_in = nullptr;
+  float* d_xs = nullptr;
+  MpcResult* d_res = nullptr;
+  CUDA_TRY(e, cudaMalloc(&d_in, nin * sizeof(float)));
+  cudaError_t crc = cudaMalloc(&d_xs, kN * sizeof(float));
+  if (crc == cudaSuccess) crc = cudaMalloc(&d_res, sizeof(MpcResult));
+  if (crc == cudaSuccess)
+    crc = cudaMemcpyAsync(d_in, hi.data(), nin * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+  int rc = MPC_OK;
+  std::vector<float> hx(kN);
+  MpcResult hr{};
+  if (crc == cudaSuccess) {
+    rc = launch_solve(e, d_in, d_in + kN * kN, d_in + kN * kN + kN, d_in + kN * kN + kN + kM, nullptr,
+                      d_res, d_xs, 1);
+    if (rc == MPC_OK) {
+      crc = cudaMemcpyAsync(hx.data(), d_xs, kN * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+      if (crc == cudaSuccess)
+        crc = cudaMemcpyAsync(&hr, d_res, sizeof(MpcResult), cudaMemcpyDeviceToHost, e->stream);
+      if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
+    }
+  }
+  cudaFree(d_in);
+  cudaFree(d_xs);
+  cudaFree(d_res);
+  if (rc) return rc;
+  if (crc != cudaSuccess) return fail(e, MPC_ERR_CUDA, cudaGetErrorString(crc));
+  for (int i = 0; i < kN; ++i) solution[i] = hx[i];
+  if (status) *status = hr.status;
+  if (iters) *iters = hr.iters;
+  return MPC_OK;
+}
+
+// ---- stance-balance QP --------------------------------------------------------
+
+int balance_load_states(MpcEngine* e, const BalanceStateIn* host, int32_t n) {
+  if (!e || e->kind != 1) return MPC_ERR_INVALID;
+  if (n < 0 || (n > 0 && !host)) return fail(e, MPC_ERR_INVALID, "bad state buffer");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  int rc = reserve(e, n);
+  if (rc) return rc;
+  if (n > 0)
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_bstates, host, size_t(n) * sizeof(BalanceStateIn),
+                                cudaMemcpyHostToDevice, e->stream));
+  e->n = n;
+  e->built = true;  // build and solve are one fused kernel for the 12-variable QP
+  e->solved = false;
+  return MPC_OK;
+}
+
+int balance_solve(MpcEngine* e) {
+  if (!e || e->kind != 1) return MPC_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (e->n > 0) {
+    const int warps_per_cta = kBalanceThreads / 32;
+    const int grid = (e->n + warps_per_cta - 1) / warps_per_cta;
+    balance_qp_kernel<<<grid, kBalanceThreads, 0, e->stream>>>(e->d_bstates, e->n, e->d_P, e->d_q, e->d_l,
+                                                               e->d_u, e->d_results, e->bal);
+    ++e->launches;
+    CUDA_TRY(e, cudaGetLastError());
+  }
+  e->solved = true;
+  return MPC_OK;
+}
+
+int balance_get_qp(MpcEngine* e, int32_t idx, float* P, float* q, float* l, float* u) {
+  if (!e || e->kind != 1) return MPC_ERR_INVALID;
+  if (!e->solved) return fail(e, MPC_ERR_STATE, "balance_get_qp before balance_solve");
+  if (idx < 0 || idx >= e->n) return fail(e, MPC_ERR_INVALID, "problem index out of range");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (P) CUDA_TRY(e, cudaMemcpy(P, e->d_P + size_t(idx) * 144, 144 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (q) CUDA_TRY(e, cudaMemcpy(q, e->d_q + size_t(idx) * 12, 12 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (l) CUDA_TRY(e, cudaMemcpy(l, e->d_l + size_t(idx) * 20, 20 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (u) CUDA_TRY(e, cudaMemcpy(u, e->d_u + size_t(idx) * 20, 20 * sizeof(float), cudaMemcpyDeviceToHost));
+  return MPC_OK;
+}
+
+int balance_qp_solve(MpcEngine* e, const BalanceStateIn* host_in, MpcResult* host_out, int32_t n) {
+  int rc = balance_load_states(e, host_in, n);
+  if (rc) return rc;
+  rc = balance_solve(e);
+  if (rc) return rc;
+  return mpc_get_results(e, host_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,260 @@
+/*
+ * mpc_b200.h -- C ABI of the B200-native batched convex-MPC ground-reaction-force
+ * (GRF) engine.
+ *
+ * This header is the drop-in boundary for ONE hot path of
+ * zerenluo123/Go1-QP-MPC-Controller:
+ *
+ *   A1RobotControl::compute_grf (MPC branch and stance-QP branch)
+ *       -> ConvexMpc::{reset, calculate_A_mat_c, calculate_B_mat_c,
+ *                      state_space_discretization, calculate_qp_mats}
+ *       -> OsqpEigen::Solver::{initSolver, solve, getSolution}
+ *
+ * The reference has no FFI: the path is ordinary C++ member calls
+ * (src/a1_cpp/src/ConvexMpc.h:22-35, src/a1_cpp/src/A1RobotControl.h:44).  The
+ * entry points below are what a binding for that path would bind; every one
+ * cites the reference code it replaces.  All functions are extern "C", take
+ * plain pointers and sizes, return int (0 = ok, <0 = MpcError) and never throw.
+ * There is NO CPU fallback behind this ABI: without a CUDA device every compute
+ * entry point fails with MPC_ERR_NO_DEVICE.
+ *
+ * Conventions
+ *   - leg order FL, FR, RL, RR everywhere (A1CtrlStates.h:44-47, :400).
+ *   - 3x3 matrices are row-major float[9]; foot positions are leg-major xyz.
+ *   - caller owns all host buffers; the engine owns its device memory.
+ *   - one engine per host thread; one CUDA stream per engine.
+ *   - functions are synchronous unless suffixed _async.
+ */
+#ifndef MPC_B200_H
+#define MPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Compile-time shapes of the reference (A1Params.h:26-34). */
+#define MPC_STATE_DIM 13
+#define MPC_NUM_DOF 12
+#define MPC_CONSTRAINT_DIM 20
+#define MPC_NUM_LEG 4
+#define MPC_HORIZON_DEFAULT 10 /* PLAN_HORIZON, A1Params.h:26 */
+#define MPC_HORIZON_MAX 30
+#define MPC_INFTY 1e30 /* OsqpEigen::INFTY == OSQP_INFTY (ConvexMpc.cpp:229-237) */
+
+typedef enum MpcError {
+  MPC_OK = 0,
+  MPC_ERR_INVALID = -1,   /* bad argument / config */
+  MPC_ERR_NO_DEVICE = -2, /* no CUDA device: there is no CPU fallback */
+  MPC_ERR_CUDA = -3,      /* CUDA runtime error; text in mpc_last_error */
+  MPC_ERR_STATE = -4,     /* call order violated (e.g. solve before build) */
+  MPC_ERR_UNSUPPORTED = -5
+} MpcError;
+
+/* OSQP status codes, kept so callers of solver.solve()/getStatus see the same
+ * values (osqp 0.6.x constants.h; the reference drops the status,
+ * A1RobotControl.cpp:431,540). */
+#define MPC_STATUS_SOLVED 1
+#define MPC_STATUS_MAX_ITER_REACHED (-2)
+#define MPC_STATUS_PRIMAL_INFEASIBLE (-3)
+#define MPC_STATUS_DUAL_INFEASIBLE (-4)
+#define MPC_STATUS_UNSOLVED (-10)
+
+/* One robot state for the MPC branch: the A1CtrlStates subset read by
+ * compute_grf (A1RobotControl.cpp:452-488, :498-514; fields A1CtrlStates.h:
+ * 348-352, 373-379, 400, 412).  48 x fp32 = 192 B, 16 B aligned so a warp
+ * reads records with 128-bit loads. */
+typedef struct MpcStateIn {
+  float euler[3];        /* root_euler (roll, pitch, yaw), ZYX (Utils.cpp:7-33) */
+  float pos[3];          /* root_pos */
+  float ang_vel[3];      /* root_ang_vel (world) */
+  float lin_vel[3];      /* root_lin_vel (world) */
+  float euler_d[3];      /* root_euler_d; [2] is never read by the reference */
+  float pos_d_z;         /* root_pos_d[2] */
+  float lin_vel_d[3];    /* root_lin_vel_d, BODY frame (rotated at :470) */
+  float ang_vel_d[3];    /* root_ang_vel_d */
+  float rot_mat[9];      /* root_rot_mat, row-major */
+  float foot_pos_abs[12]; /* foot_pos_abs, leg-major xyz */
+  float contacts[4];     /* contacts[i] as 0.0f / 1.0f */
+  float pad;
+} MpcStateIn;
+
+/* One robot state for the stance-balance QP branch (A1RobotControl.cpp:377-444).
+ * 64 x fp32 = 256 B. */
+typedef struct BalanceStateIn {
+  float euler[3];
+  float pos[3];
+  float ang_vel[3];
+  float lin_vel[3];
+  float euler_d[3];
+  float pos_d[3];
+  float lin_vel_d[3]; /* body frame */
+  float ang_vel_d[3];
+  float rot_mat[9];   /* root_rot_mat */
+  float rot_mat_z[9]; /* root_rot_mat_z (yaw only) */
+  float foot_pos_abs[12];
+  float contacts[4];
+  float pad[6];
+} BalanceStateIn;
+
+/* One result: first-step GRF in the BODY frame (Rᵀ·f, A1RobotControl.cpp:
+ * 439-444, :558-561), 3 floats per leg.  On a NaN solution the reference leaves
+ * the force untouched (:559); the engine writes zeros and flags status.
+ * 64 B. */
+typedef struct MpcResult {
+  float grf[12];
+  int32_t status;      /* MPC_STATUS_* */
+  int32_t iters;       /* ADMM iterations run */
+  int32_t rho_updates; /* refactorisations after the first */
+  float pri_res;       /* unscaled primal residual at exit */
+} MpcResult;
+
+/* OSQP settings (osqp 0.6.x names).  The reference leaves all but verbose and
+ * warm_start at library defaults (A1RobotControl.cpp:523-524). */
+typedef struct MpcSolverSettings {
+  double rho;
+  double sigma;
+  double alpha;
+  double eps_abs;
+  double eps_rel;
+  double eps_prim_inf;
+  double eps_dual_inf;
+  int32_t max_iter;
+  int32_t check_termination;
+  int32_t scaling; /* Ruiz iterations */
+  int32_t adaptive_rho;
+  int32_t adaptive_rho_interval; /* pinned: the library default is wall-clock dependent */
+  double adaptive_rho_tolerance;
+} MpcSolverSettings;
+
+/* Engine-wide constants: what ConvexMpc's constructor and A1CtrlStates hold
+ * once per robot model (ConvexMpc.cpp:7-68; A1CtrlStates.h:359-367). */
+typedef struct MpcConfig {
+  int32_t horizon;      /* PLAN_HORIZON; 10 or 30 */
+  int32_t reserved0;
+  double dt;            /* mpc_dt, A1RobotControl.cpp:462 */
+  double mu;            /* ConvexMpc.cpp:8 */
+  double fz_min;        /* ConvexMpc.cpp:223 */
+  double fz_max;        /* ConvexMpc.cpp:224 */
+  double mass;          /* robot_mass */
+  double inertia[9];    /* a1_trunk_inertia, row-major */
+  double q_weights[13]; /* state.q_weights */
+  double r_weights[12]; /* state.r_weights */
+  MpcSolverSettings osqp;
+} MpcConfig;
+
+/* Constants of the stance-balance QP (A1RobotControl.cpp:11-15) plus the PD
+ * gains it reads from A1CtrlStates (A1CtrlStates.h:429-432). */
+typedef struct BalanceConfig {
+  double Q[6];  /* 1,1,1,400,400,100 */
+  double R;     /* 1e-3 */
+  double mu;    /* 0.7 */
+  double F_min; /* 0 */
+  double F_max; /* 180 */
+  double mass;
+  double kp_linear[3];
+  double kd_linear[3];
+  double kp_angular[3];
+  double kd_angular[3];
+  MpcSolverSettings osqp;
+} BalanceConfig;
+
+typedef struct MpcEngine MpcEngine;
+
+/* ---- configuration ------------------------------------------------------ */
+
+/* OSQP 0.6.x library defaults, i.e. what the reference runs with. */
+int mpc_settings_osqp_default(MpcSolverSettings *s);
+/* BASELINE.json benchmark settings: eps_abs = eps_rel = 1e-5, interval 50. */
+int mpc_settings_benchmark(MpcSolverSettings *s);
+/* config/gazebo_a1_mpc.yaml weights and mass, H=10, dt 0.0025, mu 0.3,
+ * fz in [0,180], benchmark solver settings. */
+int mpc_config_default(MpcConfig *cfg);
+/* config/hardware_a1_mpc.yaml weights and mass (the well-conditioned set). */
+int mpc_config_hardware(MpcConfig *cfg);
+/* A1RobotControl.cpp:11-15 constants + config/gazebo_a1_qp.yaml gains. */
+int balance_config_default(BalanceConfig *cfg);
+
+/* ---- synthetic inputs (SURVEY.md 8d generator; host only, no device) ----- */
+
+/* Fills out[0..n) with the states first_index .. first_index+n-1 of the
+ * counter-based stream `seed`.  Deterministic and order independent. */
+int mpc_generate_states(uint64_t seed, uint64_t first_index, int32_t n, MpcStateIn *out);
+int balance_generate_states(uint64_t seed, uint64_t first_index, int32_t n, BalanceStateIn *out);
+
+/* ---- engine life cycle --------------------------------------------------- */
+
+/* Replaces constructing ConvexMpc + the OsqpEigen::Solver member
+ * (A1RobotControl.cpp:447, A1RobotControl.h:67).  `device` is a CUDA ordinal. */
+int mpc_engine_create(const MpcConfig *cfg, int32_t device, MpcEngine **out);
+void mpc_engine_destroy(MpcEngine *e);
+/* Text of the last error on this engine (or of the last create failure when
+ * e == NULL).  Never NULL. */
+const char *mpc_last_error(const MpcEngine *e);
+/* Make all engine work run on a caller-owned cudaStream_t (e.g. torch's current
+ * stream) instead of the engine's own stream. */
+int mpc_set_stream(MpcEngine *e, void *cuda_stream);
+int mpc_synchronize(MpcEngine *e);
+/* Number of kernels this engine has launched since creation. */
+int64_t mpc_kernel_launches(const MpcEngine *e);
+
+/* ---- batched MPC GRF solve (compute_grf, MPC branch) ---------------------- */
+
+/* K0 loader: host AoS records -> device (A1RobotControl.cpp:452-456 packing
+ * happens on the device). */
+int mpc_load_states(MpcEngine *e, const MpcStateIn *host, int32_t n);
+/* Same, but the records already live in device memory (no copy is made; the
+ * buffer must stay valid until results are read). */
+int mpc_set_states_device(MpcEngine *e, const MpcStateIn *dev, int32_t n);
+/* K1+K2: ConvexMpc::calculate_A_mat_c .. calculate_qp_mats for every loaded
+ * state (ConvexMpc.cpp:110-245; A1RobotControl.cpp:472-518). */
+int mpc_build_qp(MpcEngine *e);
+int mpc_build_qp_async(MpcEngine *e);
+/* Parity/debug read-back of one problem: P (n x n row-major), q (n), l, u (m),
+ * with n = 12 H, m = 20 H.  Any pointer may be NULL. */
+int mpc_get_qp(MpcEngine *e, int32_t idx, float *P, float *q, float *l, float *u);
+/* K3+K4+K5: OSQP-equivalent ADMM on every built problem, then the first-step
+ * rotation to the body frame (A1RobotControl.cpp:522-561). */
+int mpc_solve(MpcEngine *e);
+int mpc_solve_async(MpcEngine *e);
+/* K5 writer read-back: n results to host. */
+int mpc_get_results(MpcEngine *e, MpcResult *host);
+/* Device pointer of the result array (n x MpcResult), valid until the next
+ * load/solve. */
+int mpc_results_device(MpcEngine *e, const MpcResult **dev);
+/* Full primal solution of one problem (n floats, world frame, unscaled). */
+int mpc_get_solution(MpcEngine *e, int32_t idx, float *x);
+/* The whole compute_grf MPC branch for n robots: host records in, host results
+ * out (H2D + build + solve + D2H). */
+int mpc_compute_grf_batch(MpcEngine *e, const MpcStateIn *host_in, MpcResult *host_out, int32_t n);
+
+/* ---- ConvexMpc surface, one problem (ConvexMpc.h:22-35) -------------------- */
+
+/* calculate_qp_mats for ONE problem from caller-written model matrices, the way
+ * the reference's callers use the public members: A_mat_d (13x13 row-major),
+ * B_mat_d_list (13H x 12 row-major, A1RobotControl.cpp:513), mpc_states (13),
+ * mpc_states_d (13H), contacts[4].  Outputs hessian (n x n), gradient (n),
+ * lb, ub (m).  Runs the general dense build kernel on the device. */
+int mpc_qp_mats_from_model(MpcEngine *e, const double *A_mat_d, const double *B_mat_d_list,
+                           const double *mpc_states, const double *mpc_states_d,
+                           const int32_t *contacts, double *hessian, double *gradient,
+                           double *lb, double *ub);
+/* OsqpEigen initSolver+solve+getSolution for ONE dense problem with the MPC
+ * friction-pyramid constraint matrix (ConvexMpc.cpp:46-58): cold start. */
+int mpc_solve_qp(MpcEngine *e, const double *hessian, const double *gradient, const double *lb,
+                 const double *ub, double *solution, int32_t *status, int32_t *iters);
+
+/* ---- stance-balance QP (compute_grf, QP branch) --------------------------- */
+
+int balance_engine_create(const BalanceConfig *cfg, int32_t device, MpcEngine **out);
+/* A1RobotControl.cpp:377-444 for n robots: host in, host out. */
+int balance_qp_solve(MpcEngine *e, const BalanceStateIn *host_in, MpcResult *host_out, int32_t n);
+int balance_load_states(MpcEngine *e, const BalanceStateIn *host, int32_t n);
+int balance_solve(MpcEngine *e);
+int balance_get_qp(MpcEngine *e, int32_t idx, float *P, float *q, float *l, float *u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPC_B200_H */
