@@ -11,14 +11,20 @@
 // Precision (measured on the CPU arithmetic model, see DESIGN.md "precision"):
 // the GRF parity gate (1e-3 vs the fp64 oracle at eps 1e-5) needs the Hessian
 // ACCUMULATED in fp64 and K, K^-1 and the ADMM iterates in fp64; fp32 is fine
-// for STORAGE of P, q, l, u and for the Ruiz norm passes.  B200 runs DFMA at
-// half the FFMA rate, so the path computes in f64 and stores QP data in f32.
+// for STORAGE of P, q, l, u.  B200 runs DFMA at half the FFMA rate (measured
+// 17.1 T DFMA/s), so the path computes in f64 and stores QP data in f32.
 //
 // Thread layout shared by both kernels (H = 10, n = 120): 480 threads =
-// 120 rows x 4 parts; thread (r, part) owns columns part*30 .. part*30+29 of
-// row r.  Rows of operand vectors / matrices are stored "chunk padded": chunk
-// `part` starts at element part*32 so every thread's 30 operands are 16 B
-// aligned (LDS.128) and bank-conflict free (4 distinct addresses per warp).
+// 30 row groups x 16 column groups; thread (rg, cg) owns the 4 x 8 register
+// tile rows 4rg..4rg+3 x columns {32i + 2cg, 32i + 2cg + 1 : i = 0..3}.
+// Columns are interleaved in pairs at stride 32 so that one LDS.128 per i
+// fetches a thread's column pair and the 16 lanes of a half-warp read 256
+// contiguous bytes (no bank conflicts); the other half-warp (next row group)
+// reads the same addresses (broadcast).  Row sums are finished with a
+// reduce-scatter over the 16 lanes (5 double shuffles for 4 rows).  Matrices
+// are padded to 128 columns; columns 120..127 are structurally zero.
+// v1 of this file used a 1 x 30 tile: 4-way bank conflicts and 3x the operand
+// traffic (profiles/r01_v1_admm_solve_ncu_summary.txt).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -34,9 +40,7 @@ constexpr int kS = 13 * kH;  // 130 stacked states
 constexpr int kM = 20 * kH;  // 200 constraint rows
 constexpr int kLegSteps = 4 * kH;
 constexpr int kThreads = 480;
-constexpr int kChunk = 30;
-constexpr int kChunkPad = 32;
-constexpr int kRowPad = 128;
+constexpr int kNP = 128;     // padded column count
 constexpr int kWarps = kThreads / 32;
 
 // float offsets inside MpcStateIn
@@ -56,13 +60,46 @@ struct SolveParams {
   int max_iter, check_termination, scaling, adaptive_rho, adaptive_rho_interval;
 };
 
-__host__ __device__ constexpr int padj(int j) { return (j / kChunk) * kChunkPad + (j % kChunk); }
+// column owned by column group cg at tile position jj (0..7)
+__host__ __device__ constexpr int tile_col(int cg, int jj) { return 32 * (jj >> 1) + 2 * cg + (jj & 1); }
+
+// Reduce 4 per-row partials over the 16 column-group lanes of a half-warp.
+// Returns the total of row `owned_row(cg)`; lanes cg, cg+1, cg+2, cg+3 (cg%4==0)
+// all hold the same value.
+__device__ __forceinline__ int owned_row(int cg) { return 2 * ((cg >> 3) & 1) + ((cg >> 2) & 1); }
+
+__device__ __forceinline__ double reduce_scatter_sum(const double (&s)[4], int cg) {
+  const bool h8 = (cg & 8) != 0, h4 = (cg & 4) != 0;
+  double k0 = h8 ? s[2] : s[0], k1 = h8 ? s[3] : s[1];
+  const double t0 = h8 ? s[0] : s[2], t1 = h8 ? s[1] : s[3];
+  k0 += __shfl_xor_sync(0xffffffffu, t0, 8);
+  k1 += __shfl_xor_sync(0xffffffffu, t1, 8);
+  double k = h4 ? k1 : k0;
+  const double t = h4 ? k0 : k1;
+  k += __shfl_xor_sync(0xffffffffu, t, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
+__device__ __forceinline__ double reduce_scatter_max(const double (&s)[4], int cg) {
+  const bool h8 = (cg & 8) != 0, h4 = (cg & 4) != 0;
+  double k0 = h8 ? s[2] : s[0], k1 = h8 ? s[3] : s[1];
+  const double t0 = h8 ? s[0] : s[2], t1 = h8 ? s[1] : s[3];
+  k0 = fmax(k0, __shfl_xor_sync(0xffffffffu, t0, 8));
+  k1 = fmax(k1, __shfl_xor_sync(0xffffffffu, t1, 8));
+  double k = h4 ? k1 : k0;
+  const double t = h4 ? k0 : k1;
+  k = fmax(k, __shfl_xor_sync(0xffffffffu, t, 4));
+  k = fmax(k, __shfl_xor_sync(0xffffffffu, k, 2));
+  k = fmax(k, __shfl_xor_sync(0xffffffffu, k, 1));
+  return k;
+}
 
 // ---------------------------------------------------------------------------
 // K0+K1+K2: QP build.  One CTA per problem, grid-stride over problems.
 // ---------------------------------------------------------------------------
 struct BuildSmem {
-  double Bq[kS * kRowPad];       // B_qp, rows chunk-padded (133,120 B)
+  double Bq[kS * kNP];           // B_qp, row stride 128 (133,120 B); cols 120..127 zero
   double Apow[(kH + 1) * 169];   // A_d^0 .. A_d^H
   double Bd[kH * 156];           // B_mat_d_list
   double xref[kS];
@@ -89,7 +126,7 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, f
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BuildSmem& sm = *reinterpret_cast<BuildSmem*>(smem_raw);
   const int tid = threadIdx.x;
-  const int r = tid >> 2, part = tid & 3;
+  const int rg = tid >> 4, cg = tid & 15;
 
   for (int p = blockIdx.x; p < num; p += gridDim.x) {
     __syncthreads();  // smem reuse across problems
@@ -218,7 +255,7 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, f
       if (tid < 4) sm.contacts[tid] = model.contacts[size_t(p) * 4 + tid] != 0;
     }
     // zero B_qp (upper blocks stay zero, ConvexMpc.cpp:94)
-    for (int idx = tid; idx < kS * kRowPad / 2; idx += kThreads)
+    for (int idx = tid; idx < kS * kNP / 2; idx += kThreads)
       reinterpret_cast<double2*>(sm.Bq)[idx] = make_double2(0.0, 0.0);
     __syncthreads();
     // ---- A_qp powers: block i = block (i-1) * A_d (ConvexMpc.cpp:185-191) ----
@@ -247,7 +284,7 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, f
       double s = 0.0;
 #pragma unroll
       for (int k = 0; k < 13; ++k) s += Ap[rr * 13 + k] * Bj[k * 12 + cc];
-      sm.Bq[(13 * i + rr) * kRowPad + padj(12 * j + cc)] = s;
+      sm.Bq[(13 * i + rr) * kNP + 12 * j + cc] = s;
     }
     // tmp = Q (A_qp x0 - x_ref) (ConvexMpc.cpp:215-216)
     if (tid < kS) {
@@ -261,37 +298,51 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, f
     __syncthreads();
     // ---- K2: Hessian = B_qp' Q B_qp + R, fp64 accumulate (ConvexMpc.cpp:207-211) ----
     {
-      double acc[kChunk];
+      double acc[4][8];
 #pragma unroll
-      for (int jj = 0; jj < kChunk; ++jj) acc[jj] = 0.0;
-      const int rb = r / 12, cb0 = (part * kChunk) / 12;
-      const int kstart = 13 * (rb > cb0 ? rb : cb0);  // rows above are structurally zero
-      const int rp = padj(r);
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) acc[rr][jj] = 0.0;
+      // rows of B_qp above step block (4rg)/12 are structurally zero in these columns of B_qp'
+      const int kstart = 13 * (rg / 3);
       for (int k = kstart; k < kS; ++k) {
-        const double b = sm.Bq[k * kRowPad + rp] * bp.Qd[k % 13];
-        const double2* row = reinterpret_cast<const double2*>(&sm.Bq[k * kRowPad + part * kChunkPad]);
+        const double qk = bp.Qd[k % 13];
+        const double2* rowp = reinterpret_cast<const double2*>(&sm.Bq[k * kNP + 4 * rg]);
+        const double2 r01 = rowp[0], r23 = rowp[1];
+        const double rop[4] = {r01.x * qk, r01.y * qk, r23.x * qk, r23.y * qk};
+        const double2* colp = reinterpret_cast<const double2*>(&sm.Bq[k * kNP + 2 * cg]);
+        double cop[8];
 #pragma unroll
-        for (int j2 = 0; j2 < kChunk / 2; ++j2) {
-          const double2 v = row[j2];
-          acc[2 * j2] = fma(b, v.x, acc[2 * j2]);
-          acc[2 * j2 + 1] = fma(b, v.y, acc[2 * j2 + 1]);
+        for (int i = 0; i < 4; ++i) {
+          const double2 v = colp[16 * i];
+          cop[2 * i] = v.x;
+          cop[2 * i + 1] = v.y;
         }
-      }
-      float* Pp = P_out + size_t(p) * kN * kN + r * kN + part * kChunk;
 #pragma unroll
-      for (int j2 = 0; j2 < kChunk / 2; ++j2) {
-        const int c0 = part * kChunk + 2 * j2;
-        double v0 = acc[2 * j2], v1 = acc[2 * j2 + 1];
-        if (c0 == r) v0 += bp.Rd[r % 12];
-        if (c0 + 1 == r) v1 += bp.Rd[r % 12];
-        reinterpret_cast<float2*>(Pp)[j2] = make_float2((float)v0, (float)v1);
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) acc[rr][jj] = fma(rop[rr], cop[jj], acc[rr][jj]);
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int row = 4 * rg + rr;
+        float* Pp = P_out + size_t(p) * kN * kN + row * kN;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = 32 * i + 2 * cg;
+          if (c0 < kN) {
+            double v0 = acc[rr][2 * i], v1 = acc[rr][2 * i + 1];
+            if (c0 == row) v0 += bp.Rd[row % 12];
+            if (c0 + 1 == row) v1 += bp.Rd[row % 12];
+            *reinterpret_cast<float2*>(Pp + c0) = make_float2((float)v0, (float)v1);
+          }
+        }
       }
     }
     // ---- gradient = B_qp' tmp (ConvexMpc.cpp:217) ----
     if (tid < kN) {
-      const int cp = padj(tid);
       double s = 0.0;
-      for (int k = 13 * (tid / 12); k < kS; ++k) s = fma(sm.Bq[k * kRowPad + cp], sm.tmp[k], s);
+      for (int k = 13 * (tid / 12); k < kS; ++k) s = fma(sm.Bq[k * kNP + tid], sm.tmp[k], s);
       q_out[size_t(p) * kN + tid] = (float)s;
     }
     // ---- bounds, contacts replicated over the horizon (ConvexMpc.cpp:223-245) ----
@@ -314,19 +365,18 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, f
 // counter (iteration counts vary 100..400, so static assignment leaves a tail).
 // ---------------------------------------------------------------------------
 struct SolveSmem {
-  float P[kN * kRowPad];    // unscaled Hessian, rows chunk-padded (61,440 B)
-  double rhs[kRowPad];      // chunk-padded: operand of the K^-1 matvec
-  double xD[kRowPad];       // chunk-padded: D .* x for P x
-  double Dp[kRowPad];       // chunk-padded D
-  double buf[2][kRowPad];   // sweep: published pivot row
-  float Df[kRowPad];        // chunk-padded float copy of D for the norm passes
+  double P[kN * kNP];       // unscaled Hessian as f64, row stride 128, cols 120..127 zero (122,880 B)
+  double rhs[kNP];          // operand of the K^-1 matvec (pad = 0)
+  double xD[kNP];           // D .* x for P x (pad = 0)
+  double Dp[kNP];           // D (pad = 0)
+  double buf[2][kNP];       // sweep: published pivot row (pad = 0)
   double piv[2][2];
-  double x[kN], xt[kN], qb[kN], D[kN], Dinv[kN], q0[kN];
+  double x[kN], xt[kN], qb[kN], Dinv[kN], q0[kN];
   double z[kM], y[kM], lb[kM], ub[kM], E[kM], Einv[kM], rv[kM], rinv[kM], w[kM];
   double Av[kLegSteps * 9];  // scaled constraint entries per leg-step
   double G[kLegSteps * 9];   // A' diag(rho) A, 3x3 block per leg-step
   double red[kWarps * 16];
-  double scal[8];            // 0:c 1:cinv 2:rho 3:ct
+  double scal[8];            // 0:c 1:cinv 2:rho 3:ct 4:pri_res
   int flags[8];              // 0:done 1:status 2:refactor 3:problem index
   int ctype[kM];
 };
@@ -346,33 +396,40 @@ __device__ __forceinline__ double limit_scaling(double v) {  // osqp scaling.c
   return v > 1e4 ? 1e4 : v;
 }
 
-// max_j |P_rj| * D_j over the whole row r (fp32), valid on all 4 lanes of the row
-__device__ __forceinline__ float row_norm_pass(const SolveSmem& sm, int r, int part) {
-  const float4* prow = reinterpret_cast<const float4*>(&sm.P[r * kRowPad + part * kChunkPad]);
-  const float4* drow = reinterpret_cast<const float4*>(&sm.Df[part * kChunkPad]);
-  float m = 0.0f;
+// max_j |P_rj| * D_j for the thread's owned row (valid on the 4 lanes sharing it)
+__device__ __forceinline__ double row_norm_pass(const SolveSmem& sm, int rg, int cg) {
+  double dcol[8];
+  const double2* dp = reinterpret_cast<const double2*>(&sm.Dp[2 * cg]);
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {  // pad lanes hold P = 0
-    const float4 a = prow[j4], d = drow[j4];
-    m = fmaxf(m, fabsf(a.x) * d.x);
-    m = fmaxf(m, fabsf(a.y) * d.y);
-    m = fmaxf(m, fabsf(a.z) * d.z);
-    m = fmaxf(m, fabsf(a.w) * d.w);
+  for (int i = 0; i < 4; ++i) {
+    const double2 v = dp[16 * i];
+    dcol[2 * i] = v.x;
+    dcol[2 * i + 1] = v.y;
   }
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-  return m;
+  double m[4];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const double2* pp = reinterpret_cast<const double2*>(&sm.P[(4 * rg + rr) * kNP + 2 * cg]);
+    double mm = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double2 v = pp[16 * i];
+      mm = fmax(mm, fabs(v.x) * dcol[2 * i]);
+      mm = fmax(mm, fabs(v.y) * dcol[2 * i + 1]);
+    }
+    m[rr] = mm;
+  }
+  return reduce_scatter_max(m, cg);
 }
 
-// Build K = c D P D + sigma I + A' diag(rho) A into registers, then overwrite it
-// with -K^-1 by the symmetric sweep operator (one pivot per step, n steps).
-// Step k: the 4 threads of row k publish the row (with the pivot replaced by
-// d-1 so the generic rank-1 update also produces column k), everybody applies
+// Build K = c D P D + sigma I + A' diag(rho) A into the register tiles, then
+// overwrite it with -K^-1 by the symmetric sweep operator (one pivot per step).
+// Step k: the 16 threads of row group k/4 publish row k (the pivot d replaced
+// by d-1 so the generic rank-1 update also produces column k); everybody applies
 //   a_rj <- a_rj - (a_kr / d) * a'_kj      (r != k)
 //   a_kj <- a_kj / d,  a_kk <- -1/d        (r == k)
-__device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kChunk], int r, int part,
+__device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[4][8], int rg, int cg,
                                                int tid, double sigma) {
-  // G blocks
   if (tid < kLegSteps * 9) {
     const int k = tid / 9, rr = (tid % 9) / 3, cc = tid % 3;
     const double* av = &sm.Av[k * 9];
@@ -390,82 +447,113 @@ __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kChunk
   }
   __syncthreads();
   {
-    const double cDr = sm.scal[0] * sm.D[r];
-    const float* prow = &sm.P[r * kRowPad + part * kChunkPad];
-    const double* drow = &sm.Dp[part * kChunkPad];
+    const double c = sm.scal[0];
+    double dcol[8];
+    const double2* dp = reinterpret_cast<const double2*>(&sm.Dp[2 * cg]);
 #pragma unroll
-    for (int jj = 0; jj < kChunk; ++jj) {
-      const int col = part * kChunk + jj;
-      double v = cDr * (double)prow[jj] * drow[jj];
-      if (col == r) v += sigma;
-      if (col / 3 == r / 3) v += sm.G[(r / 3) * 9 + (r % 3) * 3 + (col % 3)];
-      a[jj] = v;
+    for (int i = 0; i < 4; ++i) {
+      const double2 v = dp[16 * i];
+      dcol[2 * i] = v.x;
+      dcol[2 * i + 1] = v.y;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int row = 4 * rg + rr;
+      const double cDr = c * sm.Dp[row];
+      const double2* pp = reinterpret_cast<const double2*>(&sm.P[row * kNP + 2 * cg]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double2 v = pp[16 * i];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 32 * i + 2 * cg + e;
+          double val = cDr * (e ? v.y : v.x) * dcol[2 * i + e];
+          if (col == row) val += sigma;
+          if (col / 3 == row / 3) val += sm.G[(row / 3) * 9 + (row % 3) * 3 + (col % 3)];
+          a[rr][2 * i + e] = val;
+        }
+      }
     }
   }
-  const int rp = padj(r);
   for (int k = 0; k < kN; ++k) {
     const int cur = k & 1;
-    if (r == k) {
-      double2* dst = reinterpret_cast<double2*>(&sm.buf[cur][part * kChunkPad]);
-      const bool has_pivot = (k / kChunk) == part;
-      const int kj = k - part * kChunk;
+    const bool mine = (rg == (k >> 2));
+    const int kr = k & 3;
+    if (mine) {
+      // publish row k; its owner of column k swaps the pivot d for d-1
+      double v[8];
 #pragma unroll
-      for (int j2 = 0; j2 < kChunk / 2; ++j2) {
-        double v0 = a[2 * j2], v1 = a[2 * j2 + 1];
-        if (has_pivot && kj == 2 * j2) { sm.piv[cur][0] = v0; v0 -= 1.0; }
-        if (has_pivot && kj == 2 * j2 + 1) { sm.piv[cur][0] = v1; v1 -= 1.0; }
-        dst[j2] = make_double2(v0, v1);
+      for (int jj = 0; jj < 8; ++jj)
+        v[jj] = (kr == 0) ? a[0][jj] : (kr == 1) ? a[1][jj] : (kr == 2) ? a[2][jj] : a[3][jj];
+      if (((k >> 1) & 15) == cg) {
+        const int kj = 2 * (k >> 5) + (k & 1);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          if (jj == kj) { sm.piv[cur][0] = v[jj]; v[jj] -= 1.0; }
       }
+      double2* dst = reinterpret_cast<double2*>(&sm.buf[cur][2 * cg]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[16 * i] = make_double2(v[2 * i], v[2 * i + 1]);
     }
     __syncthreads();
-    const double d = sm.piv[cur][0];
-    const double dinv = __drcp_rn(d);
-    const double2* src = reinterpret_cast<const double2*>(&sm.buf[cur][part * kChunkPad]);
-    if (r != k) {
-      // a_rk == a_kr by symmetry, so the published row also supplies column k;
-      // buf[k] itself was replaced by d-1 (r != k never reads it as vr)
-      const double vr = sm.buf[cur][rp];
-      const double w = -vr * dinv;
+    const double dinv = __drcp_rn(sm.piv[cur][0]);
+    double vcol[8];
+    {
+      const double2* src = reinterpret_cast<const double2*>(&sm.buf[cur][2 * cg]);
 #pragma unroll
-      for (int j2 = 0; j2 < kChunk / 2; ++j2) {
-        const double2 v = src[j2];
-        a[2 * j2] = fma(w, v.x, a[2 * j2]);
-        a[2 * j2 + 1] = fma(w, v.y, a[2 * j2 + 1]);
+      for (int i = 0; i < 4; ++i) {
+        const double2 v = src[16 * i];
+        vcol[2 * i] = v.x;
+        vcol[2 * i + 1] = v.y;
       }
-    } else {
-      const int kj = k - part * kChunk;  // only meaningful when this part holds the pivot
-      const bool has_pivot = (k / kChunk) == part;
+    }
+    // a_rk == a_kr by symmetry, so the published row also supplies column k
+    const double2* rsrc = reinterpret_cast<const double2*>(&sm.buf[cur][4 * rg]);
+    const double2 w01 = rsrc[0], w23 = rsrc[1];
+    const double w[4] = {-w01.x * dinv, -w01.y * dinv, -w23.x * dinv, -w23.y * dinv};
 #pragma unroll
-      for (int jj = 0; jj < kChunk; ++jj) {
-        double v = a[jj] * dinv;
-        if (has_pivot && jj == kj) v = -dinv;
-        a[jj] = v;
+    for (int rr = 0; rr < 4; ++rr) {
+      if (mine && rr == kr) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int col = 32 * (jj >> 1) + 2 * cg + (jj & 1);
+          a[rr][jj] = (col == k) ? -dinv : a[rr][jj] * dinv;
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) a[rr][jj] = fma(w[rr], vcol[jj], a[rr][jj]);
       }
     }
   }
   __syncthreads();
 }
 
-// x~ = K^-1 rhs with a = -K^-1 in registers; result valid on all 4 lanes of row r
-__device__ __forceinline__ double kinv_matvec(const SolveSmem& sm, const double (&a)[kChunk], int part) {
-  const double2* src = reinterpret_cast<const double2*>(&sm.rhs[part * kChunkPad]);
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+// x~ = K^-1 rhs with a = -K^-1 in the register tiles; returns x~ of the thread's owned row
+__device__ __forceinline__ double kinv_matvec(const SolveSmem& sm, const double (&a)[4][8], int cg) {
+  const double2* src = reinterpret_cast<const double2*>(&sm.rhs[2 * cg]);
+  double v[8];
 #pragma unroll
-  for (int j2 = 0; j2 < kChunk / 2; j2 += 3) {
-    const double2 v0 = src[j2], v1 = src[j2 + 1], v2 = src[j2 + 2];
-    s0 = fma(a[2 * j2], v0.x, s0);
-    s0 = fma(a[2 * j2 + 1], v0.y, s0);
-    s1 = fma(a[2 * j2 + 2], v1.x, s1);
-    s1 = fma(a[2 * j2 + 3], v1.y, s1);
-    s2 = fma(a[2 * j2 + 4], v2.x, s2);
-    s2 = fma(a[2 * j2 + 5], v2.y, s2);
+  for (int i = 0; i < 4; ++i) {
+    const double2 t = src[16 * i];
+    v[2 * i] = t.x;
+    v[2 * i + 1] = t.y;
   }
-  double s = (s0 + s1) + s2;
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  return -s;
+  double s[4];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    double s0 = a[rr][0] * v[0], s1 = a[rr][1] * v[1];
+#pragma unroll
+    for (int jj = 2; jj < 8; jj += 2) {
+      s0 = fma(a[rr][jj], v[jj], s0);
+      s1 = fma(a[rr][jj + 1], v[jj + 1], s1);
+    }
+    s[rr] = s0 + s1;
+  }
+  return -reduce_scatter_sum(s, cg);
 }
 
+// registers are allocated per 4 warps: 480 threads count as 16 warps, so 128 is the cap
+// (__maxnreg__(136) fails to launch: "too many resources requested")
 __global__ void __launch_bounds__(kThreads, 1)
 admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_all,
                   const float* __restrict__ l_all, const float* __restrict__ u_all,
@@ -476,17 +564,20 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int r = tid >> 2, part = tid & 3;
+  const int rg = tid >> 4, cg = tid & 15;
+  // variable ownership: lanes with cg % 4 == 0 own row r of their row group
+  const bool vown = (cg & 3) == 0;
+  const int r = 4 * rg + owned_row(cg);
   // constraint-row ownership: 6 leg-steps (30 lanes) per warp, warps 0..6
   const int ck = warp * 6 + lane / 5;  // leg-step
   const int ce = lane % 5;             // row inside the leg-step
   const bool crow = (warp < 7) && (lane < 30) && (ck < kLegSteps);
-  const int ci = 5 * ck + ce;          // constraint row
-  const int cja = 3 * ck + ((ce < 2) ? 0 : 1);  // lateral variable of the row
-  const int cjz = 3 * ck + 2;
+  const int ci = crow ? 5 * ck + ce : 0;                   // constraint row
+  const int cja = crow ? 3 * ck + ((ce < 2) ? 0 : 1) : 0;  // lateral variable of the row
+  const int cjz = crow ? 3 * ck + 2 : 0;
   const double mu = sp.mu;
 
-  double a[kChunk];  // row r, columns part*30.. of -K^-1
+  double a[4][8];  // register tile of -K^-1
 
   for (;;) {
     __syncthreads();
@@ -495,26 +586,23 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
     const int p = sm.flags[3];
     if (p >= num) break;
 
-    // ---- load P (coalesced float4), q, l, u ----
+    // ---- load P (coalesced float4 -> f64 smem), q, l, u ----
     {
       const float4* src = reinterpret_cast<const float4*>(P_all + size_t(p) * kN * kN);
       for (int idx = tid; idx < kN * kN / 4; idx += kThreads) {
-        const float4 v = src[idx];
-        const int e = idx * 4, rr = e / kN, cc = e % kN;  // 120 % 4 == 0: a float4 never straddles rows
-        float* dst = &sm.P[rr * kRowPad];
-        dst[padj(cc)] = v.x;
-        dst[padj(cc + 1)] = v.y;
-        dst[padj(cc + 2)] = v.z;
-        dst[padj(cc + 3)] = v.w;
+        const float4 v = __ldg(src + idx);
+        const int e = idx * 4, rr = e / kN, cc = e % kN;  // 120 % 4 == 0: never straddles rows
+        double2* dst = reinterpret_cast<double2*>(&sm.P[rr * kNP + cc]);
+        dst[0] = make_double2((double)v.x, (double)v.y);
+        dst[1] = make_double2((double)v.z, (double)v.w);
       }
-      // pad lanes of every chunk must read as zero in the norm passes
-      if (tid < kN * 4) {
-        sm.P[(tid >> 2) * kRowPad + (tid & 3) * kChunkPad + 30] = 0.0f;
-        sm.P[(tid >> 2) * kRowPad + (tid & 3) * kChunkPad + 31] = 0.0f;
+      if (tid < kN) {
+        double2* padp = reinterpret_cast<double2*>(&sm.P[tid * kNP + kN]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) padp[i] = make_double2(0.0, 0.0);
       }
-      if (tid < kRowPad) {
-        sm.Df[tid] = 1.0f;
-        sm.Dp[tid] = 1.0;
+      if (tid < kNP) {
+        sm.Dp[tid] = (tid < kN) ? 1.0 : 0.0;
         sm.rhs[tid] = 0.0;
         sm.xD[tid] = 0.0;
         sm.buf[0][tid] = 0.0;
@@ -522,7 +610,6 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
       }
       if (tid < kN) {
         sm.q0[tid] = (double)q_all[size_t(p) * kN + tid];
-        sm.D[tid] = 1.0;
         sm.x[tid] = 0.0;
         sm.xt[tid] = 0.0;
       }
@@ -546,10 +633,10 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
     // ---- K3a: modified Ruiz equilibration (osqp scaling.c scale_data) ----
     // scaled quantities are never materialised: P_bar = c D P D, A_bar = E A D.
     if (sp.scaling > 0) {
-      double nP = (double)row_norm_pass(sm, r, part);  // c = 1, D = 1
+      double nP = row_norm_pass(sm, rg, cg);  // c = 1, D = 1
       for (int it = 0; it < sp.scaling; ++it) {
         double Dt = 1.0, Et = 1.0;
-        if (part == 0) {
+        if (vown) {
           // column norm of [P; A] for variable r
           const int k = r / 3, c3 = r % 3;
           const double* Ek = &sm.E[5 * k];
@@ -557,29 +644,24 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
           if (c3 == 0) nA = fmax(Ek[0], Ek[1]);
           else if (c3 == 1) nA = fmax(Ek[2], Ek[3]);
           else nA = fmax(mu * fmax(fmax(Ek[0], Ek[1]), fmax(Ek[2], Ek[3])), Ek[4]);
-          nA *= sm.D[r];
+          nA *= sm.Dp[r];
           Dt = rsqrt(limit_scaling(fmax(nP, nA)));
         }
         if (crow) {
           // row norm of A for constraint ci
-          const double dz = sm.D[cjz];
-          const double nrow = (ce == 4) ? dz : fmax(sm.D[cja], mu * dz);
+          const double dz = sm.Dp[cjz];
+          const double nrow = (ce == 4) ? dz : fmax(sm.Dp[cja], mu * dz);
           Et = rsqrt(limit_scaling(sm.E[ci] * nrow));
         }
         __syncthreads();
-        if (part == 0) {
-          const double dn = sm.D[r] * Dt;
-          sm.D[r] = dn;
-          sm.Dp[padj(r)] = dn;
-          sm.Df[padj(r)] = (float)dn;
-        }
+        if (vown) sm.Dp[r] *= Dt;
         if (crow) sm.E[ci] *= Et;
         __syncthreads();
         // cost normalisation with the new D and the old c
         const double c_old = sm.scal[0];
-        const double nP2 = c_old * sm.D[r] * (double)row_norm_pass(sm, r, part);
-        double part_sum = (part == 0) ? nP2 : 0.0;
-        double part_q = (part == 0) ? fabs(c_old * sm.D[r] * sm.q0[r]) : 0.0;
+        const double nP2 = c_old * sm.Dp[r] * row_norm_pass(sm, rg, cg);
+        double part_sum = vown ? nP2 : 0.0;
+        double part_q = vown ? fabs(c_old * sm.Dp[r] * sm.q0[r]) : 0.0;
         part_sum = warp_sum(part_sum);
         part_q = warp_max(part_q);
         if (lane == 0) {
@@ -607,8 +689,9 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
       const double c = sm.scal[0];
       if (tid == 0) sm.scal[1] = 1.0 / c;
       if (tid < kN) {
-        sm.qb[tid] = c * sm.D[tid] * sm.q0[tid];
-        sm.Dinv[tid] = 1.0 / sm.D[tid];
+        const double d = sm.Dp[tid];
+        sm.qb[tid] = c * d * sm.q0[tid];
+        sm.Dinv[tid] = 1.0 / d;
       }
       if (crow) {
         const double e = sm.E[ci];
@@ -627,7 +710,7 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
       }
       if (tid >= 256 && tid < 256 + kLegSteps) {
         const int k = tid - 256;
-        const double dx = sm.D[3 * k], dy = sm.D[3 * k + 1], dz = sm.D[3 * k + 2];
+        const double dx = sm.Dp[3 * k], dy = sm.Dp[3 * k + 1], dz = sm.Dp[3 * k + 2];
         const double* e = &sm.E[5 * k];
         double* av = &sm.Av[9 * k];
         av[0] = e[0] * dx;  av[1] = mu * e[0] * dz;
@@ -646,10 +729,10 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
       else { cca = 0.0; ccz = av[8]; }
     }
     // first rhs: x = z = y = 0  ->  rhs = -q_bar
-    if (tid < kN) sm.rhs[padj(tid)] = -sm.qb[tid];
+    if (tid < kN) sm.rhs[tid] = -sm.qb[tid];
 
     // ---- K3b: factor (explicit inverse in registers) ----
-    factor_inverse(sm, a, r, part, tid, sp.sigma);
+    factor_inverse(sm, a, rg, cg, tid, sp.sigma);
 
     // ---- K4: ADMM iterations (osqp.c osqp_solve) ----
     const double sigma = sp.sigma, alpha = sp.alpha;
@@ -657,8 +740,8 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
     double pri_res_out = 0.0;
     for (iter = 1; iter <= sp.max_iter; ++iter) {
       // x~ = K^-1 rhs ; x <- alpha x~ + (1-alpha) x
-      const double xt = kinv_matvec(sm, a, part);
-      if (part == 0) {
+      const double xt = kinv_matvec(sm, a, cg);
+      if (vown) {
         sm.xt[r] = xt;
         sm.x[r] = alpha * xt + (1.0 - alpha) * sm.x[r];
       }
@@ -686,7 +769,7 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
           if (ce == 0) s = av[0] * w[0] + av[2] * w[1];
           else if (ce == 1) s = av[4] * w[2] + av[6] * w[3];
           else s = av[1] * w[0] + av[3] * w[1] + av[5] * w[2] + av[7] * w[3] + av[8] * w[4];
-          sm.rhs[padj(j)] = sigma * sm.x[j] - sm.qb[j] + s;
+          sm.rhs[j] = sigma * sm.x[j] - sm.qb[j] + s;
         }
       }
       const bool can_check = sp.check_termination > 0 && (iter % sp.check_termination == 0);
@@ -698,11 +781,11 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
         continue;
       }
       // ---- residuals (auxil.c compute_pri_res / compute_dua_res / tolerances) ----
-      if (tid < kN) sm.xD[padj(tid)] = sm.D[tid] * sm.x[tid];
+      if (tid < kN) sm.xD[tid] = sm.Dp[tid] * sm.x[tid];
       __syncthreads();
-      double v[12];
+      double v[10];
 #pragma unroll
-      for (int i = 0; i < 12; ++i) v[i] = 0.0;
+      for (int i = 0; i < 10; ++i) v[i] = 0.0;
       if (crow) {
         const double Ax = cca * sm.x[cja] + ccz * sm.x[cjz];
         const double zz = sm.z[ci];
@@ -717,23 +800,30 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
       }
       {
         // P_bar x = c D (P (D x))
-        const float4* prow = reinterpret_cast<const float4*>(&sm.P[r * kRowPad + part * kChunkPad]);
-        const double2* xrow = reinterpret_cast<const double2*>(&sm.xD[part * kChunkPad]);
-        double s0 = 0.0, s1 = 0.0;
+        double xv[8];
+        const double2* xp = reinterpret_cast<const double2*>(&sm.xD[2 * cg]);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {  // pad lanes: P = 0, xD = 0
-          const float4 pv = prow[j4];
-          const double2 x0 = xrow[2 * j4], x1 = xrow[2 * j4 + 1];
-          s0 = fma((double)pv.x, x0.x, s0);
-          s1 = fma((double)pv.y, x0.y, s1);
-          s0 = fma((double)pv.z, x1.x, s0);
-          s1 = fma((double)pv.w, x1.y, s1);
+        for (int i = 0; i < 4; ++i) {
+          const double2 t = xp[16 * i];
+          xv[2 * i] = t.x;
+          xv[2 * i + 1] = t.y;
         }
-        double s = s0 + s1;
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (part == 0) {
-          const double Px = sm.scal[0] * sm.D[r] * s;
+        double s[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const double2* pp = reinterpret_cast<const double2*>(&sm.P[(4 * rg + rr) * kNP + 2 * cg]);
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double2 t = pp[16 * i];
+            s0 = fma(t.x, xv[2 * i], s0);
+            s1 = fma(t.y, xv[2 * i + 1], s1);
+          }
+          s[rr] = s0 + s1;
+        }
+        const double sr = reduce_scatter_sum(s, cg);
+        if (vown) {
+          const double Px = sm.scal[0] * sm.Dp[r] * sr;
           const int k = r / 3, c3 = r % 3;
           const double* av = &sm.Av[9 * k];
           const double* yy = &sm.y[5 * k];
@@ -805,10 +895,9 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
           const double rvv = (ct == -1) ? 1e-6 : (ct == 1) ? 1e3 * rho : rho;
           sm.rv[ci] = rvv;
           sm.rinv[ci] = 1.0 / rvv;
+          // rhs was built with the old rho vector: rebuild it
+          sm.w[ci] = rvv * sm.z[ci] - sm.y[ci];
         }
-        __syncthreads();
-        // rhs was built with the old rho vector: rebuild it
-        if (crow) sm.w[ci] = sm.rv[ci] * sm.z[ci] - sm.y[ci];
         __syncwarp();
         if (crow && ce < 3) {
           const int j = 3 * ck + ce;
@@ -818,21 +907,22 @@ admm_solve_kernel(const float* __restrict__ P_all, const float* __restrict__ q_a
           if (ce == 0) s = av[0] * w[0] + av[2] * w[1];
           else if (ce == 1) s = av[4] * w[2] + av[6] * w[3];
           else s = av[1] * w[0] + av[3] * w[1] + av[5] * w[2] + av[7] * w[3] + av[8] * w[4];
-          sm.rhs[padj(j)] = sigma * sm.x[j] - sm.qb[j] + s;
+          sm.rhs[j] = sigma * sm.x[j] - sm.qb[j] + s;
         }
-        factor_inverse(sm, a, r, part, tid, sigma);
+        __syncthreads();
+        factor_inverse(sm, a, rg, cg, tid, sigma);
       }
     }
     if (iter > sp.max_iter) iter = sp.max_iter;
 
     // ---- K5: unscale, rotate the first step to the body frame, write ----
     __syncthreads();
-    if (x_all != nullptr && tid < kN) x_all[size_t(p) * kN + tid] = (float)(sm.D[tid] * sm.x[tid]);
+    if (x_all != nullptr && tid < kN) x_all[size_t(p) * kN + tid] = (float)(sm.Dp[tid] * sm.x[tid]);
     if (tid < 12) {
       const int leg = tid / 3, rr = tid % 3;
-      const double f0 = sm.D[3 * leg] * sm.x[3 * leg];
-      const double f1 = sm.D[3 * leg + 1] * sm.x[3 * leg + 1];
-      const double f2 = sm.D[3 * leg + 2] * sm.x[3 * leg + 2];
+      const double f0 = sm.Dp[3 * leg] * sm.x[3 * leg];
+      const double f1 = sm.Dp[3 * leg + 1] * sm.x[3 * leg + 1];
+      const double f2 = sm.Dp[3 * leg + 2] * sm.x[3 * leg + 2];
       double g;
       if (states != nullptr) {
         // R' f (A1RobotControl.cpp:558-561)
