@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- batched MPC QP solves/sec (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (QP build + ADMM solve + result write) over one batch
+of synthetic robot states.  Workload = BASELINE.json configs[1]: 4096 synthetic Go1 states,
+horizon 10, gazebo_a1_mpc.yaml weights, eps_abs = eps_rel = 1e-5, per GPU (weak scaling:
+every rank gets its own 4096-state shard of the counter-based stream; no data-path
+collective, one final gather).  One JSON line on rank 0:
+
+  value      whole-job solves/s with the state records already resident in HBM
+  e2e        the same metric through the reference-facing C ABI call with HOST buffers
+             (mpc_compute_grf_batch: H2D + build + solve + D2H inside the timed region)
+  roofline   dominant kernel (admm_solve_kernel): algorithmic flops / CUDA-event duration
+             against this box's measured FP64 FMA peak
+  cpu_baseline  the oracle (CPU port of the reference path) timed on the host cores
+
+--impl reference times the reference's own CPU algorithm (the oracle port: the real
+Eigen/OsqpEigen/OSQP stack cannot be built here) on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 4096
+SEED = 1002
+WORKLOAD = "batched Go1 MPC H=10, 4096 synthetic robot states per GPU (BASELINE configs[1])"
+# SURVEY.md 8d algorithmic-flop model, dense formulation the reference executes, H = 10
+F_BUILD = 4.00e6
+F_FACTOR = 0.576e6
+F_ITER = 33.0e3
+# FP64 FMA peak of this pool's B200, measured with scripts/fp64_bench.cu
+# (profiles/r01_fp64_peak.txt): 17.07 T DFMA/s = 34.1 TFLOP/s
+FP64_PEAK_TFLOPS = 34.1
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nme, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def run_reference(args):
+    """The reference's CPU algorithm (oracle port) on the host cores, same config and metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import go1_qp_mpc_controller_b200 as pkg
+    import oracle_binding as ob
+    cfg = pkg.config_default()
+    threads = ob.max_threads()
+    sample = 1024  # bounded sample of the 4096-state batch per step
+    times = []
+    for step in range(args.warmup + args.steps):
+        states = pkg.generate_states(SEED, step * BATCH, sample)
+        t0 = time.perf_counter()
+        res = ob.mpc_compute_grf(cfg, states, threads=threads)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    value = sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": "batched MPC QP solves/sec (H=10)", "value": value,
+        "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "horizon": 10, "eps_abs": 1e-5, "eps_rel": 1e-5,
+                   "sample_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} states of the 4096-state batch per step, OpenMP one problem per thread"},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mean_iters": float(res["iters"].mean()),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import go1_qp_mpc_controller_b200 as pkg
+    from go1_qp_mpc_controller_b200.sharding import gather_results
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    cfg = pkg.config_default()
+    eng = pkg.MpcEngine(cfg, local_rank)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+
+    nsteps = args.warmup + args.steps
+    rec = pkg.abi.STATE_DTYPE.itemsize
+    # fresh batch per step and per rank: global state index = (step * world + rank) * BATCH + i
+    host_batches = [pkg.generate_states(SEED, (s * world + rank) * BATCH, BATCH) for s in range(nsteps)]
+    pinned_in = torch.empty(nsteps * BATCH * rec, dtype=torch.uint8).pin_memory()
+    pin_np = pinned_in.numpy().view(pkg.abi.STATE_DTYPE)
+    for s in range(nsteps):
+        pin_np[s * BATCH:(s + 1) * BATCH] = host_batches[s]
+    dev_in = pinned_in.cuda()
+    pinned_out = torch.empty(BATCH * pkg.abi.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    out_np = pinned_out.numpy().view(pkg.abi.RESULT_DTYPE)
+
+    def step_device(s):
+        eng.set_states_device(dev_in.data_ptr() + s * BATCH * rec, BATCH)
+        eng.build_qp(sync=False)
+        eng.solve(sync=False)
+
+    # ---------------- value: inputs resident in HBM, device-timed ----------------
+    with torch.cuda.stream(stream):
+        for s in range(args.warmup):
+            step_device(s)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.kernel_launches()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+        for k in range(args.steps):
+            s = args.warmup + k
+            eng.set_states_device(dev_in.data_ptr() + s * BATCH * rec, BATCH)
+            ev[k][0].record()
+            eng.build_qp(sync=False)
+            ev[k][1].record()
+            eng.solve(sync=False)
+            ev[k][2].record()
+        e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.kernel_launches() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    build_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]))
+    solve_ms = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)]))
+    last = eng.get_results()
+    ok = bool((last["status"] == 1).all())
+    mean_iters = sum_over_ranks(float(last["iters"].mean())) / world
+    mean_fac = 1.0 + sum_over_ranks(float(last["rho_updates"].mean())) / world
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # ---------------- e2e: host buffers through the C ABI, H2D and D2H inside ----------------
+    lat = []
+    for s in range(args.warmup):
+        eng.compute_grf_batch(pin_np[s * BATCH:(s + 1) * BATCH], out_np)
+    barrier()
+    t_start = time.perf_counter()
+    for k in range(args.steps):
+        s = args.warmup + k
+        t0 = time.perf_counter()
+        eng.compute_grf_batch(pin_np[s * BATCH:(s + 1) * BATCH], out_np)
+        lat.append(time.perf_counter() - t0)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t_start)
+    barrier()
+    e2e_value = world * BATCH * args.steps / e2e_s
+    # the single exchange of the path: final gather of the 64 B records (outside the step loop)
+    if world > 1:
+        g0 = time.perf_counter()
+        full = gather_results(out_np.copy(), BATCH * world)
+        torch.cuda.synchronize()
+        gather_ms = 1e3 * (time.perf_counter() - g0)
+        assert rank != 0 or len(full) == BATCH * world
+    else:
+        gather_ms = 0.0
+
+    # ---------------- CPU baseline: the oracle on the host cores (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_binding as ob
+        threads = ob.max_threads()
+        sample = 2048
+        t0 = time.perf_counter()
+        ref = ob.mpc_compute_grf(cfg, host_batches[nsteps - 1][:sample], threads=threads)
+        cdt = time.perf_counter() - t0
+        den = np.maximum(np.linalg.norm(ref["grf"], axis=1), 1.0)
+        rel = np.linalg.norm(out_np["grf"][:sample].astype(np.float64) - ref["grf"], axis=1) / den
+        cpu = {"value": sample / cdt, "unit": "solves/s", "cores": threads, "kind": "port",
+               "sample": f"first {sample} states of the last timed batch, OpenMP one problem per thread, fp64",
+               "parity_max_rel_grf_err": float(rel.max()),
+               "parity_same_iters": float((ref["iters"] == out_np["iters"][:sample]).mean())}
+
+    if rank == 0:
+        flops_solve = mean_fac * F_FACTOR + mean_iters * F_ITER          # admm_solve_kernel, per solve
+        achieved = BATCH * flops_solve / (solve_ms * 1e-3) / 1e12
+        line = {
+            "metric": "batched MPC QP solves/sec (H=10)", "value": value, "unit": "solves/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "horizon": 10, "states_per_gpu": BATCH,
+                       "weights": "config/gazebo_a1_mpc.yaml", "eps_abs": 1e-5, "eps_rel": 1e-5,
+                       "max_iter": 4000, "adaptive_rho_interval": 50, "cold_start": True,
+                       "l2": "fresh state batch per step; per-step working set (P, 236 MB) exceeds the 126 MB L2",
+                       "parallelism": f"shard{world}"},
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": BATCH * rec,
+                    "d2h_bytes_per_step": BATCH * pkg.abi.RESULT_DTYPE.itemsize,
+                    "p50_batch_ms": 1e3 * float(np.percentile(lat, 50)),
+                    "p99_batch_ms": 1e3 * float(np.percentile(lat, 99))},
+            "gpu_launches": int(launches),
+            "kernels": {"qp_build_kernel_ms": build_ms, "admm_solve_kernel_ms": solve_ms,
+                        "final_gather_ms": gather_ms},
+            "roofline": {"bound": "fp64-fma (compute/latency; neither hbm nor tensor, SURVEY.md 8d)",
+                         "kernel": "admm_solve_kernel", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+                         "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                         "peak_source": "measured on this pool: scripts/fp64_bench.cu, profiles/r01_fp64_peak.txt",
+                         "algorithmic_flops_per_solve": flops_solve,
+                         "hbm_algorithmic_bytes_per_solve": 256},
+            "solver": {"mean_iters": mean_iters, "mean_factorisations": mean_fac, "all_solved": ok},
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    import __graft_entry__ as g
+    if not os.path.exists(g.LIB):
+        g.build()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

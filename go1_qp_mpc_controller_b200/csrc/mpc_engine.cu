@@ -445,8 +445,10 @@ int mpc_qp_mats_from_model(MpcEngine* e, const double* A_mat_d, const double* B_
   if (crc != cudaSuccess) return fail(e, MPC_ERR_CUDA, cudaGetErrorString(crc));
   if (hessian) for (size_t i = 0; i < size_t(kN) * kN; ++i) hessian[i] = ho[i];
   if (gradient) for (int i = 0; i < kN; ++i) gradient[i] = ho[size_t(kN) * kN + i];
-  if (lb) for (int i = 0; i < kM; ++i) lb[i] = ho[size_t(kN) * kN + kN + i];
-  if (ub) for (int i = 0; i < kM; ++i) ub[i] = ho[size_t(kN) * kN + kN + kM + i];
+  // the device stores bounds in fp32; hand back exactly +-OsqpEigen::INFTY like the reference
+  auto snap = [](float v) -> double { return v >= 1e29f ? MPC_INFTY : (v <= -1e29f ? -MPC_INFTY : (double)v); };
+  if (lb) for (int i = 0; i < kM; ++i) lb[i] = snap(ho[size_t(kN) * kN + kN + i]);
+  if (ub) for (int i = 0; i < kM; ++i) ub[i] = snap(ho[size_t(kN) * kN + kN + kM + i]);
   return MPC_OK;
 }
 

@@ -1,0 +1,358 @@
+"""GPU parity tests: the CUDA path through the C ABI against the oracle on the same seeded
+inputs, against the committed golden fixtures, and -- at BASELINE.json's full sizes --
+through size-independent properties.
+
+Gates (BASELINE.json north_star / SURVEY.md 8d):
+  QP matrices  max|dP| / max|P| <= 1e-5 (fp32 storage vs double), bounds exact
+  GRF          ||f_gpu - f_oracle||_2 / max(||f_oracle||_2, 1 N) <= 1e-3, same solver settings
+  constraints  friction-cone / bound violation of the returned x <= 1e-4 * fz_max
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+TOL_QP = 1e-5
+TOL_GRF = 1e-3
+TOL_CONE = 1e-4
+
+
+def grf_rel(gpu, ref):
+    den = np.maximum(np.linalg.norm(ref, axis=1), 1.0)
+    return np.linalg.norm(gpu.astype(np.float64) - ref, axis=1) / den
+
+
+@pytest.fixture(scope="module")
+def eng(pkg):
+    e = pkg.MpcEngine(pkg.config_default(), 0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("which", ["gazebo", "hardware"])
+def test_qp_build_parity(pkg, ob, which):
+    cfg = pkg.config_default() if which == "gazebo" else pkg.config_hardware()
+    e = pkg.MpcEngine(cfg, 0)
+    states = pkg.generate_states(1002, 0, 1024)
+    e.load_states(states)
+    e.build_qp()
+    worstP = worstq = 0.0
+    for i in range(0, 1024, 4):
+        P, q, l, u = e.get_qp(i)
+        Po, qo, lo, uo = ob.mpc_build_qp(cfg, states[i])
+        worstP = max(worstP, np.abs(P - Po).max() / np.abs(Po).max())
+        worstq = max(worstq, np.abs(q - qo).max() / np.abs(qo).max())
+        assert np.array_equal(l, lo.astype(np.float32)) and np.array_equal(u, uo.astype(np.float32))
+        assert np.abs(P - P.T).max() <= 2e-7 * np.abs(P).max()  # symmetric up to fp32 rounding
+    assert worstP <= TOL_QP and worstq <= TOL_QP, (worstP, worstq)
+    e.close()
+
+
+@pytest.mark.parametrize("which,seed", [("gazebo", 1002), ("gazebo", 1003), ("hardware", 1002)])
+def test_grf_parity_vs_oracle(pkg, ob, which, seed):
+    cfg = pkg.config_default() if which == "gazebo" else pkg.config_hardware()
+    e = pkg.MpcEngine(cfg, 0)
+    states = pkg.generate_states(seed, 0, 1024)
+    res = e.compute_grf_batch(states)
+    ref = ob.mpc_compute_grf(cfg, states)
+    assert (res["status"] == 1).all() and (ref["status"] == 1).all()
+    rel = grf_rel(res["grf"], ref["grf"])
+    assert rel.max() <= TOL_GRF, (rel.max(), int(np.argmax(rel)))
+    # same iterate sequence: identical iteration and refactorisation counts
+    assert (res["iters"] == ref["iters"]).mean() >= 0.995
+    assert (res["rho_updates"] == ref["rho_updates"]).mean() >= 0.995
+    np.testing.assert_allclose(res["pri_res"], ref["pri_res"], rtol=0.2, atol=1e-6)
+    e.close()
+
+
+def test_reference_default_tolerances(pkg, ob):
+    """The reference itself runs OSQP at eps 1e-3 (A1RobotControl.cpp:523-524 changes nothing else)."""
+    cfg = pkg.config_default()
+    d = pkg.settings_osqp_default()
+    cfg.osqp.eps_abs, cfg.osqp.eps_rel = d.eps_abs, d.eps_rel
+    e = pkg.MpcEngine(cfg, 0)
+    states = pkg.generate_states(1002, 2000, 512)
+    res = e.compute_grf_batch(states)
+    ref = ob.mpc_compute_grf(cfg, states)
+    assert (res["iters"] == ref["iters"]).mean() >= 0.995
+    assert grf_rel(res["grf"], ref["grf"]).max() <= TOL_GRF
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["gazebo", "hardware"])
+def test_golden_fixtures(pkg, name):
+    g = np.load(os.path.join(GOLD, f"mpc_{name}.npz"))
+    cfg = pkg.config_default() if name == "gazebo" else pkg.config_hardware()
+    e = pkg.MpcEngine(cfg, 0)
+    e.load_states(g["states"])
+    e.build_qp()
+    P, q, l, u = e.get_qp(0)
+    assert np.abs(P - g["P0"]).max() / np.abs(g["P0"]).max() <= TOL_QP
+    assert np.abs(q - g["q0"]).max() / np.abs(g["q0"]).max() <= TOL_QP
+    assert np.array_equal(l, g["l0"].astype(np.float32)) and np.array_equal(u, g["u0"].astype(np.float32))
+    for i in range(8):
+        Pi, qi, _, _ = e.get_qp(i)
+        assert abs(Pi.astype(np.float64).sum() - g["Psum"][i]) <= 1e-5 * np.abs(g["P0"]).max() * 120
+        assert np.abs(qi - g["q8"][i]).max() <= TOL_QP * np.abs(g["q8"][i]).max()
+    e.solve()
+    res = e.get_results()
+    assert np.array_equal(res["iters"], g["iters"]) and np.array_equal(res["status"], g["status"])
+    assert np.array_equal(res["rho_updates"], g["rho_updates"])
+    assert grf_rel(res["grf"], g["grf"]).max() <= TOL_GRF
+    x = np.stack([e.get_solution(i) for i in range(16)])
+    den = np.maximum(np.linalg.norm(g["solutions"][:16], axis=1), 1.0)
+    assert (np.linalg.norm(x - g["solutions"][:16], axis=1) / den).max() <= TOL_GRF
+    e.close()
+
+
+def test_cone_and_bound_violation(pkg, eng):
+    """Returned x (world frame, all H steps): |fx|,|fy| <= mu fz, 0 <= fz <= 180 c, to 1e-4 * fz_max."""
+    states = pkg.generate_states(1004, 0, 512)
+    eng.compute_grf_batch(states)
+    worst = 0.0
+    for i in range(0, 512, 8):
+        x = eng.get_solution(i).astype(np.float64).reshape(10, 4, 3)
+        c = states["contacts"][i].astype(np.float64)
+        v = np.maximum(np.abs(x[..., :2]).max(-1) - 0.3 * x[..., 2], 0).max()
+        v = max(v, np.maximum(-x[..., 2], 0).max(), np.maximum(x[..., 2] - 180.0 * c[None, :], 0).max())
+        worst = max(worst, v)
+    assert worst <= TOL_CONE * 180.0, worst
+
+
+def test_convexmpc_surface_like_test_mpc_cpp(pkg, ob):
+    """The reference's own driver (test/test_mpc.cpp:14-159) restated against this surface."""
+    from go1_qp_mpc_controller_b200 import A1CtrlStates, ConvexMpc
+    g = np.load(os.path.join(GOLD, "test_mpc_case.npz"))
+    state = A1CtrlStates()
+    state.robot_mass = 15
+    state.a1_trunk_inertia = np.diag([0.0158533, 0.0377999, 0.0456542])
+    state.root_euler = np.zeros(3)
+    state.root_rot_mat = np.eye(3)
+    state.root_pos = np.array([0.0, 0.0, 0.15])
+    state.foot_pos_rel = np.array([[0.17, 0.17, -0.17, -0.17], [0.15, -0.15, 0.15, -0.15], [-0.35] * 4])
+    state.contacts = [True, False, True, False]
+    dt = 0.0025
+    q_weights = np.array([1.0, 1.0, 1.0, 0.0, 0.0, 50.0, 0.0, 0.0, 1.0, 1.0, 1.0, 1.0, 0.0])
+    r_weights = np.full(12, 1e-6)
+    mpc_solver = ConvexMpc(q_weights, r_weights)
+    mpc_solver.reset()
+    state.mpc_states = np.concatenate([state.root_euler, state.root_pos, state.root_ang_vel,
+                                       state.root_lin_vel, [-9.8]])
+    state.root_lin_vel_d_world = state.root_rot_mat @ state.root_lin_vel_d
+    xr = np.zeros(130)
+    for i in range(10):  # test_mpc.cpp:77-92 (zero commands -> constant reference)
+        xr[13 * i:13 * i + 13] = [0, 0, 0, 0, 0, state.root_pos[2], 0, 0, 0, 0, 0, 0, -9.8]
+    state.mpc_states_d = xr
+    mpc_solver.calculate_A_mat_c(np.zeros(3))
+    foot = state.foot_pos_rel.copy()
+    for i in range(10):
+        mpc_solver.calculate_B_mat_c(state.robot_mass, state.a1_trunk_inertia, state.root_rot_mat, foot)
+        mpc_solver.state_space_discretization(dt)
+        mpc_solver.B_mat_d_list[13 * i:13 * i + 13, :] = mpc_solver.B_mat_d
+    mpc_solver.calculate_qp_mats(state)
+    assert np.abs(mpc_solver.hessian - g["P"]).max() / np.abs(g["P"]).max() <= TOL_QP
+    assert np.abs(mpc_solver.gradient - g["q"]).max() / np.abs(g["q"]).max() <= TOL_QP
+    assert mpc_solver.ub[4] == 180.0 and mpc_solver.ub[9] == 0.0 and mpc_solver.lb[1] == -1e30
+    # OsqpEigen initSolver + solve + getSolution (test_mpc.cpp:131-151), cold start
+    sol, status, iters = mpc_solver._engine.solve_qp(mpc_solver.hessian, mpc_solver.gradient,
+                                                     mpc_solver.lb, mpc_solver.ub)
+    assert status == 1 and iters == int(g["iters_eps1e-5"])
+    grf = sol[:12]                         # world frame == body frame here (R = I)
+    assert np.linalg.norm(grf - g["grf_eps1e-5"]) / np.linalg.norm(g["grf_eps1e-5"]) <= TOL_GRF
+    np.testing.assert_allclose(grf[[1, 2]], [-12.782, 42.606], atol=5e-3)   # SURVEY.md 8c probe
+
+
+def test_compute_grf_single_robot(pkg, ob):
+    """A1RobotControl::compute_grf, both branches, one robot (BASELINE config 1)."""
+    from go1_qp_mpc_controller_b200 import A1CtrlStates, A1RobotControl
+    cfg = pkg.config_default()
+    rec = pkg.generate_states(1001, 5, 1)
+    st = A1CtrlStates()
+    st.robot_mass = cfg.mass
+    st.q_weights = np.array(cfg.q_weights[:])
+    st.r_weights = np.array(cfg.r_weights[:])
+    st.root_euler = rec["euler"][0].astype(np.float64)
+    st.root_pos = rec["pos"][0].astype(np.float64)
+    st.root_ang_vel = rec["ang_vel"][0].astype(np.float64)
+    st.root_lin_vel = rec["lin_vel"][0].astype(np.float64)
+    st.root_euler_d = rec["euler_d"][0].astype(np.float64)
+    st.root_pos_d = np.array([0.0, 0.0, float(rec["pos_d_z"][0])])
+    st.root_lin_vel_d = rec["lin_vel_d"][0].astype(np.float64)
+    st.root_ang_vel_d = rec["ang_vel_d"][0].astype(np.float64)
+    st.root_rot_mat = rec["rot_mat"][0].astype(np.float64).reshape(3, 3)
+    st.foot_pos_abs = rec["foot_pos_abs"][0].astype(np.float64).reshape(4, 3).T
+    st.contacts = [bool(c) for c in rec["contacts"][0]]
+    ctl = A1RobotControl(cfg)
+    grf = ctl.compute_grf(st, 0.0025)
+    ref = ob.mpc_compute_grf(cfg, rec)["grf"][0].reshape(4, 3).T
+    assert grf.shape == (3, 4)
+    assert np.linalg.norm(grf - ref) / max(np.linalg.norm(ref), 1.0) <= TOL_GRF
+    assert st.mpc_states[12] == -9.8
+    # QP branch
+    brec = pkg.generate_balance_states(1005, 11, 1)
+    bcfg = pkg.balance_config_default()
+    st.stance_leg_control_type = 0
+    st.robot_mass = bcfg.mass
+    st.kp_linear, st.kd_linear = np.array(bcfg.kp_linear[:]), np.array(bcfg.kd_linear[:])
+    st.kp_angular, st.kd_angular = np.array(bcfg.kp_angular[:]), np.array(bcfg.kd_angular[:])
+    for f, k in (("root_euler", "euler"), ("root_pos", "pos"), ("root_ang_vel", "ang_vel"),
+                 ("root_lin_vel", "lin_vel"), ("root_euler_d", "euler_d"), ("root_pos_d", "pos_d"),
+                 ("root_lin_vel_d", "lin_vel_d"), ("root_ang_vel_d", "ang_vel_d")):
+        setattr(st, f, brec[k][0].astype(np.float64))
+    st.root_rot_mat = brec["rot_mat"][0].astype(np.float64).reshape(3, 3)
+    st.root_rot_mat_z = brec["rot_mat_z"][0].astype(np.float64).reshape(3, 3)
+    st.foot_pos_abs = brec["foot_pos_abs"][0].astype(np.float64).reshape(4, 3).T
+    st.contacts = [bool(c) for c in brec["contacts"][0]]
+    grf = ctl.compute_grf(st, 0.0025)
+    ref = ob.balance_compute_grf(bcfg, brec)["grf"][0].reshape(4, 3).T
+    assert np.linalg.norm(grf - ref) / max(np.linalg.norm(ref), 1.0) <= TOL_GRF
+
+
+def test_edge_cases(pkg, ob, eng):
+    cfg = pkg.config_default()
+    # empty batch
+    out = eng.compute_grf_batch(np.zeros(0, dtype=pkg.abi.STATE_DTYPE))
+    assert len(out) == 0
+    # one state, and ragged sizes around the SM count (148) and the warp size
+    for n in (1, 31, 147, 149, 297):
+        states = pkg.generate_states(1002, 5000, n)
+        res = eng.compute_grf_batch(states)
+        ref = ob.mpc_compute_grf(cfg, states)
+        assert np.array_equal(res["iters"], ref["iters"])
+        assert grf_rel(res["grf"], ref["grf"]).max() <= TOL_GRF
+    # every leg in swing: all fz rows are equalities [0,0] -> zero force
+    states = pkg.generate_states(1002, 0, 8)
+    states["contacts"][:] = 0.0
+    res = eng.compute_grf_batch(states)
+    ref = ob.mpc_compute_grf(cfg, states)
+    assert np.abs(res["grf"]).max() < 1e-3 and np.abs(ref["grf"]).max() < 1e-3
+    assert np.array_equal(res["status"], ref["status"]) and np.array_equal(res["iters"], ref["iters"])
+    # single stance leg, three-leg stance: contact patterns the generator never draws
+    for pat in ([1, 0, 0, 0], [1, 1, 1, 0], [0, 0, 1, 1]):
+        states = pkg.generate_states(1002, 40, 16)
+        states["contacts"][:] = pat
+        res = eng.compute_grf_batch(states)
+        ref = ob.mpc_compute_grf(cfg, states)
+        assert np.array_equal(res["status"], ref["status"])
+        assert (res["iters"] == ref["iters"]).mean() >= 0.9
+        ok = res["iters"] == ref["iters"]
+        assert grf_rel(res["grf"][ok], ref["grf"][ok]).max() <= TOL_GRF
+
+
+def test_max_iter_status(pkg, ob):
+    """Hitting max_iter reports OSQP's codes (-2, or 2 = solved inaccurate), like the oracle."""
+    cfg = pkg.config_default()
+    cfg.osqp.max_iter = 60
+    e = pkg.MpcEngine(cfg, 0)
+    states = pkg.generate_states(1002, 0, 128)
+    res = e.compute_grf_batch(states)
+    ref = ob.mpc_compute_grf(cfg, states)
+    assert np.array_equal(res["status"], ref["status"])
+    assert set(np.unique(res["status"])) <= {1, 2, -2}
+    assert (res["iters"] <= 60).all() and np.array_equal(res["iters"], ref["iters"])
+    e.close()
+
+
+def test_error_behaviour(pkg):
+    cfg = pkg.config_default()
+    e = pkg.MpcEngine(cfg, 0)
+    with pytest.raises(pkg.MpcError) as ei:
+        e.solve()
+    assert ei.value.code == pkg.abi.MPC_ERR_STATE
+    with pytest.raises(pkg.MpcError):
+        e.get_results()
+    e.load_states(pkg.generate_states(1, 0, 4))
+    e.build_qp()
+    with pytest.raises(pkg.MpcError):
+        e.get_qp(4)
+    e.close()
+    cfg.horizon = 30
+    with pytest.raises(pkg.MpcError) as ei:
+        pkg.MpcEngine(cfg, 0)
+    assert ei.value.code == pkg.abi.MPC_ERR_UNSUPPORTED
+    cfg = pkg.config_default()
+    cfg.osqp.adaptive_rho_interval = 0   # the wall-clock dependent library default is refused
+    with pytest.raises(pkg.MpcError) as ei:
+        pkg.MpcEngine(cfg, 0)
+    assert ei.value.code == pkg.abi.MPC_ERR_INVALID
+
+
+def test_full_size_properties(pkg, ob, eng):
+    """BASELINE configs 2 and 3 (4096 and 65536 states): determinism, permutation invariance,
+    feasibility, and a sampled oracle comparison."""
+    cfg = pkg.config_default()
+    states = pkg.generate_states(1002, 0, 4096)
+    a = eng.compute_grf_batch(states).copy()
+    b = eng.compute_grf_batch(states).copy()
+    assert a.tobytes() == b.tobytes()                       # bit-identical repeat
+    perm = np.random.default_rng(0).permutation(4096)
+    c = eng.compute_grf_batch(states[perm]).copy()
+    assert c.tobytes() == a[perm].tobytes()                 # a result depends on its own state only
+    big = pkg.generate_states(1003, 0, 65536)
+    r = eng.compute_grf_batch(big)
+    assert (r["status"] == 1).all()
+    assert r["iters"].min() >= 50 and r["iters"].max() <= 1000
+    # body-frame forces rotate back to world-frame forces that respect fz in [0, 180 c]
+    Rm = big["rot_mat"].reshape(-1, 3, 3).astype(np.float64)
+    fw = np.einsum("nij,nlj->nli", Rm, r["grf"].reshape(-1, 4, 3).astype(np.float64))
+    cmask = big["contacts"].astype(np.float64)
+    assert (fw[..., 2] >= -TOL_CONE * 180).all() and (fw[..., 2] <= 180.0 * cmask + TOL_CONE * 180 + 2e-3).all()
+    assert (np.abs(fw[..., :2]).max(-1) <= 0.3 * fw[..., 2] + TOL_CONE * 180 + 2e-3).all()
+    idx = np.arange(0, 65536, 128)
+    ref = ob.mpc_compute_grf(cfg, big[idx])
+    assert (r["iters"][idx] == ref["iters"]).mean() >= 0.995
+    assert grf_rel(r["grf"][idx], ref["grf"]).max() <= TOL_GRF
+    # the first 4096 of a shard of the 65536 batch equal the stand-alone solve (sharding = slicing)
+    lo = 8192
+    s = eng.compute_grf_batch(big[lo:lo + 512])
+    assert s.tobytes() == r[lo:lo + 512].tobytes()
+
+
+def test_device_resident_path_and_external_stream(pkg, ob):
+    """Inputs already in HBM (torch tensor) and kernels on a caller-owned stream."""
+    import torch
+    cfg = pkg.config_default()
+    e = pkg.MpcEngine(cfg, 0)
+    states = pkg.generate_states(1002, 123, 300)
+    t = torch.from_numpy(states.view(np.uint8).reshape(-1).copy()).cuda()
+    s = torch.cuda.Stream()
+    e.set_stream(s.cuda_stream)
+    with torch.cuda.stream(s):
+        e.set_states_device(t.data_ptr(), 300)
+        e.build_qp(sync=False)
+        e.solve(sync=False)
+    s.synchronize()
+    res = e.get_results()
+    e.set_stream(0)
+    ref = e.compute_grf_batch(states)
+    assert res.tobytes() == ref.tobytes()
+    assert e.kernel_launches() == 4
+    e.close()
+
+
+def test_balance_qp_parity(pkg, ob):
+    bcfg = pkg.balance_config_default()
+    be = pkg.MpcEngine(bcfg, 0, balance=True)
+    g = np.load(os.path.join(GOLD, "balance.npz"))
+    res = be.compute_grf_batch(g["states"])
+    assert np.array_equal(res["iters"], g["iters"]) and np.array_equal(res["status"], g["status"])
+    assert grf_rel(res["grf"], g["grf"]).max() <= TOL_GRF
+    P, q, l, u = be.get_qp(0)
+    assert np.abs(P - g["P0"]).max() / np.abs(g["P0"]).max() <= TOL_QP
+    assert np.abs(q - g["q0"]).max() / np.abs(g["q0"]).max() <= TOL_QP
+    assert np.array_equal(l, g["l0"].astype(np.float32)) and np.array_equal(u, g["u0"].astype(np.float32))
+    states = pkg.generate_balance_states(1005, 0, 8192)
+    res = be.compute_grf_batch(states)
+    ref = ob.balance_compute_grf(bcfg, states)
+    assert np.array_equal(res["status"], ref["status"])
+    assert (res["iters"] == ref["iters"]).mean() >= 0.995
+    ok = res["iters"] == ref["iters"]
+    assert grf_rel(res["grf"][ok], ref["grf"][ok]).max() <= TOL_GRF
+    # ragged / empty
+    assert len(be.compute_grf_batch(np.zeros(0, dtype=pkg.abi.BALANCE_DTYPE))) == 0
+    r1 = be.compute_grf_batch(states[:5])
+    assert r1.tobytes() == res[:5].tobytes()
+    be.close()
