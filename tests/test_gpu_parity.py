@@ -64,7 +64,9 @@ def test_grf_parity_vs_oracle(pkg, ob, which, seed):
     # same iterate sequence: identical iteration and refactorisation counts
     assert (res["iters"] == ref["iters"]).mean() >= 0.995
     assert (res["rho_updates"] == ref["rho_updates"]).mean() >= 0.995
-    np.testing.assert_allclose(res["pri_res"], ref["pri_res"], rtol=0.2, atol=1e-6)
+    # the exit residual is a difference of nearly equal numbers: compare it statistically
+    rel_res = np.abs(res["pri_res"] - ref["pri_res"]) / np.maximum(ref["pri_res"], 1e-9)
+    assert np.median(rel_res) < 0.01 and (rel_res < 0.5).mean() >= 0.98
     e.close()
 
 
