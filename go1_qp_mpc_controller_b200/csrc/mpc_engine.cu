@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/mpc_b200.h"
+#include "admm_kernel.cuh"
 #include "balance_kernels.cuh"
 #include "mpc_kernels.cuh"
 
@@ -33,8 +34,10 @@ struct MpcEngine {
   MpcStateIn* d_states_own = nullptr;
   const MpcStateIn* d_states = nullptr;
   BalanceStateIn* d_bstates = nullptr;
-  float* d_P = nullptr;
-  float* d_q = nullptr;
+  double* d_P = nullptr;   // MPC: n x 120 x 128 f64 (padded rows)
+  double* d_q = nullptr;   // MPC: n x 120 f64
+  float* d_Pb = nullptr;   // balance QP parity read-back (f32)
+  float* d_qb = nullptr;
   float* d_l = nullptr;
   float* d_u = nullptr;
   float* d_x = nullptr;
@@ -116,13 +119,16 @@ void free_buffers(MpcEngine* e) {
   cudaFree(e->d_bstates);
   cudaFree(e->d_P);
   cudaFree(e->d_q);
+  cudaFree(e->d_Pb);
+  cudaFree(e->d_qb);
   cudaFree(e->d_l);
   cudaFree(e->d_u);
   cudaFree(e->d_x);
   cudaFree(e->d_results);
   e->d_states_own = nullptr;
   e->d_bstates = nullptr;
-  e->d_P = e->d_q = e->d_l = e->d_u = e->d_x = nullptr;
+  e->d_P = e->d_q = nullptr;
+  e->d_Pb = e->d_qb = e->d_l = e->d_u = e->d_x = nullptr;
   e->d_results = nullptr;
   e->capacity = 0;
 }
@@ -137,15 +143,15 @@ int reserve(MpcEngine* e, int n) {
   if (cap < 64) cap = 64;
   if (e->kind == 0) {
     CUDA_TRY(e, cudaMalloc(&e->d_states_own, size_t(cap) * sizeof(MpcStateIn)));
-    CUDA_TRY(e, cudaMalloc(&e->d_P, size_t(cap) * kN * kN * sizeof(float)));
-    CUDA_TRY(e, cudaMalloc(&e->d_q, size_t(cap) * kN * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_P, size_t(cap) * kN * kNP * sizeof(double)));
+    CUDA_TRY(e, cudaMalloc(&e->d_q, size_t(cap) * kN * sizeof(double)));
     CUDA_TRY(e, cudaMalloc(&e->d_l, size_t(cap) * kM * sizeof(float)));
     CUDA_TRY(e, cudaMalloc(&e->d_u, size_t(cap) * kM * sizeof(float)));
     CUDA_TRY(e, cudaMalloc(&e->d_x, size_t(cap) * kN * sizeof(float)));
   } else {
     CUDA_TRY(e, cudaMalloc(&e->d_bstates, size_t(cap) * sizeof(BalanceStateIn)));
-    CUDA_TRY(e, cudaMalloc(&e->d_P, size_t(cap) * 144 * sizeof(float)));
-    CUDA_TRY(e, cudaMalloc(&e->d_q, size_t(cap) * 12 * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_Pb, size_t(cap) * 144 * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_qb, size_t(cap) * 12 * sizeof(float)));
     CUDA_TRY(e, cudaMalloc(&e->d_l, size_t(cap) * 20 * sizeof(float)));
     CUDA_TRY(e, cudaMalloc(&e->d_u, size_t(cap) * 20 * sizeof(float)));
   }
@@ -154,7 +160,7 @@ int reserve(MpcEngine* e, int n) {
   return MPC_OK;
 }
 
-int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n, float* P, float* q,
+int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n, double* P, double* q,
                  float* l, float* u) {
   const int grid = n < e->num_sms * 8 ? n : e->num_sms * 8;
   qp_build_kernel<<<grid, kThreads, sizeof(BuildSmem), e->stream>>>(d_states, model, n, P, q, l, u, e->bp);
@@ -163,11 +169,11 @@ int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n,
   return MPC_OK;
 }
 
-int launch_solve(MpcEngine* e, const float* P, const float* q, const float* l, const float* u,
+int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l, const float* u,
                  const MpcStateIn* d_states, MpcResult* res, float* x, int n) {
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
   const int grid = n < e->num_sms ? n : e->num_sms;
-  admm_solve_kernel<<<grid, kThreads, sizeof(SolveSmem), e->stream>>>(P, q, l, u, d_states, res, x, n,
+  admm_solve_kernel<<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(P, q, l, u, d_states, res, x, n,
                                                                       e->d_counter, e->sp);
   ++e->launches;
   CUDA_TRY(e, cudaGetLastError());
@@ -331,8 +337,17 @@ int mpc_get_qp(MpcEngine* e, int32_t idx, float* P, float* q, float* l, float* u
   if (idx < 0 || idx >= e->n) return fail(e, MPC_ERR_INVALID, "problem index out of range");
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  if (P) CUDA_TRY(e, cudaMemcpy(P, e->d_P + size_t(idx) * kN * kN, kN * kN * sizeof(float), cudaMemcpyDeviceToHost));
-  if (q) CUDA_TRY(e, cudaMemcpy(q, e->d_q + size_t(idx) * kN, kN * sizeof(float), cudaMemcpyDeviceToHost));
+  if (P) {
+    std::vector<double> hp(size_t(kN) * kNP);
+    CUDA_TRY(e, cudaMemcpy(hp.data(), e->d_P + size_t(idx) * kN * kNP, hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < kN; ++r)
+      for (int c = 0; c < kN; ++c) P[r * kN + c] = (float)hp[size_t(r) * kNP + c];
+  }
+  if (q) {
+    double hq[kN];
+    CUDA_TRY(e, cudaMemcpy(hq, e->d_q + size_t(idx) * kN, kN * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < kN; ++c) q[c] = (float)hq[c];
+  }
   if (l) CUDA_TRY(e, cudaMemcpy(l, e->d_l + size_t(idx) * kM, kM * sizeof(float), cudaMemcpyDeviceToHost));
   if (u) CUDA_TRY(e, cudaMemcpy(u, e->d_u + size_t(idx) * kM, kM * sizeof(float), cudaMemcpyDeviceToHost));
   return MPC_OK;
@@ -406,13 +421,15 @@ int mpc_qp_mats_from_model(MpcEngine* e, const double* A_mat_d, const double* B_
     return fail(e, MPC_ERR_INVALID, "NULL model input");
   CUDA_TRY(e, cudaSetDevice(e->device));
   const size_t nd = 169 + size_t(kH) * 156 + 13 + kS;
+  const size_t npq = size_t(kN) * kNP + kN;  // P (padded) | q, f64
   double* d_model = nullptr;
   int* d_contacts = nullptr;
-  float* d_out = nullptr;  // P | q | l | u
-  const size_t nout = size_t(kN) * kN + kN + 2 * kM;
+  double* d_pq = nullptr;
+  float* d_lu = nullptr;
   CUDA_TRY(e, cudaMalloc(&d_model, nd * sizeof(double)));
   cudaError_t crc = cudaMalloc(&d_contacts, 4 * sizeof(int));
-  if (crc == cudaSuccess) crc = cudaMalloc(&d_out, nout * sizeof(float));
+  if (crc == cudaSuccess) crc = cudaMalloc(&d_pq, npq * sizeof(double));
+  if (crc == cudaSuccess) crc = cudaMalloc(&d_lu, 2 * kM * sizeof(float));
   std::vector<double> hm(nd);
   std::memcpy(hm.data(), A_mat_d, 169 * sizeof(double));
   std::memcpy(hm.data() + 169, B_mat_d_list, size_t(kH) * 156 * sizeof(double));
@@ -423,7 +440,8 @@ int mpc_qp_mats_from_model(MpcEngine* e, const double* A_mat_d, const double* B_
   if (crc == cudaSuccess)
     crc = cudaMemcpyAsync(d_contacts, contacts, 4 * sizeof(int), cudaMemcpyHostToDevice, e->stream);
   int rc = MPC_OK;
-  std::vector<float> ho(nout);
+  std::vector<double> hpq(npq);
+  std::vector<float> hlu(2 * kM);
   if (crc == cudaSuccess) {
     ModelIn m{};
     m.A_d = d_model;
@@ -431,24 +449,28 @@ int mpc_qp_mats_from_model(MpcEngine* e, const double* A_mat_d, const double* B_
     m.x0 = d_model + 169 + kH * 156;
     m.x_ref = d_model + 169 + kH * 156 + 13;
     m.contacts = d_contacts;
-    rc = launch_build(e, nullptr, m, 1, d_out, d_out + kN * kN, d_out + kN * kN + kN,
-                      d_out + kN * kN + kN + kM);
+    rc = launch_build(e, nullptr, m, 1, d_pq, d_pq + size_t(kN) * kNP, d_lu, d_lu + kM);
     if (rc == MPC_OK) {
-      crc = cudaMemcpyAsync(ho.data(), d_out, nout * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+      crc = cudaMemcpyAsync(hpq.data(), d_pq, npq * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+      if (crc == cudaSuccess)
+        crc = cudaMemcpyAsync(hlu.data(), d_lu, 2 * kM * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
       if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
     }
   }
   cudaFree(d_model);
   cudaFree(d_contacts);
-  cudaFree(d_out);
+  cudaFree(d_pq);
+  cudaFree(d_lu);
   if (rc) return rc;
   if (crc != cudaSuccess) return fail(e, MPC_ERR_CUDA, cudaGetErrorString(crc));
-  if (hessian) for (size_t i = 0; i < size_t(kN) * kN; ++i) hessian[i] = ho[i];
-  if (gradient) for (int i = 0; i < kN; ++i) gradient[i] = ho[size_t(kN) * kN + i];
+  if (hessian)
+    for (int r = 0; r < kN; ++r)
+      for (int c = 0; c < kN; ++c) hessian[size_t(r) * kN + c] = hpq[size_t(r) * kNP + c];
+  if (gradient) for (int i = 0; i < kN; ++i) gradient[i] = hpq[size_t(kN) * kNP + i];
   // the device stores bounds in fp32; hand back exactly +-OsqpEigen::INFTY like the reference
   auto snap = [](float v) -> double { return v >= 1e29f ? MPC_INFTY : (v <= -1e29f ? -MPC_INFTY : (double)v); };
-  if (lb) for (int i = 0; i < kM; ++i) lb[i] = snap(ho[size_t(kN) * kN + kN + i]);
-  if (ub) for (int i = 0; i < kM; ++i) ub[i] = snap(ho[size_t(kN) * kN + kN + kM + i]);
+  if (lb) for (int i = 0; i < kM; ++i) lb[i] = snap(hlu[i]);
+  if (ub) for (int i = 0; i < kM; ++i) ub[i] = snap(hlu[kM + i]);
   return MPC_OK;
 }
 
@@ -457,26 +479,30 @@ int mpc_solve_qp(MpcEngine* e, const double* hessian, const double* gradient, co
   if (!e || e->kind != 0) return MPC_ERR_INVALID;
   if (!hessian || !gradient || !lb || !ub || !solution) return fail(e, MPC_ERR_INVALID, "NULL QP input");
   CUDA_TRY(e, cudaSetDevice(e->device));
-  const size_t nin = size_t(kN) * kN + kN + 2 * kM;
-  std::vector<float> hi(nin);
-  for (size_t i = 0; i < size_t(kN) * kN; ++i) hi[i] = (float)hessian[i];
-  for (int i = 0; i < kN; ++i) hi[size_t(kN) * kN + i] = (float)gradient[i];
-  for (int i = 0; i < kM; ++i) hi[size_t(kN) * kN + kN + i] = (float)lb[i];
-  for (int i = 0; i < kM; ++i) hi[size_t(kN) * kN + kN + kM + i] = (float)ub[i];
-  float* d_in = nullptr;
+  const size_t npq = size_t(kN) * kNP + kN;
+  std::vector<double> hpq(npq, 0.0);
+  for (int r = 0; r < kN; ++r)
+    for (int c = 0; c < kN; ++c) hpq[size_t(r) * kNP + c] = hessian[size_t(r) * kN + c];
+  for (int i = 0; i < kN; ++i) hpq[size_t(kN) * kNP + i] = gradient[i];
+  std::vector<float> hlu(2 * kM);
+  for (int i = 0; i < kM; ++i) { hlu[i] = (float)lb[i]; hlu[kM + i] = (float)ub[i]; }
+  double* d_pq = nullptr;
+  float* d_lu = nullptr;
   float* d_xs = nullptr;
   MpcResult* d_res = nullptr;
-  CUDA_TRY(e, cudaMalloc(&d_in, nin * sizeof(float)));
-  cudaError_t crc = cudaMalloc(&d_xs, kN * sizeof(float));
+  CUDA_TRY(e, cudaMalloc(&d_pq, npq * sizeof(double)));
+  cudaError_t crc = cudaMalloc(&d_lu, 2 * kM * sizeof(float));
+  if (crc == cudaSuccess) crc = cudaMalloc(&d_xs, kN * sizeof(float));
   if (crc == cudaSuccess) crc = cudaMalloc(&d_res, sizeof(MpcResult));
   if (crc == cudaSuccess)
-    crc = cudaMemcpyAsync(d_in, hi.data(), nin * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+    crc = cudaMemcpyAsync(d_pq, hpq.data(), npq * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+  if (crc == cudaSuccess)
+    crc = cudaMemcpyAsync(d_lu, hlu.data(), 2 * kM * sizeof(float), cudaMemcpyHostToDevice, e->stream);
   int rc = MPC_OK;
   std::vector<float> hx(kN);
   MpcResult hr{};
   if (crc == cudaSuccess) {
-    rc = launch_solve(e, d_in, d_in + kN * kN, d_in + kN * kN + kN, d_in + kN * kN + kN + kM, nullptr,
-                      d_res, d_xs, 1);
+    rc = launch_solve(e, d_pq, d_pq + size_t(kN) * kNP, d_lu, d_lu + kM, nullptr, d_res, d_xs, 1);
     if (rc == MPC_OK) {
       crc = cudaMemcpyAsync(hx.data(), d_xs, kN * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
       if (crc == cudaSuccess)
@@ -484,7 +510,8 @@ int mpc_solve_qp(MpcEngine* e, const double* hessian, const double* gradient, co
       if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
     }
   }
-  cudaFree(d_in);
+  cudaFree(d_pq);
+  cudaFree(d_lu);
   cudaFree(d_xs);
   cudaFree(d_res);
   if (rc) return rc;
@@ -518,7 +545,7 @@ int balance_solve(MpcEngine* e) {
   if (e->n > 0) {
     const int warps_per_cta = kBalanceThreads / 32;
     const int grid = (e->n + warps_per_cta - 1) / warps_per_cta;
-    balance_qp_kernel<<<grid, kBalanceThreads, 0, e->stream>>>(e->d_bstates, e->n, e->d_P, e->d_q, e->d_l,
+    balance_qp_kernel<<<grid, kBalanceThreads, 0, e->stream>>>(e->d_bstates, e->n, e->d_Pb, e->d_qb, e->d_l,
                                                                e->d_u, e->d_results, e->bal);
     ++e->launches;
     CUDA_TRY(e, cudaGetLastError());
@@ -533,8 +560,8 @@ int balance_get_qp(MpcEngine* e, int32_t idx, float* P, float* q, float* l, floa
   if (idx < 0 || idx >= e->n) return fail(e, MPC_ERR_INVALID, "problem index out of range");
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  if (P) CUDA_TRY(e, cudaMemcpy(P, e->d_P + size_t(idx) * 144, 144 * sizeof(float), cudaMemcpyDeviceToHost));
-  if (q) CUDA_TRY(e, cudaMemcpy(q, e->d_q + size_t(idx) * 12, 12 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (P) CUDA_TRY(e, cudaMemcpy(P, e->d_Pb + size_t(idx) * 144, 144 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (q) CUDA_TRY(e, cudaMemcpy(q, e->d_qb + size_t(idx) * 12, 12 * sizeof(float), cudaMemcpyDeviceToHost));
   if (l) CUDA_TRY(e, cudaMemcpy(l, e->d_l + size_t(idx) * 20, 20 * sizeof(float), cudaMemcpyDeviceToHost));
   if (u) CUDA_TRY(e, cudaMemcpy(u, e->d_u + size_t(idx) * 20, 20 * sizeof(float), cudaMemcpyDeviceToHost));
   return MPC_OK;
