@@ -45,6 +45,14 @@ F_ITER = 33.0e3
 FP64_PEAK_TFLOPS = 34.1
 
 
+def host_cores():
+    """Host cores this process may use (all of them: the CPU arm is one problem per thread)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks and throttle reasons DURING the timed region."""
 
@@ -93,7 +101,7 @@ def run_reference(args):
     import go1_qp_mpc_controller_b200 as pkg
     import oracle_binding as ob
     cfg = pkg.config_default()
-    threads = ob.max_threads()
+    threads = host_cores()  # torchrun exports OMP_NUM_THREADS=1; num_threads() overrides it
     sample = 1024  # bounded sample of the 4096-state batch per step
     times = []
     for step in range(args.warmup + args.steps):
@@ -243,7 +251,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_binding as ob
-        threads = ob.max_threads()
+        threads = host_cores()
         sample = 2048
         t0 = time.perf_counter()
         ref = ob.mpc_compute_grf(cfg, host_batches[nsteps - 1][:sample], threads=threads)
