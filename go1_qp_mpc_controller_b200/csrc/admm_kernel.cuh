@@ -14,9 +14,10 @@
 //     lane cg = 0 : variable fx + row 0      lane cg = 1 : row 1
 //     lane cg = 4 : variable fy + row 2      lane cg = 5 : row 3
 //     lane cg = 8 : variable fz + row 4
-//   K^-1 comes from a symmetric sweep (Gauss-Jordan on the SPD matrix) over the register
-//   tiles: per pivot one published row; the row of the NEXT pivot is updated and
-//   published first (look-ahead), so the barrier never waits on the publisher.
+//   K^-1 comes from a BLOCKED symmetric sweep (Gauss-Jordan on the SPD matrix) over the
+//   register tiles: a row group is exactly 3 pivot rows, so one rank-3 update per barrier;
+//   the pivot block of the NEXT step is brought up to date, its 3x3 inverted and published
+//   first (look-ahead).  (A one-pivot-per-barrier sweep spent 40 % of its time at the barrier.)
 //   P arrives by one cp.async.bulk (TMA) per problem into shared memory.
 #pragma once
 
@@ -36,9 +37,8 @@ struct SolveSmem {
   double rhs[2][kNP];       // operand of the K^-1 matvec, double buffered by iteration parity (pad = 0)
   double xD[kNP];           // D .* x for P x (pad = 0)
   double Dp[kNP];           // D (pad = 0)
-  double buf[2][kNP];       // sweep: published pivot row v' (pivot replaced by d-1)
-  double wbuf[2][kNP];      // sweep: -v / d
-  double piv[2][2];         // sweep: 1/d
+  double Vb[2][3][kNP];     // blocked sweep: published pivot rows A_S,: with A_SS replaced by A_SS - I
+  double Wb[2][3][kNP];     // blocked sweep: -(A_SS^-1 A_S,:)
   double G[kLegSteps * 6];  // A' diag(rho) A per leg-step: xx, xz, yy, yz, zz, (pad)
   double red[kSolveWarps * 16];
   double scal[8];           // 0:c 1:cinv 2:rho 3:ct 4:pri_res
@@ -129,81 +129,81 @@ __device__ __forceinline__ double row_norm_pass(const SolveSmem& sm, int rg, int
   return reduce_scatter3_max(m[0], m[1], m[2], cg);
 }
 
-// publish row `kn` (the next pivot) held in a[nr][*] by the 16 lanes of its row group
-__device__ __forceinline__ void publish_row(SolveSmem& sm, const double (&row)[8], int kn, int cg, int hb,
-                                            int nxt) {
-  // the pivot d = a[kn][kn] lives on lane (kn >> 1) & 15 at tile position 2 * (kn >> 5) + (kn & 1)
-  const int pcg = (kn >> 1) & 15, pi = kn >> 5, pe = kn & 1;
-  double cand = 0.0;
+// Blocked symmetric sweep, one leg-step (3 pivots S = {3kb, 3kb+1, 3kb+2}) per barrier.
+// With V = A_S,: (before the step), M = A_SS^-1, W = -M V the step is
+//   A_rj <- A_rj + sum_s W[s][r] V'[s][j]   (r not in S; V' = V with A_SS - I in the S columns,
+//                                            which makes the same update produce A_rS M)
+//   A_Sj <- -W[:, j] (j not in S),  A_SS <- -M
+// (W[s][r] doubles as the column factor because A is symmetric).  The row group kb IS S, so
+// its 16 lanes hold V entirely.
+__device__ __forceinline__ void publish_block(SolveSmem& sm, double (&a)[3][8], int kb, int cg, int hb, int b) {
+  const unsigned hmask = 0xffffu << hb;  // only this half-warp executes here
+  const int c0 = 3 * kb;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (i == pi) cand = pe ? row[2 * i + 1] : row[2 * i];
-  // only this half-warp (one row group) executes here: shuffle with its 16-lane mask
-  const double d = __shfl_sync(0xffffu << hb, cand, hb + pcg);
-  const double dinv = __drcp_rn(d);
-  double2* vdst = reinterpret_cast<double2*>(&sm.buf[nxt][2 * cg]);
-  double2* wdst = reinterpret_cast<double2*>(&sm.wbuf[nxt][2 * cg]);
+  for (int s3 = 0; s3 < 3; ++s3) {
+    double2* dst = reinterpret_cast<double2*>(&sm.Vb[b][s3][2 * cg]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = 32 * i + 2 * cg;
+      double v0 = a[s3][2 * i], v1 = a[s3][2 * i + 1];
+      if (col == c0 + s3) v0 -= 1.0;
+      if (col + 1 == c0 + s3) v1 -= 1.0;
+      dst[16 * i] = make_double2(v0, v1);
+    }
+  }
+  __syncwarp(hmask);
+  // A_SS (identity added back), symmetric 3x3 cofactor inverse on every lane
+  const double m00 = sm.Vb[b][0][c0] + 1.0, m01 = sm.Vb[b][0][c0 + 1], m02 = sm.Vb[b][0][c0 + 2];
+  const double m11 = sm.Vb[b][1][c0 + 1] + 1.0, m12 = sm.Vb[b][1][c0 + 2];
+  const double m22 = sm.Vb[b][2][c0 + 2] + 1.0;
+  const double k00 = m11 * m22 - m12 * m12, k01 = m02 * m12 - m01 * m22, k02 = m01 * m12 - m02 * m11;
+  const double id = 1.0 / (m00 * k00 + m01 * k01 + m02 * k02);
+  const double i00 = k00 * id, i01 = k01 * id, i02 = k02 * id;
+  const double i11 = (m00 * m22 - m02 * m02) * id, i12 = (m01 * m02 - m00 * m12) * id;
+  const double i22 = (m00 * m11 - m01 * m01) * id;
+  double2* w0d = reinterpret_cast<double2*>(&sm.Wb[b][0][2 * cg]);
+  double2* w1d = reinterpret_cast<double2*>(&sm.Wb[b][1][2 * cg]);
+  double2* w2d = reinterpret_cast<double2*>(&sm.Wb[b][2][2 * cg]);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    double v0 = row[2 * i], v1 = row[2 * i + 1];
-    wdst[16 * i] = make_double2(-v0 * dinv, -v1 * dinv);
-    if (cg == pcg && i == pi) {
-      if (pe) v1 = d - 1.0; else v0 = d - 1.0;
+    double w0[2], w1[2], w2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int jj = 2 * i + e;
+      const double x0 = a[0][jj], x1 = a[1][jj], x2 = a[2][jj];
+      w0[e] = -(i00 * x0 + i01 * x1 + i02 * x2);
+      w1[e] = -(i01 * x0 + i11 * x1 + i12 * x2);
+      w2[e] = -(i02 * x0 + i12 * x1 + i22 * x2);
+      const int t = 32 * i + 2 * cg + e - c0;  // position inside S, if any
+      a[0][jj] = (t == 0) ? -i00 : (t == 1) ? -i01 : (t == 2) ? -i02 : -w0[e];
+      a[1][jj] = (t == 0) ? -i01 : (t == 1) ? -i11 : (t == 2) ? -i12 : -w1[e];
+      a[2][jj] = (t == 0) ? -i02 : (t == 1) ? -i12 : (t == 2) ? -i22 : -w2[e];
     }
-    vdst[16 * i] = make_double2(v0, v1);
+    w0d[16 * i] = make_double2(w0[0], w0[1]);
+    w1d[16 * i] = make_double2(w1[0], w1[1]);
+    w2d[16 * i] = make_double2(w2[0], w2[1]);
   }
-  if (cg == pcg) sm.piv[nxt][0] = dinv;
 }
 
-// One pivot of the sweep: k = 3 kb + KR (KR is a template parameter so that every register
-// index below is static).
-template <int KR>
-__device__ __forceinline__ void sweep_step(SolveSmem& sm, double (&a)[3][8], int kb, int rg, int cg, int hb) {
-  constexpr int NR = (KR + 1) % 3;  // tile row of the next pivot
-  const int k = 3 * kb + KR;
-  const int cur = k & 1, nxt = cur ^ 1;
-  __syncthreads();  // row k (published one step ahead) is visible
-  double vcol[8];
-  load_cols(sm.buf[cur], cg, vcol);
-  const double* wr = &sm.wbuf[cur][3 * rg];
-  double w[3];
-  w[0] = wr[0];
-  w[1] = wr[1];
-  w[2] = wr[2];
-  const bool piv_rg = (rg == kb);
-  // look-ahead: the row of the next pivot is updated and published first
-  const bool next_rg = (KR < 2) ? piv_rg : (rg == kb + 1);
-  if (next_rg) {
+// rank-3 update of this thread's tile with the published block in buffer b
+__device__ __forceinline__ void apply_block(const SolveSmem& sm, double (&a)[3][8], int rg, int cg, int b) {
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) a[NR][jj] = fma(w[NR], vcol[jj], a[NR][jj]);
-    if (k + 1 < kN) publish_row(sm, a[NR], k + 1, cg, hb, nxt);
-  }
+  for (int s3 = 0; s3 < 3; ++s3) {
+    double v[8];
+    load_cols(sm.Vb[b][s3], cg, v);
+    const double* wp = &sm.Wb[b][s3][3 * rg];
+    const double w0 = wp[0], w1 = wp[1], w2 = wp[2];
 #pragma unroll
-  for (int rr = 0; rr < 3; ++rr) {
-    if (rr == NR) {
-      if (!next_rg) {
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) a[rr][jj] = fma(w[rr], vcol[jj], a[rr][jj]);
-      }
-    } else if (rr == KR && piv_rg) {
-      const double dinv = sm.piv[cur][0];
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int col = 32 * (jj >> 1) + 2 * cg + (jj & 1);
-        a[rr][jj] = (col == k) ? -dinv : a[rr][jj] * dinv;
-      }
-    } else {
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) a[rr][jj] = fma(w[rr], vcol[jj], a[rr][jj]);
+    for (int jj = 0; jj < 8; ++jj) {
+      a[0][jj] = fma(w0, v[jj], a[0][jj]);
+      a[1][jj] = fma(w1, v[jj], a[1][jj]);
+      a[2][jj] = fma(w2, v[jj], a[2][jj]);
     }
   }
 }
 
 // Build K = c D P D + sigma I + A' diag(rho) A into the register tiles, then overwrite it
-// with -K^-1 by the symmetric sweep operator.  Step k applies, with v = row k before the step,
-//   a_rj <- a_rj - (v_r / d) v'_j   (r != k; v'_k = d - 1 makes the same update produce column k)
-//   a_kj <- v_j / d,  a_kk <- -1/d
-// and relies on a_rk == a_kr (symmetry) so the published ROW also supplies column k.
+// with -K^-1 by the blocked symmetric sweep (40 rank-3 steps, one barrier each).
 __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[3][8], int rg, int cg, int hb,
                                                double sigma) {
   {
@@ -235,11 +235,13 @@ __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[3][8],
       }
     }
   }
-  if (rg == 0) publish_row(sm, a[0], 0, cg, hb, 0);
+  if (rg == 0) publish_block(sm, a, 0, cg, hb, 0);
   for (int kb = 0; kb < kLegSteps; ++kb) {
-    sweep_step<0>(sm, a, kb, rg, cg, hb);
-    sweep_step<1>(sm, a, kb, rg, cg, hb);
-    sweep_step<2>(sm, a, kb, rg, cg, hb);
+    const int b = kb & 1;
+    __syncthreads();  // block kb (published one step ahead) is visible
+    if (rg != kb) apply_block(sm, a, rg, cg, b);
+    // look-ahead: the next pivot block is brought up to date and published first
+    if (rg == kb + 1) publish_block(sm, a, kb + 1, cg, hb, b ^ 1);
   }
 }
 
@@ -252,7 +254,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
                   const float* __restrict__ l_all, const float* __restrict__ u_all,
                   const MpcStateIn* __restrict__ states, MpcResult* __restrict__ results,
                   float* __restrict__ x_all, int num, int* __restrict__ counter,
-                  const __grid_constant__ SolveParams sp) {
+                  long long* __restrict__ phase_clk, const __grid_constant__ SolveParams sp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -275,6 +277,10 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
   }
   uint32_t phase = 0;
   double a[3][8];  // register tile of -K^-1
+  // optional per-phase cycle counters (thread 0; phase_clk == nullptr in production)
+  long long pc[6] = {0, 0, 0, 0, 0, 0};  // 0 load+ruiz 1 factor 2 iterations 3 checks 4 output 5 problems
+  long long tmark = 0;
+#define PHASE_MARK(i) do { if (phase_clk != nullptr && tid == 0) { const long long _t = clock64(); pc[i] += _t - tmark; tmark = _t; } } while (0)
 
   for (;;) {
     __syncthreads();
@@ -295,16 +301,20 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     __syncthreads();
     const int p = sm.flags[3];
     if (p >= num) break;
+    if (phase_clk != nullptr && tid == 0) { tmark = clock64(); pc[5] += 1; }
 
     if (tid < kNP) {
       sm.Dp[tid] = (tid < kN) ? 1.0 : 0.0;
       sm.rhs[0][tid] = 0.0;
       sm.rhs[1][tid] = 0.0;
       sm.xD[tid] = 0.0;
-      sm.buf[0][tid] = 0.0;
-      sm.buf[1][tid] = 0.0;
-      sm.wbuf[0][tid] = 0.0;
-      sm.wbuf[1][tid] = 0.0;
+#pragma unroll
+      for (int s3 = 0; s3 < 3; ++s3) {
+        sm.Vb[0][s3][tid] = 0.0;
+        sm.Vb[1][s3][tid] = 0.0;
+        sm.Wb[0][s3][tid] = 0.0;
+        sm.Wb[1][s3][tid] = 0.0;
+      }
     }
     if (tid == 0) {
       sm.scal[0] = 1.0;
@@ -417,8 +427,10 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     if (vown) sm.rhs[1][vj] = -qb;  // rhs of iteration 1: x = z = y = 0
     __syncthreads();
 
+    PHASE_MARK(0);
     // ---- K3b: factor (explicit inverse in registers) ----
     factor_inverse(sm, a, rg, cg, hb, sigma);
+    PHASE_MARK(1);
 
     // ---- K4: ADMM iterations (osqp.c osqp_solve) ----
     double x = 0.0, z = 0.0, y = 0.0;  // x on variable lanes; z, y on row lanes
@@ -465,6 +477,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
                              (iter % sp.adaptive_rho_interval == 0);
       const bool last = (iter == sp.max_iter);
       if (!(can_check || can_adapt || last)) continue;
+      PHASE_MARK(2);
 
       // ---- residuals (auxil.c compute_pri_res / compute_dua_res / tolerances) ----
       if (vown) sm.xD[vj] = D * x;
@@ -556,6 +569,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         sm.flags[2] = refactor;
       }
       __syncthreads();
+      PHASE_MARK(3);
       if (sm.flags[0]) {
         status = sm.flags[1];
         pri_res_out = sm.scal[4];
@@ -575,6 +589,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         build_G();
         __syncthreads();
         factor_inverse(sm, a, rg, cg, hb, sigma);
+        PHASE_MARK(1);
       }
     }
     if (iter > sp.max_iter) iter = sp.max_iter;
@@ -604,7 +619,13 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       results[p].rho_updates = rho_updates;
       results[p].pri_res = (float)pri_res_out;
     }
+    PHASE_MARK(4);
   }
+  if (phase_clk != nullptr && tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) phase_clk[blockIdx.x * 6 + i] = pc[i];
+  }
+#undef PHASE_MARK
 }
 
 }  // namespace mpcb200

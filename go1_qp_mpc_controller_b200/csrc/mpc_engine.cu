@@ -43,6 +43,7 @@ struct MpcEngine {
   float* d_x = nullptr;
   MpcResult* d_results = nullptr;
   int* d_counter = nullptr;
+  long long* d_phase_clk = nullptr;  // optional per-phase cycle counters (mpc_debug_phase_cycles)
   bool built = false, solved = false;
   int64_t launches = 0;
   BuildParams bp{};
@@ -174,7 +175,7 @@ int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l,
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
   const int grid = n < e->num_sms ? n : e->num_sms;
   admm_solve_kernel<<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(P, q, l, u, d_states, res, x, n,
-                                                                      e->d_counter, e->sp);
+                                                                           e->d_counter, e->d_phase_clk, e->sp);
   ++e->launches;
   CUDA_TRY(e, cudaGetLastError());
   return MPC_OK;
@@ -261,6 +262,7 @@ void mpc_engine_destroy(MpcEngine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   free_buffers(e);
   cudaFree(e->d_counter);
+  cudaFree(e->d_phase_clk);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -283,6 +285,27 @@ int mpc_synchronize(MpcEngine* e) {
 }
 
 int64_t mpc_kernel_launches(const MpcEngine* e) { return e ? e->launches : 0; }
+
+int mpc_debug_phase_cycles(MpcEngine* e, int32_t enable, int64_t* out6) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  const size_t n = size_t(e->num_sms) * 6;
+  if (out6 && e->d_phase_clk) {
+    std::vector<long long> h(n);
+    CUDA_TRY(e, cudaMemcpy(h.data(), e->d_phase_clk, n * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; ++i) out6[i] = 0;
+    for (size_t k = 0; k < n; ++k) out6[k % 6] += h[k];
+  }
+  if (enable && !e->d_phase_clk) {
+    CUDA_TRY(e, cudaMalloc(&e->d_phase_clk, n * sizeof(long long)));
+  } else if (!enable && e->d_phase_clk) {
+    cudaFree(e->d_phase_clk);
+    e->d_phase_clk = nullptr;
+  }
+  if (e->d_phase_clk) CUDA_TRY(e, cudaMemset(e->d_phase_clk, 0, n * sizeof(long long)));
+  return MPC_OK;
+}
 
 int mpc_load_states(MpcEngine* e, const MpcStateIn* host, int32_t n) {
   if (!e || e->kind != 0) return MPC_ERR_INVALID;

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "mpc_settings_osqp_default", "mpc_settings_benchmark", "mpc_config_default",
     "mpc_config_hardware", "balance_config_default", "mpc_generate_states",
     "balance_generate_states", "mpc_engine_create", "mpc_engine_destroy", "mpc_last_error",
-    "mpc_set_stream", "mpc_synchronize", "mpc_kernel_launches", "mpc_load_states",
+    "mpc_set_stream", "mpc_synchronize", "mpc_kernel_launches", "mpc_debug_phase_cycles", "mpc_load_states",
     "mpc_set_states_device", "mpc_build_qp", "mpc_build_qp_async", "mpc_get_qp", "mpc_solve",
     "mpc_solve_async", "mpc_get_results", "mpc_results_device", "mpc_get_solution",
     "mpc_compute_grf_batch", "mpc_qp_mats_from_model", "mpc_solve_qp", "balance_engine_create",
@@ -173,6 +173,13 @@ class MpcEngine:
 
     def kernel_launches(self):
         return int(self._lib.mpc_kernel_launches(self._h))
+
+    def phase_cycles(self, enable=True):
+        """Developer aid: read and reset admm_solve_kernel's per-phase cycle counters."""
+        out = (C.c_int64 * 6)()
+        self._lib.mpc_debug_phase_cycles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        self._check(self._lib.mpc_debug_phase_cycles(self._h, 1 if enable else 0, out))
+        return dict(zip(["load_scale", "factor", "iterations", "checks", "output", "problems"], list(out)))
 
     def load_states(self, states):
         states = np.ascontiguousarray(states)
