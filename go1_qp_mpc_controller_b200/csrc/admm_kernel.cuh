@@ -16,8 +16,9 @@
 //     lane cg = 8 : variable fz + row 4
 //   K^-1 comes from a BLOCKED symmetric sweep (Gauss-Jordan on the SPD matrix) over the
 //   register tiles: a row group is exactly 3 pivot rows, so one rank-3 update per barrier;
-//   the pivot block of the NEXT step is brought up to date, its 3x3 inverted and published
-//   first (look-ahead).  (A one-pivot-per-barrier sweep spent 40 % of its time at the barrier.)
+//   the publisher stores only its three rows, every thread inverts the 3x3 pivot block itself.
+//   (One pivot per barrier, or M/W computed by the publisher alone, left 40-50 % of the sweep
+//   time at the barrier: profiles/r01_v3_*, r01_v4_*.)
 //   P arrives by one cp.async.bulk (TMA) per problem into shared memory.
 #pragma once
 
@@ -38,8 +39,10 @@ struct SolveSmem {
   double xD[kNP];           // D .* x for P x (pad = 0)
   double Dp[kNP];           // D (pad = 0)
   double Vb[2][3][kNP];     // blocked sweep: published pivot rows A_S,: with A_SS replaced by A_SS - I
-  double Wb[2][3][kNP];     // blocked sweep: -(A_SS^-1 A_S,:)
   double G[kLegSteps * 6];  // A' diag(rho) A per leg-step: xx, xz, yy, yz, zz, (pad)
+  // per-lane constants of the ADMM loop (slot [k][tid]); registers are kept for the K^-1 tile
+  double lane_lb[kSolveThreads], lane_ub[kSolveThreads], lane_rv[kSolveThreads], lane_rinv[kSolveThreads];
+  double lane_qb[kSolveThreads], lane_D[kSolveThreads], lane_Einv[kSolveThreads];
   double red[kSolveWarps * 16];
   double scal[8];           // 0:c 1:cinv 2:rho 3:ct 4:pri_res
   unsigned long long mbar;
@@ -135,9 +138,10 @@ __device__ __forceinline__ double row_norm_pass(const SolveSmem& sm, int rg, int
 //                                            which makes the same update produce A_rS M)
 //   A_Sj <- -W[:, j] (j not in S),  A_SS <- -M
 // (W[s][r] doubles as the column factor because A is symmetric).  The row group kb IS S, so
-// its 16 lanes hold V entirely.
-__device__ __forceinline__ void publish_block(SolveSmem& sm, double (&a)[3][8], int kb, int cg, int hb, int b) {
-  const unsigned hmask = 0xffffu << hb;  // only this half-warp executes here
+// its 16 lanes hold V entirely and publish ONLY V' (12 stores): every thread inverts the 3x3
+// pivot block itself and forms the 3x3 block of W it needs.  Doing M and W on the publishing
+// half-warp alone left the other 19 warps at the barrier for half of every step.
+__device__ __forceinline__ void publish_rows(SolveSmem& sm, const double (&a)[3][8], int kb, int cg, int b) {
   const int c0 = 3 * kb;
 #pragma unroll
   for (int s3 = 0; s3 < 3; ++s3) {
@@ -151,53 +155,51 @@ __device__ __forceinline__ void publish_block(SolveSmem& sm, double (&a)[3][8], 
       dst[16 * i] = make_double2(v0, v1);
     }
   }
-  __syncwarp(hmask);
-  // A_SS (identity added back), symmetric 3x3 cofactor inverse on every lane
+}
+
+// One step of the blocked sweep for this thread's tile, block kb published in buffer b.
+__device__ __forceinline__ void sweep_block(const SolveSmem& sm, double (&a)[3][8], int kb, int rg, int cg,
+                                            int b) {
+  const int c0 = 3 * kb;
+  // A_SS (identity added back) and its symmetric 3x3 cofactor inverse, on every thread
   const double m00 = sm.Vb[b][0][c0] + 1.0, m01 = sm.Vb[b][0][c0 + 1], m02 = sm.Vb[b][0][c0 + 2];
   const double m11 = sm.Vb[b][1][c0 + 1] + 1.0, m12 = sm.Vb[b][1][c0 + 2];
   const double m22 = sm.Vb[b][2][c0 + 2] + 1.0;
   const double k00 = m11 * m22 - m12 * m12, k01 = m02 * m12 - m01 * m22, k02 = m01 * m12 - m02 * m11;
-  const double id = 1.0 / (m00 * k00 + m01 * k01 + m02 * k02);
+  const double id = __drcp_rn(m00 * k00 + m01 * k01 + m02 * k02);
   const double i00 = k00 * id, i01 = k01 * id, i02 = k02 * id;
   const double i11 = (m00 * m22 - m02 * m02) * id, i12 = (m01 * m02 - m00 * m12) * id;
   const double i22 = (m00 * m11 - m01 * m01) * id;
-  double2* w0d = reinterpret_cast<double2*>(&sm.Wb[b][0][2 * cg]);
-  double2* w1d = reinterpret_cast<double2*>(&sm.Wb[b][1][2 * cg]);
-  double2* w2d = reinterpret_cast<double2*>(&sm.Wb[b][2][2 * cg]);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double w0[2], w1[2], w2[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int jj = 2 * i + e;
-      const double x0 = a[0][jj], x1 = a[1][jj], x2 = a[2][jj];
-      w0[e] = -(i00 * x0 + i01 * x1 + i02 * x2);
-      w1[e] = -(i01 * x0 + i11 * x1 + i12 * x2);
-      w2[e] = -(i02 * x0 + i12 * x1 + i22 * x2);
-      const int t = 32 * i + 2 * cg + e - c0;  // position inside S, if any
-      a[0][jj] = (t == 0) ? -i00 : (t == 1) ? -i01 : (t == 2) ? -i02 : -w0[e];
-      a[1][jj] = (t == 0) ? -i01 : (t == 1) ? -i11 : (t == 2) ? -i12 : -w1[e];
-      a[2][jj] = (t == 0) ? -i02 : (t == 1) ? -i12 : (t == 2) ? -i22 : -w2[e];
-    }
-    w0d[16 * i] = make_double2(w0[0], w0[1]);
-    w1d[16 * i] = make_double2(w1[0], w1[1]);
-    w2d[16 * i] = make_double2(w2[0], w2[1]);
-  }
-}
-
-// rank-3 update of this thread's tile with the published block in buffer b
-__device__ __forceinline__ void apply_block(const SolveSmem& sm, double (&a)[3][8], int rg, int cg, int b) {
-#pragma unroll
-  for (int s3 = 0; s3 < 3; ++s3) {
-    double v[8];
-    load_cols(sm.Vb[b][s3], cg, v);
-    const double* wp = &sm.Wb[b][s3][3 * rg];
-    const double w0 = wp[0], w1 = wp[1], w2 = wp[2];
+  if (rg == kb) {
+    // pivot rows: A_Sj <- M A_Sj, A_SS <- -M
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-      a[0][jj] = fma(w0, v[jj], a[0][jj]);
-      a[1][jj] = fma(w1, v[jj], a[1][jj]);
-      a[2][jj] = fma(w2, v[jj], a[2][jj]);
+      const double x0 = a[0][jj], x1 = a[1][jj], x2 = a[2][jj];
+      const int t = 32 * (jj >> 1) + 2 * cg + (jj & 1) - c0;  // position inside S, if any
+      a[0][jj] = (t == 0) ? -i00 : (t == 1) ? -i01 : (t == 2) ? -i02 : (i00 * x0 + i01 * x1 + i02 * x2);
+      a[1][jj] = (t == 0) ? -i01 : (t == 1) ? -i11 : (t == 2) ? -i12 : (i01 * x0 + i11 * x1 + i12 * x2);
+      a[2][jj] = (t == 0) ? -i02 : (t == 1) ? -i12 : (t == 2) ? -i22 : (i02 * x0 + i12 * x1 + i22 * x2);
+    }
+  } else {
+    // W[s][r] = -(M V[:, r])[s] for the thread's three rows (V = V' there: r is not in S)
+    double w[3][3];
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) {
+      const double x0 = sm.Vb[b][0][3 * rg + rr], x1 = sm.Vb[b][1][3 * rg + rr], x2 = sm.Vb[b][2][3 * rg + rr];
+      w[0][rr] = -(i00 * x0 + i01 * x1 + i02 * x2);
+      w[1][rr] = -(i01 * x0 + i11 * x1 + i12 * x2);
+      w[2][rr] = -(i02 * x0 + i12 * x1 + i22 * x2);
+    }
+#pragma unroll
+    for (int s3 = 0; s3 < 3; ++s3) {
+      double v[8];
+      load_cols(sm.Vb[b][s3], cg, v);
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        a[0][jj] = fma(w[s3][0], v[jj], a[0][jj]);
+        a[1][jj] = fma(w[s3][1], v[jj], a[1][jj]);
+        a[2][jj] = fma(w[s3][2], v[jj], a[2][jj]);
+      }
     }
   }
 }
@@ -235,13 +237,13 @@ __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[3][8],
       }
     }
   }
-  if (rg == 0) publish_block(sm, a, 0, cg, hb, 0);
+  if (rg == 0) publish_rows(sm, a, 0, cg, 0);
   for (int kb = 0; kb < kLegSteps; ++kb) {
     const int b = kb & 1;
-    __syncthreads();  // block kb (published one step ahead) is visible
-    if (rg != kb) apply_block(sm, a, rg, cg, b);
-    // look-ahead: the next pivot block is brought up to date and published first
-    if (rg == kb + 1) publish_block(sm, a, kb + 1, cg, hb, b ^ 1);
+    __syncthreads();  // rows of block kb (published one step ahead) are visible
+    sweep_block(sm, a, kb, rg, cg, b);
+    // look-ahead: the next pivot rows are now up to date; publish them for step kb + 1
+    if (rg == kb + 1) publish_rows(sm, a, kb + 1, cg, b ^ 1);
   }
 }
 
@@ -249,6 +251,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+template <bool kProfile>
 __global__ void __launch_bounds__(kSolveThreads, 1)
 admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q_all,
                   const float* __restrict__ l_all, const float* __restrict__ u_all,
@@ -277,10 +280,11 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
   }
   uint32_t phase = 0;
   double a[3][8];  // register tile of -K^-1
-  // optional per-phase cycle counters (thread 0; phase_clk == nullptr in production)
-  long long pc[6] = {0, 0, 0, 0, 0, 0};  // 0 load+ruiz 1 factor 2 iterations 3 checks 4 output 5 problems
+  // per-phase cycle counters of thread 0: compiled in only for the kProfile instantiation
+  // (they cost 14 registers the production kernel cannot spare)
+  long long pc[kProfile ? 6 : 1] = {0};  // 0 load+ruiz 1 factor 2 iterations 3 checks 4 output 5 problems
   long long tmark = 0;
-#define PHASE_MARK(i) do { if (phase_clk != nullptr && tid == 0) { const long long _t = clock64(); pc[i] += _t - tmark; tmark = _t; } } while (0)
+#define PHASE_MARK(i) do { if (kProfile && tid == 0) { const long long _t = clock64(); pc[kProfile ? (i) : 0] += _t - tmark; tmark = _t; } } while (0)
 
   for (;;) {
     __syncthreads();
@@ -301,7 +305,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     __syncthreads();
     const int p = sm.flags[3];
     if (p >= num) break;
-    if (phase_clk != nullptr && tid == 0) { tmark = clock64(); pc[5] += 1; }
+    if (kProfile && tid == 0) { tmark = clock64(); pc[kProfile ? 5 : 0] += 1; }
 
     if (tid < kNP) {
       sm.Dp[tid] = (tid < kN) ? 1.0 : 0.0;
@@ -312,8 +316,6 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       for (int s3 = 0; s3 < 3; ++s3) {
         sm.Vb[0][s3][tid] = 0.0;
         sm.Vb[1][s3][tid] = 0.0;
-        sm.Wb[0][s3][tid] = 0.0;
-        sm.Wb[1][s3][tid] = 0.0;
       }
     }
     if (tid == 0) {
@@ -393,19 +395,15 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         nP = nP2 * sm.scal[3];
       }
     }
-    // ---- scaled data on the owning lanes ----
+    // ---- scaled data on the owning lanes (constants go to per-lane shared-memory slots) ----
     const double c = sm.scal[0];
-    const double cinv = 1.0 / c;
-    const double Dinv = 1.0 / D, Einv = 1.0 / E;
-    const double qb = c * D * q0;
+    const double qb0 = c * D * q0;
     lb *= E;
     ub *= E;
     int ctype = 0;
     if (lb < -MPC_INFTY * 1e-4 && ub > MPC_INFTY * 1e-4) ctype = -1;
     else if (ub - lb < 1e-4) ctype = 1;
-    double rho = sp.rho;
-    double rv = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * rho : rho;
-    double rinv = 1.0 / rv;
+    double rv = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * sp.rho : sp.rho;
     // scaled constraint coefficients of the owned row: z~_i = cca * x~_lat + ccz * x~_z
     double cca, ccz;
     {
@@ -414,9 +412,17 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       ccz = (re == 4) ? E * Dz : ((re & 1) ? -mu : mu) * E * Dz;
       if (!rown) { cca = 0.0; ccz = 0.0; }
     }
+    sm.lane_lb[tid] = lb;
+    sm.lane_ub[tid] = ub;
+    sm.lane_rv[tid] = rv;
+    sm.lane_rinv[tid] = 1.0 / rv;
+    sm.lane_qb[tid] = qb0;
+    sm.lane_D[tid] = D;
+    sm.lane_Einv[tid] = 1.0 / E;
+    if (tid == 0) sm.scal[1] = 1.0 / c;
     auto build_G = [&]() {
       // A' diag(rho) A of this leg-step from the five row lanes
-      const double r0 = rown ? rv : 0.0;
+      const double r0 = rown ? sm.lane_rv[tid] : 0.0;
       const LegSums s1 = leg_reduce(r0 * cca * cca, r0 * ccz * ccz, hb);  // xx|yy on lanes 0|4, zz on lane 8
       const LegSums s2 = leg_reduce(r0 * cca * ccz, 0.0, hb);             // xz|yz on lanes 0|4
       if (cg == 0) { sm.G[rg * 6 + 0] = s1.lat; sm.G[rg * 6 + 1] = s2.lat; }
@@ -424,7 +430,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       if (cg == 8) sm.G[rg * 6 + 4] = s1.z;
     };
     build_G();
-    if (vown) sm.rhs[1][vj] = -qb;  // rhs of iteration 1: x = z = y = 0
+    if (vown) sm.rhs[1][vj] = -qb0;  // rhs of iteration 1: x = z = y = 0
     __syncthreads();
 
     PHASE_MARK(0);
@@ -436,6 +442,9 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     double x = 0.0, z = 0.0, y = 0.0;  // x on variable lanes; z, y on row lanes
     int iter = 0, rho_updates = 0, status = MPC_STATUS_UNSOLVED;
     double pri_res_out = 0.0;
+    // countdowns instead of iter % interval (runtime divisors cost ~50 instructions per iteration)
+    int until_check = sp.check_termination > 0 ? sp.check_termination : 0x7fffffff;
+    int until_adapt = (sp.adaptive_rho && sp.adaptive_rho_interval > 0) ? sp.adaptive_rho_interval : 0x7fffffff;
     for (iter = 1; iter <= sp.max_iter; ++iter) {
       __syncthreads();  // rhs[iter & 1] is complete; rhs[(iter + 1) & 1] is free to rewrite
       // x~ = K^-1 rhs
@@ -459,28 +468,33 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       // x <- alpha x~ + (1 - alpha) x
       x = alpha * xt + (1.0 - alpha) * x;
       // z~ = A x~ ; z, y update on the row lanes
-      const double xt_lat = shfl(xt, latsrc), xt_z = shfl(xt, zsrc);
-      const double zt = cca * xt_lat + ccz * xt_z;
-      const double zr = alpha * zt + (1.0 - alpha) * z;
-      double zn = zr + rinv * y;
-      zn = fmin(fmax(zn, lb), ub);
-      y = y + rv * (zr - zn);
-      z = zn;
+      const double rvv = sm.lane_rv[tid];
+      {
+        const double xt_lat = shfl(xt, latsrc), xt_z = shfl(xt, zsrc);
+        const double zt = cca * xt_lat + ccz * xt_z;
+        const double zr = alpha * zt + (1.0 - alpha) * z;
+        double zn = zr + sm.lane_rinv[tid] * y;
+        zn = fmin(fmax(zn, sm.lane_lb[tid]), sm.lane_ub[tid]);
+        y = y + rvv * (zr - zn);
+        z = zn;
+      }
       // next rhs = sigma x - q + A'(rho z - y)
       {
-        const double w = rown ? (rv * z - y) : 0.0;
+        const double w = rown ? (rvv * z - y) : 0.0;
         const LegSums s = leg_reduce(cca * w, ccz * w, hb);
-        if (vown) sm.rhs[(iter + 1) & 1][vj] = sigma * x - qb + ((vc == 2) ? s.z : s.lat);
+        if (vown) sm.rhs[(iter + 1) & 1][vj] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
       }
-      const bool can_check = sp.check_termination > 0 && (iter % sp.check_termination == 0);
-      const bool can_adapt = sp.adaptive_rho && sp.adaptive_rho_interval > 0 &&
-                             (iter % sp.adaptive_rho_interval == 0);
+      const bool can_check = (--until_check == 0);
+      const bool can_adapt = (--until_adapt == 0);
+      if (can_check) until_check = sp.check_termination;
+      if (can_adapt) until_adapt = sp.adaptive_rho_interval;
       const bool last = (iter == sp.max_iter);
       if (!(can_check || can_adapt || last)) continue;
       PHASE_MARK(2);
 
       // ---- residuals (auxil.c compute_pri_res / compute_dua_res / tolerances) ----
-      if (vown) sm.xD[vj] = D * x;
+      const double Dl = sm.lane_D[tid], cinv = sm.scal[1], c_s = sm.scal[0];
+      if (vown) sm.xD[vj] = Dl * x;
       __syncthreads();
       double v[10];
 #pragma unroll
@@ -488,6 +502,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       {
         const double x_lat = shfl(x, latsrc), x_z = shfl(x, zsrc);
         if (rown) {
+          const double Einv = sm.lane_Einv[tid];
           const double Ax = cca * x_lat + ccz * x_z;
           const double rp_ = Ax - z;
           v[0] = fabs(rp_);          // scaled primal residual
@@ -519,7 +534,8 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         const double yy = rown ? y : 0.0;
         const LegSums ay = leg_reduce(cca * yy, ccz * yy, hb);
         if (vown) {
-          const double Px = c * D * sr;
+          const double qb = sm.lane_qb[tid], Dinv = 1.0 / Dl;
+          const double Px = c_s * Dl * sr;
           const double Aty = (vc == 2) ? ay.z : ay.lat;
           const double rd = Px + qb + Aty;
           v[6] = fabs(rd);          // scaled dual residual
@@ -577,14 +593,15 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       }
       if (sm.flags[2]) {
         ++rho_updates;
-        rho = sm.scal[2];
-        rv = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * rho : rho;
-        rinv = 1.0 / rv;
+        const double rho = sm.scal[2];
+        const double rvn = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * rho : rho;
+        sm.lane_rv[tid] = rvn;
+        sm.lane_rinv[tid] = 1.0 / rvn;
         // the rhs was built with the old rho vector: rebuild it, then refactor
         {
-          const double w = rown ? (rv * z - y) : 0.0;
+          const double w = rown ? (rvn * z - y) : 0.0;
           const LegSums s = leg_reduce(cca * w, ccz * w, hb);
-          if (vown) sm.rhs[(iter + 1) & 1][vj] = sigma * x - qb + ((vc == 2) ? s.z : s.lat);
+          if (vown) sm.rhs[(iter + 1) & 1][vj] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
         }
         build_G();
         __syncthreads();
@@ -595,7 +612,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     if (iter > sp.max_iter) iter = sp.max_iter;
 
     // ---- K5: unscale, rotate the first step to the body frame, write ----
-    const double xo = D * x;
+    const double xo = sm.lane_D[tid] * x;
     if (x_all != nullptr && vown) x_all[size_t(p) * kN + vj] = (float)xo;
     if (rg < 4) {
       // leg rg of the first horizon step: f = (x, y, z) on lanes 0, 4, 8 of this half-warp
@@ -621,9 +638,9 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     }
     PHASE_MARK(4);
   }
-  if (phase_clk != nullptr && tid == 0) {
+  if (kProfile && tid == 0 && phase_clk != nullptr) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) phase_clk[blockIdx.x * 6 + i] = pc[i];
+    for (int i = 0; i < (kProfile ? 6 : 1); ++i) phase_clk[blockIdx.x * 6 + i] = pc[i];
   }
 #undef PHASE_MARK
 }

@@ -174,8 +174,12 @@ int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l,
                  const MpcStateIn* d_states, MpcResult* res, float* x, int n) {
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
   const int grid = n < e->num_sms ? n : e->num_sms;
-  admm_solve_kernel<<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(P, q, l, u, d_states, res, x, n,
-                                                                           e->d_counter, e->d_phase_clk, e->sp);
+  if (e->d_phase_clk)
+    admm_solve_kernel<true><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
+        P, q, l, u, d_states, res, x, n, e->d_counter, e->d_phase_clk, e->sp);
+  else
+    admm_solve_kernel<false><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
+        P, q, l, u, d_states, res, x, n, e->d_counter, nullptr, e->sp);
   ++e->launches;
   CUDA_TRY(e, cudaGetLastError());
   return MPC_OK;
@@ -199,7 +203,10 @@ int create_common(int kind, int device, MpcEngine** out) {
     crc = cudaFuncSetAttribute(qp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)sizeof(BuildSmem));
   if (crc == cudaSuccess)
-    crc = cudaFuncSetAttribute(admm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    crc = cudaFuncSetAttribute(admm_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(SolveSmem));
+  if (crc == cudaSuccess)
+    crc = cudaFuncSetAttribute(admm_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)sizeof(SolveSmem));
   if (crc != cudaSuccess) {
     std::string msg = std::string("engine setup: ") + cudaGetErrorString(crc);
