@@ -4,21 +4,22 @@
 // K = P + sigma I + A' diag(rho) A, ADMM with alpha-relaxation, residual termination
 // every check_termination iterations, rho adaptation with refactorisation.
 //
-// v3 layout (v1/v2 history in profiles/):
-//   640 threads = 40 row groups x 16 column groups; thread (rg, cg) holds the 3 x 8
-//   register tile rows 3rg..3rg+2 x columns {32i + 2cg, 32i + 2cg + 1 : i < 4} of -K^-1.
-//   A row group IS a leg-step: variables 3rg..3rg+2, constraint rows 5rg..5rg+4.  The 16
-//   lanes of a half-warp therefore finish x~ for one leg-step (reduce-scatter), and the
-//   same lanes do that leg-step's z/y update and next right-hand side through shuffles:
-//   ONE block barrier per ADMM iteration, no shared-memory vectors except rhs.
-//     lane cg = 0 : variable fx + row 0      lane cg = 1 : row 1
-//     lane cg = 4 : variable fy + row 2      lane cg = 5 : row 3
-//     lane cg = 8 : variable fz + row 4
+// v5 layout (history and measurements of v1..v4 in profiles/ and DESIGN.md):
+//   320 threads = 20 row groups x 16 column groups; thread (rg, cg) holds the 6 x 8
+//   register tile rows 6rg..6rg+5 x columns {32i + 2cg, 32i + 2cg + 1 : i < 4} of -K^-1
+//   (96 registers; 10 warps leave 204 registers per thread, nothing spills).
+//   A row group is TWO leg-steps (variables 6rg..6rg+5, constraint rows 10rg..10rg+9).
+//   After the reduce-scatter, lanes (2r, 2r+1) of a half-warp hold x~ of tile row r, so the
+//   16 lanes run both leg-steps' z/y update and next right-hand side through shuffles:
+//   ONE block barrier per ADMM iteration, x/z/y in registers of their owning lanes.
+//     leg-step A (rows 0-2): lanes 0..4 = constraint rows 0..4, lanes 0/2/4 own fx/fy/fz
+//     leg-step B (rows 3-5): lanes 6..10 likewise
+//   Tall tiles matter: every half-warp re-reads the same operand vector / published rows, so
+//   shared-memory traffic per step is (row groups) x 1 KB; 3 x 8 tiles (40 row groups, 640
+//   threads) were bound by that traffic and by 20 warps issuing the same scalar code.
 //   K^-1 comes from a BLOCKED symmetric sweep (Gauss-Jordan on the SPD matrix) over the
-//   register tiles: a row group is exactly 3 pivot rows, so one rank-3 update per barrier;
-//   the publisher stores only its three rows, every thread inverts the 3x3 pivot block itself.
-//   (One pivot per barrier, or M/W computed by the publisher alone, left 40-50 % of the sweep
-//   time at the barrier: profiles/r01_v3_*, r01_v4_*.)
+//   register tiles: rank-3 steps (one leg-step of pivots per barrier); the publisher stores
+//   only its three rows one step ahead, every thread inverts the 3x3 pivot block itself.
 //   P arrives by one cp.async.bulk (TMA) per problem into shared memory.
 #pragma once
 
@@ -29,8 +30,10 @@
 
 namespace mpcb200 {
 
-constexpr int kSolveThreads = 640;
+constexpr int kSolveThreads = 320;
 constexpr int kSolveWarps = kSolveThreads / 32;
+constexpr int kRowGroups = 20;
+constexpr int kTR = 6;                 // tile rows
 constexpr int kPBytes = kN * kNP * 8;  // 122,880
 
 struct SolveSmem {
@@ -40,7 +43,8 @@ struct SolveSmem {
   double Dp[kNP];           // D (pad = 0)
   double Vb[2][3][kNP];     // blocked sweep: published pivot rows A_S,: with A_SS replaced by A_SS - I
   double G[kLegSteps * 6];  // A' diag(rho) A per leg-step: xx, xz, yy, yz, zz, (pad)
-  // per-lane constants of the ADMM loop (slot [k][tid]); registers are kept for the K^-1 tile
+  double Wg[kRowGroups][24];  // blocked sweep: W[s][row] of each row group, [6 s + rr] (18 used)
+  // per-lane constants of the ADMM loop (slot [tid]); registers are kept for the K^-1 tile
   double lane_lb[kSolveThreads], lane_ub[kSolveThreads], lane_rv[kSolveThreads], lane_rinv[kSolveThreads];
   double lane_qb[kSolveThreads], lane_D[kSolveThreads], lane_Einv[kSolveThreads];
   double red[kSolveWarps * 16];
@@ -64,44 +68,43 @@ __device__ __forceinline__ double limit_scaling(double v) {  // osqp scaling.c
   return v > 1e4 ? 1e4 : v;
 }
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-// Reduce three per-row partials over the 16 lanes of a half-warp: lanes 4c..4c+3 end up
-// with the total of row c (c = 0, 1, 2); lanes 12..15 hold nothing useful.
-__device__ __forceinline__ double reduce_scatter3_sum(double s0, double s1, double s2, int cg) {
-  const bool h8 = (cg & 8) != 0, h4 = (cg & 4) != 0;
-  double k0 = h8 ? s2 : s0, k1 = h8 ? 0.0 : s1;
-  const double t0 = h8 ? s0 : s2, t1 = h8 ? s1 : 0.0;
-  k0 += __shfl_xor_sync(0xffffffffu, t0, 8);
-  k1 += __shfl_xor_sync(0xffffffffu, t1, 8);
-  double k = h4 ? k1 : k0;
-  const double t = h4 ? k0 : k1;
-  k += __shfl_xor_sync(0xffffffffu, t, 4);
-  k += __shfl_xor_sync(0xffffffffu, k, 2);
-  k += __shfl_xor_sync(0xffffffffu, k, 1);
-  return k;
-}
-__device__ __forceinline__ double reduce_scatter3_max(double s0, double s1, double s2, int cg) {
-  const bool h8 = (cg & 8) != 0, h4 = (cg & 4) != 0;
-  double k0 = h8 ? s2 : s0, k1 = h8 ? 0.0 : s1;
-  const double t0 = h8 ? s0 : s2, t1 = h8 ? s1 : 0.0;
-  k0 = fmax(k0, __shfl_xor_sync(0xffffffffu, t0, 8));
-  k1 = fmax(k1, __shfl_xor_sync(0xffffffffu, t1, 8));
-  double k = h4 ? k1 : k0;
-  const double t = h4 ? k0 : k1;
-  k = fmax(k, __shfl_xor_sync(0xffffffffu, t, 4));
-  k = fmax(k, __shfl_xor_sync(0xffffffffu, k, 2));
-  k = fmax(k, __shfl_xor_sync(0xffffffffu, k, 1));
-  return k;
+// Reduce six per-row partials over the 16 lanes of a half-warp (reduce-scatter, 8 double
+// shuffles): lanes 2r and 2r+1 end up with the total of tile row r (r < 6); lanes 12..15
+// hold nothing useful.
+struct AddOp { __device__ __forceinline__ double operator()(double a, double b) const { return a + b; } };
+struct MaxOp { __device__ __forceinline__ double operator()(double a, double b) const { return fmax(a, b); } };
+template <class Op>
+__device__ __forceinline__ double reduce_scatter6(const double (&s)[kTR], int cg, Op op) {
+  const bool b3 = (cg & 8) != 0, b2 = (cg & 4) != 0, b1 = (cg & 2) != 0;
+  // slots 0..7 (6 and 7 are zero); xor 8 exchanges slot groups {0..3} and {4..7}
+  double k0 = b3 ? s[4] : s[0], k1 = b3 ? s[5] : s[1], k2 = b3 ? 0.0 : s[2], k3 = b3 ? 0.0 : s[3];
+  const double t0 = b3 ? s[0] : s[4], t1 = b3 ? s[1] : s[5], t2 = b3 ? s[2] : 0.0, t3 = b3 ? s[3] : 0.0;
+  k0 = op(k0, shfl_xor(t0, 8));
+  k1 = op(k1, shfl_xor(t1, 8));
+  k2 = op(k2, shfl_xor(t2, 8));
+  k3 = op(k3, shfl_xor(t3, 8));
+  double m0 = b2 ? k2 : k0, m1 = b2 ? k3 : k1;
+  const double u0 = b2 ? k0 : k2, u1 = b2 ? k1 : k3;
+  m0 = op(m0, shfl_xor(u0, 4));
+  m1 = op(m1, shfl_xor(u1, 4));
+  double r = b1 ? m1 : m0;
+  const double w = b1 ? m0 : m1;
+  r = op(r, shfl_xor(w, 2));
+  r = op(r, shfl_xor(r, 1));
+  return r;
 }
 
-// Sums over the five row lanes {0,1,4,5,8} of a half-warp (hb = lane & 16):
-//   returns on lane 0: pa@0 + pa@1 (in .x) ; lane 4: pa@4 + pa@5 (in .x) ; lane 8: sum of pz over all five (in .y)
+// Sums over the five row lanes bl..bl+4 of a leg-step (bl = 0 or 6 inside the half-warp):
+//   .lat on lane bl: pa@bl + pa@(bl+1);  on lane bl+2: pa@(bl+2) + pa@(bl+3)
+//   .z   on lane bl+4: sum of pz over the five lanes
 struct LegSums { double lat, z; };
-__device__ __forceinline__ LegSums leg_reduce(double pa, double pz, int hb) {
+__device__ __forceinline__ LegSums leg_reduce(double pa, double pz, int lbase) {
   LegSums r;
   r.lat = pa + __shfl_down_sync(0xffffffffu, pa, 1);
   const double t = pz + __shfl_down_sync(0xffffffffu, pz, 1);
-  r.z = pz + shfl(t, hb) + shfl(t, hb + 4);
+  r.z = pz + shfl(t, lbase) + shfl(t, lbase + 2);
   return r;
 }
 
@@ -115,41 +118,42 @@ __device__ __forceinline__ void load_cols(const double* base, int cg, double (&v
   }
 }
 
-// max_j |P_rj| D_j of the rows of this row group; lanes 4c..4c+3 get row c
+// max_j |P_rj| D_j of the rows of this row group; lanes 2r, 2r+1 get tile row r
 __device__ __forceinline__ double row_norm_pass(const SolveSmem& sm, int rg, int cg) {
   double dcol[8];
   load_cols(sm.Dp, cg, dcol);
-  double m[3];
+  double m[kTR];
 #pragma unroll
-  for (int rr = 0; rr < 3; ++rr) {
+  for (int rr = 0; rr < kTR; ++rr) {
     double pv[8];
-    load_cols(&sm.P[(3 * rg + rr) * kNP], cg, pv);
+    load_cols(&sm.P[(kTR * rg + rr) * kNP], cg, pv);
     double mm = 0.0;
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) mm = fmax(mm, fabs(pv[jj]) * dcol[jj]);
     m[rr] = mm;
   }
-  return reduce_scatter3_max(m[0], m[1], m[2], cg);
+  return reduce_scatter6(m, cg, MaxOp());
 }
 
 // Blocked symmetric sweep, one leg-step (3 pivots S = {3kb, 3kb+1, 3kb+2}) per barrier.
 // With V = A_S,: (before the step), M = A_SS^-1, W = -M V the step is
 //   A_rj <- A_rj + sum_s W[s][r] V'[s][j]   (r not in S; V' = V with A_SS - I in the S columns,
 //                                            which makes the same update produce A_rS M)
-//   A_Sj <- -W[:, j] (j not in S),  A_SS <- -M
-// (W[s][r] doubles as the column factor because A is symmetric).  The row group kb IS S, so
-// its 16 lanes hold V entirely and publish ONLY V' (12 stores): every thread inverts the 3x3
-// pivot block itself and forms the 3x3 block of W it needs.  Doing M and W on the publishing
-// half-warp alone left the other 19 warps at the barrier for half of every step.
-__device__ __forceinline__ void publish_rows(SolveSmem& sm, const double (&a)[3][8], int kb, int cg, int b) {
+//   A_Sj <- M A_Sj (j not in S),  A_SS <- -M
+// (W[s][r] doubles as the column factor because A is symmetric).  Block kb lives in row group
+// kb / 2, tile rows 3 (kb & 1) .. +2 (HALF is a template parameter: static register indices).
+// The publisher stores ONLY V' (12 stores, one step ahead); every thread inverts the 3x3 pivot
+// block itself and forms the 3 x 6 block of W it needs.
+template <int HALF>
+__device__ __forceinline__ void publish_rows(SolveSmem& sm, const double (&a)[kTR][8], int kb, int cg) {
   const int c0 = 3 * kb;
 #pragma unroll
   for (int s3 = 0; s3 < 3; ++s3) {
-    double2* dst = reinterpret_cast<double2*>(&sm.Vb[b][s3][2 * cg]);
+    double2* dst = reinterpret_cast<double2*>(&sm.Vb[HALF][s3][2 * cg]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int col = 32 * i + 2 * cg;
-      double v0 = a[s3][2 * i], v1 = a[s3][2 * i + 1];
+      double v0 = a[3 * HALF + s3][2 * i], v1 = a[3 * HALF + s3][2 * i + 1];
       if (col == c0 + s3) v0 -= 1.0;
       if (col + 1 == c0 + s3) v1 -= 1.0;
       dst[16 * i] = make_double2(v0, v1);
@@ -157,48 +161,70 @@ __device__ __forceinline__ void publish_rows(SolveSmem& sm, const double (&a)[3]
   }
 }
 
-// One step of the blocked sweep for this thread's tile, block kb published in buffer b.
-__device__ __forceinline__ void sweep_block(const SolveSmem& sm, double (&a)[3][8], int kb, int rg, int cg,
-                                            int b) {
+template <int HALF>
+__device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][8], int kb, int rg, int cg) {
   const int c0 = 3 * kb;
+  const double(*V)[kNP] = sm.Vb[HALF];
   // A_SS (identity added back) and its symmetric 3x3 cofactor inverse, on every thread
-  const double m00 = sm.Vb[b][0][c0] + 1.0, m01 = sm.Vb[b][0][c0 + 1], m02 = sm.Vb[b][0][c0 + 2];
-  const double m11 = sm.Vb[b][1][c0 + 1] + 1.0, m12 = sm.Vb[b][1][c0 + 2];
-  const double m22 = sm.Vb[b][2][c0 + 2] + 1.0;
+  const double m00 = V[0][c0] + 1.0, m01 = V[0][c0 + 1], m02 = V[0][c0 + 2];
+  const double m11 = V[1][c0 + 1] + 1.0, m12 = V[1][c0 + 2];
+  const double m22 = V[2][c0 + 2] + 1.0;
   const double k00 = m11 * m22 - m12 * m12, k01 = m02 * m12 - m01 * m22, k02 = m01 * m12 - m02 * m11;
   const double id = __drcp_rn(m00 * k00 + m01 * k01 + m02 * k02);
   const double i00 = k00 * id, i01 = k01 * id, i02 = k02 * id;
   const double i11 = (m00 * m22 - m02 * m02) * id, i12 = (m01 * m02 - m00 * m12) * id;
   const double i22 = (m00 * m11 - m01 * m01) * id;
-  if (rg == kb) {
-    // pivot rows: A_Sj <- M A_Sj, A_SS <- -M
+  const bool piv = (rg == (kb >> 1));
+  // W[s][r] = -(M V[:, r])[s] for the six rows of this row group depends on rg only: the 16
+  // lanes of the half-warp compute its 18 entries cooperatively and stage them in shared memory
+  {
+    auto wentry = [&](int e) {
+      const int s3 = e / kTR, rr = e - kTR * s3;
+      const double x0 = V[0][kTR * rg + rr], x1 = V[1][kTR * rg + rr], x2 = V[2][kTR * rg + rr];
+      const double a0 = (s3 == 0) ? i00 : (s3 == 1) ? i01 : i02;
+      const double a1 = (s3 == 0) ? i01 : (s3 == 1) ? i11 : i12;
+      const double a2 = (s3 == 0) ? i02 : (s3 == 1) ? i12 : i22;
+      return -(a0 * x0 + a1 * x1 + a2 * x2);
+    };
+    sm.Wg[rg][cg] = wentry(cg);
+    if (cg < 2) sm.Wg[rg][16 + cg] = wentry(16 + cg);
+    __syncwarp();
+  }
+  if (piv) {
+    // pivot rows: A_Sj <- M A_Sj, A_SS <- -M (uses the rows' old values; they skip the generic update)
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-      const double x0 = a[0][jj], x1 = a[1][jj], x2 = a[2][jj];
+      const double x0 = a[3 * HALF][jj], x1 = a[3 * HALF + 1][jj], x2 = a[3 * HALF + 2][jj];
       const int t = 32 * (jj >> 1) + 2 * cg + (jj & 1) - c0;  // position inside S, if any
-      a[0][jj] = (t == 0) ? -i00 : (t == 1) ? -i01 : (t == 2) ? -i02 : (i00 * x0 + i01 * x1 + i02 * x2);
-      a[1][jj] = (t == 0) ? -i01 : (t == 1) ? -i11 : (t == 2) ? -i12 : (i01 * x0 + i11 * x1 + i12 * x2);
-      a[2][jj] = (t == 0) ? -i02 : (t == 1) ? -i12 : (t == 2) ? -i22 : (i02 * x0 + i12 * x1 + i22 * x2);
+      a[3 * HALF][jj] = (t == 0) ? -i00 : (t == 1) ? -i01 : (t == 2) ? -i02 : (i00 * x0 + i01 * x1 + i02 * x2);
+      a[3 * HALF + 1][jj] = (t == 0) ? -i01 : (t == 1) ? -i11 : (t == 2) ? -i12 : (i01 * x0 + i11 * x1 + i12 * x2);
+      a[3 * HALF + 2][jj] = (t == 0) ? -i02 : (t == 1) ? -i12 : (t == 2) ? -i22 : (i02 * x0 + i12 * x1 + i22 * x2);
     }
-  } else {
-    // W[s][r] = -(M V[:, r])[s] for the thread's three rows (V = V' there: r is not in S)
-    double w[3][3];
+  }
 #pragma unroll
-    for (int rr = 0; rr < 3; ++rr) {
-      const double x0 = sm.Vb[b][0][3 * rg + rr], x1 = sm.Vb[b][1][3 * rg + rr], x2 = sm.Vb[b][2][3 * rg + rr];
-      w[0][rr] = -(i00 * x0 + i01 * x1 + i02 * x2);
-      w[1][rr] = -(i01 * x0 + i11 * x1 + i12 * x2);
-      w[2][rr] = -(i02 * x0 + i12 * x1 + i22 * x2);
+  for (int s3 = 0; s3 < 3; ++s3) {
+    double v[8], w[kTR];
+    load_cols(V[s3], cg, v);
+    {
+      const double2* wp = reinterpret_cast<const double2*>(&sm.Wg[rg][kTR * s3]);
+#pragma unroll
+      for (int h = 0; h < 3; ++h) {
+        const double2 t = wp[h];
+        w[2 * h] = t.x;
+        w[2 * h + 1] = t.y;
+      }
     }
 #pragma unroll
-    for (int s3 = 0; s3 < 3; ++s3) {
-      double v[8];
-      load_cols(sm.Vb[b][s3], cg, v);
+    for (int rr = 0; rr < kTR; ++rr) {
+      const bool is_pivot_row = (rr >= 3 * HALF) && (rr < 3 * HALF + 3);  // static
+      if (is_pivot_row) {
+        if (!piv) {
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        a[0][jj] = fma(w[s3][0], v[jj], a[0][jj]);
-        a[1][jj] = fma(w[s3][1], v[jj], a[1][jj]);
-        a[2][jj] = fma(w[s3][2], v[jj], a[2][jj]);
+          for (int jj = 0; jj < 8; ++jj) a[rr][jj] = fma(w[rr], v[jj], a[rr][jj]);
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) a[rr][jj] = fma(w[rr], v[jj], a[rr][jj]);
       }
     }
   }
@@ -206,16 +232,16 @@ __device__ __forceinline__ void sweep_block(const SolveSmem& sm, double (&a)[3][
 
 // Build K = c D P D + sigma I + A' diag(rho) A into the register tiles, then overwrite it
 // with -K^-1 by the blocked symmetric sweep (40 rank-3 steps, one barrier each).
-__device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[3][8], int rg, int cg, int hb,
-                                               double sigma) {
+__device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][8], int rg, int cg, double sigma) {
   {
     const double c = sm.scal[0];
     double dcol[8];
     load_cols(sm.Dp, cg, dcol);
-    const double* g = &sm.G[rg * 6];
 #pragma unroll
-    for (int rr = 0; rr < 3; ++rr) {
-      const int row = 3 * rg + rr;
+    for (int rr = 0; rr < kTR; ++rr) {
+      const int row = kTR * rg + rr;
+      const int ls = 2 * rg + rr / 3, rc = rr % 3;  // leg-step and component of this row (static rc)
+      const double* g = &sm.G[ls * 6];
       const double cDr = c * sm.Dp[row];
       double pv[8];
       load_cols(&sm.P[row * kNP], cg, pv);
@@ -224,12 +250,12 @@ __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[3][8],
         const int col = 32 * (jj >> 1) + 2 * cg + (jj & 1);
         double val = cDr * pv[jj] * dcol[jj];
         if (col == row) val += sigma;
-        if (col / 3 == rg) {
-          const int cc = col - 3 * rg;
+        const int cc = col - 3 * ls;
+        if (cc >= 0 && cc < 3) {
           // G = [[xx, 0, xz], [0, yy, yz], [xz, yz, zz]]
           double gv;
-          if (rr == 0) gv = (cc == 0) ? g[0] : (cc == 1) ? 0.0 : g[1];
-          else if (rr == 1) gv = (cc == 0) ? 0.0 : (cc == 1) ? g[2] : g[3];
+          if (rc == 0) gv = (cc == 0) ? g[0] : (cc == 1) ? 0.0 : g[1];
+          else if (rc == 1) gv = (cc == 0) ? 0.0 : (cc == 1) ? g[2] : g[3];
           else gv = (cc == 0) ? g[1] : (cc == 1) ? g[3] : g[4];
           val += gv;
         }
@@ -237,13 +263,15 @@ __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[3][8],
       }
     }
   }
-  if (rg == 0) publish_rows(sm, a, 0, cg, 0);
-  for (int kb = 0; kb < kLegSteps; ++kb) {
-    const int b = kb & 1;
-    __syncthreads();  // rows of block kb (published one step ahead) are visible
-    sweep_block(sm, a, kb, rg, cg, b);
-    // look-ahead: the next pivot rows are now up to date; publish them for step kb + 1
-    if (rg == kb + 1) publish_rows(sm, a, kb + 1, cg, b ^ 1);
+  if (rg == 0) publish_rows<0>(sm, a, 0, cg);
+  for (int kp = 0; kp < kRowGroups; ++kp) {
+    __syncthreads();  // rows of block 2kp (published one step ahead) are visible
+    sweep_block<0>(sm, a, 2 * kp, rg, cg);
+    // look-ahead: the next pivot rows are now up to date; publish them for the next step
+    if (rg == kp) publish_rows<1>(sm, a, 2 * kp + 1, cg);
+    __syncthreads();
+    sweep_block<1>(sm, a, 2 * kp + 1, rg, cg);
+    if (rg == kp + 1) publish_rows<0>(sm, a, 2 * kp + 2, cg);
   }
 }
 
@@ -263,14 +291,18 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int rg = tid >> 4, cg = tid & 15, hb = lane & 16;
-  // lane roles inside the half-warp (= leg-step rg)
-  const bool vown = (cg == 0) || (cg == 4) || (cg == 8);
-  const int vc = cg >> 2;                 // variable component owned (x, y, z)
-  const int vj = 3 * rg + (vown ? vc : 0);
-  const bool rown = (cg == 0) || (cg == 1) || (cg == 4) || (cg == 5) || (cg == 8);
-  const int re = (cg & 1) + ((cg >> 2) << 1);  // row inside the leg-step (valid on row lanes)
-  const int ri = 5 * rg + (rown ? re : 0);
-  const int latsrc = hb + (cg & 4), zsrc = hb + 8;
+  // lane roles inside the half-warp (two leg-steps: lanes 0..4 and 6..10)
+  const int lg = (cg >= 6) ? 1 : 0;
+  const int pos = cg - 6 * lg;
+  const bool active = cg < 12;
+  const bool rown = active && pos <= 4;                         // owns constraint row `pos` of its leg-step
+  const bool vown = active && (pos == 0 || pos == 2 || pos == 4);  // owns variable component pos / 2
+  const int vc = pos >> 1;
+  const int ls = 2 * rg + lg;                                   // leg-step
+  const int vj = 3 * ls + (vown ? vc : 0);
+  const int ri = 5 * ls + (rown ? pos : 0);
+  const int lbase = hb + 6 * lg;
+  const int latsrc = lbase + ((pos < 2) ? 0 : 2), zsrc = lbase + 4;
   const double mu = sp.mu;
   const double sigma = sp.sigma, alpha = sp.alpha;
 
@@ -279,9 +311,8 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   uint32_t phase = 0;
-  double a[3][8];  // register tile of -K^-1
+  double a[kTR][8];  // register tile of -K^-1
   // per-phase cycle counters of thread 0: compiled in only for the kProfile instantiation
-  // (they cost 14 registers the production kernel cannot spare)
   long long pc[kProfile ? 6 : 1] = {0};  // 0 load+ruiz 1 factor 2 iterations 3 checks 4 output 5 problems
   long long tmark = 0;
 #define PHASE_MARK(i) do { if (kProfile && tid == 0) { const long long _t = clock64(); pc[kProfile ? (i) : 0] += _t - tmark; tmark = _t; } } while (0)
@@ -346,27 +377,29 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     // scaled quantities are never materialised: P_bar = c D P D, A_bar = E A D.
     double D = 1.0, E = 1.0;  // D on variable lanes, E on row lanes
     if (sp.scaling > 0) {
-      double nP = row_norm_pass(sm, rg, cg);  // c = 1, D = 1
+      double nP = row_norm_pass(sm, rg, cg);  // c = 1, D = 1 (valid on the variable lanes)
       __syncthreads();                        // Dp is rewritten inside the loop
       for (int it = 0; it < sp.scaling; ++it) {
-        // column norm of [P; A] for the owned variable
-        const double E0 = shfl(E, hb), E1 = shfl(E, hb + 1), E2 = shfl(E, hb + 4), E3 = shfl(E, hb + 5),
-                     E4 = shfl(E, hb + 8);
-        const double Dx = shfl(D, hb), Dy = shfl(D, hb + 4), Dz = shfl(D, hb + 8);
+        // column norm of [P; A] for the owned variable, row norm of A for the owned row
+        const double E0 = shfl(E, lbase), E1 = shfl(E, lbase + 1), E2 = shfl(E, lbase + 2),
+                     E3 = shfl(E, lbase + 3), E4 = shfl(E, lbase + 4);
+        const double Dx = shfl(D, lbase), Dy = shfl(D, lbase + 2), Dz = shfl(D, lbase + 4);
+        double Dn = D, En = E;
         if (vown) {
           double nA;
           if (vc == 0) nA = fmax(E0, E1);
           else if (vc == 1) nA = fmax(E2, E3);
           else nA = fmax(mu * fmax(fmax(E0, E1), fmax(E2, E3)), E4);
           nA *= D;
-          D *= rsqrt(limit_scaling(fmax(nP, nA)));
-          sm.Dp[vj] = D;
+          Dn = D * rsqrt(limit_scaling(fmax(nP, nA)));
+          sm.Dp[vj] = Dn;
         }
         if (rown) {
-          // row norm of A for the owned constraint row
-          const double nrow = (re == 4) ? Dz : fmax((re < 2) ? Dx : Dy, mu * Dz);
-          E *= rsqrt(limit_scaling(E * nrow));
+          const double nrow = (pos == 4) ? Dz : fmax((pos < 2) ? Dx : Dy, mu * Dz);
+          En = E * rsqrt(limit_scaling(E * nrow));
         }
+        D = Dn;
+        E = En;
         __syncthreads();
         // cost normalisation with the new D and the old c
         const double c_old = sm.scal[0];
@@ -403,31 +436,31 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     int ctype = 0;
     if (lb < -MPC_INFTY * 1e-4 && ub > MPC_INFTY * 1e-4) ctype = -1;
     else if (ub - lb < 1e-4) ctype = 1;
-    double rv = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * sp.rho : sp.rho;
+    const double rv0 = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * sp.rho : sp.rho;
     // scaled constraint coefficients of the owned row: z~_i = cca * x~_lat + ccz * x~_z
     double cca, ccz;
     {
       const double Dlat = shfl(D, latsrc), Dz = shfl(D, zsrc);
-      cca = (re == 4) ? 0.0 : E * Dlat;
-      ccz = (re == 4) ? E * Dz : ((re & 1) ? -mu : mu) * E * Dz;
+      cca = (pos == 4) ? 0.0 : E * Dlat;
+      ccz = (pos == 4) ? E * Dz : ((pos & 1) ? -mu : mu) * E * Dz;
       if (!rown) { cca = 0.0; ccz = 0.0; }
     }
     sm.lane_lb[tid] = lb;
     sm.lane_ub[tid] = ub;
-    sm.lane_rv[tid] = rv;
-    sm.lane_rinv[tid] = 1.0 / rv;
+    sm.lane_rv[tid] = rv0;
+    sm.lane_rinv[tid] = 1.0 / rv0;
     sm.lane_qb[tid] = qb0;
     sm.lane_D[tid] = D;
     sm.lane_Einv[tid] = 1.0 / E;
     if (tid == 0) sm.scal[1] = 1.0 / c;
     auto build_G = [&]() {
-      // A' diag(rho) A of this leg-step from the five row lanes
+      // A' diag(rho) A of this lane's leg-step from its five row lanes
       const double r0 = rown ? sm.lane_rv[tid] : 0.0;
-      const LegSums s1 = leg_reduce(r0 * cca * cca, r0 * ccz * ccz, hb);  // xx|yy on lanes 0|4, zz on lane 8
-      const LegSums s2 = leg_reduce(r0 * cca * ccz, 0.0, hb);             // xz|yz on lanes 0|4
-      if (cg == 0) { sm.G[rg * 6 + 0] = s1.lat; sm.G[rg * 6 + 1] = s2.lat; }
-      if (cg == 4) { sm.G[rg * 6 + 2] = s1.lat; sm.G[rg * 6 + 3] = s2.lat; }
-      if (cg == 8) sm.G[rg * 6 + 4] = s1.z;
+      const LegSums s1 = leg_reduce(r0 * cca * cca, r0 * ccz * ccz, lbase);  // xx|yy on lanes 0|2, zz on lane 4
+      const LegSums s2 = leg_reduce(r0 * cca * ccz, 0.0, lbase);             // xz|yz on lanes 0|2
+      if (active && pos == 0) { sm.G[ls * 6 + 0] = s1.lat; sm.G[ls * 6 + 1] = s2.lat; }
+      if (active && pos == 2) { sm.G[ls * 6 + 2] = s1.lat; sm.G[ls * 6 + 3] = s2.lat; }
+      if (active && pos == 4) sm.G[ls * 6 + 4] = s1.z;
     };
     build_G();
     if (vown) sm.rhs[1][vj] = -qb0;  // rhs of iteration 1: x = z = y = 0
@@ -435,7 +468,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
 
     PHASE_MARK(0);
     // ---- K3b: factor (explicit inverse in registers) ----
-    factor_inverse(sm, a, rg, cg, hb, sigma);
+    factor_inverse(sm, a, rg, cg, sigma);
     PHASE_MARK(1);
 
     // ---- K4: ADMM iterations (osqp.c osqp_solve) ----
@@ -452,9 +485,9 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       {
         double v[8];
         load_cols(sm.rhs[iter & 1], cg, v);
-        double s[3];
+        double s[kTR];
 #pragma unroll
-        for (int rr = 0; rr < 3; ++rr) {
+        for (int rr = 0; rr < kTR; ++rr) {
           double s0 = a[rr][0] * v[0], s1 = a[rr][1] * v[1];
 #pragma unroll
           for (int jj = 2; jj < 8; jj += 2) {
@@ -463,7 +496,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
           }
           s[rr] = s0 + s1;
         }
-        xt = -reduce_scatter3_sum(s[0], s[1], s[2], cg);  // lanes 4c..4c+3: x~ of variable c
+        xt = -reduce_scatter6(s, cg, AddOp());  // lanes 2r, 2r+1: x~ of tile row r
       }
       // x <- alpha x~ + (1 - alpha) x
       x = alpha * xt + (1.0 - alpha) * x;
@@ -481,7 +514,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       // next rhs = sigma x - q + A'(rho z - y)
       {
         const double w = rown ? (rvv * z - y) : 0.0;
-        const LegSums s = leg_reduce(cca * w, ccz * w, hb);
+        const LegSums s = leg_reduce(cca * w, ccz * w, lbase);
         if (vown) sm.rhs[(iter + 1) & 1][vj] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
       }
       const bool can_check = (--until_check == 0);
@@ -517,11 +550,11 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         // P_bar x = c D (P (D x)) ; A' y
         double xv[8];
         load_cols(sm.xD, cg, xv);
-        double s[3];
+        double s[kTR];
 #pragma unroll
-        for (int rr = 0; rr < 3; ++rr) {
+        for (int rr = 0; rr < kTR; ++rr) {
           double pv[8];
-          load_cols(&sm.P[(3 * rg + rr) * kNP], cg, pv);
+          load_cols(&sm.P[(kTR * rg + rr) * kNP], cg, pv);
           double s0 = 0.0, s1 = 0.0;
 #pragma unroll
           for (int jj = 0; jj < 8; jj += 2) {
@@ -530,9 +563,9 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
           }
           s[rr] = s0 + s1;
         }
-        const double sr = reduce_scatter3_sum(s[0], s[1], s[2], cg);
+        const double sr = reduce_scatter6(s, cg, AddOp());
         const double yy = rown ? y : 0.0;
-        const LegSums ay = leg_reduce(cca * yy, ccz * yy, hb);
+        const LegSums ay = leg_reduce(cca * yy, ccz * yy, lbase);
         if (vown) {
           const double qb = sm.lane_qb[tid], Dinv = 1.0 / Dl;
           const double Px = c_s * Dl * sr;
@@ -600,12 +633,12 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         // the rhs was built with the old rho vector: rebuild it, then refactor
         {
           const double w = rown ? (rvn * z - y) : 0.0;
-          const LegSums s = leg_reduce(cca * w, ccz * w, hb);
+          const LegSums s = leg_reduce(cca * w, ccz * w, lbase);
           if (vown) sm.rhs[(iter + 1) & 1][vj] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
         }
         build_G();
         __syncthreads();
-        factor_inverse(sm, a, rg, cg, hb, sigma);
+        factor_inverse(sm, a, rg, cg, sigma);
         PHASE_MARK(1);
       }
     }
@@ -614,9 +647,10 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     // ---- K5: unscale, rotate the first step to the body frame, write ----
     const double xo = sm.lane_D[tid] * x;
     if (x_all != nullptr && vown) x_all[size_t(p) * kN + vj] = (float)xo;
-    if (rg < 4) {
-      // leg rg of the first horizon step: f = (x, y, z) on lanes 0, 4, 8 of this half-warp
-      const double f0 = shfl(xo, hb), f1 = shfl(xo, hb + 4), f2 = shfl(xo, hb + 8);
+    if (rg < 2) {
+      // legs 0..3 of the first horizon step are leg-steps 0..3 = warp 0; f = (x, y, z) on lanes
+      // lbase, lbase + 2, lbase + 4
+      const double f0 = shfl(xo, lbase), f1 = shfl(xo, lbase + 2), f2 = shfl(xo, lbase + 4);
       if (vown) {
         double g;
         if (states != nullptr) {
@@ -627,7 +661,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
           g = (vc == 0) ? f0 : (vc == 1) ? f1 : f2;
         }
         const bool bad = isnan(f0) || isnan(f1) || isnan(f2);  // NaN guard (:559)
-        results[p].grf[3 * rg + vc] = bad ? 0.0f : (float)g;
+        results[p].grf[3 * ls + vc] = bad ? 0.0f : (float)g;
       }
     }
     if (tid == 0) {
