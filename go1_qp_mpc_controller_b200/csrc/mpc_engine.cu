@@ -13,6 +13,7 @@
 #include "../../include/mpc_b200.h"
 #include "admm_kernel.cuh"
 #include "balance_kernels.cuh"
+#include "gen_kernels.cuh"
 #include "mpc_kernels.cuh"
 
 using namespace mpcb200;
@@ -43,6 +44,11 @@ struct MpcEngine {
   float* d_x = nullptr;
   MpcResult* d_results = nullptr;
   int* d_counter = nullptr;
+  double* d_workspace = nullptr;  // long-horizon path: per-CTA B_qp / -K^-1 scratch
+  int H = kH;                     // horizon
+  int nvar() const { return 12 * H; }
+  int ncon() const { return 20 * H; }
+  size_t p_stride() const { return H == kH ? size_t(kN) * kNP : size_t(nvar()) * nvar(); }  // doubles per problem
   long long* d_phase_clk = nullptr;  // optional per-phase cycle counters (mpc_debug_phase_cycles)
   bool built = false, solved = false;
   int64_t launches = 0;
@@ -142,13 +148,14 @@ int reserve(MpcEngine* e, int n) {
   int cap = 1;
   while (cap < n) cap <<= 1;
   if (cap < 64) cap = 64;
+  if (e->kind == 0 && e->H != kH && cap > n) cap = n < 64 ? 64 : n;  // 1 MB per problem: no slack
   if (e->kind == 0) {
     CUDA_TRY(e, cudaMalloc(&e->d_states_own, size_t(cap) * sizeof(MpcStateIn)));
-    CUDA_TRY(e, cudaMalloc(&e->d_P, size_t(cap) * kN * kNP * sizeof(double)));
-    CUDA_TRY(e, cudaMalloc(&e->d_q, size_t(cap) * kN * sizeof(double)));
-    CUDA_TRY(e, cudaMalloc(&e->d_l, size_t(cap) * kM * sizeof(float)));
-    CUDA_TRY(e, cudaMalloc(&e->d_u, size_t(cap) * kM * sizeof(float)));
-    CUDA_TRY(e, cudaMalloc(&e->d_x, size_t(cap) * kN * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_P, size_t(cap) * e->p_stride() * sizeof(double)));
+    CUDA_TRY(e, cudaMalloc(&e->d_q, size_t(cap) * e->nvar() * sizeof(double)));
+    CUDA_TRY(e, cudaMalloc(&e->d_l, size_t(cap) * e->ncon() * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_u, size_t(cap) * e->ncon() * sizeof(float)));
+    CUDA_TRY(e, cudaMalloc(&e->d_x, size_t(cap) * e->nvar() * sizeof(float)));
   } else {
     CUDA_TRY(e, cudaMalloc(&e->d_bstates, size_t(cap) * sizeof(BalanceStateIn)));
     CUDA_TRY(e, cudaMalloc(&e->d_Pb, size_t(cap) * 144 * sizeof(float)));
@@ -163,8 +170,14 @@ int reserve(MpcEngine* e, int n) {
 
 int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n, double* P, double* q,
                  float* l, float* u) {
-  const int grid = n < e->num_sms * 8 ? n : e->num_sms * 8;
-  qp_build_kernel<<<grid, kThreads, sizeof(BuildSmem), e->stream>>>(d_states, model, n, P, q, l, u, e->bp);
+  if (e->H == kH) {
+    const int grid = n < e->num_sms * 8 ? n : e->num_sms * 8;
+    qp_build_kernel<<<grid, kThreads, sizeof(BuildSmem), e->stream>>>(d_states, model, n, P, q, l, u, e->bp);
+  } else {
+    const int grid = n < e->num_sms ? n : e->num_sms;
+    gen_build_kernel<30><<<grid, kGenBuildThreads, sizeof(GenBuildSmem<30>), e->stream>>>(
+        d_states, model, n, P, q, l, u, e->d_workspace, e->bp);
+  }
   ++e->launches;
   CUDA_TRY(e, cudaGetLastError());
   return MPC_OK;
@@ -174,7 +187,10 @@ int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l,
                  const MpcStateIn* d_states, MpcResult* res, float* x, int n) {
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
   const int grid = n < e->num_sms ? n : e->num_sms;
-  if (e->d_phase_clk)
+  if (e->H != kH)
+    gen_solve_kernel<30><<<grid, kGenSolveThreads, sizeof(GenSolveSmem<30>), e->stream>>>(
+        P, q, l, u, d_states, res, x, n, e->d_counter, e->d_workspace, e->sp);
+  else if (e->d_phase_clk)
     admm_solve_kernel<true><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
         P, q, l, u, d_states, res, x, n, e->d_counter, e->d_phase_clk, e->sp);
   else
@@ -208,6 +224,12 @@ int create_common(int kind, int device, MpcEngine** out) {
   if (crc == cudaSuccess)
     crc = cudaFuncSetAttribute(admm_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)sizeof(SolveSmem));
+  if (crc == cudaSuccess)
+    crc = cudaFuncSetAttribute(gen_build_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(GenBuildSmem<30>));
+  if (crc == cudaSuccess)
+    crc = cudaFuncSetAttribute(gen_solve_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(GenSolveSmem<30>));
   if (crc != cudaSuccess) {
     std::string msg = std::string("engine setup: ") + cudaGetErrorString(crc);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -226,9 +248,9 @@ extern "C" {
 
 int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
   if (!cfg) return fail(nullptr, MPC_ERR_INVALID, "cfg is NULL");
-  if (cfg->horizon != kH)
+  if (cfg->horizon != kH && cfg->horizon != 30)
     return fail(nullptr, MPC_ERR_UNSUPPORTED,
-                "horizon " + std::to_string(cfg->horizon) + " not built; this build has H = 10 kernels");
+                "horizon " + std::to_string(cfg->horizon) + " not built; this build has H = 10 and H = 30 kernels");
   std::string why;
   if (validate_settings(cfg->osqp, &why)) return fail(nullptr, MPC_ERR_INVALID, why);
   if (!(cfg->dt > 0) || !(cfg->mass > 0) || !(cfg->mu > 0))
@@ -237,6 +259,17 @@ int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
   int rc = create_common(0, device, &e);
   if (rc != MPC_OK) return rc;
   e->cfg = *cfg;
+  e->H = cfg->horizon;
+  if (e->H != kH) {
+    // long-horizon path: one scratch matrix per persistent CTA (B_qp is 13H x 12H, -K^-1 is 12H x 12H)
+    const size_t per_cta = size_t(13 * e->H) * (12 * e->H);
+    cudaError_t wrc = cudaMalloc(&e->d_workspace, size_t(e->num_sms) * per_cta * sizeof(double));
+    if (wrc != cudaSuccess) {
+      const std::string msg = std::string("workspace: ") + cudaGetErrorString(wrc);
+      mpc_engine_destroy(e);
+      return fail(nullptr, MPC_ERR_CUDA, msg);
+    }
+  }
   e->bp.dt = cfg->dt;
   e->bp.mu = cfg->mu;
   e->bp.fz_min = cfg->fz_min;
@@ -270,6 +303,7 @@ void mpc_engine_destroy(MpcEngine* e) {
   free_buffers(e);
   cudaFree(e->d_counter);
   cudaFree(e->d_phase_clk);
+  cudaFree(e->d_workspace);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -367,19 +401,21 @@ int mpc_get_qp(MpcEngine* e, int32_t idx, float* P, float* q, float* l, float* u
   if (idx < 0 || idx >= e->n) return fail(e, MPC_ERR_INVALID, "problem index out of range");
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  const int nv = e->nvar(), nc = e->ncon();
+  const size_t stride = e->H == kH ? size_t(kNP) : size_t(nv);
   if (P) {
-    std::vector<double> hp(size_t(kN) * kNP);
-    CUDA_TRY(e, cudaMemcpy(hp.data(), e->d_P + size_t(idx) * kN * kNP, hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int r = 0; r < kN; ++r)
-      for (int c = 0; c < kN; ++c) P[r * kN + c] = (float)hp[size_t(r) * kNP + c];
+    std::vector<double> hp(e->p_stride());
+    CUDA_TRY(e, cudaMemcpy(hp.data(), e->d_P + size_t(idx) * e->p_stride(), hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < nv; ++r)
+      for (int c = 0; c < nv; ++c) P[size_t(r) * nv + c] = (float)hp[size_t(r) * stride + c];
   }
   if (q) {
-    double hq[kN];
-    CUDA_TRY(e, cudaMemcpy(hq, e->d_q + size_t(idx) * kN, kN * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int c = 0; c < kN; ++c) q[c] = (float)hq[c];
+    std::vector<double> hq(nv);
+    CUDA_TRY(e, cudaMemcpy(hq.data(), e->d_q + size_t(idx) * nv, nv * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < nv; ++c) q[c] = (float)hq[c];
   }
-  if (l) CUDA_TRY(e, cudaMemcpy(l, e->d_l + size_t(idx) * kM, kM * sizeof(float), cudaMemcpyDeviceToHost));
-  if (u) CUDA_TRY(e, cudaMemcpy(u, e->d_u + size_t(idx) * kM, kM * sizeof(float), cudaMemcpyDeviceToHost));
+  if (l) CUDA_TRY(e, cudaMemcpy(l, e->d_l + size_t(idx) * nc, nc * sizeof(float), cudaMemcpyDeviceToHost));
+  if (u) CUDA_TRY(e, cudaMemcpy(u, e->d_u + size_t(idx) * nc, nc * sizeof(float), cudaMemcpyDeviceToHost));
   return MPC_OK;
 }
 
@@ -426,7 +462,7 @@ int mpc_get_solution(MpcEngine* e, int32_t idx, float* x) {
   if (idx < 0 || idx >= e->n) return fail(e, MPC_ERR_INVALID, "problem index out of range");
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  CUDA_TRY(e, cudaMemcpy(x, e->d_x + size_t(idx) * kN, kN * sizeof(float), cudaMemcpyDeviceToHost));
+  CUDA_TRY(e, cudaMemcpy(x, e->d_x + size_t(idx) * e->nvar(), e->nvar() * sizeof(float), cudaMemcpyDeviceToHost));
   return MPC_OK;
 }
 
@@ -450,8 +486,10 @@ int mpc_qp_mats_from_model(MpcEngine* e, const double* A_mat_d, const double* B_
   if (!A_mat_d || !B_mat_d_list || !mpc_states || !mpc_states_d || !contacts)
     return fail(e, MPC_ERR_INVALID, "NULL model input");
   CUDA_TRY(e, cudaSetDevice(e->device));
-  const size_t nd = 169 + size_t(kH) * 156 + 13 + kS;
-  const size_t npq = size_t(kN) * kNP + kN;  // P (padded) | q, f64
+  const int Hh = e->H, nv = e->nvar(), nc = e->ncon(), ns = 13 * e->H;
+  const size_t rs = (Hh == kH) ? size_t(kNP) : size_t(nv);  // row stride of P on the device
+  const size_t nd = 169 + size_t(Hh) * 156 + 13 + ns;
+  const size_t npq = e->p_stride() + nv;  // P | q, f64
   double* d_model = nullptr;
   int* d_contacts = nullptr;
   double* d_pq = nullptr;
@@ -459,31 +497,31 @@ int mpc_qp_mats_from_model(MpcEngine* e, const double* A_mat_d, const double* B_
   CUDA_TRY(e, cudaMalloc(&d_model, nd * sizeof(double)));
   cudaError_t crc = cudaMalloc(&d_contacts, 4 * sizeof(int));
   if (crc == cudaSuccess) crc = cudaMalloc(&d_pq, npq * sizeof(double));
-  if (crc == cudaSuccess) crc = cudaMalloc(&d_lu, 2 * kM * sizeof(float));
+  if (crc == cudaSuccess) crc = cudaMalloc(&d_lu, 2 * nc * sizeof(float));
   std::vector<double> hm(nd);
   std::memcpy(hm.data(), A_mat_d, 169 * sizeof(double));
-  std::memcpy(hm.data() + 169, B_mat_d_list, size_t(kH) * 156 * sizeof(double));
-  std::memcpy(hm.data() + 169 + kH * 156, mpc_states, 13 * sizeof(double));
-  std::memcpy(hm.data() + 169 + kH * 156 + 13, mpc_states_d, kS * sizeof(double));
+  std::memcpy(hm.data() + 169, B_mat_d_list, size_t(Hh) * 156 * sizeof(double));
+  std::memcpy(hm.data() + 169 + Hh * 156, mpc_states, 13 * sizeof(double));
+  std::memcpy(hm.data() + 169 + Hh * 156 + 13, mpc_states_d, ns * sizeof(double));
   if (crc == cudaSuccess)
     crc = cudaMemcpyAsync(d_model, hm.data(), nd * sizeof(double), cudaMemcpyHostToDevice, e->stream);
   if (crc == cudaSuccess)
     crc = cudaMemcpyAsync(d_contacts, contacts, 4 * sizeof(int), cudaMemcpyHostToDevice, e->stream);
   int rc = MPC_OK;
   std::vector<double> hpq(npq);
-  std::vector<float> hlu(2 * kM);
+  std::vector<float> hlu(2 * nc);
   if (crc == cudaSuccess) {
     ModelIn m{};
     m.A_d = d_model;
     m.B_d_list = d_model + 169;
-    m.x0 = d_model + 169 + kH * 156;
-    m.x_ref = d_model + 169 + kH * 156 + 13;
+    m.x0 = d_model + 169 + Hh * 156;
+    m.x_ref = d_model + 169 + Hh * 156 + 13;
     m.contacts = d_contacts;
-    rc = launch_build(e, nullptr, m, 1, d_pq, d_pq + size_t(kN) * kNP, d_lu, d_lu + kM);
+    rc = launch_build(e, nullptr, m, 1, d_pq, d_pq + e->p_stride(), d_lu, d_lu + nc);
     if (rc == MPC_OK) {
       crc = cudaMemcpyAsync(hpq.data(), d_pq, npq * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
       if (crc == cudaSuccess)
-        crc = cudaMemcpyAsync(hlu.data(), d_lu, 2 * kM * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+        crc = cudaMemcpyAsync(hlu.data(), d_lu, 2 * nc * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
       if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
     }
   }
@@ -494,13 +532,13 @@ int mpc_qp_mats_from_model(MpcEngine* e, const double* A_mat_d, const double* B_
   if (rc) return rc;
   if (crc != cudaSuccess) return fail(e, MPC_ERR_CUDA, cudaGetErrorString(crc));
   if (hessian)
-    for (int r = 0; r < kN; ++r)
-      for (int c = 0; c < kN; ++c) hessian[size_t(r) * kN + c] = hpq[size_t(r) * kNP + c];
-  if (gradient) for (int i = 0; i < kN; ++i) gradient[i] = hpq[size_t(kN) * kNP + i];
+    for (int r = 0; r < nv; ++r)
+      for (int c = 0; c < nv; ++c) hessian[size_t(r) * nv + c] = hpq[size_t(r) * rs + c];
+  if (gradient) for (int i = 0; i < nv; ++i) gradient[i] = hpq[e->p_stride() + i];
   // the device stores bounds in fp32; hand back exactly +-OsqpEigen::INFTY like the reference
   auto snap = [](float v) -> double { return v >= 1e29f ? MPC_INFTY : (v <= -1e29f ? -MPC_INFTY : (double)v); };
-  if (lb) for (int i = 0; i < kM; ++i) lb[i] = snap(hlu[i]);
-  if (ub) for (int i = 0; i < kM; ++i) ub[i] = snap(hlu[kM + i]);
+  if (lb) for (int i = 0; i < nc; ++i) lb[i] = snap(hlu[i]);
+  if (ub) for (int i = 0; i < nc; ++i) ub[i] = snap(hlu[nc + i]);
   return MPC_OK;
 }
 
@@ -509,32 +547,34 @@ int mpc_solve_qp(MpcEngine* e, const double* hessian, const double* gradient, co
   if (!e || e->kind != 0) return MPC_ERR_INVALID;
   if (!hessian || !gradient || !lb || !ub || !solution) return fail(e, MPC_ERR_INVALID, "NULL QP input");
   CUDA_TRY(e, cudaSetDevice(e->device));
-  const size_t npq = size_t(kN) * kNP + kN;
+  const int Hh = e->H, nv = e->nvar(), nc = e->ncon();
+  const size_t rs = (Hh == kH) ? size_t(kNP) : size_t(nv);
+  const size_t npq = e->p_stride() + nv;
   std::vector<double> hpq(npq, 0.0);
-  for (int r = 0; r < kN; ++r)
-    for (int c = 0; c < kN; ++c) hpq[size_t(r) * kNP + c] = hessian[size_t(r) * kN + c];
-  for (int i = 0; i < kN; ++i) hpq[size_t(kN) * kNP + i] = gradient[i];
-  std::vector<float> hlu(2 * kM);
-  for (int i = 0; i < kM; ++i) { hlu[i] = (float)lb[i]; hlu[kM + i] = (float)ub[i]; }
+  for (int r = 0; r < nv; ++r)
+    for (int c = 0; c < nv; ++c) hpq[size_t(r) * rs + c] = hessian[size_t(r) * nv + c];
+  for (int i = 0; i < nv; ++i) hpq[e->p_stride() + i] = gradient[i];
+  std::vector<float> hlu(2 * nc);
+  for (int i = 0; i < nc; ++i) { hlu[i] = (float)lb[i]; hlu[nc + i] = (float)ub[i]; }
   double* d_pq = nullptr;
   float* d_lu = nullptr;
   float* d_xs = nullptr;
   MpcResult* d_res = nullptr;
   CUDA_TRY(e, cudaMalloc(&d_pq, npq * sizeof(double)));
-  cudaError_t crc = cudaMalloc(&d_lu, 2 * kM * sizeof(float));
-  if (crc == cudaSuccess) crc = cudaMalloc(&d_xs, kN * sizeof(float));
+  cudaError_t crc = cudaMalloc(&d_lu, 2 * nc * sizeof(float));
+  if (crc == cudaSuccess) crc = cudaMalloc(&d_xs, nv * sizeof(float));
   if (crc == cudaSuccess) crc = cudaMalloc(&d_res, sizeof(MpcResult));
   if (crc == cudaSuccess)
     crc = cudaMemcpyAsync(d_pq, hpq.data(), npq * sizeof(double), cudaMemcpyHostToDevice, e->stream);
   if (crc == cudaSuccess)
-    crc = cudaMemcpyAsync(d_lu, hlu.data(), 2 * kM * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+    crc = cudaMemcpyAsync(d_lu, hlu.data(), 2 * nc * sizeof(float), cudaMemcpyHostToDevice, e->stream);
   int rc = MPC_OK;
-  std::vector<float> hx(kN);
+  std::vector<float> hx(nv);
   MpcResult hr{};
   if (crc == cudaSuccess) {
-    rc = launch_solve(e, d_pq, d_pq + size_t(kN) * kNP, d_lu, d_lu + kM, nullptr, d_res, d_xs, 1);
+    rc = launch_solve(e, d_pq, d_pq + e->p_stride(), d_lu, d_lu + nc, nullptr, d_res, d_xs, 1);
     if (rc == MPC_OK) {
-      crc = cudaMemcpyAsync(hx.data(), d_xs, kN * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+      crc = cudaMemcpyAsync(hx.data(), d_xs, nv * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
       if (crc == cudaSuccess)
         crc = cudaMemcpyAsync(&hr, d_res, sizeof(MpcResult), cudaMemcpyDeviceToHost, e->stream);
       if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
@@ -546,7 +586,7 @@ int mpc_solve_qp(MpcEngine* e, const double* hessian, const double* gradient, co
   cudaFree(d_res);
   if (rc) return rc;
   if (crc != cudaSuccess) return fail(e, MPC_ERR_CUDA, cudaGetErrorString(crc));
-  for (int i = 0; i < kN; ++i) solution[i] = hx[i];
+  for (int i = 0; i < nv; ++i) solution[i] = hx[i];
   if (status) *status = hr.status;
   if (iters) *iters = hr.iters;
   return MPC_OK;

@@ -30,6 +30,13 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"mpc_{name}.npz"), states=states, grf=res["grf"],
                             iters=res["iters"], status=res["status"], rho_updates=res["rho_updates"],
                             solutions=sol, P0=P0, q0=q0, l0=l0, u0=u0, Psum=Psum, q8=qs)
+    # --- long horizon, H = 30 (BASELINE config 4) ---
+    cfg = pkg.config_default()
+    cfg.horizon = 30
+    states = pkg.generate_states(1004, 0, 16)
+    res = ob.mpc_compute_grf(cfg, states)
+    np.savez_compressed(os.path.join(HERE, "mpc_h30.npz"), states=states, grf=res["grf"], iters=res["iters"],
+                        status=res["status"], rho_updates=res["rho_updates"])
     # --- the reference's own driver input, test/test_mpc.cpp:15-60 ---
     cfg = pkg.config_default()
     cfg.mass = 15.0

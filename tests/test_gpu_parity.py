@@ -271,7 +271,7 @@ def test_error_behaviour(pkg):
     with pytest.raises(pkg.MpcError):
         e.get_qp(4)
     e.close()
-    cfg.horizon = 30
+    cfg.horizon = 20   # kernels exist for H = 10 and H = 30
     with pytest.raises(pkg.MpcError) as ei:
         pkg.MpcEngine(cfg, 0)
     assert ei.value.code == pkg.abi.MPC_ERR_UNSUPPORTED
@@ -358,3 +358,42 @@ def test_balance_qp_parity(pkg, ob):
     r1 = be.compute_grf_batch(states[:5])
     assert r1.tobytes() == res[:5].tobytes()
     be.close()
+
+
+def test_long_horizon_h30(pkg, ob):
+    """BASELINE config 4: H = 30 (360 variables, 600 constraints) through the generic-horizon kernels."""
+    cfg = pkg.config_default()
+    cfg.horizon = 30
+    e = pkg.MpcEngine(cfg, 0)
+    states = pkg.generate_states(1004, 0, 200)
+    e.load_states(states)
+    e.build_qp()
+    for i in (0, 7, 199):
+        P, q, l, u = e.get_qp(i)
+        Po, qo, lo, uo = ob.mpc_build_qp(cfg, states[i])
+        assert P.shape == (360, 360) and l.shape == (600,)
+        assert np.abs(P - Po).max() / np.abs(Po).max() <= TOL_QP
+        assert np.abs(q - qo).max() / np.abs(qo).max() <= TOL_QP
+        assert np.array_equal(l, lo.astype(np.float32)) and np.array_equal(u, uo.astype(np.float32))
+        assert np.array_equal(P, P.T)
+    e.solve()
+    res = e.get_results()
+    ref = ob.mpc_compute_grf(cfg, states)
+    assert np.array_equal(res["status"], ref["status"]) and (res["status"] == 1).all()
+    assert (res["iters"] == ref["iters"]).mean() >= 0.99
+    assert (res["rho_updates"] == ref["rho_updates"]).mean() >= 0.99
+    ok = res["iters"] == ref["iters"]
+    assert grf_rel(res["grf"][ok], ref["grf"][ok]).max() <= TOL_GRF
+    x = e.get_solution(3).astype(np.float64).reshape(30, 4, 3)
+    c = states["contacts"][3].astype(np.float64)
+    assert np.maximum(np.abs(x[..., :2]).max(-1) - 0.3 * x[..., 2], 0).max() <= TOL_CONE * 180.0
+    assert np.maximum(x[..., 2] - 180.0 * c[None, :], 0).max() <= TOL_CONE * 180.0
+    g = np.load(os.path.join(GOLD, "mpc_h30.npz"))                 # committed fixture
+    rg = e.compute_grf_batch(g["states"])
+    assert np.array_equal(rg["iters"], g["iters"]) and np.array_equal(rg["rho_updates"], g["rho_updates"])
+    assert grf_rel(rg["grf"], g["grf"]).max() <= TOL_GRF
+    # ragged sizes around the SM count, and a repeat is bit-identical
+    r2 = e.compute_grf_batch(states[:149])
+    assert r2.tobytes() == res[:149].tobytes()
+    assert len(e.compute_grf_batch(np.zeros(0, dtype=pkg.abi.STATE_DTYPE))) == 0
+    e.close()

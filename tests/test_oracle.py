@@ -92,6 +92,17 @@ def test_golden_regression(pkg, ob):
         assert np.array_equal(l, g["l0"]) and np.array_equal(u, g["u0"])
 
 
+def test_golden_regression_h30(pkg, ob):
+    g = np.load(os.path.join(GOLD, "mpc_h30.npz"))
+    cfg = pkg.config_default()
+    cfg.horizon = 30
+    res = ob.mpc_compute_grf(cfg, g["states"])
+    assert np.array_equal(res["iters"], g["iters"]) and np.array_equal(res["status"], g["status"])
+    np.testing.assert_allclose(res["grf"], g["grf"], rtol=0, atol=1e-9)
+    P, q, l, u = ob.mpc_build_qp(cfg, g["states"][0])
+    assert P.shape == (360, 360) and abs(np.linalg.eigvalsh(P)[0] - 2e-7) < 1e-11
+
+
 def test_generator_known_answer(pkg):
     g = np.load(os.path.join(GOLD, "generator.npz"))
     assert pkg.generate_states(1001, 0, 4).tobytes() == g["s1001"].tobytes()
