@@ -4,19 +4,18 @@
 // K = P + sigma I + A' diag(rho) A, ADMM with alpha-relaxation, residual termination
 // every check_termination iterations, rho adaptation with refactorisation.
 //
-// v5 layout (history and measurements of v1..v4 in profiles/ and DESIGN.md):
-//   320 threads = 20 row groups x 16 column groups; thread (rg, cg) holds the 6 x 8
-//   register tile rows 6rg..6rg+5 x columns {32i + 2cg, 32i + 2cg + 1 : i < 4} of -K^-1
-//   (96 registers; 10 warps leave 204 registers per thread, nothing spills).
-//   A row group is TWO leg-steps (variables 6rg..6rg+5, constraint rows 10rg..10rg+9).
-//   After the reduce-scatter, lanes (2r, 2r+1) of a half-warp hold x~ of tile row r, so the
-//   16 lanes run both leg-steps' z/y update and next right-hand side through shuffles:
-//   ONE block barrier per ADMM iteration, x/z/y in registers of their owning lanes.
-//     leg-step A (rows 0-2): lanes 0..4 = constraint rows 0..4, lanes 0/2/4 own fx/fy/fz
-//     leg-step B (rows 3-5): lanes 6..10 likewise
-//   Tall tiles matter: every half-warp re-reads the same operand vector / published rows, so
-//   shared-memory traffic per step is (row groups) x 1 KB; 3 x 8 tiles (40 row groups, 640
-//   threads) were bound by that traffic and by 20 warps issuing the same scalar code.
+// v6 layout (history and measurements of v1..v5 in profiles/ and DESIGN.md):
+//   256 threads = 8 warps; WARP w holds rows 15w..15w+14 of -K^-1 (five leg-steps), lane cg
+//   holds the 15 x 4 register tile of columns {64i + 2cg, 64i + 2cg + 1 : i < 2}
+//   (120 registers; 8 warps leave 255 registers per thread, nothing spills).
+//   8 warps = 2 per SM sub-partition: the FP64-bound phases are balanced (10 warps were
+//   3:3:2:2 and left a third of the sweep at the barrier, profiles/r01_v5_*).
+//   Row sums go through a padded per-warp shared-memory transpose: afterwards lanes (2r, 2r+1)
+//   hold x~ of tile row r, i.e. leg-step g of the warp has fx/fy/fz on lanes 6g, 6g+2, 6g+4,
+//   and lanes 6g..6g+4 own its five constraint rows: the z/y update and the next right-hand
+//   side run through shuffles, ONE block barrier per ADMM iteration, x/z/y in registers.
+//   Tall tiles matter: every warp re-reads the same operand vector / published rows, so
+//   shared-memory traffic per step is (row groups) x 1 KB.
 //   K^-1 comes from a BLOCKED symmetric sweep (Gauss-Jordan on the SPD matrix) over the
 //   register tiles: rank-3 steps (one leg-step of pivots per barrier); the publisher stores
 //   only its three rows one step ahead, every thread inverts the 3x3 pivot block itself.
@@ -30,10 +29,13 @@
 
 namespace mpcb200 {
 
-constexpr int kSolveThreads = 320;
+constexpr int kSolveThreads = 256;
 constexpr int kSolveWarps = kSolveThreads / 32;
-constexpr int kRowGroups = 20;
-constexpr int kTR = 6;                 // tile rows
+constexpr int kRowGroups = 8;          // one per warp
+constexpr int kTR = 15;                // tile rows = 5 leg-steps
+constexpr int kTC = 4;                 // tile columns
+constexpr int kLegPerWarp = 5;
+constexpr int kRedStride = 36;         // padded row stride of the transpose scratch (conflict-free LDS.128)
 constexpr int kPBytes = kN * kNP * 8;  // 122,880
 
 struct SolveSmem {
@@ -43,7 +45,8 @@ struct SolveSmem {
   double Dp[kNP];           // D (pad = 0)
   double Vb[2][3][kNP];     // blocked sweep: published pivot rows A_S,: with A_SS replaced by A_SS - I
   double G[kLegSteps * 6];  // A' diag(rho) A per leg-step: xx, xz, yy, yz, zz, (pad)
-  double Wg[kRowGroups][24];  // blocked sweep: W[s][row] of each row group, [6 s + rr] (18 used)
+  double Wg[kRowGroups][3][16];  // blocked sweep: W[s][row] of each row group (15 used per s)
+  double redt[kSolveWarps][kTR][kRedStride];  // per-warp transpose scratch of the row reductions
   // per-lane constants of the ADMM loop (slot [tid]); registers are kept for the K^-1 tile
   double lane_lb[kSolveThreads], lane_ub[kSolveThreads], lane_rv[kSolveThreads], lane_rinv[kSolveThreads];
   double lane_qb[kSolveThreads], lane_D[kSolveThreads], lane_Einv[kSolveThreads];
@@ -70,33 +73,31 @@ __device__ __forceinline__ double limit_scaling(double v) {  // osqp scaling.c
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-// Reduce six per-row partials over the 16 lanes of a half-warp (reduce-scatter, 8 double
-// shuffles): lanes 2r and 2r+1 end up with the total of tile row r (r < 6); lanes 12..15
-// hold nothing useful.
+// Reduce fifteen per-row partials over the 32 lanes of a warp through a padded shared-memory
+// transpose: lanes 2r and 2r+1 end up with the total of tile row r (r < 15); lanes 30, 31 hold
+// nothing useful.  Row stride 36 doubles keeps the 16 B reads of a quarter-warp on distinct banks.
 struct AddOp { __device__ __forceinline__ double operator()(double a, double b) const { return a + b; } };
 struct MaxOp { __device__ __forceinline__ double operator()(double a, double b) const { return fmax(a, b); } };
 template <class Op>
-__device__ __forceinline__ double reduce_scatter6(const double (&s)[kTR], int cg, Op op) {
-  const bool b3 = (cg & 8) != 0, b2 = (cg & 4) != 0, b1 = (cg & 2) != 0;
-  // slots 0..7 (6 and 7 are zero); xor 8 exchanges slot groups {0..3} and {4..7}
-  double k0 = b3 ? s[4] : s[0], k1 = b3 ? s[5] : s[1], k2 = b3 ? 0.0 : s[2], k3 = b3 ? 0.0 : s[3];
-  const double t0 = b3 ? s[0] : s[4], t1 = b3 ? s[1] : s[5], t2 = b3 ? s[2] : 0.0, t3 = b3 ? s[3] : 0.0;
-  k0 = op(k0, shfl_xor(t0, 8));
-  k1 = op(k1, shfl_xor(t1, 8));
-  k2 = op(k2, shfl_xor(t2, 8));
-  k3 = op(k3, shfl_xor(t3, 8));
-  double m0 = b2 ? k2 : k0, m1 = b2 ? k3 : k1;
-  const double u0 = b2 ? k0 : k2, u1 = b2 ? k1 : k3;
-  m0 = op(m0, shfl_xor(u0, 4));
-  m1 = op(m1, shfl_xor(u1, 4));
-  double r = b1 ? m1 : m0;
-  const double w = b1 ? m0 : m1;
-  r = op(r, shfl_xor(w, 2));
-  r = op(r, shfl_xor(r, 1));
-  return r;
+__device__ __forceinline__ double reduce_rows(double (*scr)[kRedStride], const double (&s)[kTR], int lane, Op op) {
+  __syncwarp();  // the previous use of the scratch is over
+#pragma unroll
+  for (int r = 0; r < kTR; ++r) scr[r][lane] = s[r];
+  __syncwarp();
+  const int r = (lane < 30) ? (lane >> 1) : 14, h = lane & 1;
+  const double2* src = reinterpret_cast<const double2*>(&scr[r][0]);
+  double2 t[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t[k] = src[2 * k + h];  // interleaved 16 B chunks: lanes 2r, 2r+1 read neighbours
+  double p0 = op(op(t[0].x, t[0].y), op(t[1].x, t[1].y));
+  double p1 = op(op(t[2].x, t[2].y), op(t[3].x, t[3].y));
+  double p2 = op(op(t[4].x, t[4].y), op(t[5].x, t[5].y));
+  double p3 = op(op(t[6].x, t[6].y), op(t[7].x, t[7].y));
+  double part = op(op(p0, p1), op(p2, p3));
+  return op(part, shfl_xor(part, 1));
 }
 
-// Sums over the five row lanes bl..bl+4 of a leg-step (bl = 0 or 6 inside the half-warp):
+// Sums over the five row lanes lbase..lbase+4 of a leg-step (lbase = 6 g inside the warp):
 //   .lat on lane bl: pa@bl + pa@(bl+1);  on lane bl+2: pa@(bl+2) + pa@(bl+3)
 //   .z   on lane bl+4: sum of pz over the five lanes
 struct LegSums { double lat, z; };
@@ -108,31 +109,32 @@ __device__ __forceinline__ LegSums leg_reduce(double pa, double pz, int lbase) {
   return r;
 }
 
-__device__ __forceinline__ void load_cols(const double* base, int cg, double (&v)[8]) {
+__device__ __forceinline__ void load_cols(const double* base, int cg, double (&v)[kTC]) {
   const double2* p = reinterpret_cast<const double2*>(base + 2 * cg);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const double2 t = p[16 * i];
+  for (int i = 0; i < 2; ++i) {
+    const double2 t = p[32 * i];
     v[2 * i] = t.x;
     v[2 * i + 1] = t.y;
   }
 }
+__device__ __forceinline__ int solve_col(int cg, int jj) { return 64 * (jj >> 1) + 2 * cg + (jj & 1); }
 
-// max_j |P_rj| D_j of the rows of this row group; lanes 2r, 2r+1 get tile row r
-__device__ __forceinline__ double row_norm_pass(const SolveSmem& sm, int rg, int cg) {
-  double dcol[8];
+// max_j |P_rj| D_j of the rows of this warp's row group; lanes 2r, 2r+1 get tile row r
+__device__ __forceinline__ double row_norm_pass(SolveSmem& sm, int rg, int cg) {
+  double dcol[kTC];
   load_cols(sm.Dp, cg, dcol);
   double m[kTR];
 #pragma unroll
   for (int rr = 0; rr < kTR; ++rr) {
-    double pv[8];
+    double pv[kTC];
     load_cols(&sm.P[(kTR * rg + rr) * kNP], cg, pv);
     double mm = 0.0;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) mm = fmax(mm, fabs(pv[jj]) * dcol[jj]);
+    for (int jj = 0; jj < kTC; ++jj) mm = fmax(mm, fabs(pv[jj]) * dcol[jj]);
     m[rr] = mm;
   }
-  return reduce_scatter6(m, cg, MaxOp());
+  return reduce_rows(sm.redt[rg], m, cg, MaxOp());
 }
 
 // Blocked symmetric sweep, one leg-step (3 pivots S = {3kb, 3kb+1, 3kb+2}) per barrier.
@@ -140,31 +142,31 @@ __device__ __forceinline__ double row_norm_pass(const SolveSmem& sm, int rg, int
 //   A_rj <- A_rj + sum_s W[s][r] V'[s][j]   (r not in S; V' = V with A_SS - I in the S columns,
 //                                            which makes the same update produce A_rS M)
 //   A_Sj <- M A_Sj (j not in S),  A_SS <- -M
-// (W[s][r] doubles as the column factor because A is symmetric).  Block kb lives in row group
-// kb / 2, tile rows 3 (kb & 1) .. +2 (HALF is a template parameter: static register indices).
-// The publisher stores ONLY V' (12 stores, one step ahead); every thread inverts the 3x3 pivot
-// block itself and forms the 3 x 6 block of W it needs.
-template <int HALF>
-__device__ __forceinline__ void publish_rows(SolveSmem& sm, const double (&a)[kTR][8], int kb, int cg) {
+// (W[s][r] doubles as the column factor because A is symmetric).  Block kb lives in warp
+// kb / 5, tile rows 3 (kb % 5) .. +2 (SUB is a template parameter: static register indices).
+// The publisher stores ONLY V' (6 stores per lane, one step ahead); every thread inverts the 3x3
+// pivot block itself; the 45 entries of W a warp needs are computed cooperatively by its lanes.
+template <int SUB>
+__device__ __forceinline__ void publish_rows(SolveSmem& sm, const double (&a)[kTR][kTC], int kb, int cg, int b) {
   const int c0 = 3 * kb;
 #pragma unroll
   for (int s3 = 0; s3 < 3; ++s3) {
-    double2* dst = reinterpret_cast<double2*>(&sm.Vb[HALF][s3][2 * cg]);
+    double2* dst = reinterpret_cast<double2*>(&sm.Vb[b][s3][2 * cg]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int col = 32 * i + 2 * cg;
-      double v0 = a[3 * HALF + s3][2 * i], v1 = a[3 * HALF + s3][2 * i + 1];
+    for (int i = 0; i < 2; ++i) {
+      const int col = 64 * i + 2 * cg;
+      double v0 = a[3 * SUB + s3][2 * i], v1 = a[3 * SUB + s3][2 * i + 1];
       if (col == c0 + s3) v0 -= 1.0;
       if (col + 1 == c0 + s3) v1 -= 1.0;
-      dst[16 * i] = make_double2(v0, v1);
+      dst[32 * i] = make_double2(v0, v1);
     }
   }
 }
 
-template <int HALF>
-__device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][8], int kb, int rg, int cg) {
+template <int SUB>
+__device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][kTC], int kb, int rg, int cg, int b) {
   const int c0 = 3 * kb;
-  const double(*V)[kNP] = sm.Vb[HALF];
+  const double(*V)[kNP] = sm.Vb[b];
   // A_SS (identity added back) and its symmetric 3x3 cofactor inverse, on every thread
   const double m00 = V[0][c0] + 1.0, m01 = V[0][c0 + 1], m02 = V[0][c0 + 2];
   const double m11 = V[1][c0 + 1] + 1.0, m12 = V[1][c0 + 2];
@@ -174,9 +176,9 @@ __device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][8], 
   const double i00 = k00 * id, i01 = k01 * id, i02 = k02 * id;
   const double i11 = (m00 * m22 - m02 * m02) * id, i12 = (m01 * m02 - m00 * m12) * id;
   const double i22 = (m00 * m11 - m01 * m01) * id;
-  const bool piv = (rg == (kb >> 1));
-  // W[s][r] = -(M V[:, r])[s] for the six rows of this row group depends on rg only: the 16
-  // lanes of the half-warp compute its 18 entries cooperatively and stage them in shared memory
+  const bool piv = (rg * kLegPerWarp + SUB == kb);
+  // W[s][r] = -(M V[:, r])[s] for the 15 rows of this warp depends on the warp only: its lanes
+  // compute the 45 entries cooperatively and stage them in shared memory
   {
     auto wentry = [&](int e) {
       const int s3 = e / kTR, rr = e - kTR * s3;
@@ -184,31 +186,31 @@ __device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][8], 
       const double a0 = (s3 == 0) ? i00 : (s3 == 1) ? i01 : i02;
       const double a1 = (s3 == 0) ? i01 : (s3 == 1) ? i11 : i12;
       const double a2 = (s3 == 0) ? i02 : (s3 == 1) ? i12 : i22;
-      return -(a0 * x0 + a1 * x1 + a2 * x2);
+      sm.Wg[rg][s3][rr] = -(a0 * x0 + a1 * x1 + a2 * x2);
     };
-    sm.Wg[rg][cg] = wentry(cg);
-    if (cg < 2) sm.Wg[rg][16 + cg] = wentry(16 + cg);
+    wentry(cg);
+    if (cg < 3 * kTR - 32) wentry(32 + cg);
     __syncwarp();
   }
   if (piv) {
     // pivot rows: A_Sj <- M A_Sj, A_SS <- -M (uses the rows' old values; they skip the generic update)
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      const double x0 = a[3 * HALF][jj], x1 = a[3 * HALF + 1][jj], x2 = a[3 * HALF + 2][jj];
-      const int t = 32 * (jj >> 1) + 2 * cg + (jj & 1) - c0;  // position inside S, if any
-      a[3 * HALF][jj] = (t == 0) ? -i00 : (t == 1) ? -i01 : (t == 2) ? -i02 : (i00 * x0 + i01 * x1 + i02 * x2);
-      a[3 * HALF + 1][jj] = (t == 0) ? -i01 : (t == 1) ? -i11 : (t == 2) ? -i12 : (i01 * x0 + i11 * x1 + i12 * x2);
-      a[3 * HALF + 2][jj] = (t == 0) ? -i02 : (t == 1) ? -i12 : (t == 2) ? -i22 : (i02 * x0 + i12 * x1 + i22 * x2);
+    for (int jj = 0; jj < kTC; ++jj) {
+      const double x0 = a[3 * SUB][jj], x1 = a[3 * SUB + 1][jj], x2 = a[3 * SUB + 2][jj];
+      const int t = solve_col(cg, jj) - c0;  // position inside S, if any
+      a[3 * SUB][jj] = (t == 0) ? -i00 : (t == 1) ? -i01 : (t == 2) ? -i02 : (i00 * x0 + i01 * x1 + i02 * x2);
+      a[3 * SUB + 1][jj] = (t == 0) ? -i01 : (t == 1) ? -i11 : (t == 2) ? -i12 : (i01 * x0 + i11 * x1 + i12 * x2);
+      a[3 * SUB + 2][jj] = (t == 0) ? -i02 : (t == 1) ? -i12 : (t == 2) ? -i22 : (i02 * x0 + i12 * x1 + i22 * x2);
     }
   }
 #pragma unroll
   for (int s3 = 0; s3 < 3; ++s3) {
-    double v[8], w[kTR];
+    double v[kTC], w[16];
     load_cols(V[s3], cg, v);
     {
-      const double2* wp = reinterpret_cast<const double2*>(&sm.Wg[rg][kTR * s3]);
+      const double2* wp = reinterpret_cast<const double2*>(&sm.Wg[rg][s3][0]);
 #pragma unroll
-      for (int h = 0; h < 3; ++h) {
+      for (int h = 0; h < 8; ++h) {
         const double2 t = wp[h];
         w[2 * h] = t.x;
         w[2 * h + 1] = t.y;
@@ -216,38 +218,52 @@ __device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][8], 
     }
 #pragma unroll
     for (int rr = 0; rr < kTR; ++rr) {
-      const bool is_pivot_row = (rr >= 3 * HALF) && (rr < 3 * HALF + 3);  // static
+      const bool is_pivot_row = (rr >= 3 * SUB) && (rr < 3 * SUB + 3);  // static
       if (is_pivot_row) {
         if (!piv) {
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) a[rr][jj] = fma(w[rr], v[jj], a[rr][jj]);
+          for (int jj = 0; jj < kTC; ++jj) a[rr][jj] = fma(w[rr], v[jj], a[rr][jj]);
         }
       } else {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) a[rr][jj] = fma(w[rr], v[jj], a[rr][jj]);
+        for (int jj = 0; jj < kTC; ++jj) a[rr][jj] = fma(w[rr], v[jj], a[rr][jj]);
       }
     }
   }
 }
 
+// one leg-step of the sweep: barrier, update, look-ahead publication of the next pivot rows
+template <int SUB>
+__device__ __forceinline__ void sweep_step(SolveSmem& sm, double (&a)[kTR][kTC], int kp, int rg, int cg) {
+  const int kb = kLegPerWarp * kp + SUB;
+  const int b = kb & 1;
+  __syncthreads();  // rows of block kb (published one step ahead) are visible
+  sweep_block<SUB>(sm, a, kb, rg, cg, b);
+  if (SUB < kLegPerWarp - 1) {
+    if (rg == kp) publish_rows<(SUB + 1) % kLegPerWarp>(sm, a, kb + 1, cg, b ^ 1);
+  } else {
+    if (rg == kp + 1) publish_rows<0>(sm, a, kb + 1, cg, b ^ 1);
+  }
+}
+
 // Build K = c D P D + sigma I + A' diag(rho) A into the register tiles, then overwrite it
 // with -K^-1 by the blocked symmetric sweep (40 rank-3 steps, one barrier each).
-__device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][8], int rg, int cg, double sigma) {
+__device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][kTC], int rg, int cg, double sigma) {
   {
     const double c = sm.scal[0];
-    double dcol[8];
+    double dcol[kTC];
     load_cols(sm.Dp, cg, dcol);
 #pragma unroll
     for (int rr = 0; rr < kTR; ++rr) {
       const int row = kTR * rg + rr;
-      const int ls = 2 * rg + rr / 3, rc = rr % 3;  // leg-step and component of this row (static rc)
+      const int ls = kLegPerWarp * rg + rr / 3, rc = rr % 3;  // leg-step and component of this row (static rc)
       const double* g = &sm.G[ls * 6];
       const double cDr = c * sm.Dp[row];
-      double pv[8];
+      double pv[kTC];
       load_cols(&sm.P[row * kNP], cg, pv);
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int col = 32 * (jj >> 1) + 2 * cg + (jj & 1);
+      for (int jj = 0; jj < kTC; ++jj) {
+        const int col = solve_col(cg, jj);
         double val = cDr * pv[jj] * dcol[jj];
         if (col == row) val += sigma;
         const int cc = col - 3 * ls;
@@ -263,15 +279,13 @@ __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][8
       }
     }
   }
-  if (rg == 0) publish_rows<0>(sm, a, 0, cg);
+  if (rg == 0) publish_rows<0>(sm, a, 0, cg, 0);
   for (int kp = 0; kp < kRowGroups; ++kp) {
-    __syncthreads();  // rows of block 2kp (published one step ahead) are visible
-    sweep_block<0>(sm, a, 2 * kp, rg, cg);
-    // look-ahead: the next pivot rows are now up to date; publish them for the next step
-    if (rg == kp) publish_rows<1>(sm, a, 2 * kp + 1, cg);
-    __syncthreads();
-    sweep_block<1>(sm, a, 2 * kp + 1, rg, cg);
-    if (rg == kp + 1) publish_rows<0>(sm, a, 2 * kp + 2, cg);
+    sweep_step<0>(sm, a, kp, rg, cg);
+    sweep_step<1>(sm, a, kp, rg, cg);
+    sweep_step<2>(sm, a, kp, rg, cg);
+    sweep_step<3>(sm, a, kp, rg, cg);
+    sweep_step<4>(sm, a, kp, rg, cg);
   }
 }
 
@@ -290,18 +304,18 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int rg = tid >> 4, cg = tid & 15, hb = lane & 16;
-  // lane roles inside the half-warp (two leg-steps: lanes 0..4 and 6..10)
-  const int lg = (cg >= 6) ? 1 : 0;
-  const int pos = cg - 6 * lg;
-  const bool active = cg < 12;
-  const bool rown = active && pos <= 4;                         // owns constraint row `pos` of its leg-step
+  const int rg = warp, cg = lane;  // row group = warp, column group = lane
+  // lane roles inside the warp (five leg-steps: lanes 6g .. 6g+4, g < 5)
+  const int lg = lane / 6;
+  const int pos = lane - 6 * lg;
+  const bool active = lane < 30;
+  const bool rown = active && pos <= 4;                            // owns constraint row `pos` of its leg-step
   const bool vown = active && (pos == 0 || pos == 2 || pos == 4);  // owns variable component pos / 2
   const int vc = pos >> 1;
-  const int ls = 2 * rg + lg;                                   // leg-step
+  const int ls = kLegPerWarp * rg + (active ? lg : 0);             // leg-step
   const int vj = 3 * ls + (vown ? vc : 0);
   const int ri = 5 * ls + (rown ? pos : 0);
-  const int lbase = hb + 6 * lg;
+  const int lbase = active ? 6 * lg : 24;
   const int latsrc = lbase + ((pos < 2) ? 0 : 2), zsrc = lbase + 4;
   const double mu = sp.mu;
   const double sigma = sp.sigma, alpha = sp.alpha;
@@ -311,7 +325,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   uint32_t phase = 0;
-  double a[kTR][8];  // register tile of -K^-1
+  double a[kTR][kTC];  // register tile of -K^-1
   // per-phase cycle counters of thread 0: compiled in only for the kProfile instantiation
   long long pc[kProfile ? 6 : 1] = {0};  // 0 load+ruiz 1 factor 2 iterations 3 checks 4 output 5 problems
   long long tmark = 0;
@@ -483,20 +497,13 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       // x~ = K^-1 rhs
       double xt;
       {
-        double v[8];
+        double v[kTC];
         load_cols(sm.rhs[iter & 1], cg, v);
         double s[kTR];
 #pragma unroll
-        for (int rr = 0; rr < kTR; ++rr) {
-          double s0 = a[rr][0] * v[0], s1 = a[rr][1] * v[1];
-#pragma unroll
-          for (int jj = 2; jj < 8; jj += 2) {
-            s0 = fma(a[rr][jj], v[jj], s0);
-            s1 = fma(a[rr][jj + 1], v[jj + 1], s1);
-          }
-          s[rr] = s0 + s1;
-        }
-        xt = -reduce_scatter6(s, cg, AddOp());  // lanes 2r, 2r+1: x~ of tile row r
+        for (int rr = 0; rr < kTR; ++rr)
+          s[rr] = fma(a[rr][0], v[0], a[rr][1] * v[1]) + fma(a[rr][2], v[2], a[rr][3] * v[3]);
+        xt = -reduce_rows(sm.redt[rg], s, lane, AddOp());  // lanes 2r, 2r+1: x~ of tile row r
       }
       // x <- alpha x~ + (1 - alpha) x
       x = alpha * xt + (1.0 - alpha) * x;
@@ -548,22 +555,16 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       }
       {
         // P_bar x = c D (P (D x)) ; A' y
-        double xv[8];
+        double xv[kTC];
         load_cols(sm.xD, cg, xv);
         double s[kTR];
 #pragma unroll
         for (int rr = 0; rr < kTR; ++rr) {
-          double pv[8];
+          double pv[kTC];
           load_cols(&sm.P[(kTR * rg + rr) * kNP], cg, pv);
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int jj = 0; jj < 8; jj += 2) {
-            s0 = fma(pv[jj], xv[jj], s0);
-            s1 = fma(pv[jj + 1], xv[jj + 1], s1);
-          }
-          s[rr] = s0 + s1;
+          s[rr] = fma(pv[0], xv[0], pv[1] * xv[1]) + fma(pv[2], xv[2], pv[3] * xv[3]);
         }
-        const double sr = reduce_scatter6(s, cg, AddOp());
+        const double sr = reduce_rows(sm.redt[rg], s, lane, AddOp());
         const double yy = rown ? y : 0.0;
         const LegSums ay = leg_reduce(cca * yy, ccz * yy, lbase);
         if (vown) {
@@ -647,11 +648,11 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     // ---- K5: unscale, rotate the first step to the body frame, write ----
     const double xo = sm.lane_D[tid] * x;
     if (x_all != nullptr && vown) x_all[size_t(p) * kN + vj] = (float)xo;
-    if (rg < 2) {
-      // legs 0..3 of the first horizon step are leg-steps 0..3 = warp 0; f = (x, y, z) on lanes
-      // lbase, lbase + 2, lbase + 4
+    if (rg == 0) {
+      // legs 0..3 of the first horizon step are leg-steps 0..3 = lanes 0..23 of warp 0;
+      // f = (x, y, z) on lanes lbase, lbase + 2, lbase + 4
       const double f0 = shfl(xo, lbase), f1 = shfl(xo, lbase + 2), f2 = shfl(xo, lbase + 4);
-      if (vown) {
+      if (vown && lg < 4) {
         double g;
         if (states != nullptr) {
           // R' f (A1RobotControl.cpp:558-561)
