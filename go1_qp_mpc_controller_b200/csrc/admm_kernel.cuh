@@ -29,6 +29,10 @@
 
 namespace mpcb200 {
 
+// fine-grained cycle probes of the profiling instantiation (thread 0 of every CTA accumulates
+// into registers-free shared slots; see scripts/phase_profile.py)
+#define FINE_PROBE(sm, i) do { if (kProfile && threadIdx.x == 0) { const long long _t = clock64(); (sm).fine[i] += _t - (sm).fine_mark; (sm).fine_mark = _t; } } while (0)
+
 constexpr int kSolveThreads = 256;
 constexpr int kSolveWarps = kSolveThreads / 32;
 constexpr int kRowGroups = 8;          // one per warp
@@ -53,6 +57,8 @@ struct SolveSmem {
   double red[kSolveWarps * 16];
   double scal[8];           // 0:c 1:cinv 2:rho 3:ct 4:pri_res
   unsigned long long mbar;
+  long long fine[16];       // profiling instantiation only
+  long long fine_mark;
   int flags[8];             // 0:done 1:status 2:refactor 3:problem index
 };
 
@@ -163,7 +169,7 @@ __device__ __forceinline__ void publish_rows(SolveSmem& sm, const double (&a)[kT
   }
 }
 
-template <int SUB>
+template <int SUB, bool kProfile>
 __device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][kTC], int kb, int rg, int cg, int b) {
   const int c0 = 3 * kb;
   const double(*V)[kNP] = sm.Vb[b];
@@ -177,6 +183,7 @@ __device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][kTC]
   const double i11 = (m00 * m22 - m02 * m02) * id, i12 = (m01 * m02 - m00 * m12) * id;
   const double i22 = (m00 * m11 - m01 * m01) * id;
   const bool piv = (rg * kLegPerWarp + SUB == kb);
+  FINE_PROBE(sm, 1);  // 3x3 inverse
   // W[s][r] = -(M V[:, r])[s] for the 15 rows of this warp depends on the warp only: its lanes
   // compute the 45 entries cooperatively and stage them in shared memory
   {
@@ -192,6 +199,7 @@ __device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][kTC]
     if (cg < 3 * kTR - 32) wentry(32 + cg);
     __syncwarp();
   }
+  FINE_PROBE(sm, 2);  // W staging
   if (piv) {
     // pivot rows: A_Sj <- M A_Sj, A_SS <- -M (uses the rows' old values; they skip the generic update)
 #pragma unroll
@@ -203,6 +211,7 @@ __device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][kTC]
       a[3 * SUB + 2][jj] = (t == 0) ? -i02 : (t == 1) ? -i12 : (t == 2) ? -i22 : (i02 * x0 + i12 * x1 + i22 * x2);
     }
   }
+  FINE_PROBE(sm, 3);  // pivot rows
 #pragma unroll
   for (int s3 = 0; s3 < 3; ++s3) {
     double v[kTC], w[16];
@@ -230,24 +239,28 @@ __device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][kTC]
       }
     }
   }
+  FINE_PROBE(sm, 4);  // rank-3 update
 }
 
 // one leg-step of the sweep: barrier, update, look-ahead publication of the next pivot rows
-template <int SUB>
+template <int SUB, bool kProfile>
 __device__ __forceinline__ void sweep_step(SolveSmem& sm, double (&a)[kTR][kTC], int kp, int rg, int cg) {
   const int kb = kLegPerWarp * kp + SUB;
   const int b = kb & 1;
   __syncthreads();  // rows of block kb (published one step ahead) are visible
-  sweep_block<SUB>(sm, a, kb, rg, cg, b);
+  FINE_PROBE(sm, 0);  // barrier wait
+  sweep_block<SUB, kProfile>(sm, a, kb, rg, cg, b);
   if (SUB < kLegPerWarp - 1) {
     if (rg == kp) publish_rows<(SUB + 1) % kLegPerWarp>(sm, a, kb + 1, cg, b ^ 1);
   } else {
     if (rg == kp + 1) publish_rows<0>(sm, a, kb + 1, cg, b ^ 1);
   }
+  FINE_PROBE(sm, 5);  // publication
 }
 
 // Build K = c D P D + sigma I + A' diag(rho) A into the register tiles, then overwrite it
 // with -K^-1 by the blocked symmetric sweep (40 rank-3 steps, one barrier each).
+template <bool kProfile>
 __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][kTC], int rg, int cg, double sigma) {
   {
     const double c = sm.scal[0];
@@ -280,12 +293,13 @@ __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][k
     }
   }
   if (rg == 0) publish_rows<0>(sm, a, 0, cg, 0);
+  if (kProfile && threadIdx.x == 0) sm.fine_mark = clock64();
   for (int kp = 0; kp < kRowGroups; ++kp) {
-    sweep_step<0>(sm, a, kp, rg, cg);
-    sweep_step<1>(sm, a, kp, rg, cg);
-    sweep_step<2>(sm, a, kp, rg, cg);
-    sweep_step<3>(sm, a, kp, rg, cg);
-    sweep_step<4>(sm, a, kp, rg, cg);
+    sweep_step<0, kProfile>(sm, a, kp, rg, cg);
+    sweep_step<1, kProfile>(sm, a, kp, rg, cg);
+    sweep_step<2, kProfile>(sm, a, kp, rg, cg);
+    sweep_step<3, kProfile>(sm, a, kp, rg, cg);
+    sweep_step<4, kProfile>(sm, a, kp, rg, cg);
   }
 }
 
@@ -325,6 +339,10 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   uint32_t phase = 0;
+  if (kProfile && tid == 0) {
+    for (int i = 0; i < 16; ++i) sm.fine[i] = 0;
+    sm.fine_mark = clock64();
+  }
   double a[kTR][kTC];  // register tile of -K^-1
   // per-phase cycle counters of thread 0: compiled in only for the kProfile instantiation
   long long pc[kProfile ? 6 : 1] = {0};  // 0 load+ruiz 1 factor 2 iterations 3 checks 4 output 5 problems
@@ -482,7 +500,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
 
     PHASE_MARK(0);
     // ---- K3b: factor (explicit inverse in registers) ----
-    factor_inverse(sm, a, rg, cg, sigma);
+    factor_inverse<kProfile>(sm, a, rg, cg, sigma);
     PHASE_MARK(1);
 
     // ---- K4: ADMM iterations (osqp.c osqp_solve) ----
@@ -493,7 +511,9 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     int until_check = sp.check_termination > 0 ? sp.check_termination : 0x7fffffff;
     int until_adapt = (sp.adaptive_rho && sp.adaptive_rho_interval > 0) ? sp.adaptive_rho_interval : 0x7fffffff;
     for (iter = 1; iter <= sp.max_iter; ++iter) {
+      if (kProfile && tid == 0) sm.fine_mark = clock64();
       __syncthreads();  // rhs[iter & 1] is complete; rhs[(iter + 1) & 1] is free to rewrite
+      FINE_PROBE(sm, 8);  // iteration: barrier
       // x~ = K^-1 rhs
       double xt;
       {
@@ -503,7 +523,11 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
 #pragma unroll
         for (int rr = 0; rr < kTR; ++rr)
           s[rr] = fma(a[rr][0], v[0], a[rr][1] * v[1]) + fma(a[rr][2], v[2], a[rr][3] * v[3]);
+        if (kProfile) { double chk = 0.0; for (int rr = 0; rr < kTR; ++rr) chk += s[rr]; if (chk == 1.2345e300) sm.fine[15] += 1; }
+        FINE_PROBE(sm, 9);  // iteration: rhs load + 60 FMA
         xt = -reduce_rows(sm.redt[rg], s, lane, AddOp());  // lanes 2r, 2r+1: x~ of tile row r
+        if (kProfile && xt == 1.2345e300) sm.fine[15] += 1;
+        FINE_PROBE(sm, 10);  // iteration: row reduction
       }
       // x <- alpha x~ + (1 - alpha) x
       x = alpha * xt + (1.0 - alpha) * x;
@@ -518,12 +542,15 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         y = y + rvv * (zr - zn);
         z = zn;
       }
+      if (kProfile && z == 1.2345e300) sm.fine[15] += 1;
+      FINE_PROBE(sm, 11);  // iteration: z / y update
       // next rhs = sigma x - q + A'(rho z - y)
       {
         const double w = rown ? (rvv * z - y) : 0.0;
         const LegSums s = leg_reduce(cca * w, ccz * w, lbase);
         if (vown) sm.rhs[(iter + 1) & 1][vj] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
       }
+      FINE_PROBE(sm, 12);  // iteration: next rhs
       const bool can_check = (--until_check == 0);
       const bool can_adapt = (--until_adapt == 0);
       if (can_check) until_check = sp.check_termination;
@@ -639,7 +666,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         }
         build_G();
         __syncthreads();
-        factor_inverse(sm, a, rg, cg, sigma);
+        factor_inverse<kProfile>(sm, a, rg, cg, sigma);
         PHASE_MARK(1);
       }
     }
@@ -676,6 +703,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
   if (kProfile && tid == 0 && phase_clk != nullptr) {
 #pragma unroll
     for (int i = 0; i < (kProfile ? 6 : 1); ++i) phase_clk[blockIdx.x * 6 + i] = pc[i];
+    for (int i = 0; i < 16; ++i) phase_clk[gridDim.x * 6 + blockIdx.x * 16 + i] = sm.fine[i];
   }
 #undef PHASE_MARK
 }

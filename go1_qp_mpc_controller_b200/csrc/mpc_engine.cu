@@ -331,12 +331,14 @@ int mpc_debug_phase_cycles(MpcEngine* e, int32_t enable, int64_t* out6) {
   if (!e || e->kind != 0) return MPC_ERR_INVALID;
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  const size_t n = size_t(e->num_sms) * 6;
+  const size_t n6 = size_t(e->num_sms) * 6;
+  const size_t n = size_t(e->num_sms) * 22;  // 6 phase + 16 fine counters per CTA
   if (out6 && e->d_phase_clk) {
     std::vector<long long> h(n);
     CUDA_TRY(e, cudaMemcpy(h.data(), e->d_phase_clk, n * sizeof(long long), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 6; ++i) out6[i] = 0;
-    for (size_t k = 0; k < n; ++k) out6[k % 6] += h[k];
+    for (int i = 0; i < 22; ++i) out6[i] = 0;
+    for (size_t k = 0; k < n6; ++k) out6[k % 6] += h[k];
+    for (size_t k = n6; k < n; ++k) out6[6 + (k - n6) % 16] += h[k];
   }
   if (enable && !e->d_phase_clk) {
     CUDA_TRY(e, cudaMalloc(&e->d_phase_clk, n * sizeof(long long)));

@@ -176,10 +176,12 @@ class MpcEngine:
 
     def phase_cycles(self, enable=True):
         """Developer aid: read and reset admm_solve_kernel's per-phase cycle counters."""
-        out = (C.c_int64 * 6)()
+        out = (C.c_int64 * 22)()
         self._lib.mpc_debug_phase_cycles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         self._check(self._lib.mpc_debug_phase_cycles(self._h, 1 if enable else 0, out))
-        return dict(zip(["load_scale", "factor", "iterations", "checks", "output", "problems"], list(out)))
+        d = dict(zip(["load_scale", "factor", "iterations", "checks", "output", "problems"], list(out)[:6]))
+        d["fine"] = list(out)[6:]
+        return d
 
     def load_states(self, states):
         states = np.ascontiguousarray(states)

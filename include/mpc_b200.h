@@ -199,8 +199,9 @@ int mpc_synchronize(MpcEngine *e);
 /* Number of kernels this engine has launched since creation. */
 int64_t mpc_kernel_launches(const MpcEngine *e);
 /* Developer aid: per-phase SM cycle counters of admm_solve_kernel, summed over CTAs since the
- * last call (out6: load+scaling, factorisations, ADMM iterations, residual checks, output,
- * problems).  enable != 0 switches the counters on for later launches, 0 off. */
+ * last call (out6[0..5]: load+scaling, factorisations, ADMM iterations, residual checks, output,
+ * problems; out6[6..21]: fine probes inside the sweep step and the iteration; the buffer must
+ * hold 22 values).  enable != 0 switches the counters on for later launches, 0 off. */
 int mpc_debug_phase_cycles(MpcEngine *e, int32_t enable, int64_t *out6);
 
 /* ---- batched MPC GRF solve (compute_grf, MPC branch) ---------------------- */
