@@ -39,6 +39,9 @@ constexpr int kRowGroups = 8;          // one per warp
 constexpr int kTR = 15;                // tile rows = 5 leg-steps
 constexpr int kTC = 4;                 // tile columns
 constexpr int kLegPerWarp = 5;
+// one warm-start slot (doubles): scaled x | previous unscaled q | scaled z | scaled y | rho | live
+constexpr int kWarmX = 0, kWarmQ = kN, kWarmZ = 2 * kN, kWarmY = 2 * kN + kM, kWarmRho = 2 * kN + 2 * kM,
+              kWarmLive = kWarmRho + 1, kWarmStride = 648;
 constexpr int kRedStride = 36;         // padded row stride of the transpose scratch (conflict-free LDS.128)
 constexpr int kPBytes = kN * kNP * 8;  // 122,880
 
@@ -307,13 +310,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-template <bool kProfile>
+template <bool kProfile, bool kWarm>
 __global__ void __launch_bounds__(kSolveThreads, 1)
 admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q_all,
                   const float* __restrict__ l_all, const float* __restrict__ u_all,
                   const MpcStateIn* __restrict__ states, MpcResult* __restrict__ results,
                   float* __restrict__ x_all, int num, int* __restrict__ counter,
-                  long long* __restrict__ phase_clk, const __grid_constant__ SolveParams sp) {
+                  long long* __restrict__ phase_clk, double* __restrict__ warm,
+                  const __grid_constant__ SolveParams sp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -370,6 +374,13 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     if (p >= num) break;
     if (kProfile && tid == 0) { tmark = clock64(); pc[kProfile ? 5 : 0] += 1; }
 
+    // kWarm: slot p of `warm` is the solver this robot keeps alive between control ticks
+    // (A1RobotControl.cpp:522-538).  A live slot makes this an update + warm solve: scale_data
+    // still sees the PREVIOUS tick's gradient (osqp_update_P runs before osqp_update_lin_cost),
+    // and x, z, y (in the old scaled coordinates) and rho carry over.
+    double* const ws = kWarm ? warm + size_t(p) * kWarmStride : nullptr;
+    const bool live = kWarm && ws[kWarmLive] != 0.0;
+    const double rho0 = live ? ws[kWarmRho] : sp.rho;
     if (tid < kNP) {
       sm.Dp[tid] = (tid < kN) ? 1.0 : 0.0;
       sm.rhs[0][tid] = 0.0;
@@ -383,11 +394,12 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     }
     if (tid == 0) {
       sm.scal[0] = 1.0;
-      sm.scal[2] = sp.rho;
+      sm.scal[2] = rho0;
       sm.flags[0] = 0;
       sm.flags[1] = MPC_STATUS_UNSOLVED;
     }
     const double q0 = vown ? q_all[size_t(p) * kN + vj] : 0.0;
+    const double q_scale = (live && vown) ? ws[kWarmQ + vj] : q0;
     double lb = rown ? (double)l_all[size_t(p) * kM + ri] : 0.0;
     double ub = rown ? (double)u_all[size_t(p) * kM + ri] : 0.0;
     {
@@ -437,7 +449,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         const double c_old = sm.scal[0];
         const double nP2 = c_old * D * row_norm_pass(sm, rg, cg);
         double part_sum = vown ? nP2 : 0.0;
-        double part_q = vown ? fabs(c_old * D * q0) : 0.0;
+        double part_q = vown ? fabs(c_old * D * q_scale) : 0.0;
         part_sum = warp_sum(part_sum);
         part_q = warp_max(part_q);
         if (lane == 0) {
@@ -468,7 +480,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     int ctype = 0;
     if (lb < -MPC_INFTY * 1e-4 && ub > MPC_INFTY * 1e-4) ctype = -1;
     else if (ub - lb < 1e-4) ctype = 1;
-    const double rv0 = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * sp.rho : sp.rho;
+    const double rv0 = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * rho0 : rho0;
     // scaled constraint coefficients of the owned row: z~_i = cca * x~_lat + ccz * x~_z
     double cca, ccz;
     {
@@ -495,7 +507,16 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       if (active && pos == 4) sm.G[ls * 6 + 4] = s1.z;
     };
     build_G();
-    if (vown) sm.rhs[1][vj] = -qb0;  // rhs of iteration 1: x = z = y = 0
+    double x = 0.0, z = 0.0, y = 0.0;  // x on variable lanes; z, y on row lanes
+    if (live) {
+      if (vown) x = ws[kWarmX + vj];
+      if (rown) { z = ws[kWarmZ + ri]; y = ws[kWarmY + ri]; }
+      const double w = rown ? (rv0 * z - y) : 0.0;
+      const LegSums s = leg_reduce(cca * w, ccz * w, lbase);
+      if (vown) sm.rhs[1][vj] = sigma * x - qb0 + ((vc == 2) ? s.z : s.lat);
+    } else {
+      if (vown) sm.rhs[1][vj] = -qb0;  // rhs of iteration 1: x = z = y = 0
+    }
     __syncthreads();
 
     PHASE_MARK(0);
@@ -504,7 +525,6 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     PHASE_MARK(1);
 
     // ---- K4: ADMM iterations (osqp.c osqp_solve) ----
-    double x = 0.0, z = 0.0, y = 0.0;  // x on variable lanes; z, y on row lanes
     int iter = 0, rho_updates = 0, status = MPC_STATUS_UNSOLVED;
     double pri_res_out = 0.0;
     // countdowns instead of iter % interval (runtime divisors cost ~50 instructions per iteration)
@@ -686,6 +706,12 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     }
     if (iter > sp.max_iter) iter = sp.max_iter;
 
+    if (kWarm) {
+      // keep the solver alive for the next tick
+      if (vown) { ws[kWarmX + vj] = x; ws[kWarmQ + vj] = q0; }
+      if (rown) { ws[kWarmZ + ri] = z; ws[kWarmY + ri] = y; }
+      if (tid == 0) { ws[kWarmRho] = sm.scal[2]; ws[kWarmLive] = 1.0; }
+    }
     // ---- K5: unscale, rotate the first step to the body frame, write ----
     const double xo = sm.lane_D[tid] * x;
     if (x_all != nullptr && vown) x_all[size_t(p) * kN + vj] = (float)xo;

@@ -136,8 +136,17 @@ const double kDefaultFoot[12] = {0.17, 0.15, -0.35, 0.17, -0.15, -0.35,
                                  -0.17, 0.15, -0.35, -0.17, -0.15, -0.35};
 
 struct CommonDraw {
-  double euler[3], pos[3], w[3], v[3], R[9], foot_abs[12];
+  double euler[3], pos[3], w[3], v[3], R[9], foot_abs[12], rel[12];
 };
+
+void place_feet(CommonDraw& d) {
+  euler_to_rot(d.euler[0], d.euler[1], d.euler[2], d.R);
+  // foot_pos_abs = R * foot_pos_rel (GazeboA1ROS.cpp:283)
+  for (int leg = 0; leg < 4; ++leg)
+    for (int r = 0; r < 3; ++r)
+      d.foot_abs[3 * leg + r] = d.R[3 * r] * d.rel[3 * leg] + d.R[3 * r + 1] * d.rel[3 * leg + 1] +
+                                d.R[3 * r + 2] * d.rel[3 * leg + 2];
+}
 
 void draw_common(SplitMix& g, CommonDraw& d) {
   d.euler[0] = g.uni(-0.2, 0.2);
@@ -150,52 +159,73 @@ void draw_common(SplitMix& g, CommonDraw& d) {
   d.v[0] = g.uni(-0.6, 0.6);
   d.v[1] = g.uni(-0.3, 0.3);
   d.v[2] = g.uni(-0.2, 0.2);
-  euler_to_rot(d.euler[0], d.euler[1], d.euler[2], d.R);
-  double rel[12];
-  for (int i = 0; i < 12; ++i) rel[i] = kDefaultFoot[i] + g.uni(-0.05, 0.05);
-  // foot_pos_abs = R * foot_pos_rel (GazeboA1ROS.cpp:283)
-  for (int leg = 0; leg < 4; ++leg)
-    for (int r = 0; r < 3; ++r)
-      d.foot_abs[3 * leg + r] = d.R[3 * r] * rel[3 * leg] + d.R[3 * r + 1] * rel[3 * leg + 1] +
-                                d.R[3 * r + 2] * rel[3 * leg + 2];
+  for (int i = 0; i < 12; ++i) d.rel[i] = kDefaultFoot[i] + g.uni(-0.05, 0.05);
+  place_feet(d);
 }
 
 }  // namespace
 
+// State `index` of stream `seed`, `tick` control periods (2.5 ms, the main loop period of
+// GazeboA1ROS.cpp / HardwareA1ROS.cpp) after its draw: velocities relax towards the commanded
+// ones with a 0.1 s time constant, the pose integrates them, trot pairs swap every 48 ticks.
+// tick = 0 is exactly the draw.
+static void make_mpc_state(uint64_t seed, uint64_t index, int64_t tick, MpcStateIn& s) {
+  SplitMix g(seed, index);
+  CommonDraw d;
+  draw_common(g, d);
+  std::memset(&s, 0, sizeof(s));
+  s.euler_d[0] = 0.0f;
+  s.euler_d[1] = float(g.uni(-0.1, 0.1));
+  s.euler_d[2] = 0.0f;
+  s.pos_d_z = float(g.uni(0.25, 0.32));        // JOY_CMD_BODY_HEIGHT_MAX, A1Params.h:16
+  s.lin_vel_d[0] = float(g.uni(-0.6, 0.6));    // JOY_CMD_VELX_MAX, A1Params.h:19
+  s.lin_vel_d[1] = float(g.uni(-0.3, 0.3));    // JOY_CMD_VELY_MAX, A1Params.h:20
+  s.lin_vel_d[2] = 0.0f;
+  s.ang_vel_d[0] = 0.0f;
+  s.ang_vel_d[1] = 0.0f;
+  s.ang_vel_d[2] = float(g.uni(-0.8, 0.8));    // JOY_CMD_YAW_MAX, A1Params.h:21
+  // trot pairs {FL,RR} / {FR,RL} 45 % each, four-stance 10 %
+  const double c = g.u01();
+  bool a = c < 0.45, b = c >= 0.45 && c < 0.90;
+  if (tick > 0) {
+    const double tau = 0.0025 * double(tick);
+    const double relax = 1.0 - std::exp(-tau / 0.1);
+    for (int i = 0; i < 3; ++i) {
+      const double v0 = d.v[i], w0 = d.w[i];
+      const double v1 = v0 + (double(s.lin_vel_d[i]) - v0) * relax;
+      const double w1 = w0 + (double(s.ang_vel_d[i]) - w0) * relax;
+      d.pos[i] += 0.5 * (v0 + v1) * tau;
+      d.euler[i] += 0.5 * (w0 + w1) * tau * (i == 2 ? 1.0 : 0.25);
+      d.v[i] = v1;
+      d.w[i] = w1;
+    }
+    place_feet(d);
+    if (((tick / 48) & 1) && (a || b)) { a = !a; b = !b; }
+  }
+  for (int i = 0; i < 3; ++i) {
+    s.euler[i] = float(d.euler[i]);
+    s.pos[i] = float(d.pos[i]);
+    s.ang_vel[i] = float(d.w[i]);
+    s.lin_vel[i] = float(d.v[i]);
+  }
+  for (int i = 0; i < 9; ++i) s.rot_mat[i] = float(d.R[i]);
+  for (int i = 0; i < 12; ++i) s.foot_pos_abs[i] = float(d.foot_abs[i]);
+  s.contacts[0] = (a || (!a && !b)) ? 1.0f : 0.0f;
+  s.contacts[3] = s.contacts[0];
+  s.contacts[1] = (b || (!a && !b)) ? 1.0f : 0.0f;
+  s.contacts[2] = s.contacts[1];
+}
+
 int mpc_generate_states(uint64_t seed, uint64_t first_index, int32_t n, MpcStateIn* out) {
   if (!out || n < 0) return MPC_ERR_INVALID;
-  for (int32_t k = 0; k < n; ++k) {
-    SplitMix g(seed, first_index + uint64_t(k));
-    CommonDraw d;
-    draw_common(g, d);
-    MpcStateIn& s = out[k];
-    std::memset(&s, 0, sizeof(s));
-    for (int i = 0; i < 3; ++i) {
-      s.euler[i] = float(d.euler[i]);
-      s.pos[i] = float(d.pos[i]);
-      s.ang_vel[i] = float(d.w[i]);
-      s.lin_vel[i] = float(d.v[i]);
-    }
-    s.euler_d[0] = 0.0f;
-    s.euler_d[1] = float(g.uni(-0.1, 0.1));
-    s.euler_d[2] = 0.0f;
-    s.pos_d_z = float(g.uni(0.25, 0.32));        // JOY_CMD_BODY_HEIGHT_MAX, A1Params.h:16
-    s.lin_vel_d[0] = float(g.uni(-0.6, 0.6));    // JOY_CMD_VELX_MAX, A1Params.h:19
-    s.lin_vel_d[1] = float(g.uni(-0.3, 0.3));    // JOY_CMD_VELY_MAX, A1Params.h:20
-    s.lin_vel_d[2] = 0.0f;
-    s.ang_vel_d[0] = 0.0f;
-    s.ang_vel_d[1] = 0.0f;
-    s.ang_vel_d[2] = float(g.uni(-0.8, 0.8));    // JOY_CMD_YAW_MAX, A1Params.h:21
-    for (int i = 0; i < 9; ++i) s.rot_mat[i] = float(d.R[i]);
-    for (int i = 0; i < 12; ++i) s.foot_pos_abs[i] = float(d.foot_abs[i]);
-    // trot pairs {FL,RR} / {FR,RL} 45 % each, four-stance 10 %
-    const double c = g.u01();
-    const bool a = c < 0.45, b = c >= 0.45 && c < 0.90;
-    s.contacts[0] = (a || (!a && !b)) ? 1.0f : 0.0f;
-    s.contacts[3] = s.contacts[0];
-    s.contacts[1] = (b || (!a && !b)) ? 1.0f : 0.0f;
-    s.contacts[2] = s.contacts[1];
-  }
+  for (int32_t k = 0; k < n; ++k) make_mpc_state(seed, first_index + uint64_t(k), 0, out[k]);
+  return MPC_OK;
+}
+
+int mpc_generate_stream_states(uint64_t seed, uint64_t first_index, int32_t n, int64_t tick,
+                               MpcStateIn* out) {
+  if (!out || n < 0 || tick < 0) return MPC_ERR_INVALID;
+  for (int32_t k = 0; k < n; ++k) make_mpc_state(seed, first_index + uint64_t(k), tick, out[k]);
   return MPC_OK;
 }
 

@@ -49,6 +49,8 @@ struct MpcEngine {
   int nvar() const { return 12 * H; }
   int ncon() const { return 20 * H; }
   size_t p_stride() const { return H == kH ? size_t(kN) * kNP : size_t(nvar()) * nvar(); }  // doubles per problem
+  double* d_warm = nullptr;       // kWarmStride doubles per robot: the solver kept alive between ticks
+  int warm_capacity = 0;
   long long* d_phase_clk = nullptr;  // optional per-phase cycle counters (mpc_debug_phase_cycles)
   bool built = false, solved = false;
   int64_t launches = 0;
@@ -184,18 +186,21 @@ int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n,
 }
 
 int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l, const float* u,
-                 const MpcStateIn* d_states, MpcResult* res, float* x, int n) {
+                 const MpcStateIn* d_states, MpcResult* res, float* x, int n, double* warm = nullptr) {
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
   const int grid = n < e->num_sms ? n : e->num_sms;
-  if (e->H != kH)
+  if (warm)
+    admm_solve_kernel<false, true><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
+        P, q, l, u, d_states, res, x, n, e->d_counter, nullptr, warm, e->sp);
+  else if (e->H != kH)
     gen_solve_kernel<30><<<grid, kGenSolveThreads, sizeof(GenSolveSmem<30>), e->stream>>>(
         P, q, l, u, d_states, res, x, n, e->d_counter, e->d_workspace, e->sp);
   else if (e->d_phase_clk)
-    admm_solve_kernel<true><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
-        P, q, l, u, d_states, res, x, n, e->d_counter, e->d_phase_clk, e->sp);
+    admm_solve_kernel<true, false><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
+        P, q, l, u, d_states, res, x, n, e->d_counter, e->d_phase_clk, nullptr, e->sp);
   else
-    admm_solve_kernel<false><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
-        P, q, l, u, d_states, res, x, n, e->d_counter, nullptr, e->sp);
+    admm_solve_kernel<false, false><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
+        P, q, l, u, d_states, res, x, n, e->d_counter, nullptr, nullptr, e->sp);
   ++e->launches;
   CUDA_TRY(e, cudaGetLastError());
   return MPC_OK;
@@ -219,10 +224,13 @@ int create_common(int kind, int device, MpcEngine** out) {
     crc = cudaFuncSetAttribute(qp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)sizeof(BuildSmem));
   if (crc == cudaSuccess)
-    crc = cudaFuncSetAttribute(admm_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    crc = cudaFuncSetAttribute(admm_solve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)sizeof(SolveSmem));
   if (crc == cudaSuccess)
-    crc = cudaFuncSetAttribute(admm_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    crc = cudaFuncSetAttribute(admm_solve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(SolveSmem));
+  if (crc == cudaSuccess)
+    crc = cudaFuncSetAttribute(admm_solve_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)sizeof(SolveSmem));
   if (crc == cudaSuccess)
     crc = cudaFuncSetAttribute(gen_build_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -304,6 +312,7 @@ void mpc_engine_destroy(MpcEngine* e) {
   cudaFree(e->d_counter);
   cudaFree(e->d_phase_clk);
   cudaFree(e->d_workspace);
+  cudaFree(e->d_warm);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -437,6 +446,62 @@ int mpc_solve(MpcEngine* e) {
   int rc = mpc_solve_async(e);
   if (rc) return rc;
   return mpc_synchronize(e);
+}
+
+// ---- warm-started streaming (one persistent solver per robot slot) ------------
+
+int mpc_stream_reset(MpcEngine* e) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (e->d_warm)
+    CUDA_TRY(e, cudaMemsetAsync(e->d_warm, 0, size_t(e->warm_capacity) * kWarmStride * sizeof(double), e->stream));
+  return MPC_OK;
+}
+
+int mpc_solve_warm_async(MpcEngine* e) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (e->H != kH) return fail(e, MPC_ERR_UNSUPPORTED, "warm-started streaming is built for horizon 10 only");
+  if (!e->built) return fail(e, MPC_ERR_STATE, "mpc_solve_warm before mpc_build_qp");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (e->n > e->warm_capacity) {
+    // growing the slot array keeps the live solvers of the slots that already exist
+    double* grown = nullptr;
+    CUDA_TRY(e, cudaMalloc(&grown, size_t(e->n) * kWarmStride * sizeof(double)));
+    cudaError_t crc = cudaMemsetAsync(grown, 0, size_t(e->n) * kWarmStride * sizeof(double), e->stream);
+    if (crc == cudaSuccess && e->d_warm)
+      crc = cudaMemcpyAsync(grown, e->d_warm, size_t(e->warm_capacity) * kWarmStride * sizeof(double),
+                            cudaMemcpyDeviceToDevice, e->stream);
+    if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
+    if (crc != cudaSuccess) {
+      cudaFree(grown);
+      return fail(e, MPC_ERR_CUDA, cudaGetErrorString(crc));
+    }
+    cudaFree(e->d_warm);
+    e->d_warm = grown;
+    e->warm_capacity = e->n;
+  }
+  if (e->n > 0) {
+    int rc = launch_solve(e, e->d_P, e->d_q, e->d_l, e->d_u, e->d_states, e->d_results, e->d_x, e->n, e->d_warm);
+    if (rc) return rc;
+  }
+  e->solved = true;
+  return MPC_OK;
+}
+
+int mpc_solve_warm(MpcEngine* e) {
+  int rc = mpc_solve_warm_async(e);
+  if (rc) return rc;
+  return mpc_synchronize(e);
+}
+
+int mpc_stream_step(MpcEngine* e, const MpcStateIn* host_in, MpcResult* host_out, int32_t n) {
+  int rc = mpc_load_states(e, host_in, n);
+  if (rc) return rc;
+  rc = mpc_build_qp_async(e);
+  if (rc) return rc;
+  rc = mpc_solve_warm_async(e);
+  if (rc) return rc;
+  return mpc_get_results(e, host_out);
 }
 
 int mpc_get_results(MpcEngine* e, MpcResult* host) {

@@ -25,6 +25,8 @@ EXPORTED_SYMBOLS = [
     "mpc_solve_async", "mpc_get_results", "mpc_results_device", "mpc_get_solution",
     "mpc_compute_grf_batch", "mpc_qp_mats_from_model", "mpc_solve_qp", "balance_engine_create",
     "balance_qp_solve", "balance_load_states", "balance_solve", "balance_get_qp",
+    "mpc_generate_stream_states", "mpc_solve_warm", "mpc_solve_warm_async", "mpc_stream_reset",
+    "mpc_stream_step",
 ]
 
 
@@ -70,6 +72,11 @@ def load_library():
     lib.mpc_results_device.argtypes = [vp, C.POINTER(vp)]
     lib.mpc_get_solution.argtypes = [vp, i32, vp]
     lib.mpc_compute_grf_batch.argtypes = [vp, vp, vp, i32]
+    lib.mpc_generate_stream_states.argtypes = [u64, u64, i32, C.c_int64, vp]
+    lib.mpc_solve_warm.argtypes = [vp]
+    lib.mpc_solve_warm_async.argtypes = [vp]
+    lib.mpc_stream_reset.argtypes = [vp]
+    lib.mpc_stream_step.argtypes = [vp, vp, vp, i32]
     lib.mpc_qp_mats_from_model.argtypes = [vp] + [vp] * 9
     lib.mpc_solve_qp.argtypes = [vp] + [vp] * 7
     lib.balance_qp_solve.argtypes = [vp, vp, vp, i32]
@@ -115,6 +122,15 @@ def generate_states(seed, first_index, n):
     rc = load_library().mpc_generate_states(seed, first_index, n, _ptr(out))
     if rc:
         raise MpcError(rc, "mpc_generate_states")
+    return out
+
+
+def generate_stream_states(seed, first_index, n, tick):
+    """The robots of generate_states(seed, first_index, n), `tick` control periods later."""
+    out = np.zeros(n, dtype=abi.STATE_DTYPE)
+    rc = load_library().mpc_generate_stream_states(seed, first_index, n, tick, _ptr(out))
+    if rc:
+        raise MpcError(rc, "mpc_generate_stream_states")
     return out
 
 
@@ -250,6 +266,23 @@ class MpcEngine:
             self._check(self._lib.balance_qp_solve(self._h, _ptr(states), _ptr(out), len(states)))
         else:
             self._check(self._lib.mpc_compute_grf_batch(self._h, _ptr(states), _ptr(out), len(states)))
+        self.n = len(states)
+        return out
+
+    # warm-started streaming: slot i keeps robot i's solver alive between ticks
+    # (A1RobotControl.cpp:522-538)
+    def solve_warm(self, sync=True):
+        self._check((self._lib.mpc_solve_warm if sync else self._lib.mpc_solve_warm_async)(self._h))
+
+    def stream_reset(self):
+        self._check(self._lib.mpc_stream_reset(self._h))
+
+    def stream_step(self, states, out=None):
+        """One control tick for every robot: host in, host out, warm-started solve."""
+        states = np.ascontiguousarray(states)
+        if out is None:
+            out = np.zeros(len(states), dtype=abi.RESULT_DTYPE)
+        self._check(self._lib.mpc_stream_step(self._h, _ptr(states), _ptr(out), len(states)))
         self.n = len(states)
         return out
 

@@ -182,6 +182,10 @@ int balance_config_default(BalanceConfig *cfg);
  * counter-based stream `seed`.  Deterministic and order independent. */
 int mpc_generate_states(uint64_t seed, uint64_t first_index, int32_t n, MpcStateIn *out);
 int balance_generate_states(uint64_t seed, uint64_t first_index, int32_t n, BalanceStateIn *out);
+/* The same robots `tick` control periods (2.5 ms) later: velocities relax to the commanded
+ * ones, the pose integrates them, trot pairs swap every 48 ticks.  tick 0 = mpc_generate_states. */
+int mpc_generate_stream_states(uint64_t seed, uint64_t first_index, int32_t n, int64_t tick,
+                               MpcStateIn *out);
 
 /* ---- engine life cycle --------------------------------------------------- */
 
@@ -233,6 +237,25 @@ int mpc_get_solution(MpcEngine *e, int32_t idx, float *x);
 /* The whole compute_grf MPC branch for n robots: host records in, host results
  * out (H2D + build + solve + D2H). */
 int mpc_compute_grf_batch(MpcEngine *e, const MpcStateIn *host_in, MpcResult *host_out, int32_t n);
+
+/* ---- warm-started streaming: the solver the controller keeps alive --------- *
+ * A1RobotControl.h:67 holds ONE OsqpEigen::Solver for the controller's life;
+ * A1RobotControl.cpp:522-531 initialises it on the first MPC tick (initSolver,
+ * setWarmStart(true)) and :532-538 only updates Hessian, gradient and bounds
+ * afterwards, so every later solve starts from the previous tick's iterates
+ * and adapted rho.  Problem slot i of the engine is robot i's solver:
+ *   - a fresh slot behaves exactly like mpc_solve (cold start);
+ *   - a live slot follows OSQP's update semantics: osqp_update_P re-runs the
+ *     Ruiz scaling on the new Hessian with the previous gradient still in place,
+ *     then gradient and bounds are replaced and rho_vec re-typed; x, z, y stay
+ *     in the old scaled coordinates and rho keeps its adapted value.
+ * Horizon 10 only (MPC_ERR_UNSUPPORTED otherwise). */
+int mpc_solve_warm(MpcEngine *e);
+int mpc_solve_warm_async(MpcEngine *e);
+/* Forget every live solver (the next warm solve of each slot is an initSolver). */
+int mpc_stream_reset(MpcEngine *e);
+/* One control tick for n robots: load + build + warm solve + results. */
+int mpc_stream_step(MpcEngine *e, const MpcStateIn *host_in, MpcResult *host_out, int32_t n);
 
 /* ---- ConvexMpc surface, one problem (ConvexMpc.h:22-35) -------------------- */
 

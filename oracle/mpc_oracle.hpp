@@ -331,6 +331,8 @@ struct Osqp {
   Settings st;
   std::vector<T> P, q, l, u;  // scaled in place by setup()
   Csr<T> A;
+  Csr<T> A0;                  // unscaled constraint matrix (for osqp_update_P's unscale/scale)
+  std::vector<T> q_unscaled;  // the linear cost as last passed by the caller
   std::vector<T> D, E, Dinv, Einv;
   T c = 1, cinv = 1;
   std::vector<T> rho_vec, rho_inv_vec;
@@ -502,6 +504,8 @@ struct Osqp {
     l.assign(l_, l_ + m);
     u.assign(u_, u_ + m);
     A = A_;
+    A0 = A_;
+    q_unscaled = q;
     if (st.scaling > 0) {
       scale_data();
     } else {
@@ -516,6 +520,35 @@ struct Osqp {
     Ax.assign(m, 0); Px.assign(n, 0); Aty.assign(n, 0);
     info = Info();
     n_factor = 0;
+    return factor();
+  }
+
+  // The warm path of the live controller (A1RobotControl.cpp:532-538): updateHessianMatrix,
+  // updateGradient, updateLowerBound, updateUpperBound on a solver that stays alive.
+  //   osqp_update_P        unscale_data; new P; scale_data (from D = E = c = 1, with the OLD q
+  //                        still in place: the cost scaling c sees the previous gradient);
+  //                        refactor; reset_info
+  //   osqp_update_lin_cost q <- c D q_new
+  //   osqp_update_bounds   l, u <- E l_new, E u_new; update_rho_vec (constraint types may change)
+  // The iterates x, z, y (in the OLD scaled coordinates) and settings->rho are kept: warm start.
+  bool update(const T* P_new, const T* q_new, const T* l_new, const T* u_new) {
+    P.assign(P_new, P_new + size_t(n) * n);
+    q = q_unscaled;  // old gradient, unscaled
+    A = A0;
+    if (st.scaling > 0) {
+      // l, u are rescaled by scale_data and then overwritten below: give it neutral values
+      std::fill(l.begin(), l.end(), T(0));
+      std::fill(u.begin(), u.end(), T(0));
+      scale_data();
+    }
+    q_unscaled.assign(q_new, q_new + n);
+    for (int j = 0; j < n; ++j) q[j] = c * D[j] * q_unscaled[j];
+    for (int i = 0; i < m; ++i) {
+      l[i] = E[i] * l_new[i];
+      u[i] = E[i] * u_new[i];
+    }
+    set_rho_vec(true);  // recomputes the constraint types from the new scaled bounds, keeps st.rho
+    info = Info();
     return factor();
   }
 
@@ -836,6 +869,40 @@ void mpc_solve(const MpcParams& p, const RobotState<T>& st, MpcProblem<T>& pb, G
   out.pri_res = solver.info.pri_res;
   out.dua_res = solver.info.dua_res;
 }
+
+// One robot's persistent MPC solver over control ticks (A1RobotControl.h:67 `solver` member,
+// A1RobotControl.cpp:522-540): initSolver on the first tick, update* + warm solve afterwards.
+template <class T>
+struct MpcStream {
+  Osqp<T> solver;
+  bool initialised = false;
+  void tick(const MpcParams& p, const RobotState<T>& st, MpcProblem<T>& pb, GrfResult<T>& out) {
+    ConvexMpc<T>& mpc = pb.mpc;
+    if (!initialised) {
+      Csr<T> A;
+      A.m = mpc.m; A.n = mpc.n;
+      A.row_ptr = mpc.Ac_row_ptr; A.col = mpc.Ac_col; A.val = mpc.Ac_val;
+      solver.setup(mpc.n, mpc.m, mpc.hessian.data(), mpc.gradient.data(), A, mpc.lb.data(), mpc.ub.data(), p.osqp);
+      initialised = true;
+    } else {
+      solver.update(mpc.hessian.data(), mpc.gradient.data(), mpc.lb.data(), mpc.ub.data());
+    }
+    solver.solve();
+    std::vector<T> sol(mpc.n);
+    solver.solution(sol.data(), nullptr);
+    for (int i = 0; i < kNumLeg; ++i) {
+      const T* f = &sol[3 * i];
+      const bool bad = std::isnan(f[0]) || std::isnan(f[1]) || std::isnan(f[2]);
+      for (int r = 0; r < 3; ++r)
+        out.grf[3 * i + r] = bad ? T(0) : st.rot_mat[r] * f[0] + st.rot_mat[3 + r] * f[1] + st.rot_mat[6 + r] * f[2];
+    }
+    out.status = solver.info.status;
+    out.iters = solver.info.iters;
+    out.rho_updates = solver.info.rho_updates;
+    out.pri_res = solver.info.pri_res;
+    out.dua_res = solver.info.dua_res;
+  }
+};
 
 // ---------------------------------------------------------------------------
 // stance-balance QP (A1RobotControl.cpp:11-48 constants, :321-332, :377-444)

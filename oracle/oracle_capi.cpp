@@ -262,6 +262,30 @@ int oracle_balance_compute_grf(const BalanceConfig* cfg, const BalanceStateIn* s
   return 0;
 }
 
+// Warm-started streaming: `ticks` consecutive control ticks of n robots, states tick-major
+// (states[t * n + i]); one persistent solver per robot, like the controller's member solver.
+int oracle_mpc_stream(const MpcConfig* cfg, const MpcStateIn* states, int32_t n, int32_t ticks,
+                      OracleResult* out, int32_t threads) {
+  const MpcParams p = to_params(cfg);
+  if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads)
+  {
+    MpcProblem<double> pb(p);
+#pragma omp for schedule(dynamic, 1)
+    for (int i = 0; i < n; ++i) {
+      MpcStream<double> stream;
+      for (int t = 0; t < ticks; ++t) {
+        RobotState<double> st = widen<double>(states[size_t(t) * n + i]);
+        GrfResult<double> g;
+        mpc_build(p, st, pb);
+        stream.tick(p, st, pb, g);
+        to_result(g, &out[size_t(t) * n + i]);
+      }
+    }
+  }
+  return 0;
+}
+
 int oracle_max_threads(void) { return omp_get_max_threads(); }
 
 }  // extern "C"

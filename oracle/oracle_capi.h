@@ -47,6 +47,9 @@ int oracle_balance_build_qp(const BalanceConfig *cfg, const BalanceStateIn *stat
                             double *q, double *l, double *u);
 int oracle_balance_compute_grf(const BalanceConfig *cfg, const BalanceStateIn *states, int32_t n,
                                OracleResult *out, int32_t threads);
+/* A1RobotControl.cpp:522-540 kept alive over `ticks` control ticks (states tick-major). */
+int oracle_mpc_stream(const MpcConfig *cfg, const MpcStateIn *states, int32_t n, int32_t ticks,
+                      OracleResult *out, int32_t threads);
 int oracle_max_threads(void);
 
 #ifdef __cplusplus

@@ -19,7 +19,19 @@ import go1_qp_mpc_controller_b200 as pkg  # noqa: E402
 import oracle_binding as ob  # noqa: E402
 
 
+def stream():
+    # --- warm-started streaming: 8 consecutive ticks across a trot swap (ticks 44..51) ---
+    for name, cfg in (("gazebo", pkg.config_default()), ("hardware", pkg.config_hardware())):
+        st = np.stack([pkg.generate_stream_states(1006, 0, 48, 44 + t) for t in range(8)])
+        res = ob.mpc_stream(cfg, st)
+        np.savez_compressed(os.path.join(HERE, f"stream_{name}.npz"), states=st, grf=res["grf"], iters=res["iters"],
+                            status=res["status"], rho_updates=res["rho_updates"])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "stream":
+        return stream()
+    stream()
     # --- MPC, gazebo weights (primary) and hardware weights (secondary) ---
     for name, cfg in (("gazebo", pkg.config_default()), ("hardware", pkg.config_hardware())):
         states = pkg.generate_states(1002, 0, 96)

@@ -162,6 +162,16 @@ def balance_compute_grf(cfg, states, threads=0):
     return out
 
 
+def mpc_stream(cfg, states_tn, threads=0):
+    """states_tn: (ticks, n) record array; returns (ticks, n) oracle results (warm-started solver per robot)."""
+    st = np.ascontiguousarray(states_tn)
+    ticks, n = st.shape
+    out = np.zeros((ticks, n), dtype=ORACLE_RESULT_DTYPE)
+    rc = lib().oracle_mpc_stream(C.byref(cfg), _vp(st), C.c_int32(n), C.c_int32(ticks), _vp(out), C.c_int32(threads))
+    assert rc == 0
+    return out
+
+
 def max_threads():
     return int(lib().oracle_max_threads())
 

@@ -397,3 +397,64 @@ def test_long_horizon_h30(pkg, ob):
     assert r2.tobytes() == res[:149].tobytes()
     assert len(e.compute_grf_batch(np.zeros(0, dtype=pkg.abi.STATE_DTYPE))) == 0
     e.close()
+
+
+@pytest.mark.parametrize("which", ["gazebo", "hardware"])
+def test_warm_started_stream_parity(pkg, ob, which):
+    """The solver kept alive between control ticks (A1RobotControl.cpp:522-538): the GPU slots
+    follow the oracle's OSQP update semantics tick by tick -- same iteration counts, same rho
+    updates, GRF inside the gate -- across a trot contact swap (bounds change type)."""
+    cfg = pkg.config_default() if which == "gazebo" else pkg.config_hardware()
+    N, T = 256, 8
+    st = np.stack([pkg.generate_stream_states(1006, 0, N, 44 + t) for t in range(T)])
+    ref = ob.mpc_stream(cfg, st)
+    e = pkg.MpcEngine(cfg, 0)
+    cold = e.compute_grf_batch(st[1]).copy()
+    for t in range(T):
+        res = e.stream_step(st[t])
+        assert (res["status"] == ref["status"][t]).all()
+        same = (res["iters"] == ref["iters"][t]).mean()
+        assert same >= 0.98, (t, same)
+        ok = res["iters"] == ref["iters"][t]
+        assert grf_rel(res["grf"][ok], ref["grf"][t][ok]).max() <= TOL_GRF, t
+        assert (res["rho_updates"][ok] == ref["rho_updates"][t][ok]).all()
+        if t == 0:
+            first = res.copy()
+    # a warm tick is cheaper than the cold solve of the same problem
+    res1 = None
+    e.stream_reset()
+    e.stream_step(st[0])
+    res1 = e.stream_step(st[1])
+    assert res1["iters"].mean() < 0.7 * cold["iters"].mean()
+    # reset makes the next tick an initSolver again: identical to the plain cold path
+    e.stream_reset()
+    again = e.stream_step(st[0])
+    plain = e.compute_grf_batch(st[0])
+    assert np.array_equal(again["iters"], plain["iters"]) and np.array_equal(again["grf"], plain["grf"])
+    assert np.array_equal(again["grf"], first["grf"])
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["gazebo", "hardware"])
+def test_warm_stream_golden(pkg, name):
+    g = np.load(os.path.join(GOLD, f"stream_{name}.npz"))
+    cfg = pkg.config_default() if name == "gazebo" else pkg.config_hardware()
+    e = pkg.MpcEngine(cfg, 0)
+    for t in range(g["states"].shape[0]):
+        res = e.stream_step(g["states"][t])
+        ok = res["iters"] == g["iters"][t]
+        assert ok.mean() >= 0.95, t
+        assert grf_rel(res["grf"][ok], g["grf"][t][ok]).max() <= TOL_GRF
+    e.close()
+
+
+def test_warm_stream_unsupported_horizon(pkg):
+    cfg = pkg.config_default()
+    cfg.horizon = 30
+    e = pkg.MpcEngine(cfg, 0)
+    e.load_states(pkg.generate_states(1, 0, 2))
+    e.build_qp()
+    with pytest.raises(pkg.MpcError) as ei:
+        e.solve_warm()
+    assert ei.value.code == pkg.abi.MPC_ERR_UNSUPPORTED
+    e.close()

@@ -268,3 +268,46 @@ def test_f32_model_drifts(pkg, ob):
     rel = np.linalg.norm(r32["grf"] - r64["grf"], axis=1) / den
     assert (rel > 1e-3).mean() > 0.002       # f32 misses the 1e-3 gate on a visible fraction
     assert (r32["iters"] == r64["iters"]).mean() < 0.99
+
+
+# ---- warm-started streaming (A1RobotControl.cpp:522-538) --------------------------------
+
+def test_stream_generator_tick0_is_the_draw(pkg):
+    assert pkg.generate_stream_states(1002, 7, 33, 0).tobytes() == pkg.generate_states(1002, 7, 33).tobytes()
+    a = pkg.generate_stream_states(1002, 0, 64, 48)
+    b = pkg.generate_states(1002, 0, 64)
+    trot = b["contacts"].sum(1) == 2
+    assert (a["contacts"][trot] == 1 - b["contacts"][trot]).all()       # pairs swapped after 48 ticks
+    assert (a["contacts"][~trot] == b["contacts"][~trot]).all()
+    R = a["rot_mat"].reshape(-1, 3, 3).astype(np.float64)
+    assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["gazebo", "hardware"])
+def test_stream_golden_regression(pkg, ob, name):
+    g = np.load(os.path.join(GOLD, f"stream_{name}.npz"))
+    cfg = pkg.config_default() if name == "gazebo" else pkg.config_hardware()
+    assert g["states"].tobytes() == np.stack(
+        [pkg.generate_stream_states(1006, 0, 48, 44 + t) for t in range(8)]).tobytes()
+    res = ob.mpc_stream(cfg, g["states"])
+    assert np.array_equal(res["iters"], g["iters"]) and np.array_equal(res["status"], g["status"])
+    assert np.abs(res["grf"] - g["grf"]).max() <= 1e-9 * np.abs(g["grf"]).max()
+
+
+def test_stream_semantics(pkg, ob):
+    """First tick = initSolver = the cold path; later ticks start from the previous iterates and
+    cost fewer iterations; at a tight tolerance warm and cold ticks reach the same optimum."""
+    cfg = pkg.config_hardware()
+    N, T = 24, 4
+    st = np.stack([pkg.generate_stream_states(1002, 0, N, t) for t in range(T)])
+    warm = ob.mpc_stream(cfg, st)
+    cold0 = ob.mpc_compute_grf(cfg, st[0])
+    assert np.array_equal(warm["iters"][0], cold0["iters"]) and np.array_equal(warm["grf"][0], cold0["grf"])
+    cold = np.stack([ob.mpc_compute_grf(cfg, st[t]) for t in range(T)])
+    assert (warm["status"] == 1).all()
+    assert warm["iters"][1:].mean() < 0.7 * cold["iters"][1:].mean()
+    cfg.osqp.eps_abs = cfg.osqp.eps_rel = 1e-9
+    cfg.osqp.max_iter = 50000
+    warm = ob.mpc_stream(cfg, st)
+    cold = np.stack([ob.mpc_compute_grf(cfg, st[t]) for t in range(T)])
+    assert np.abs(warm["grf"] - cold["grf"]).max() <= 1e-5 * np.abs(cold["grf"]).max()
