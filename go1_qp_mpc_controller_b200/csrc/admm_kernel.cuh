@@ -42,7 +42,6 @@ constexpr int kLegPerWarp = 5;
 // one warm-start slot (doubles): scaled x | previous unscaled q | scaled z | scaled y | rho | live
 constexpr int kWarmX = 0, kWarmQ = kN, kWarmZ = 2 * kN, kWarmY = 2 * kN + kM, kWarmRho = 2 * kN + 2 * kM,
               kWarmLive = kWarmRho + 1, kWarmStride = 648;
-constexpr int kRedStride = 36;         // padded row stride of the transpose scratch (conflict-free LDS.128)
 constexpr int kPBytes = kN * kNP * 8;  // 122,880
 
 struct SolveSmem {
@@ -53,7 +52,6 @@ struct SolveSmem {
   double Vb[2][3][kNP];     // blocked sweep: published pivot rows A_S,: with A_SS replaced by A_SS - I
   double G[kLegSteps * 6];  // A' diag(rho) A per leg-step: xx, xz, yy, yz, zz, (pad)
   double Wg[kRowGroups][3][16];  // blocked sweep: W[s][row] of each row group (15 used per s)
-  double redt[kSolveWarps][kTR][kRedStride];  // per-warp transpose scratch of the row reductions
   // per-lane constants of the ADMM loop (slot [tid]); registers are kept for the K^-1 tile
   double lane_lb[kSolveThreads], lane_ub[kSolveThreads], lane_rv[kSolveThreads], lane_rinv[kSolveThreads];
   double lane_qb[kSolveThreads], lane_D[kSolveThreads], lane_Einv[kSolveThreads];
@@ -82,28 +80,29 @@ __device__ __forceinline__ double limit_scaling(double v) {  // osqp scaling.c
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-// Reduce fifteen per-row partials over the 32 lanes of a warp through a padded shared-memory
-// transpose: lanes 2r and 2r+1 end up with the total of tile row r (r < 15); lanes 30, 31 hold
-// nothing useful.  Row stride 36 doubles keeps the 16 B reads of a quarter-warp on distinct banks.
+// Reduce fifteen per-row partials over the 32 lanes of a warp by recursive halving: at the stage
+// with lane mask m a lane keeps the half of its rows whose index bit matches its own lane bit and
+// hands the other half to lane ^ m, so 8 + 4 + 2 + 1 + 1 = 16 shuffles do the whole transpose-
+// reduction (a naive butterfly needs 75).  Lanes 2r and 2r+1 end up with the total of tile row r
+// (r < 15); lanes 30, 31 hold the padding row.  No shared memory, no warp barrier.
 struct AddOp { __device__ __forceinline__ double operator()(double a, double b) const { return a + b; } };
 struct MaxOp { __device__ __forceinline__ double operator()(double a, double b) const { return fmax(a, b); } };
 template <class Op>
-__device__ __forceinline__ double reduce_rows(double (*scr)[kRedStride], const double (&s)[kTR], int lane, Op op) {
-  __syncwarp();  // the previous use of the scratch is over
+__device__ __forceinline__ double reduce_rows(const double (&s)[kTR], int lane, Op op) {
+  static_assert(kTR == 15, "recursive halving is written for 15 (padded to 16) rows");
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+  double a8[8], a4[4], a2[2];
 #pragma unroll
-  for (int r = 0; r < kTR; ++r) scr[r][lane] = s[r];
-  __syncwarp();
-  const int r = (lane < 30) ? (lane >> 1) : 14, h = lane & 1;
-  const double2* src = reinterpret_cast<const double2*>(&scr[r][0]);
-  double2 t[8];
+  for (int k = 0; k < 8; ++k) {
+    const double lo = s[k], hi = (k + 8 < kTR) ? s[k + 8] : 0.0;  // 0 is neutral for both ops (max of norms)
+    a8[k] = op(b4 ? hi : lo, shfl_xor(b4 ? lo : hi, 16));
+  }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) t[k] = src[2 * k + h];  // interleaved 16 B chunks: lanes 2r, 2r+1 read neighbours
-  double p0 = op(op(t[0].x, t[0].y), op(t[1].x, t[1].y));
-  double p1 = op(op(t[2].x, t[2].y), op(t[3].x, t[3].y));
-  double p2 = op(op(t[4].x, t[4].y), op(t[5].x, t[5].y));
-  double p3 = op(op(t[6].x, t[6].y), op(t[7].x, t[7].y));
-  double part = op(op(p0, p1), op(p2, p3));
-  return op(part, shfl_xor(part, 1));
+  for (int k = 0; k < 4; ++k) a4[k] = op(b3 ? a8[k + 4] : a8[k], shfl_xor(b3 ? a8[k] : a8[k + 4], 8));
+#pragma unroll
+  for (int k = 0; k < 2; ++k) a2[k] = op(b2 ? a4[k + 2] : a4[k], shfl_xor(b2 ? a4[k] : a4[k + 2], 4));
+  const double a1 = op(b1 ? a2[1] : a2[0], shfl_xor(b1 ? a2[0] : a2[1], 2));
+  return op(a1, shfl_xor(a1, 1));
 }
 
 // Sums over the five row lanes lbase..lbase+4 of a leg-step (lbase = 6 g inside the warp):
@@ -143,7 +142,7 @@ __device__ __forceinline__ double row_norm_pass(SolveSmem& sm, int rg, int cg) {
     for (int jj = 0; jj < kTC; ++jj) mm = fmax(mm, fabs(pv[jj]) * dcol[jj]);
     m[rr] = mm;
   }
-  return reduce_rows(sm.redt[rg], m, cg, MaxOp());
+  return reduce_rows(m, cg, MaxOp());
 }
 
 // Blocked symmetric sweep, one leg-step (3 pivots S = {3kb, 3kb+1, 3kb+2}) per barrier.
@@ -542,10 +541,10 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         double s[kTR];
 #pragma unroll
         for (int rr = 0; rr < kTR; ++rr)
-          s[rr] = fma(a[rr][0], v[0], a[rr][1] * v[1]) + fma(a[rr][2], v[2], a[rr][3] * v[3]);
+          s[rr] = fma(a[rr][3], v[3], fma(a[rr][2], v[2], fma(a[rr][1], v[1], a[rr][0] * v[0])));
         if (kProfile) { double chk = 0.0; for (int rr = 0; rr < kTR; ++rr) chk += s[rr]; if (chk == 1.2345e300) sm.fine[15] += 1; }
         FINE_PROBE(sm, 9);  // iteration: rhs load + 60 FMA
-        xt = -reduce_rows(sm.redt[rg], s, lane, AddOp());  // lanes 2r, 2r+1: x~ of tile row r
+        xt = -reduce_rows(s, lane, AddOp());  // lanes 2r, 2r+1: x~ of tile row r
         if (kProfile && xt == 1.2345e300) sm.fine[15] += 1;
         FINE_PROBE(sm, 10);  // iteration: row reduction
       }
@@ -616,7 +615,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
           load_cols(&sm.P[(kTR * rg + rr) * kNP], cg, pv);
           s[rr] = fma(pv[0], xv[0], pv[1] * xv[1]) + fma(pv[2], xv[2], pv[3] * xv[3]);
         }
-        const double sr = reduce_rows(sm.redt[rg], s, lane, AddOp());
+        const double sr = reduce_rows(s, lane, AddOp());
         const double yy = rown ? y : 0.0;
         const LegSums ay = leg_reduce(cca * yy, ccz * yy, lbase);
         if (vown) {
