@@ -49,9 +49,10 @@ struct SolveSmem {
   double rhs[2][kNP];       // operand of the K^-1 matvec, double buffered by iteration parity (pad = 0)
   double xD[kNP];           // D .* x for P x (pad = 0)
   double Dp[kNP];           // D (pad = 0)
-  double Vb[2][3][kNP];     // blocked sweep: published pivot rows A_S,: with A_SS replaced by A_SS - I
+  double Vb[10][3][kNP];    // blocked sweep, ten slots: published pivot rows V' = A_S,: with A_SS - I
+  double Wb[10][3][kNP];    //   W = -A_SS^-1 V' of the same block, 16 entries per row group (15 used)
+  double Mb[10][8];         //   A_SS^-1: 00 01 02 11 12 22
   double G[kLegSteps * 6];  // A' diag(rho) A per leg-step: xx, xz, yy, yz, zz, (pad)
-  double Wg[kRowGroups][3][16];  // blocked sweep: W[s][row] of each row group (15 used per s)
   // per-lane constants of the ADMM loop (slot [tid]); registers are kept for the K^-1 tile
   double lane_lb[kSolveThreads], lane_ub[kSolveThreads], lane_rv[kSolveThreads], lane_rinv[kSolveThreads];
   double lane_qb[kSolveThreads], lane_D[kSolveThreads], lane_Einv[kSolveThreads];
@@ -60,7 +61,9 @@ struct SolveSmem {
   unsigned long long mbar;
   long long fine[16];       // profiling instantiation only
   long long fine_mark;
-  int flags[8];             // 0:done 1:status 2:refactor 3:problem index
+  int flags[8];             // 0:done 1:status 2:refactor 3:problem index 4:sweep flag wait timed out
+  int pub_ready;            // blocked sweep: number of blocks published so far (monotone, release/acquire)
+  int grp_done;             // blocked sweep: warps x groups finished so far (monotone): slot recycling
 };
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -79,6 +82,9 @@ __device__ __forceinline__ double limit_scaling(double v) {  // osqp scaling.c
 }
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
 
 // Reduce fifteen per-row partials over the 32 lanes of a warp by recursive halving: at the stage
 // with lane mask m a lane keeps the half of its rows whose index bit matches its own lane bit and
@@ -145,37 +151,54 @@ __device__ __forceinline__ double row_norm_pass(SolveSmem& sm, int rg, int cg) {
   return reduce_rows(m, cg, MaxOp());
 }
 
-// Blocked symmetric sweep, one leg-step (3 pivots S = {3kb, 3kb+1, 3kb+2}) per barrier.
-// With V = A_S,: (before the step), M = A_SS^-1, W = -M V the step is
+// Blocked symmetric sweep (Gauss-Jordan on the SPD matrix), one leg-step (3 pivots
+// S = {3kb, 3kb+1, 3kb+2}) per step.  With V = A_S,: (before the step), M = A_SS^-1, W = -M V:
 //   A_rj <- A_rj + sum_s W[s][r] V'[s][j]   (r not in S; V' = V with A_SS - I in the S columns,
 //                                            which makes the same update produce A_rS M)
 //   A_Sj <- M A_Sj (j not in S),  A_SS <- -M
 // (W[s][r] doubles as the column factor because A is symmetric).  Block kb lives in warp
 // kb / 5, tile rows 3 (kb % 5) .. +2 (SUB is a template parameter: static register indices).
-// The publisher stores ONLY V' (6 stores per lane, one step ahead); every thread inverts the 3x3
-// pivot block itself; the 45 entries of W a warp needs are computed cooperatively by its lanes.
-template <int SUB>
-__device__ __forceinline__ void publish_rows(SolveSmem& sm, const double (&a)[kTR][kTC], int kb, int cg, int b) {
-  const int c0 = 3 * kb;
+//
+// Synchronisation is producer/consumer, not a block barrier per step: the owner of a block
+// publishes V', M and W = -M V' for it and releases a monotone flag; every warp only acquires
+// the flag of the block it is about to apply (sweep_group below).  Warps drift apart, so one
+// warp's latency chain (flag, loads, publication) overlaps its sub-partition partner's FMAs and
+// the step cost falls towards the FP64 pipe time.  Ten slots (two groups of five blocks) are
+// recycled; a monotone "warps x groups done" counter guards the rewrite, no block barrier at all.
+__device__ __forceinline__ void flag_release(int* f, int v) {
+  asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(f)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int flag_acquire(const int* f) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(f)) : "memory");
+  return v;
+}
+// position of row/column r inside a published W row: 16 slots per row group (15 used)
+__device__ __forceinline__ int wpos(int r) { return r + r / kTR; }
+
+// Executed by the warp that owns block kbn once its tile rows 3 SUBN .. 3 SUBN + 2 are up to date.
+template <int SUBN>
+__device__ __forceinline__ void publish_block(SolveSmem& sm, const double (&a)[kTR][kTC], int kbn, int cg, int slot,
+                                              int flag_value) {
+  const int c0 = 3 * kbn;
+  double vp[3][kTC];  // V' entries of this lane
 #pragma unroll
   for (int s3 = 0; s3 < 3; ++s3) {
-    double2* dst = reinterpret_cast<double2*>(&sm.Vb[b][s3][2 * cg]);
+    double2* dst = reinterpret_cast<double2*>(&sm.Vb[slot][s3][2 * cg]);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int col = 64 * i + 2 * cg;
-      double v0 = a[3 * SUB + s3][2 * i], v1 = a[3 * SUB + s3][2 * i + 1];
+      double v0 = a[3 * SUBN + s3][2 * i], v1 = a[3 * SUBN + s3][2 * i + 1];
       if (col == c0 + s3) v0 -= 1.0;
       if (col + 1 == c0 + s3) v1 -= 1.0;
+      vp[s3][2 * i] = v0;
+      vp[s3][2 * i + 1] = v1;
       dst[32 * i] = make_double2(v0, v1);
     }
   }
-}
-
-template <int SUB, bool kProfile>
-__device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][kTC], int kb, int rg, int cg, int b) {
-  const int c0 = 3 * kb;
-  const double(*V)[kNP] = sm.Vb[b];
-  // A_SS (identity added back) and its symmetric 3x3 cofactor inverse, on every thread
+  __syncwarp();
+  // A_SS (identity added back) and its symmetric 3x3 cofactor inverse, redundantly on every lane
+  const double(*V)[kNP] = sm.Vb[slot];
   const double m00 = V[0][c0] + 1.0, m01 = V[0][c0 + 1], m02 = V[0][c0 + 2];
   const double m11 = V[1][c0 + 1] + 1.0, m12 = V[1][c0 + 2];
   const double m22 = V[2][c0 + 2] + 1.0;
@@ -184,86 +207,144 @@ __device__ __forceinline__ void sweep_block(SolveSmem& sm, double (&a)[kTR][kTC]
   const double i00 = k00 * id, i01 = k01 * id, i02 = k02 * id;
   const double i11 = (m00 * m22 - m02 * m02) * id, i12 = (m01 * m02 - m00 * m12) * id;
   const double i22 = (m00 * m11 - m01 * m01) * id;
-  const bool piv = (rg * kLegPerWarp + SUB == kb);
-  FINE_PROBE(sm, 1);  // 3x3 inverse
-  // W[s][r] = -(M V[:, r])[s] for the 15 rows of this warp depends on the warp only: its lanes
-  // compute the 45 entries cooperatively and stage them in shared memory
-  {
-    auto wentry = [&](int e) {
-      const int s3 = e / kTR, rr = e - kTR * s3;
-      const double x0 = V[0][kTR * rg + rr], x1 = V[1][kTR * rg + rr], x2 = V[2][kTR * rg + rr];
-      const double a0 = (s3 == 0) ? i00 : (s3 == 1) ? i01 : i02;
-      const double a1 = (s3 == 0) ? i01 : (s3 == 1) ? i11 : i12;
-      const double a2 = (s3 == 0) ? i02 : (s3 == 1) ? i12 : i22;
-      sm.Wg[rg][s3][rr] = -(a0 * x0 + a1 * x1 + a2 * x2);
-    };
-    wentry(cg);
-    if (cg < 3 * kTR - 32) wentry(32 + cg);
-    __syncwarp();
-  }
-  FINE_PROBE(sm, 2);  // W staging
-  if (piv) {
-    // pivot rows: A_Sj <- M A_Sj, A_SS <- -M (uses the rows' old values; they skip the generic update)
+  // W = -M V' for this lane's four columns
 #pragma unroll
-    for (int jj = 0; jj < kTC; ++jj) {
-      const double x0 = a[3 * SUB][jj], x1 = a[3 * SUB + 1][jj], x2 = a[3 * SUB + 2][jj];
-      const int t = solve_col(cg, jj) - c0;  // position inside S, if any
-      a[3 * SUB][jj] = (t == 0) ? -i00 : (t == 1) ? -i01 : (t == 2) ? -i02 : (i00 * x0 + i01 * x1 + i02 * x2);
-      a[3 * SUB + 1][jj] = (t == 0) ? -i01 : (t == 1) ? -i11 : (t == 2) ? -i12 : (i01 * x0 + i11 * x1 + i12 * x2);
-      a[3 * SUB + 2][jj] = (t == 0) ? -i02 : (t == 1) ? -i12 : (t == 2) ? -i22 : (i02 * x0 + i12 * x1 + i22 * x2);
+  for (int jj = 0; jj < kTC; ++jj) {
+    const int col = solve_col(cg, jj);
+    if (col < kN) {  // pad columns have no row
+      const int wp = wpos(col);
+      const double x0 = vp[0][jj], x1 = vp[1][jj], x2 = vp[2][jj];
+      sm.Wb[slot][0][wp] = -(i00 * x0 + i01 * x1 + i02 * x2);
+      sm.Wb[slot][1][wp] = -(i01 * x0 + i11 * x1 + i12 * x2);
+      sm.Wb[slot][2][wp] = -(i02 * x0 + i12 * x1 + i22 * x2);
     }
   }
-  FINE_PROBE(sm, 3);  // pivot rows
+  if (cg == 0) {
+    double* m = sm.Mb[slot];
+    m[0] = i00; m[1] = i01; m[2] = i02; m[3] = i11; m[4] = i12; m[5] = i22;
+  }
+  __syncwarp();
+  if (cg == 0) flag_release(&sm.pub_ready, flag_value);
+}
+
+// rows [R0, R0 + NR) of the rank-3 update with the block published in `slot`
+template <int R0, int NR>
+__device__ __forceinline__ void update_rows(SolveSmem& sm, double (&a)[kTR][kTC], int slot, int rg, int cg) {
+  if (NR <= 0) return;
 #pragma unroll
   for (int s3 = 0; s3 < 3; ++s3) {
     double v[kTC], w[16];
-    load_cols(V[s3], cg, v);
+    load_cols(sm.Vb[slot][s3], cg, v);
     {
-      const double2* wp = reinterpret_cast<const double2*>(&sm.Wg[rg][s3][0]);
+      const double2* wp = reinterpret_cast<const double2*>(&sm.Wb[slot][s3][16 * rg]);
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
+      for (int h = R0 / 2; h < (R0 + NR + 1) / 2; ++h) {
         const double2 t = wp[h];
         w[2 * h] = t.x;
         w[2 * h + 1] = t.y;
       }
     }
 #pragma unroll
-    for (int rr = 0; rr < kTR; ++rr) {
-      const bool is_pivot_row = (rr >= 3 * SUB) && (rr < 3 * SUB + 3);  // static
-      if (is_pivot_row) {
-        if (!piv) {
+    for (int rr = R0; rr < R0 + NR; ++rr) {
 #pragma unroll
-          for (int jj = 0; jj < kTC; ++jj) a[rr][jj] = fma(w[rr], v[jj], a[rr][jj]);
-        }
-      } else {
-#pragma unroll
-        for (int jj = 0; jj < kTC; ++jj) a[rr][jj] = fma(w[rr], v[jj], a[rr][jj]);
-      }
+      for (int jj = 0; jj < kTC; ++jj) a[rr][jj] = fma(w[rr], v[jj], a[rr][jj]);
     }
   }
-  FINE_PROBE(sm, 4);  // rank-3 update
 }
 
-// one leg-step of the sweep: barrier, update, look-ahead publication of the next pivot rows
-template <int SUB, bool kProfile>
-__device__ __forceinline__ void sweep_step(SolveSmem& sm, double (&a)[kTR][kTC], int kp, int rg, int cg) {
-  const int kb = kLegPerWarp * kp + SUB;
-  const int b = kb & 1;
-  __syncthreads();  // rows of block kb (published one step ahead) are visible
-  FINE_PROBE(sm, 0);  // barrier wait
-  sweep_block<SUB, kProfile>(sm, a, kb, rg, cg, b);
-  if (SUB < kLegPerWarp - 1) {
-    if (rg == kp) publish_rows<(SUB + 1) % kLegPerWarp>(sm, a, kb + 1, cg, b ^ 1);
-  } else {
-    if (rg == kp + 1) publish_rows<0>(sm, a, kb + 1, cg, b ^ 1);
+// pivot rows of block kb (tile rows 3 SUB ..): A_Sj <- M A_Sj (j not in S), A_SS <- -M
+template <int SUB>
+__device__ __forceinline__ void pivot_rows(SolveSmem& sm, double (&a)[kTR][kTC], int kb, int slot, int cg) {
+  const int c0 = 3 * kb;
+  const double* m = sm.Mb[slot];
+  const double i00 = m[0], i01 = m[1], i02 = m[2], i11 = m[3], i12 = m[4], i22 = m[5];
+#pragma unroll
+  for (int jj = 0; jj < kTC; ++jj) {
+    const double x0 = a[3 * SUB][jj], x1 = a[3 * SUB + 1][jj], x2 = a[3 * SUB + 2][jj];
+    const int t = solve_col(cg, jj) - c0;  // position inside S, if any
+    a[3 * SUB][jj] = (t == 0) ? -i00 : (t == 1) ? -i01 : (t == 2) ? -i02 : (i00 * x0 + i01 * x1 + i02 * x2);
+    a[3 * SUB + 1][jj] = (t == 0) ? -i01 : (t == 1) ? -i11 : (t == 2) ? -i12 : (i01 * x0 + i11 * x1 + i12 * x2);
+    a[3 * SUB + 2][jj] = (t == 0) ? -i02 : (t == 1) ? -i12 : (t == 2) ? -i22 : (i02 * x0 + i12 * x1 + i22 * x2);
   }
-  FINE_PROBE(sm, 5);  // publication
+}
+
+// bounded spins: a publication is at most a few thousand cycles away; a lost one must not hang the GPU
+__device__ __forceinline__ void wait_flag(SolveSmem& sm, const int* f, int want) {
+  int spins = 0;
+  while (flag_acquire(f) < want) {
+    if (++spins > (1 << 20)) { sm.flags[4] = 1; break; }
+  }
+}
+
+// One group of the sweep = the five leg-steps whose pivot rows live in warp kp.
+//   warp kp (owner): PANEL first -- with block j (already published) update only the rows of its
+//     later blocks j+1..4 and publish block j+1 at once, so publications run ahead of the
+//     consumers; then the DEFERRED part: pivot transform of block j and the update of the rows of
+//     the earlier blocks, j = 0..4.  (Row updates with different blocks are additive and commute;
+//     each row only needs its own pivot transform in sequence, which this order keeps.)
+//   other warps: apply the five blocks as their flags come in; warp kp + 1 updates its rows 0..2
+//     first on the last block and publishes block 0 of the next group.
+// A slot set is rewritten two groups later: the first write waits until every warp has reported
+// the old group done (grp_done counts warps x groups, monotone).
+template <bool kProfile>
+__device__ __forceinline__ void sweep_group(SolveSmem& sm, double (&a)[kTR][kTC], int kp, int rg, int cg, int base,
+                                            int done_base) {
+  const int set = (kp & 1) * kLegPerWarp;
+  const int kb0 = kLegPerWarp * kp;
+  if (rg == kp) {
+    wait_flag(sm, &sm.pub_ready, base + kb0 + 1);
+    FINE_PROBE(sm, 0);  // flag wait
+    update_rows<3, 12>(sm, a, set + 0, rg, cg);
+    publish_block<1>(sm, a, kb0 + 1, cg, set + 1, base + kb0 + 2);
+    update_rows<6, 9>(sm, a, set + 1, rg, cg);
+    publish_block<2>(sm, a, kb0 + 2, cg, set + 2, base + kb0 + 3);
+    update_rows<9, 6>(sm, a, set + 2, rg, cg);
+    publish_block<3>(sm, a, kb0 + 3, cg, set + 3, base + kb0 + 4);
+    update_rows<12, 3>(sm, a, set + 3, rg, cg);
+    publish_block<4>(sm, a, kb0 + 4, cg, set + 4, base + kb0 + 5);
+    FINE_PROBE(sm, 5);  // panel
+    pivot_rows<0>(sm, a, kb0 + 0, set + 0, cg);
+    pivot_rows<1>(sm, a, kb0 + 1, set + 1, cg);
+    update_rows<0, 3>(sm, a, set + 1, rg, cg);
+    pivot_rows<2>(sm, a, kb0 + 2, set + 2, cg);
+    update_rows<0, 6>(sm, a, set + 2, rg, cg);
+    pivot_rows<3>(sm, a, kb0 + 3, set + 3, cg);
+    update_rows<0, 9>(sm, a, set + 3, rg, cg);
+    pivot_rows<4>(sm, a, kb0 + 4, set + 4, cg);
+    update_rows<0, 12>(sm, a, set + 4, rg, cg);
+    FINE_PROBE(sm, 3);  // deferred part
+  } else {
+#pragma unroll 1
+    for (int sub = 0; sub < kLegPerWarp - 1; ++sub) {
+      wait_flag(sm, &sm.pub_ready, base + kb0 + sub + 1);
+      FINE_PROBE(sm, 0);  // flag wait
+      update_rows<0, kTR>(sm, a, set + sub, rg, cg);
+      FINE_PROBE(sm, 4);  // rank-3 update
+    }
+    wait_flag(sm, &sm.pub_ready, base + kb0 + kLegPerWarp);
+    FINE_PROBE(sm, 0);
+    if (rg == kp + 1) {
+      update_rows<0, 3>(sm, a, set + 4, rg, cg);
+      // first write into the other slot set in its new life: everyone must be done with group kp - 1
+      if (kp >= 1) wait_flag(sm, &sm.grp_done, done_base + kSolveWarps * kp);
+      publish_block<0>(sm, a, kb0 + kLegPerWarp, cg, ((kp + 1) & 1) * kLegPerWarp, base + kb0 + kLegPerWarp + 1);
+      update_rows<3, 12>(sm, a, set + 4, rg, cg);
+    } else {
+      update_rows<0, kTR>(sm, a, set + 4, rg, cg);
+    }
+    FINE_PROBE(sm, 4);
+  }
+  // this warp no longer reads the slots of group kp
+  __syncwarp();
+  if (cg == 0) asm volatile("red.release.cta.shared::cta.add.s32 [%0], 1;" ::"r"(smem_u32(&sm.grp_done)) : "memory");
 }
 
 // Build K = c D P D + sigma I + A' diag(rho) A into the register tiles, then overwrite it
-// with -K^-1 by the blocked symmetric sweep (40 rank-3 steps, one barrier each).
+// with -K^-1 by the blocked symmetric sweep (40 rank-3 steps).  `base` counts the blocks this CTA
+// has published so far (the flag is monotone over the CTA's life).
 template <bool kProfile>
-__device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][kTC], int rg, int cg, double sigma) {
+__device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][kTC], int rg, int cg, double sigma,
+                                               int& base, int& done_base) {
   {
     const double c = sm.scal[0];
     double dcol[kTC];
@@ -294,19 +375,12 @@ __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][k
       }
     }
   }
-  if (rg == 0) publish_rows<0>(sm, a, 0, cg, 0);
+  // callers arrive here behind a block barrier: nobody reads the slots of an earlier factorisation
+  if (rg == 0) publish_block<0>(sm, a, 0, cg, 0, base + 1);
   if (kProfile && threadIdx.x == 0) sm.fine_mark = clock64();
-  for (int kp = 0; kp < kRowGroups; ++kp) {
-    sweep_step<0, kProfile>(sm, a, kp, rg, cg);
-    sweep_step<1, kProfile>(sm, a, kp, rg, cg);
-    sweep_step<2, kProfile>(sm, a, kp, rg, cg);
-    sweep_step<3, kProfile>(sm, a, kp, rg, cg);
-    sweep_step<4, kProfile>(sm, a, kp, rg, cg);
-  }
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  for (int kp = 0; kp < kRowGroups; ++kp) sweep_group<kProfile>(sm, a, kp, rg, cg, base, done_base);
+  base += kLegSteps;
+  done_base += kSolveWarps * kRowGroups;
 }
 
 template <bool kProfile, bool kWarm>
@@ -342,6 +416,8 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   uint32_t phase = 0;
+  int sweep_base = 0, sweep_done = 0;  // blocks published / (warps x groups) finished by this CTA so far
+  if (tid == 0) { sm.pub_ready = 0; sm.grp_done = 0; }
   if (kProfile && tid == 0) {
     for (int i = 0; i < 16; ++i) sm.fine[i] = 0;
     sm.fine_mark = clock64();
@@ -385,16 +461,12 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       sm.rhs[0][tid] = 0.0;
       sm.rhs[1][tid] = 0.0;
       sm.xD[tid] = 0.0;
-#pragma unroll
-      for (int s3 = 0; s3 < 3; ++s3) {
-        sm.Vb[0][s3][tid] = 0.0;
-        sm.Vb[1][s3][tid] = 0.0;
-      }
     }
     if (tid == 0) {
       sm.scal[0] = 1.0;
       sm.scal[2] = rho0;
       sm.flags[0] = 0;
+      sm.flags[4] = 0;
       sm.flags[1] = MPC_STATUS_UNSOLVED;
     }
     const double q0 = vown ? q_all[size_t(p) * kN + vj] : 0.0;
@@ -519,17 +591,20 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     __syncthreads();
 
     PHASE_MARK(0);
-    // ---- K3b: factor (explicit inverse in registers) ----
-    factor_inverse<kProfile>(sm, a, rg, cg, sigma);
-    PHASE_MARK(1);
-
     // ---- K4: ADMM iterations (osqp.c osqp_solve) ----
     int iter = 0, rho_updates = 0, status = MPC_STATUS_UNSOLVED;
     double pri_res_out = 0.0;
     // countdowns instead of iter % interval (runtime divisors cost ~50 instructions per iteration)
     int until_check = sp.check_termination > 0 ? sp.check_termination : 0x7fffffff;
     int until_adapt = (sp.adaptive_rho && sp.adaptive_rho_interval > 0) ? sp.adaptive_rho_interval : 0x7fffffff;
+    bool need_factor = true;
     for (iter = 1; iter <= sp.max_iter; ++iter) {
+      if (need_factor) {
+        // ---- K3b: factor (explicit inverse in registers); ONE call site keeps the code small ----
+        need_factor = false;
+        factor_inverse<kProfile>(sm, a, rg, cg, sigma, sweep_base, sweep_done);
+        PHASE_MARK(1);
+      }
       if (kProfile && tid == 0) sm.fine_mark = clock64();
       __syncthreads();  // rhs[iter & 1] is complete; rhs[(iter + 1) & 1] is free to rewrite
       FINE_PROBE(sm, 8);  // iteration: barrier
@@ -699,8 +774,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         }
         build_G();
         __syncthreads();
-        factor_inverse<kProfile>(sm, a, rg, cg, sigma);
-        PHASE_MARK(1);
+        need_factor = true;
       }
     }
     if (iter > sp.max_iter) iter = sp.max_iter;
@@ -732,7 +806,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       }
     }
     if (tid == 0) {
-      results[p].status = status;
+      results[p].status = sm.flags[4] ? MPC_STATUS_INTERNAL_ERROR : status;
       results[p].iters = iter;
       results[p].rho_updates = rho_updates;
       results[p].pri_res = (float)pri_res_out;

@@ -60,6 +60,7 @@ typedef enum MpcError {
 #define MPC_STATUS_PRIMAL_INFEASIBLE (-3)
 #define MPC_STATUS_DUAL_INFEASIBLE (-4)
 #define MPC_STATUS_UNSOLVED (-10)
+#define MPC_STATUS_INTERNAL_ERROR (-100) /* device-side synchronisation timed out: a bug, never expected */
 
 /* One robot state for the MPC branch: the A1CtrlStates subset read by
  * compute_grf (A1RobotControl.cpp:452-488, :498-514; fields A1CtrlStates.h:

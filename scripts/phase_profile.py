@@ -18,8 +18,8 @@ for k in ("load_scale", "factor", "iterations", "checks", "output"):
     print(f"  {k:11s} {100*pc[k]/tot:5.1f}%  {pc[k]/npb:9.0f} cyc/problem")
 print(f"  per ADMM iteration {pc['iterations']/it:.0f} cyc   per factorisation {pc['factor']/fac:.0f} cyc ({pc['factor']/fac/40:.0f} per block step)   per check {pc['checks']/(it/25):.0f} cyc")
 f = pc["fine"]
-names = {0: "sweep: barrier wait", 1: "sweep: 3x3 inverse", 2: "sweep: W staging", 3: "sweep: pivot rows", 4: "sweep: rank-3 update",
-         5: "sweep: publication", 8: "iter: barrier wait", 9: "iter: rhs load + 60 FMA", 10: "iter: row reduction",
+names = {0: "sweep: flag wait", 1: "sweep: (unused)", 2: "sweep: (unused)", 3: "sweep: owner deferred part", 4: "sweep: consumer updates",
+         5: "sweep: owner panel", 8: "iter: barrier wait", 9: "iter: rhs load + 60 FMA", 10: "iter: row reduction",
          11: "iter: z/y update", 12: "iter: next rhs"}
 steps = fac * 40
 print("fine probes (thread 0 of each CTA), cycles per sweep step / per iteration:")
