@@ -166,6 +166,18 @@ RESULT_DTYPE = np.dtype(
     ]
 )
 
+TORQUE_IN_DTYPE = np.dtype(
+    [
+        ("j_foot", "<f4", 36),
+        ("foot_forces_kin", "<f4", 12),
+        ("km_foot", "<f4", 3),
+        ("torques_gravity", "<f4", 12),
+        ("pad", "<f4"),
+    ]
+)
+TORQUE_OUT_DTYPE = np.dtype([("joint_torques", "<f4", 12), ("nan_mask", "<i4"), ("pad", "<i4", 3)])
+assert TORQUE_IN_DTYPE.itemsize == 256 and TORQUE_OUT_DTYPE.itemsize == 64
+
 assert C.sizeof(MpcStateIn) == 192 == STATE_DTYPE.itemsize
 assert C.sizeof(BalanceStateIn) == 256 == BALANCE_DTYPE.itemsize
 assert C.sizeof(MpcResult) == 64 == RESULT_DTYPE.itemsize

@@ -60,6 +60,12 @@ class A1CtrlStates:
         self.kd_linear = np.array([200.0, 70.0, 120.0])
         self.kp_angular = np.array([650.0, 35.0, 1.0])
         self.kd_angular = np.array([4.5, 4.5, 30.0])
+        # compute_joint_torques inputs/outputs (A1CtrlStates.h:95,122,129)
+        self.j_foot = np.eye(NUM_DOF)
+        self.foot_forces_kin = np.zeros((3, NUM_LEG))
+        self.km_foot = np.array([0.1, 0.1, 0.1])
+        self.torques_gravity = np.array([0.80, 0, 0, -0.80, 0, 0, 0.80, 0, 0, -0.80, 0, 0])
+        self.joint_torques = np.zeros(NUM_DOF)
 
     def to_record(self):
         """Pack into the 192 B MpcStateIn record (include/mpc_b200.h)."""
@@ -75,6 +81,16 @@ class A1CtrlStates:
         r["rot_mat"][0] = np.asarray(self.root_rot_mat).reshape(9)
         r["foot_pos_abs"][0] = np.asarray(self.foot_pos_abs).T.reshape(12)
         r["contacts"][0] = [1.0 if c else 0.0 for c in self.contacts]
+        return r
+
+    def to_torque_record(self):
+        """Pack the compute_joint_torques inputs into the 256 B MpcTorqueIn record."""
+        r = np.zeros(1, dtype=abi.TORQUE_IN_DTYPE)
+        J = np.asarray(self.j_foot)
+        r["j_foot"][0] = np.concatenate([J[3 * i:3 * i + 3, 3 * i:3 * i + 3].reshape(9) for i in range(NUM_LEG)])
+        r["foot_forces_kin"][0] = np.asarray(self.foot_forces_kin).T.reshape(12)
+        r["km_foot"][0] = self.km_foot
+        r["torques_gravity"][0] = self.torques_gravity
         return r
 
     def to_balance_record(self):
@@ -187,6 +203,8 @@ class A1RobotControl:
         self._device = device
         self._engine = None
         self._balance = None
+        self.mpc_init_counter = 0
+        self._torques = None
 
     def _mpc_engine(self, state, mpc_dt):
         cfg = self._cfg
@@ -216,7 +234,12 @@ class A1RobotControl:
             state.mpc_states = np.concatenate([state.root_euler, state.root_pos, state.root_ang_vel,
                                                state.root_lin_vel, [-9.8]])
             state.root_lin_vel_d_world = state.root_rot_mat @ state.root_lin_vel_d
-            res = eng.compute_grf_batch(state.to_record())
+            eng.load_states(state.to_record())
+            eng.set_torque_inputs(state.to_torque_record())
+            eng.build_qp(sync=False)
+            eng.solve(sync=False)
+            res = eng.get_results()
+            self._torques = eng.get_torques()[0]
         else:
             if self._balance is None:
                 from .engine import balance_config_default
@@ -228,8 +251,27 @@ class A1RobotControl:
                     bcfg.kp_angular[i] = state.kp_angular[i]
                     bcfg.kd_angular[i] = state.kd_angular[i]
                 self._balance = MpcEngine(bcfg, self._device, balance=True)
-            res = self._balance.compute_grf_batch(state.to_balance_record())
+            self._balance.load_states(state.to_balance_record())
+            self._balance.set_torque_inputs(state.to_torque_record())
+            self._balance.solve(sync=False)
+            res = self._balance.get_results()
+            self._torques = self._balance.get_torques()[0]
         return np.asarray(res["grf"][0], dtype=np.float64).reshape(4, 3).T
+
+    def compute_joint_torques(self, state):
+        """A1RobotControl.cpp:289-319 with the torques the device wrote next to the last GRF:
+        zero for the first ten calls, NaN components keep their previous value."""
+        self.mpc_init_counter += 1
+        if self.mpc_init_counter < 10:
+            state.joint_torques = np.zeros(NUM_DOF)
+            return
+        if self._torques is None:
+            raise RuntimeError("compute_joint_torques before compute_grf")
+        tau = np.asarray(self._torques["joint_torques"], dtype=np.float64)
+        mask = int(self._torques["nan_mask"])
+        for i in range(NUM_DOF):
+            if not (mask >> i) & 1:
+                state.joint_torques[i] = tau[i]
 
     def compute_grf_batch(self, records):
         """MPC branch for a batch of MpcStateIn records (engine-wide constants from cfg)."""

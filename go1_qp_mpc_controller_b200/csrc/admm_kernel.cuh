@@ -26,6 +26,7 @@
 #include <stdint.h>
 
 #include "mpc_kernels.cuh"
+#include "torque_map.cuh"
 
 namespace mpcb200 {
 
@@ -394,6 +395,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
                   const MpcStateIn* __restrict__ states, MpcResult* __restrict__ results,
                   float* __restrict__ x_all, int num, int* __restrict__ counter,
                   long long* __restrict__ phase_clk, double* __restrict__ warm,
+                  const MpcTorqueIn* __restrict__ tin, MpcTorqueOut* __restrict__ tout,
                   const __grid_constant__ SolveParams sp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
@@ -796,6 +798,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       // legs 0..3 of the first horizon step are leg-steps 0..3 = lanes 0..23 of warp 0;
       // f = (x, y, z) on lanes lbase, lbase + 2, lbase + 4
       const double f0 = shfl(xo, lbase), f1 = shfl(xo, lbase + 2), f2 = shfl(xo, lbase + 4);
+      double gb = 0.0;  // body-frame component vc of this leg, NaN-guarded
       if (vown && lg < 4) {
         double g;
         if (states != nullptr) {
@@ -806,7 +809,32 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
           g = (vc == 0) ? f0 : (vc == 1) ? f1 : f2;
         }
         const bool bad = isnan(f0) || isnan(f1) || isnan(f2);  // NaN guard (:559)
-        results[p].grf[3 * ls + vc] = bad ? 0.0f : (float)g;
+        gb = bad ? 0.0 : g;
+        results[p].grf[3 * ls + vc] = (float)gb;
+      }
+      if (tin != nullptr) {
+        // fused torque map (A1RobotControl.cpp:289-319): the three variable lanes of a leg each
+        // write one joint torque of that leg
+        const double gx = shfl(gb, lbase), gy = shfl(gb, lbase + 2), gz = shfl(gb, lbase + 4);
+        bool tnan = false;
+        if (vown && lg < 4) {
+          const MpcTorqueIn& t = tin[p];
+          const bool contact = reinterpret_cast<const float*>(states + p)[kOffContacts + lg] != 0.0f;
+          double tau[3];
+          leg_torque(t.j_foot + 9 * lg, contact, gx, gy, gz, t.foot_forces_kin + 3 * lg, t.km_foot,
+                     t.torques_gravity + 3 * lg, tau);
+          const double tv = (vc == 0) ? tau[0] : (vc == 1) ? tau[1] : tau[2];
+          tnan = isnan(tv);
+          tout[p].joint_torques[3 * lg + vc] = tnan ? 0.0f : (float)tv;
+        }
+        // lane 6 lg + 2 vc carries component 3 lg + vc: compress the ballot to 12 bits
+        const unsigned bal = __ballot_sync(0xffffffffu, tnan);
+        if (lane == 0) {
+          unsigned m = 0;
+#pragma unroll
+          for (int i = 0; i < 12; ++i) m |= ((bal >> (6 * (i / 3) + 2 * (i % 3))) & 1u) << i;
+          tout[p].nan_mask = (int32_t)m;
+        }
       }
     }
     if (tid == 0) {

@@ -229,6 +229,52 @@ int mpc_generate_stream_states(uint64_t seed, uint64_t first_index, int32_t n, i
   return MPC_OK;
 }
 
+// ---------------------------------------------------------------------------
+// A1 leg kinematics, own derivation of the hip(x)-thigh(y)-calf(y) chain the reference's
+// generated code evaluates (legKinematics/A1Kinematics.cpp fk / jac with rho_opt = 0,
+// rho_fix = (ox, oy, d, lt, lc), GazeboA1ROS.cpp:76-97):
+//   p = (ox, oy, 0) + Rx(q0) [ (0, d, 0) + Ry(q1) ( (0,0,-lt) + Ry(q2) (0,0,-lc) ) ]
+// J = dp/dq, row-major.
+// ---------------------------------------------------------------------------
+static void a1_leg_fk_jac(int leg, const double q[3], double p[3], double J[9]) {
+  const double ox = (leg < 2) ? 0.1881 : -0.1881;
+  const double oy = (leg % 2 == 0) ? 0.04675 : -0.04675;
+  const double d = (leg % 2 == 0) ? 0.08 : -0.08;
+  const double lt = 0.213, lc = 0.213;
+  const double c0 = std::cos(q[0]), s0 = std::sin(q[0]);
+  const double c1 = std::cos(q[1]), s1 = std::sin(q[1]);
+  const double c12 = std::cos(q[1] + q[2]), s12 = std::sin(q[1] + q[2]);
+  const double L = lt * c1 + lc * c12;    // leg extension below the hip axis
+  const double X = -lt * s1 - lc * s12;   // forward reach = dL/dq1
+  p[0] = ox + X;
+  p[1] = oy + d * c0 + L * s0;
+  p[2] = d * s0 - L * c0;
+  J[0] = 0.0;              J[1] = -L;       J[2] = -lc * c12;
+  J[3] = -d * s0 + L * c0; J[4] = s0 * X;   J[5] = -s0 * lc * s12;
+  J[6] = d * c0 + L * s0;  J[7] = -c0 * X;  J[8] = c0 * lc * s12;
+}
+
+int mpc_generate_torque_inputs(uint64_t seed, uint64_t first_index, int32_t n, MpcTorqueIn* out) {
+  if (!out || n < 0) return MPC_ERR_INVALID;
+  for (int32_t k = 0; k < n; ++k) {
+    SplitMix g(seed ^ 0x746f727175653a31ULL, first_index + uint64_t(k));  // a stream of its own
+    MpcTorqueIn& t = out[k];
+    std::memset(&t, 0, sizeof(t));
+    for (int leg = 0; leg < 4; ++leg) {
+      const double q[3] = {g.uni(-0.3, 0.3), g.uni(0.5, 1.1), g.uni(-2.0, -1.2)};
+      double p[3], J[9];
+      a1_leg_fk_jac(leg, q, p, J);
+      for (int i = 0; i < 9; ++i) t.j_foot[9 * leg + i] = float(J[i]);
+      t.foot_forces_kin[3 * leg + 0] = float(g.uni(-40.0, 40.0));
+      t.foot_forces_kin[3 * leg + 1] = float(g.uni(-40.0, 40.0));
+      t.foot_forces_kin[3 * leg + 2] = float(g.uni(-60.0, 60.0));
+      t.torques_gravity[3 * leg] = (leg % 2 == 0) ? 0.80f : -0.80f;  // A1CtrlStates.h:129
+    }
+    t.km_foot[0] = t.km_foot[1] = t.km_foot[2] = 0.1f;               // A1CtrlStates.h:122
+  }
+  return MPC_OK;
+}
+
 int balance_generate_states(uint64_t seed, uint64_t first_index, int32_t n, BalanceStateIn* out) {
   if (!out || n < 0) return MPC_ERR_INVALID;
   for (int32_t k = 0; k < n; ++k) {

@@ -15,6 +15,7 @@
 #include "balance_kernels.cuh"
 #include "gen_kernels.cuh"
 #include "mpc_kernels.cuh"
+#include "torque_map.cuh"
 
 using namespace mpcb200;
 
@@ -49,6 +50,10 @@ struct MpcEngine {
   int nvar() const { return 12 * H; }
   int ncon() const { return 20 * H; }
   size_t p_stride() const { return H == kH ? size_t(kN) * kNP : size_t(nvar()) * nvar(); }  // doubles per problem
+  MpcTorqueIn* d_tin = nullptr;   // optional torque-map inputs (compute_joint_torques), n records
+  MpcTorqueOut* d_tout = nullptr;
+  int torque_capacity = 0;
+  bool torque_on = false;
   double* d_warm = nullptr;       // kWarmStride doubles per robot: the solver kept alive between ticks
   int warm_capacity = 0;
   long long* d_phase_clk = nullptr;  // optional per-phase cycle counters (mpc_debug_phase_cycles)
@@ -186,21 +191,30 @@ int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n,
 }
 
 int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l, const float* u,
-                 const MpcStateIn* d_states, MpcResult* res, float* x, int n, double* warm = nullptr) {
+                 const MpcStateIn* d_states, MpcResult* res, float* x, int n, double* warm = nullptr,
+                 bool with_torque = false) {
+  const MpcTorqueIn* tin = (with_torque && d_states) ? e->d_tin : nullptr;
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
   const int grid = n < e->num_sms ? n : e->num_sms;
   if (warm)
     admm_solve_kernel<false, true><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
-        P, q, l, u, d_states, res, x, n, e->d_counter, nullptr, warm, e->sp);
-  else if (e->H != kH)
+        P, q, l, u, d_states, res, x, n, e->d_counter, nullptr, warm, tin, e->d_tout, e->sp);
+  else if (e->H != kH) {
     gen_solve_kernel<30><<<grid, kGenSolveThreads, sizeof(GenSolveSmem<30>), e->stream>>>(
         P, q, l, u, d_states, res, x, n, e->d_counter, e->d_workspace, e->sp);
+    if (tin) {
+      // the long-horizon writer is not fused: map the written results
+      torque_map_kernel<<<(4 * n + 127) / 128, 128, 0, e->stream>>>(
+          res, reinterpret_cast<const float*>(d_states), int(sizeof(MpcStateIn) / 4), kOffContacts, tin, e->d_tout, n);
+      ++e->launches;
+    }
+  }
   else if (e->d_phase_clk)
     admm_solve_kernel<true, false><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
-        P, q, l, u, d_states, res, x, n, e->d_counter, e->d_phase_clk, nullptr, e->sp);
+        P, q, l, u, d_states, res, x, n, e->d_counter, e->d_phase_clk, nullptr, tin, e->d_tout, e->sp);
   else
     admm_solve_kernel<false, false><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
-        P, q, l, u, d_states, res, x, n, e->d_counter, nullptr, nullptr, e->sp);
+        P, q, l, u, d_states, res, x, n, e->d_counter, nullptr, nullptr, tin, e->d_tout, e->sp);
   ++e->launches;
   CUDA_TRY(e, cudaGetLastError());
   return MPC_OK;
@@ -313,6 +327,8 @@ void mpc_engine_destroy(MpcEngine* e) {
   cudaFree(e->d_phase_clk);
   cudaFree(e->d_workspace);
   cudaFree(e->d_warm);
+  cudaFree(e->d_tin);
+  cudaFree(e->d_tout);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -371,6 +387,7 @@ int mpc_load_states(MpcEngine* e, const MpcStateIn* host, int32_t n) {
   e->d_states = e->d_states_own;
   e->n = n;
   e->built = e->solved = false;
+  e->torque_on = false;  // torque inputs belong to one batch of states
   return MPC_OK;
 }
 
@@ -383,6 +400,7 @@ int mpc_set_states_device(MpcEngine* e, const MpcStateIn* dev, int32_t n) {
   e->d_states = dev;
   e->n = n;
   e->built = e->solved = false;
+  e->torque_on = false;  // torque inputs belong to one batch of states
   return MPC_OK;
 }
 
@@ -435,7 +453,8 @@ int mpc_solve_async(MpcEngine* e) {
   if (!e->built) return fail(e, MPC_ERR_STATE, "mpc_solve before mpc_build_qp");
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->n > 0) {
-    int rc = launch_solve(e, e->d_P, e->d_q, e->d_l, e->d_u, e->d_states, e->d_results, e->d_x, e->n);
+    int rc = launch_solve(e, e->d_P, e->d_q, e->d_l, e->d_u, e->d_states, e->d_results, e->d_x, e->n, nullptr,
+                          e->torque_on);
     if (rc) return rc;
   }
   e->solved = true;
@@ -446,6 +465,46 @@ int mpc_solve(MpcEngine* e) {
   int rc = mpc_solve_async(e);
   if (rc) return rc;
   return mpc_synchronize(e);
+}
+
+// ---- torque map (compute_joint_torques) ----------------------------------------
+
+int mpc_set_torque_inputs(MpcEngine* e, const MpcTorqueIn* host, int32_t n) {
+  if (!e) return MPC_ERR_INVALID;
+  if (!host) {
+    e->torque_on = false;
+    return MPC_OK;
+  }
+  if (n != e->n || (e->kind == 0 && !e->d_states && n > 0) || (e->kind == 1 && !e->built))
+    return fail(e, MPC_ERR_STATE, "mpc_set_torque_inputs: load the n states first, then give n torque records");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (n > e->torque_capacity) {
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_tin);
+    cudaFree(e->d_tout);
+    e->d_tin = nullptr;
+    e->d_tout = nullptr;
+    e->torque_capacity = 0;
+    CUDA_TRY(e, cudaMalloc(&e->d_tin, size_t(n) * sizeof(MpcTorqueIn)));
+    CUDA_TRY(e, cudaMalloc(&e->d_tout, size_t(n) * sizeof(MpcTorqueOut)));
+    e->torque_capacity = n;
+  }
+  if (n > 0)
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_tin, host, size_t(n) * sizeof(MpcTorqueIn), cudaMemcpyHostToDevice, e->stream));
+  e->torque_on = true;
+  e->solved = false;
+  return MPC_OK;
+}
+
+int mpc_get_torques(MpcEngine* e, MpcTorqueOut* host) {
+  if (!e) return MPC_ERR_INVALID;
+  if (!e->solved || !e->torque_on) return fail(e, MPC_ERR_STATE, "mpc_get_torques: no solve with torque inputs yet");
+  if (e->n > 0 && !host) return fail(e, MPC_ERR_INVALID, "host buffer is NULL");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (e->n > 0)
+    CUDA_TRY(e, cudaMemcpyAsync(host, e->d_tout, size_t(e->n) * sizeof(MpcTorqueOut), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  return MPC_OK;
 }
 
 // ---- warm-started streaming (one persistent solver per robot slot) ------------
@@ -481,7 +540,8 @@ int mpc_solve_warm_async(MpcEngine* e) {
     e->warm_capacity = e->n;
   }
   if (e->n > 0) {
-    int rc = launch_solve(e, e->d_P, e->d_q, e->d_l, e->d_u, e->d_states, e->d_results, e->d_x, e->n, e->d_warm);
+    int rc = launch_solve(e, e->d_P, e->d_q, e->d_l, e->d_u, e->d_states, e->d_results, e->d_x, e->n, e->d_warm,
+                          e->torque_on);
     if (rc) return rc;
   }
   e->solved = true;
@@ -673,6 +733,7 @@ int balance_load_states(MpcEngine* e, const BalanceStateIn* host, int32_t n) {
   e->n = n;
   e->built = true;  // build and solve are one fused kernel for the 12-variable QP
   e->solved = false;
+  e->torque_on = false;
   return MPC_OK;
 }
 
@@ -686,6 +747,13 @@ int balance_solve(MpcEngine* e) {
                                                                e->d_u, e->d_results, e->bal);
     ++e->launches;
     CUDA_TRY(e, cudaGetLastError());
+    if (e->torque_on) {
+      torque_map_kernel<<<(4 * e->n + 127) / 128, 128, 0, e->stream>>>(
+          e->d_results, reinterpret_cast<const float*>(e->d_bstates), int(sizeof(BalanceStateIn) / 4), 54, e->d_tin,
+          e->d_tout, e->n);
+      ++e->launches;
+      CUDA_TRY(e, cudaGetLastError());
+    }
   }
   e->solved = true;
   return MPC_OK;

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "mpc_compute_grf_batch", "mpc_qp_mats_from_model", "mpc_solve_qp", "balance_engine_create",
     "balance_qp_solve", "balance_load_states", "balance_solve", "balance_get_qp",
     "mpc_generate_stream_states", "mpc_solve_warm", "mpc_solve_warm_async", "mpc_stream_reset",
-    "mpc_stream_step",
+    "mpc_stream_step", "mpc_set_torque_inputs", "mpc_get_torques", "mpc_generate_torque_inputs",
 ]
 
 
@@ -73,6 +73,9 @@ def load_library():
     lib.mpc_get_solution.argtypes = [vp, i32, vp]
     lib.mpc_compute_grf_batch.argtypes = [vp, vp, vp, i32]
     lib.mpc_generate_stream_states.argtypes = [u64, u64, i32, C.c_int64, vp]
+    lib.mpc_set_torque_inputs.argtypes = [vp, vp, i32]
+    lib.mpc_get_torques.argtypes = [vp, vp]
+    lib.mpc_generate_torque_inputs.argtypes = [u64, u64, i32, vp]
     lib.mpc_solve_warm.argtypes = [vp]
     lib.mpc_solve_warm_async.argtypes = [vp]
     lib.mpc_stream_reset.argtypes = [vp]
@@ -131,6 +134,15 @@ def generate_stream_states(seed, first_index, n, tick):
     rc = load_library().mpc_generate_stream_states(seed, first_index, n, tick, _ptr(out))
     if rc:
         raise MpcError(rc, "mpc_generate_stream_states")
+    return out
+
+
+def generate_torque_inputs(seed, first_index, n):
+    """Synthetic compute_joint_torques inputs (leg Jacobians, PD forces) for the robots of generate_states."""
+    out = np.zeros(n, dtype=abi.TORQUE_IN_DTYPE)
+    rc = load_library().mpc_generate_torque_inputs(seed, first_index, n, _ptr(out))
+    if rc:
+        raise MpcError(rc, "mpc_generate_torque_inputs")
     return out
 
 
@@ -267,6 +279,22 @@ class MpcEngine:
         else:
             self._check(self._lib.mpc_compute_grf_batch(self._h, _ptr(states), _ptr(out), len(states)))
         self.n = len(states)
+        return out
+
+    # torque map fused into the result writer (compute_joint_torques, A1RobotControl.cpp:289-319)
+    def set_torque_inputs(self, torque_in):
+        """Give the torque-map inputs of the loaded states (None switches the map off)."""
+        if torque_in is None:
+            self._check(self._lib.mpc_set_torque_inputs(self._h, None, 0))
+            return
+        t = np.ascontiguousarray(torque_in)
+        assert t.dtype == abi.TORQUE_IN_DTYPE
+        self._keep_t = t  # async H2D reads this buffer until the next sync
+        self._check(self._lib.mpc_set_torque_inputs(self._h, _ptr(t), len(t)))
+
+    def get_torques(self):
+        out = np.zeros(self.n, dtype=abi.TORQUE_OUT_DTYPE)
+        self._check(self._lib.mpc_get_torques(self._h, _ptr(out)))
         return out
 
     # warm-started streaming: slot i keeps robot i's solver alive between ticks

@@ -45,6 +45,23 @@ struct A1CtrlStates {
   std::vector<double> mpc_states_d = std::vector<double>(13 * PLAN_HORIZON, 0.0);
   std::array<double, 3> kp_linear{1000, 1000, 1000}, kd_linear{200, 70, 120};
   std::array<double, 3> kp_angular{650, 35, 1}, kd_angular{4.5, 4.5, 30};
+  // compute_joint_torques inputs / output (A1CtrlStates.h:95,122,129)
+  std::array<double, 36> j_foot_blocks{1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0, 0, 0, 1, 0, 0, 0, 1,
+                                       1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0, 0, 0, 1, 0, 0, 0, 1};  // 4 x (3x3 row-major)
+  std::array<double, 12> foot_forces_kin{};  // 3 x 4, element (r, leg) at [4 r + leg]
+  std::array<double, 3> km_foot{0.1, 0.1, 0.1};
+  std::array<double, 12> torques_gravity{0.80, 0, 0, -0.80, 0, 0, 0.80, 0, 0, -0.80, 0, 0};
+  std::array<double, 12> joint_torques{};
+  MpcTorqueIn to_torque_record() const {
+    MpcTorqueIn t;
+    std::memset(&t, 0, sizeof(t));
+    for (int i = 0; i < 36; ++i) t.j_foot[i] = (float)j_foot_blocks[i];
+    for (int leg = 0; leg < 4; ++leg)
+      for (int k = 0; k < 3; ++k) t.foot_forces_kin[3 * leg + k] = (float)foot_forces_kin[4 * k + leg];
+    for (int i = 0; i < 3; ++i) t.km_foot[i] = (float)km_foot[i];
+    for (int i = 0; i < 12; ++i) t.torques_gravity[i] = (float)torques_gravity[i];
+    return t;
+  }
 
   MpcStateIn to_record() const {
     MpcStateIn r;
@@ -199,17 +216,41 @@ class A1RobotControl {
       }
       state.mpc_states[12] = -9.8;
       MpcStateIn rec = state.to_record();
-      check(mpc_compute_grf_batch(mpc_, &rec, &res, 1), mpc_);
+      MpcTorqueIn tin = state.to_torque_record();
+      check(mpc_load_states(mpc_, &rec, 1), mpc_);
+      check(mpc_set_torque_inputs(mpc_, &tin, 1), mpc_);
+      check(mpc_build_qp_async(mpc_), mpc_);
+      check(mpc_solve_async(mpc_), mpc_);
+      check(mpc_get_results(mpc_, &res), mpc_);
+      check(mpc_get_torques(mpc_, &torques_), mpc_);
     } else {
       ensure_qp(state);
       BalanceStateIn rec = state.to_balance_record();
-      check(balance_qp_solve(qp_, &rec, &res, 1), qp_);
+      MpcTorqueIn tin = state.to_torque_record();
+      check(balance_load_states(qp_, &rec, 1), qp_);
+      check(mpc_set_torque_inputs(qp_, &tin, 1), qp_);
+      check(balance_solve(qp_), qp_);
+      check(mpc_get_results(qp_, &res), qp_);
+      check(mpc_get_torques(qp_, &torques_), qp_);
     }
+    have_torques_ = true;
     std::array<double, 12> grf;
     for (int leg = 0; leg < 4; ++leg)
       for (int k = 0; k < 3; ++k) grf[4 * k + leg] = res.grf[3 * leg + k];
     return grf;
   }
+  // A1RobotControl.cpp:289-319 with the torques the device wrote next to the last GRF: zero for
+  // the first nine calls, NaN components keep their previous value
+  void compute_joint_torques(A1CtrlStates& state) {
+    if (++mpc_init_counter < 10) {
+      state.joint_torques.fill(0.0);
+      return;
+    }
+    if (!have_torques_) throw std::runtime_error("compute_joint_torques before compute_grf");
+    for (int i = 0; i < 12; ++i)
+      if (!((torques_.nan_mask >> i) & 1)) state.joint_torques[i] = torques_.joint_torques[i];
+  }
+  int mpc_init_counter = 0;
   // the MPC branch for n robots sharing the engine-wide constants of `cfg`
   void compute_grf_batch(const MpcConfig& cfg, const MpcStateIn* states, MpcResult* out, int n) {
     if (!mpc_) check(mpc_engine_create(&cfg, device_, &mpc_), nullptr);
@@ -246,6 +287,8 @@ class A1RobotControl {
   MpcEngine* mpc_ = nullptr;
   MpcEngine* qp_ = nullptr;
   MpcConfig cfg_{};
+  MpcTorqueOut torques_{};
+  bool have_torques_ = false;
 };
 
 }  // namespace mpc_b200

@@ -111,6 +111,24 @@ typedef struct MpcResult {
   float pri_res;       /* unscaled primal residual at exit */
 } MpcResult;
 
+/* Inputs of the torque map (compute_joint_torques, A1RobotControl.cpp:289-319)
+ * that compute_grf does not already read; 256 B. */
+typedef struct MpcTorqueIn {
+  float j_foot[36];          /* the four 3x3 diagonal blocks of state.j_foot, leg-major, each ROW-major */
+  float foot_forces_kin[12]; /* swing-leg PD force, robot frame, 3 per leg (A1RobotControl.cpp:254-255) */
+  float km_foot[3];          /* A1CtrlStates.h:122 */
+  float torques_gravity[12]; /* A1CtrlStates.h:129 */
+  float pad;
+} MpcTorqueIn;
+
+/* joint_torques of one robot; bit i of nan_mask set = component i was NaN and the
+ * caller keeps its previous value (A1RobotControl.cpp:314-317); 64 B. */
+typedef struct MpcTorqueOut {
+  float joint_torques[12];
+  int32_t nan_mask;
+  int32_t pad[3];
+} MpcTorqueOut;
+
 /* OSQP settings (osqp 0.6.x names).  The reference leaves all but verbose and
  * warm_start at library defaults (A1RobotControl.cpp:523-524). */
 typedef struct MpcSolverSettings {
@@ -238,6 +256,20 @@ int mpc_get_solution(MpcEngine *e, int32_t idx, float *x);
 /* The whole compute_grf MPC branch for n robots: host records in, host results
  * out (H2D + build + solve + D2H). */
 int mpc_compute_grf_batch(MpcEngine *e, const MpcStateIn *host_in, MpcResult *host_out, int32_t n);
+
+/* ---- torque map fused into the result writer ----------- *
+ * compute_joint_torques (A1RobotControl.cpp:289-319): stance leg tau = J^T (-f_grf), swing leg
+ * J tau = km .* f_kin (3x3 partial-pivot LU like Eigen's lu().solve), + torques_gravity; NaN
+ * components are flagged, not written.  Give the n records once the states are loaded; the next
+ * solve (cold, warm, H = 10 or 30, or the stance-balance QP) writes the torques next to the GRF.
+ * NULL switches the map off again.  The first-ten-ticks zero-torque rule (:292-295) is host
+ * state and lives in the host mirrors (A1RobotControl::compute_joint_torques). */
+int mpc_set_torque_inputs(MpcEngine *e, const MpcTorqueIn *host, int32_t n);
+int mpc_get_torques(MpcEngine *e, MpcTorqueOut *host);
+/* Synthetic torque-map inputs for the robots of mpc_generate_states: Jacobians of the A1 leg at
+ * drawn joint angles (own derivation of the hip-thigh-calf chain, rho_opt = 0 as in
+ * GazeboA1ROS.cpp:95), PD forces, km and gravity terms of A1CtrlStates.h:122,129. */
+int mpc_generate_torque_inputs(uint64_t seed, uint64_t first_index, int32_t n, MpcTorqueIn *out);
 
 /* ---- warm-started streaming: the solver the controller keeps alive --------- *
  * A1RobotControl.h:67 holds ONE OsqpEigen::Solver for the controller's life;

@@ -905,6 +905,63 @@ struct MpcStream {
 };
 
 // ---------------------------------------------------------------------------
+// compute_joint_torques (A1RobotControl.cpp:289-319) for one robot.
+//   j_foot      : the four 3x3 diagonal blocks, leg-major, row-major
+//   grf, f_kin  : 3 per leg, robot frame
+// Returns the NaN mask (bit i: component i is NaN, the caller keeps its previous torque, :314-317).
+// The swing-leg solve is Eigen's jac.lu().solve(): LU with partial (row) pivoting.
+template <class T>
+inline int torque_map(const T* j_foot, const bool* contacts, const T* grf, const T* f_kin, const T* km,
+                      const T* torques_gravity, T* joint_torques) {
+  int mask = 0;
+  for (int leg = 0; leg < kNumLeg; ++leg) {
+    T A[3][3], tau[3];
+    for (int i = 0; i < 9; ++i) A[i / 3][i % 3] = j_foot[9 * leg + i];
+    if (contacts[leg]) {
+      // jac^T * -grf (:303)
+      for (int k = 0; k < 3; ++k) {
+        T acc = 0;
+        for (int r = 0; r < 3; ++r) acc += A[r][k] * -grf[3 * leg + r];
+        tau[k] = acc;
+      }
+    } else {
+      // jac * tau = km .* f_kin (:306-307)
+      T rhs[3];
+      int perm[3] = {0, 1, 2};
+      for (int i = 0; i < 3; ++i) rhs[i] = km[i] * f_kin[3 * leg + i];
+      for (int col = 0; col < 3; ++col) {
+        int best = col;
+        for (int r = col + 1; r < 3; ++r)
+          if (std::abs(A[perm[r]][col]) > std::abs(A[perm[best]][col])) best = r;
+        std::swap(perm[col], perm[best]);
+        for (int r = col + 1; r < 3; ++r) {
+          const T f = A[perm[r]][col] / A[perm[col]][col];
+          A[perm[r]][col] = f;
+          for (int c = col + 1; c < 3; ++c) A[perm[r]][c] -= f * A[perm[col]][c];
+        }
+      }
+      T yv[3];
+      for (int i = 0; i < 3; ++i) {
+        T acc = rhs[perm[i]];
+        for (int c = 0; c < i; ++c) acc -= A[perm[i]][c] * yv[c];
+        yv[i] = acc;
+      }
+      for (int i = 2; i >= 0; --i) {
+        T acc = yv[i];
+        for (int c = i + 1; c < 3; ++c) acc -= A[perm[i]][c] * tau[c];
+        tau[i] = acc / A[perm[i]][i];
+      }
+    }
+    for (int k = 0; k < 3; ++k) {
+      const T v = tau[k] + torques_gravity[3 * leg + k];  // gravity compensation (:311)
+      joint_torques[3 * leg + k] = v;
+      if (std::isnan(v)) mask |= 1 << (3 * leg + k);
+    }
+  }
+  return mask;
+}
+
+// ---------------------------------------------------------------------------
 // stance-balance QP (A1RobotControl.cpp:11-48 constants, :321-332, :377-444)
 // ---------------------------------------------------------------------------
 struct BalanceParams {

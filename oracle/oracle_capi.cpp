@@ -286,6 +286,24 @@ int oracle_mpc_stream(const MpcConfig* cfg, const MpcStateIn* states, int32_t n,
   return 0;
 }
 
+// compute_joint_torques for n robots from given body-frame GRFs (n x 12 doubles); contacts are
+// read at float word `contact_offset` of records `state_stride` floats apart (MPC 48/43,
+// stance QP 64/54).
+int oracle_torque_map(const float* state_words, int32_t state_stride, int32_t contact_offset,
+                      const MpcTorqueIn* tin, const double* grf, int32_t n, double* joint_torques,
+                      int32_t* nan_mask) {
+  for (int i = 0; i < n; ++i) {
+    double J[36], fk[12], km[3], tg[12];
+    bool contacts[4];
+    for (int k = 0; k < 36; ++k) J[k] = tin[i].j_foot[k];
+    for (int k = 0; k < 12; ++k) { fk[k] = tin[i].foot_forces_kin[k]; tg[k] = tin[i].torques_gravity[k]; }
+    for (int k = 0; k < 3; ++k) km[k] = tin[i].km_foot[k];
+    for (int k = 0; k < 4; ++k) contacts[k] = state_words[size_t(i) * state_stride + contact_offset + k] != 0.0f;
+    nan_mask[i] = torque_map<double>(J, contacts, grf + size_t(i) * 12, fk, km, tg, joint_torques + size_t(i) * 12);
+  }
+  return 0;
+}
+
 int oracle_max_threads(void) { return omp_get_max_threads(); }
 
 }  // extern "C"

@@ -50,6 +50,10 @@ int oracle_balance_compute_grf(const BalanceConfig *cfg, const BalanceStateIn *s
 /* A1RobotControl.cpp:522-540 kept alive over `ticks` control ticks (states tick-major). */
 int oracle_mpc_stream(const MpcConfig *cfg, const MpcStateIn *states, int32_t n, int32_t ticks,
                       OracleResult *out, int32_t threads);
+/* A1RobotControl.cpp:289-319 from given body-frame GRFs. */
+int oracle_torque_map(const float *state_words, int32_t state_stride, int32_t contact_offset,
+                      const MpcTorqueIn *tin, const double *grf, int32_t n, double *joint_torques,
+                      int32_t *nan_mask);
 int oracle_max_threads(void);
 
 #ifdef __cplusplus

@@ -58,7 +58,28 @@ int main() {
     const bool ok = status == MPC_STATUS_SOLVED && std::fabs(sol[1] + 12.782) < 0.01 &&
                     std::fabs(sol[2] - 42.606) < 0.01 && std::fabs(sol[8] - 42.606) < 0.01 &&
                     std::fabs(sol[5]) < 1e-3;
-    return ok ? 0 : 1;
+    // compute_grf + compute_joint_torques through the controller mirror: with the default
+    // j_foot = I (A1CtrlStates.h:95) a stance leg gets tau = -f + gravity term, and the first
+    // nine calls return zero torques (A1RobotControl.cpp:292-295)
+    mpc_b200::A1RobotControl ctl;
+    state.root_euler = {0, 0, 0};
+    state.root_pos_d = state.root_pos;
+    state.foot_pos_abs = foot_pos_rel;
+    const std::array<double, 12> grf = ctl.compute_grf(state, dt);
+    bool tok = true;
+    for (int k = 0; k < 9; ++k) {
+      ctl.compute_joint_torques(state);
+      for (int i = 0; i < 12; ++i) tok = tok && state.joint_torques[i] == 0.0;
+    }
+    ctl.compute_joint_torques(state);
+    for (int leg = 0; leg < 4; ++leg)
+      for (int k = 0; k < 3; ++k) {
+        const double want = state.contacts[leg] ? -grf[4 * k + leg] + state.torques_gravity[3 * leg + k]
+                                                : state.torques_gravity[3 * leg + k];  // f_kin = 0
+        tok = tok && std::fabs(state.joint_torques[3 * leg + k] - want) < 1e-4;
+      }
+    std::printf("torque map %s\n", tok ? "ok" : "MISMATCH");
+    return (ok && tok) ? 0 : 1;
   } catch (const std::exception& ex) {
     std::fprintf(stderr, "%s\n", ex.what());
     return 2;

@@ -172,6 +172,21 @@ def mpc_stream(cfg, states_tn, threads=0):
     return out
 
 
+def torque_map(states, torque_in, grf, balance=False):
+    """compute_joint_torques for len(states) robots from body-frame GRFs (n, 12) in double."""
+    st = np.ascontiguousarray(states)
+    tin = np.ascontiguousarray(torque_in)
+    g = np.ascontiguousarray(grf, dtype=np.float64)
+    n = len(st)
+    tau = np.zeros((n, 12))
+    mask = np.zeros(n, dtype=np.int32)
+    stride, off = (64, 54) if balance else (48, 43)
+    rc = lib().oracle_torque_map(_vp(st), C.c_int32(stride), C.c_int32(off), _vp(tin), _p(g), C.c_int32(n), _p(tau),
+                                 _p(mask, C.c_int32))
+    assert rc == 0
+    return tau, mask
+
+
 def max_threads():
     return int(lib().oracle_max_threads())
 

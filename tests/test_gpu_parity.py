@@ -458,3 +458,107 @@ def test_warm_stream_unsupported_horizon(pkg):
         e.solve_warm()
     assert ei.value.code == pkg.abi.MPC_ERR_UNSUPPORTED
     e.close()
+
+
+def _check_torques(ob, states, tin, res, tq, balance=False):
+    # (a) the map itself: oracle map applied to the GPU's own GRF (fp32 output rounding only)
+    tau_a, mask_a = ob.torque_map(states, tin, res["grf"].astype(np.float64), balance=balance)
+    assert np.array_equal(tq["nan_mask"], mask_a)
+    ok = ~np.isnan(tau_a)
+    assert np.abs(tq["joint_torques"][ok] - tau_a[ok]).max() <= 1e-5 * max(1.0, np.abs(tau_a[ok]).max())
+    return tau_a
+
+
+@pytest.mark.parametrize("path", ["cold", "warm", "h30", "balance"])
+def test_torque_map_parity(pkg, ob, path):
+    """compute_joint_torques (A1RobotControl.cpp:289-319) fused into the result writer."""
+    n = 96 if path == "h30" else 512
+    tin = pkg.generate_torque_inputs(1002, 0, n)
+    if path == "balance":
+        cfg = pkg.balance_config_default()
+        e = pkg.MpcEngine(cfg, 0, balance=True)
+        st = pkg.generate_balance_states(1005, 0, n)
+        e.load_states(st)
+        e.set_torque_inputs(tin)
+        e.solve()
+        res, tq = e.get_results(), e.get_torques()
+        ref = ob.balance_compute_grf(cfg, st)
+        _check_torques(ob, st, tin, res, tq, balance=True)
+        tau_ref, _ = ob.torque_map(st, tin, ref["grf"], balance=True)
+    else:
+        cfg = pkg.config_default()
+        if path == "h30":
+            cfg.horizon = 30
+        e = pkg.MpcEngine(cfg, 0)
+        st = pkg.generate_states(1002, 0, n)
+        e.load_states(st)
+        e.set_torque_inputs(tin)
+        e.build_qp()
+        if path == "warm":
+            e.solve_warm()
+        else:
+            e.solve()
+        res, tq = e.get_results(), e.get_torques()
+        ref = ob.mpc_compute_grf(cfg, st)
+        _check_torques(ob, st, tin, res, tq)
+        tau_ref, _ = ob.torque_map(st, tin, ref["grf"])
+    # (b) end to end against the oracle's GRF -> oracle map: the GRF gate carried through J
+    same = res["iters"] == ref["iters"]
+    err = np.abs(tq["joint_torques"][same] - tau_ref[same]).max(axis=1) / np.maximum(np.abs(tau_ref[same]).max(axis=1), 1.0)
+    assert err.max() <= TOL_GRF, err.max()
+    e.close()
+
+
+def test_torque_map_nan_guard_and_errors(pkg, ob):
+    n = 64
+    e = pkg.MpcEngine(pkg.config_default(), 0)
+    st = pkg.generate_states(1002, 0, n)
+    tin = pkg.generate_torque_inputs(1002, 0, n)
+    i, leg = np.argwhere(st["contacts"] == 0)[0]
+    tin["j_foot"][i][9 * leg:9 * leg + 9] = 0.0          # singular swing-leg Jacobian -> NaN torques
+    with pytest.raises(pkg.MpcError) as ei:
+        e.set_torque_inputs(tin)                          # states first
+    assert ei.value.code == pkg.abi.MPC_ERR_STATE
+    e.load_states(st)
+    e.build_qp()
+    e.solve()
+    with pytest.raises(pkg.MpcError):
+        e.get_torques()                                   # no torque inputs were given
+    e.load_states(st)
+    e.set_torque_inputs(tin)
+    e.build_qp()
+    e.solve()
+    tq = e.get_torques()
+    assert (tq["nan_mask"][i] >> (3 * leg)) & 7 == 7
+    assert (np.delete(tq["nan_mask"], i) == 0).all()
+    assert (tq["joint_torques"][i][3 * leg:3 * leg + 3] == 0).all()
+    _check_torques(ob, st, tin, e.get_results(), tq)
+    with pytest.raises(pkg.MpcError):
+        e.set_torque_inputs(tin[:5])                      # wrong count
+    e.close()
+
+
+def test_mirror_compute_joint_torques(pkg, ob):
+    """Host mirror: zero torques for the first nine calls, then the device map (:292-295)."""
+    ctl = pkg.A1RobotControl()
+    s = pkg.A1CtrlStates()
+    rec = pkg.generate_states(1002, 3, 1)
+    tin = pkg.generate_torque_inputs(1002, 3, 1)
+    s.root_euler, s.root_pos = rec["euler"][0].astype(float), rec["pos"][0].astype(float)
+    s.root_ang_vel, s.root_lin_vel = rec["ang_vel"][0].astype(float), rec["lin_vel"][0].astype(float)
+    s.root_euler_d = rec["euler_d"][0].astype(float)
+    s.root_pos_d = np.array([0.0, 0.0, float(rec["pos_d_z"][0])])
+    s.root_lin_vel_d, s.root_ang_vel_d = rec["lin_vel_d"][0].astype(float), rec["ang_vel_d"][0].astype(float)
+    s.root_rot_mat = rec["rot_mat"][0].astype(float).reshape(3, 3)
+    s.foot_pos_abs = rec["foot_pos_abs"][0].astype(float).reshape(4, 3).T
+    s.contacts = [bool(c) for c in rec["contacts"][0]]
+    for leg in range(4):
+        s.j_foot[3 * leg:3 * leg + 3, 3 * leg:3 * leg + 3] = tin["j_foot"][0][9 * leg:9 * leg + 9].reshape(3, 3)
+    s.foot_forces_kin = tin["foot_forces_kin"][0].astype(float).reshape(4, 3).T
+    grf = ctl.compute_grf(s, 0.0025)
+    for k in range(9):
+        ctl.compute_joint_torques(s)
+        assert (s.joint_torques == 0).all()
+    ctl.compute_joint_torques(s)
+    tau, mask = ob.torque_map(s.to_record(), s.to_torque_record(), grf.T.reshape(1, 12))
+    assert mask[0] == 0 and np.allclose(s.joint_torques, tau[0], rtol=1e-5, atol=1e-5)

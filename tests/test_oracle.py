@@ -311,3 +311,42 @@ def test_stream_semantics(pkg, ob):
     warm = ob.mpc_stream(cfg, st)
     cold = np.stack([ob.mpc_compute_grf(cfg, st[t]) for t in range(T)])
     assert np.abs(warm["grf"] - cold["grf"]).max() <= 1e-5 * np.abs(cold["grf"]).max()
+
+
+# ---- torque map (compute_joint_torques, A1RobotControl.cpp:289-319) -----------------------
+
+def test_torque_map_oracle(pkg, ob):
+    n = 64
+    st = pkg.generate_states(1002, 0, n)
+    tin = pkg.generate_torque_inputs(1002, 0, n)
+    rng = np.random.default_rng(7)
+    grf = rng.uniform(-50, 150, size=(n, 12))
+    tau, mask = ob.torque_map(st, tin, grf)
+    assert (mask == 0).all()
+    for i in range(n):
+        for leg in range(4):
+            J = tin["j_foot"][i][9 * leg:9 * leg + 9].astype(np.float64).reshape(3, 3)
+            g = tin["torques_gravity"][i][3 * leg:3 * leg + 3].astype(np.float64)
+            t = tau[i, 3 * leg:3 * leg + 3] - g
+            if st["contacts"][i][leg] != 0:
+                assert np.allclose(t, -J.T @ grf[i, 3 * leg:3 * leg + 3], rtol=1e-13, atol=1e-13)
+            else:
+                rhs = tin["km_foot"][i].astype(np.float64) * tin["foot_forces_kin"][i][3 * leg:3 * leg + 3].astype(np.float64)
+                assert np.allclose(J @ t, rhs, rtol=1e-10, atol=1e-10)       # J tau = km .* f_kin
+                assert np.allclose(t, np.linalg.solve(J, rhs), rtol=1e-9, atol=1e-12)
+    # singular Jacobian on a swing leg: NaN components are flagged, not written
+    swing = np.argwhere(st["contacts"] == 0)
+    i, leg = swing[0]
+    tin2 = tin.copy()
+    tin2["j_foot"][i][9 * leg:9 * leg + 9] = 0.0
+    tau2, mask2 = ob.torque_map(st, tin2, grf)
+    assert (mask2[i] >> (3 * leg)) & 7 == 7 and (np.delete(mask2, i) == 0).all()
+
+
+def test_torque_input_generator(pkg):
+    t = pkg.generate_torque_inputs(1002, 5, 16)
+    assert t.tobytes() == pkg.generate_torque_inputs(1002, 0, 32)[5:21].tobytes()   # counter based
+    J = t["j_foot"].reshape(16, 4, 3, 3).astype(np.float64)
+    assert (J[:, :, 0, 0] == 0).all()                       # the hip joint does not move the foot along x
+    assert (np.abs(np.linalg.det(J)) > 1e-3).all()          # drawn away from the knee singularity
+    assert np.allclose(t["torques_gravity"][0], [0.8, 0, 0, -0.8, 0, 0, 0.8, 0, 0, -0.8, 0, 0])
