@@ -43,6 +43,19 @@ F_ITER = 33.0e3
 # FP64 FMA peak of this pool's B200, measured with scripts/fp64_bench.cu
 # (profiles/r01_fp64_peak.txt): 17.07 T DFMA/s = 34.1 TFLOP/s
 FP64_PEAK_TFLOPS = 34.1
+# dram__bytes_read.sum + dram__bytes_write.sum of admm_solve_kernel per solve, from the committed
+# ncu --set full capture (profiles/r01_v9_ncu_summary.txt: 37.31 MB read, 0 written, 296 solves):
+# the padded f64 Hessian (122,880 B) + q, l, u, state.  P is an intermediate of the path, not
+# algorithmic input, hence the much smaller hbm_algorithmic_bytes_per_solve.
+NCU_DRAM_BYTES_PER_SOLVE = 37.309696e6 / 296
+
+
+def measured_hbm_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 7700.0, "fallback (B200_PROFILING.md nominal)"
 
 
 def host_cores():
@@ -285,7 +298,13 @@ def run_ours(args):
                         "final_gather_ms": gather_ms},
             "roofline": {"bound": "fp64-fma (compute/latency; neither hbm nor tensor, SURVEY.md 8d)",
                          "kernel": "admm_solve_kernel", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
-                         "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
+                         "traffic": NCU_DRAM_BYTES_PER_SOLVE * BATCH,
+                         "traffic_source": "ncu --set full, profiles/r01_v9_ncu_summary.txt, scaled to this launch's solves",
+                         "hbm": {"achieved": NCU_DRAM_BYTES_PER_SOLVE * BATCH / (solve_ms * 1e-3) / 1e9,
+                                 "peak": measured_hbm_peak_gbs()[0], "unit": "GB/s",
+                                 "frac": NCU_DRAM_BYTES_PER_SOLVE * BATCH / (solve_ms * 1e-3) / 1e9 / measured_hbm_peak_gbs()[0],
+                                 "peak_source": measured_hbm_peak_gbs()[1]},
                          "peak_source": "measured on this pool: scripts/fp64_bench.cu, profiles/r01_fp64_peak.txt",
                          "algorithmic_flops_per_solve": flops_solve,
                          "hbm_algorithmic_bytes_per_solve": 256},
