@@ -178,6 +178,39 @@ TORQUE_IN_DTYPE = np.dtype(
 TORQUE_OUT_DTYPE = np.dtype([("joint_torques", "<f4", 12), ("nan_mask", "<i4"), ("pad", "<i4", 3)])
 assert TORQUE_IN_DTYPE.itemsize == 256 and TORQUE_OUT_DTYPE.itemsize == 64
 
+SENSOR_DTYPE = np.dtype(
+    [
+        ("joint_pos", "<f4", 12), ("joint_vel", "<f4", 12), ("root_quat", "<f4", 4), ("imu_acc", "<f4", 3),
+        ("imu_ang_vel", "<f4", 3), ("foot_force", "<f4", 4), ("root_pos", "<f4", 3), ("root_lin_vel", "<f4", 3),
+        ("root_euler_d", "<f4", 3), ("root_pos_d_z", "<f4"), ("root_lin_vel_d", "<f4", 3), ("root_ang_vel_d", "<f4", 3),
+        ("contacts", "<f4", 4), ("foot_pos_recent_contact", "<f4", 12), ("foot_forces_kin", "<f4", 12),
+        ("movement_mode", "<f4"), ("dt", "<f4"), ("pad", "<f4", 12),
+    ]
+)
+PREP_OUT_DTYPE = np.dtype(
+    [
+        ("root_euler", "<f4", 3), ("root_rot_mat", "<f4", 9), ("root_ang_vel", "<f4", 3), ("foot_pos_rel", "<f4", 12),
+        ("foot_vel_rel", "<f4", 12), ("foot_pos_abs", "<f4", 12), ("foot_vel_abs", "<f4", 12),
+        ("foot_pos_world", "<f4", 12), ("foot_vel_world", "<f4", 12), ("estimated_root_pos", "<f4", 3),
+        ("estimated_root_vel", "<f4", 3), ("estimated_contacts", "<f4", 4), ("terrain_pitch_angle", "<f4"),
+        ("root_euler_d_pitch", "<f4"), ("pad", "<f4", 29),
+    ]
+)
+assert SENSOR_DTYPE.itemsize == 384 and PREP_OUT_DTYPE.itemsize == 512
+
+
+class PrepConfig(C.Structure):
+    _fields_ = [
+        ("rho_fix", C.c_double * 20),
+        ("km_foot", C.c_double * 3),
+        ("torques_gravity", C.c_double * 12),
+        ("use_estimator", C.c_int32),
+        ("assume_flat_ground", C.c_int32),
+        ("use_terrain_adapt", C.c_int32),
+        ("pad", C.c_int32),
+    ]
+
+
 assert C.sizeof(MpcStateIn) == 192 == STATE_DTYPE.itemsize
 assert C.sizeof(BalanceStateIn) == 256 == BALANCE_DTYPE.itemsize
 assert C.sizeof(MpcResult) == 64 == RESULT_DTYPE.itemsize

@@ -236,22 +236,44 @@ int mpc_generate_stream_states(uint64_t seed, uint64_t first_index, int32_t n, i
 //   p = (ox, oy, 0) + Rx(q0) [ (0, d, 0) + Ry(q1) ( (0,0,-lt) + Ry(q2) (0,0,-lc) ) ]
 // J = dp/dq, row-major.
 // ---------------------------------------------------------------------------
-static void a1_leg_fk_jac(int leg, const double q[3], double p[3], double J[9]) {
-  const double ox = (leg < 2) ? 0.1881 : -0.1881;
-  const double oy = (leg % 2 == 0) ? 0.04675 : -0.04675;
-  const double d = (leg % 2 == 0) ? 0.08 : -0.08;
-  const double lt = 0.213, lc = 0.213;
+int a1_leg_fk_jac(const double rho_fix[5], const double q[3], double* p, double* J) {
+  if (!rho_fix || !q) return MPC_ERR_INVALID;
+  const double ox = rho_fix[0], oy = rho_fix[1], d = rho_fix[2], lt = rho_fix[3], lc = rho_fix[4];
   const double c0 = std::cos(q[0]), s0 = std::sin(q[0]);
   const double c1 = std::cos(q[1]), s1 = std::sin(q[1]);
   const double c12 = std::cos(q[1] + q[2]), s12 = std::sin(q[1] + q[2]);
   const double L = lt * c1 + lc * c12;    // leg extension below the hip axis
   const double X = -lt * s1 - lc * s12;   // forward reach = dL/dq1
-  p[0] = ox + X;
-  p[1] = oy + d * c0 + L * s0;
-  p[2] = d * s0 - L * c0;
-  J[0] = 0.0;              J[1] = -L;       J[2] = -lc * c12;
-  J[3] = -d * s0 + L * c0; J[4] = s0 * X;   J[5] = -s0 * lc * s12;
-  J[6] = d * c0 + L * s0;  J[7] = -c0 * X;  J[8] = c0 * lc * s12;
+  if (p) {
+    p[0] = ox + X;
+    p[1] = oy + d * c0 + L * s0;
+    p[2] = d * s0 - L * c0;
+  }
+  if (J) {
+    J[0] = 0.0;              J[1] = -L;       J[2] = -lc * c12;
+    J[3] = -d * s0 + L * c0; J[4] = s0 * X;   J[5] = -s0 * lc * s12;
+    J[6] = d * c0 + L * s0;  J[7] = -c0 * X;  J[8] = c0 * lc * s12;
+  }
+  return MPC_OK;
+}
+
+int prep_config_default(PrepConfig* cfg) {
+  if (!cfg) return MPC_ERR_INVALID;
+  std::memset(cfg, 0, sizeof(*cfg));
+  for (int leg = 0; leg < 4; ++leg) {
+    double* r = cfg->rho_fix + 5 * leg;                 // GazeboA1ROS.cpp:76-93
+    r[0] = (leg < 2) ? 0.1881 : -0.1881;
+    r[1] = (leg % 2 == 0) ? 0.04675 : -0.04675;
+    r[2] = (leg % 2 == 0) ? 0.08 : -0.08;
+    r[3] = 0.213;
+    r[4] = 0.213;
+    cfg->torques_gravity[3 * leg] = (leg % 2 == 0) ? 0.80 : -0.80;  // A1CtrlStates.h:129
+  }
+  cfg->km_foot[0] = cfg->km_foot[1] = cfg->km_foot[2] = 0.1;        // A1CtrlStates.h:122
+  cfg->use_estimator = 1;
+  cfg->assume_flat_ground = 1;
+  cfg->use_terrain_adapt = 1;
+  return MPC_OK;
 }
 
 int mpc_generate_torque_inputs(uint64_t seed, uint64_t first_index, int32_t n, MpcTorqueIn* out) {
@@ -263,7 +285,9 @@ int mpc_generate_torque_inputs(uint64_t seed, uint64_t first_index, int32_t n, M
     for (int leg = 0; leg < 4; ++leg) {
       const double q[3] = {g.uni(-0.3, 0.3), g.uni(0.5, 1.1), g.uni(-2.0, -1.2)};
       double p[3], J[9];
-      a1_leg_fk_jac(leg, q, p, J);
+      PrepConfig pc;
+      prep_config_default(&pc);
+      a1_leg_fk_jac(pc.rho_fix + 5 * leg, q, p, J);
       for (int i = 0; i < 9; ++i) t.j_foot[9 * leg + i] = float(J[i]);
       t.foot_forces_kin[3 * leg + 0] = float(g.uni(-40.0, 40.0));
       t.foot_forces_kin[3 * leg + 1] = float(g.uni(-40.0, 40.0));
@@ -271,6 +295,69 @@ int mpc_generate_torque_inputs(uint64_t seed, uint64_t first_index, int32_t n, M
       t.torques_gravity[3 * leg] = (leg % 2 == 0) ? 0.80f : -0.80f;  // A1CtrlStates.h:129
     }
     t.km_foot[0] = t.km_foot[1] = t.km_foot[2] = 0.1f;               // A1CtrlStates.h:122
+  }
+  return MPC_OK;
+}
+
+// Sensor records consistent with make_mpc_state(seed, index, tick): the same pose, velocities,
+// commands and contacts, seen through quaternion / IMU / joint encoders / foot force sensors.
+int mpc_generate_sensors(uint64_t seed, uint64_t first_index, int32_t n, int64_t tick, RobotSensorIn* out) {
+  if (!out || n < 0 || tick < 0) return MPC_ERR_INVALID;
+  PrepConfig pc;
+  prep_config_default(&pc);
+  for (int32_t k = 0; k < n; ++k) {
+    const uint64_t index = first_index + uint64_t(k);
+    MpcStateIn st;
+    make_mpc_state(seed, index, tick, st);
+    SplitMix g(seed ^ 0x73656e736f72733aULL, index);  // per-robot constants of the sensor stream
+    RobotSensorIn& s = out[k];
+    std::memset(&s, 0, sizeof(s));
+    const double tau = 0.0025 * double(tick);
+    // quaternion of the ZYX euler angles
+    const double cr = std::cos(0.5 * st.euler[0]), sr = std::sin(0.5 * st.euler[0]);
+    const double cp = std::cos(0.5 * st.euler[1]), sp = std::sin(0.5 * st.euler[1]);
+    const double cy = std::cos(0.5 * st.euler[2]), sy = std::sin(0.5 * st.euler[2]);
+    s.root_quat[0] = float(cr * cp * cy + sr * sp * sy);
+    s.root_quat[1] = float(sr * cp * cy - cr * sp * sy);
+    s.root_quat[2] = float(cr * sp * cy + sr * cp * sy);
+    s.root_quat[3] = float(cr * cp * sy - sr * sp * cy);
+    const float* R = st.rot_mat;
+    // IMU: body-frame angular velocity and specific force (gravity + a slow sway)
+    const double acc_w[3] = {0.4 * std::sin(7.0 * tau + g.uni(0, 6.28)), 0.4 * std::cos(5.0 * tau + g.uni(0, 6.28)),
+                             9.81 + 0.3 * std::sin(9.0 * tau + g.uni(0, 6.28))};
+    for (int c = 0; c < 3; ++c) {
+      s.imu_ang_vel[c] = float(R[c] * st.ang_vel[0] + R[3 + c] * st.ang_vel[1] + R[6 + c] * st.ang_vel[2]);
+      s.imu_acc[c] = float(R[c] * acc_w[0] + R[3 + c] * acc_w[1] + R[6 + c] * acc_w[2]);
+    }
+    const double slope_x = g.uni(-0.25, 0.25), slope_y = g.uni(-0.1, 0.1);  // terrain under the feet
+    for (int leg = 0; leg < 4; ++leg) {
+      const double ph = g.uni(0, 6.28);
+      const double q[3] = {g.uni(-0.25, 0.25) + 0.05 * std::sin(6.0 * tau + ph), g.uni(0.6, 1.0) + 0.1 * std::sin(8.0 * tau + ph),
+                           g.uni(-1.9, -1.3) + 0.1 * std::cos(8.0 * tau + ph)};
+      const double qd[3] = {0.3 * std::cos(6.0 * tau + ph), 0.8 * std::cos(8.0 * tau + ph), -0.8 * std::sin(8.0 * tau + ph)};
+      for (int c = 0; c < 3; ++c) { s.joint_pos[3 * leg + c] = float(q[c]); s.joint_vel[3 * leg + c] = float(qd[c]); }
+      const bool contact = st.contacts[leg] != 0.0f;
+      s.foot_force[leg] = contact ? float(g.uni(60.0, 160.0)) : float(g.uni(0.0, 30.0));
+      double p[3];
+      a1_leg_fk_jac(pc.rho_fix + 5 * leg, q, p, nullptr);
+      s.foot_pos_recent_contact[3 * leg] = float(p[0]);
+      s.foot_pos_recent_contact[3 * leg + 1] = float(p[1]);
+      s.foot_pos_recent_contact[3 * leg + 2] = float(-0.30 + slope_x * p[0] + slope_y * p[1] + g.uni(-0.005, 0.005));
+      s.foot_forces_kin[3 * leg] = float(g.uni(-40.0, 40.0));
+      s.foot_forces_kin[3 * leg + 1] = float(g.uni(-40.0, 40.0));
+      s.foot_forces_kin[3 * leg + 2] = float(g.uni(-60.0, 60.0));
+      s.contacts[leg] = st.contacts[leg];
+    }
+    for (int c = 0; c < 3; ++c) {
+      s.root_pos[c] = st.pos[c];
+      s.root_lin_vel[c] = st.lin_vel[c];
+      s.root_euler_d[c] = st.euler_d[c];
+      s.root_lin_vel_d[c] = st.lin_vel_d[c];
+      s.root_ang_vel_d[c] = st.ang_vel_d[c];
+    }
+    s.root_pos_d_z = st.pos_d_z;
+    s.movement_mode = (g.u01() < 0.9) ? 1.0f : 0.0f;
+    s.dt = 0.0025f;
   }
   return MPC_OK;
 }

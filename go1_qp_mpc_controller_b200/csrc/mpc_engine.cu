@@ -15,6 +15,7 @@
 #include "balance_kernels.cuh"
 #include "gen_kernels.cuh"
 #include "mpc_kernels.cuh"
+#include "prep_kernel.cuh"
 #include "torque_map.cuh"
 
 using namespace mpcb200;
@@ -54,6 +55,11 @@ struct MpcEngine {
   MpcTorqueOut* d_tout = nullptr;
   int torque_capacity = 0;
   bool torque_on = false;
+  RobotSensorIn* d_sensors = nullptr;  // state preparation: inputs, derived quantities, per-robot
+  RobotPrepOut* d_extras = nullptr;    // estimator / terrain-filter slots (kPrepSlotStride doubles)
+  double* d_prep_slots = nullptr;
+  int prep_capacity = 0, prep_slot_capacity = 0;
+  bool prepared = false;
   double* d_warm = nullptr;       // kWarmStride doubles per robot: the solver kept alive between ticks
   int warm_capacity = 0;
   long long* d_phase_clk = nullptr;  // optional per-phase cycle counters (mpc_debug_phase_cycles)
@@ -220,6 +226,20 @@ int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l,
   return MPC_OK;
 }
 
+int reserve_torque(MpcEngine* e, int n) {
+  if (n <= e->torque_capacity) return MPC_OK;
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  cudaFree(e->d_tin);
+  cudaFree(e->d_tout);
+  e->d_tin = nullptr;
+  e->d_tout = nullptr;
+  e->torque_capacity = 0;
+  CUDA_TRY(e, cudaMalloc(&e->d_tin, size_t(n) * sizeof(MpcTorqueIn)));
+  CUDA_TRY(e, cudaMalloc(&e->d_tout, size_t(n) * sizeof(MpcTorqueOut)));
+  e->torque_capacity = n;
+  return MPC_OK;
+}
+
 int create_common(int kind, int device, MpcEngine** out) {
   if (!out) return fail(nullptr, MPC_ERR_INVALID, "out is NULL");
   *out = nullptr;
@@ -329,6 +349,9 @@ void mpc_engine_destroy(MpcEngine* e) {
   cudaFree(e->d_warm);
   cudaFree(e->d_tin);
   cudaFree(e->d_tout);
+  cudaFree(e->d_sensors);
+  cudaFree(e->d_extras);
+  cudaFree(e->d_prep_slots);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -388,6 +411,7 @@ int mpc_load_states(MpcEngine* e, const MpcStateIn* host, int32_t n) {
   e->n = n;
   e->built = e->solved = false;
   e->torque_on = false;  // torque inputs belong to one batch of states
+  e->prepared = false;
   return MPC_OK;
 }
 
@@ -401,6 +425,7 @@ int mpc_set_states_device(MpcEngine* e, const MpcStateIn* dev, int32_t n) {
   e->n = n;
   e->built = e->solved = false;
   e->torque_on = false;  // torque inputs belong to one batch of states
+  e->prepared = false;
   return MPC_OK;
 }
 
@@ -478,17 +503,8 @@ int mpc_set_torque_inputs(MpcEngine* e, const MpcTorqueIn* host, int32_t n) {
   if (n != e->n || (e->kind == 0 && !e->d_states && n > 0) || (e->kind == 1 && !e->built))
     return fail(e, MPC_ERR_STATE, "mpc_set_torque_inputs: load the n states first, then give n torque records");
   CUDA_TRY(e, cudaSetDevice(e->device));
-  if (n > e->torque_capacity) {
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    cudaFree(e->d_tin);
-    cudaFree(e->d_tout);
-    e->d_tin = nullptr;
-    e->d_tout = nullptr;
-    e->torque_capacity = 0;
-    CUDA_TRY(e, cudaMalloc(&e->d_tin, size_t(n) * sizeof(MpcTorqueIn)));
-    CUDA_TRY(e, cudaMalloc(&e->d_tout, size_t(n) * sizeof(MpcTorqueOut)));
-    e->torque_capacity = n;
-  }
+  int rc = reserve_torque(e, n);
+  if (rc) return rc;
   if (n > 0)
     CUDA_TRY(e, cudaMemcpyAsync(e->d_tin, host, size_t(n) * sizeof(MpcTorqueIn), cudaMemcpyHostToDevice, e->stream));
   e->torque_on = true;
@@ -504,6 +520,91 @@ int mpc_get_torques(MpcEngine* e, MpcTorqueOut* host) {
   if (e->n > 0)
     CUDA_TRY(e, cudaMemcpyAsync(host, e->d_tout, size_t(e->n) * sizeof(MpcTorqueOut), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  return MPC_OK;
+}
+
+// ---- upstream state preparation -------------------------------------------------
+
+int mpc_prepare_states(MpcEngine* e, const PrepConfig* cfg, const RobotSensorIn* host, int32_t n) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (!cfg || n < 0 || (n > 0 && !host)) return fail(e, MPC_ERR_INVALID, "bad sensor buffer or config");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  int rc = reserve(e, n);
+  if (rc) return rc;
+  rc = reserve_torque(e, n);
+  if (rc) return rc;
+  if (n > e->prep_capacity) {
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_sensors);
+    cudaFree(e->d_extras);
+    e->d_sensors = nullptr;
+    e->d_extras = nullptr;
+    e->prep_capacity = 0;
+    CUDA_TRY(e, cudaMalloc(&e->d_sensors, size_t(n) * sizeof(RobotSensorIn)));
+    CUDA_TRY(e, cudaMalloc(&e->d_extras, size_t(n) * sizeof(RobotPrepOut)));
+    e->prep_capacity = n;
+  }
+  if (n > e->prep_slot_capacity) {
+    // growing keeps the estimators of the robots that already have a slot
+    double* grown = nullptr;
+    const size_t bytes = size_t(n) * kPrepSlotStride * sizeof(double);
+    CUDA_TRY(e, cudaMalloc(&grown, bytes));
+    cudaError_t crc = cudaMemsetAsync(grown, 0, bytes, e->stream);
+    if (crc == cudaSuccess && e->d_prep_slots)
+      crc = cudaMemcpyAsync(grown, e->d_prep_slots, size_t(e->prep_slot_capacity) * kPrepSlotStride * sizeof(double),
+                            cudaMemcpyDeviceToDevice, e->stream);
+    if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
+    if (crc != cudaSuccess) {
+      cudaFree(grown);
+      return fail(e, MPC_ERR_CUDA, cudaGetErrorString(crc));
+    }
+    cudaFree(e->d_prep_slots);
+    e->d_prep_slots = grown;
+    e->prep_slot_capacity = n;
+  }
+  if (n > 0) {
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_sensors, host, size_t(n) * sizeof(RobotSensorIn), cudaMemcpyHostToDevice, e->stream));
+    PrepParams pp{};
+    for (int i = 0; i < 20; ++i) pp.rho_fix[i] = cfg->rho_fix[i];
+    for (int i = 0; i < 3; ++i) pp.km_foot[i] = cfg->km_foot[i];
+    for (int i = 0; i < 12; ++i) pp.torques_gravity[i] = cfg->torques_gravity[i];
+    pp.use_estimator = cfg->use_estimator;
+    pp.assume_flat_ground = cfg->assume_flat_ground;
+    pp.use_terrain_adapt = cfg->use_terrain_adapt;
+    const int grid = (n + kPrepWarps - 1) / kPrepWarps;
+    state_prep_kernel<<<grid, 32 * kPrepWarps, kPrepWarps * sizeof(PrepWarpSmem), e->stream>>>(
+        e->d_sensors, n, e->d_prep_slots, e->d_states_own, e->d_tin, e->d_extras, pp);
+    ++e->launches;
+    CUDA_TRY(e, cudaGetLastError());
+  }
+  e->d_states = e->d_states_own;
+  e->n = n;
+  e->built = e->solved = false;
+  e->torque_on = true;
+  e->prepared = true;
+  return MPC_OK;
+}
+
+int mpc_get_prepared(MpcEngine* e, MpcStateIn* states, MpcTorqueIn* torque_in, RobotPrepOut* extras) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (!e->prepared) return fail(e, MPC_ERR_STATE, "mpc_get_prepared before mpc_prepare_states");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const size_t n = size_t(e->n);
+  if (n > 0 && states)
+    CUDA_TRY(e, cudaMemcpyAsync(states, e->d_states_own, n * sizeof(MpcStateIn), cudaMemcpyDeviceToHost, e->stream));
+  if (n > 0 && torque_in)
+    CUDA_TRY(e, cudaMemcpyAsync(torque_in, e->d_tin, n * sizeof(MpcTorqueIn), cudaMemcpyDeviceToHost, e->stream));
+  if (n > 0 && extras)
+    CUDA_TRY(e, cudaMemcpyAsync(extras, e->d_extras, n * sizeof(RobotPrepOut), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  return MPC_OK;
+}
+
+int mpc_prepare_reset(MpcEngine* e) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (e->d_prep_slots)
+    CUDA_TRY(e, cudaMemsetAsync(e->d_prep_slots, 0, size_t(e->prep_slot_capacity) * kPrepSlotStride * sizeof(double), e->stream));
   return MPC_OK;
 }
 

@@ -27,6 +27,8 @@ EXPORTED_SYMBOLS = [
     "balance_qp_solve", "balance_load_states", "balance_solve", "balance_get_qp",
     "mpc_generate_stream_states", "mpc_solve_warm", "mpc_solve_warm_async", "mpc_stream_reset",
     "mpc_stream_step", "mpc_set_torque_inputs", "mpc_get_torques", "mpc_generate_torque_inputs",
+    "prep_config_default", "mpc_prepare_states", "mpc_get_prepared", "mpc_prepare_reset", "mpc_generate_sensors",
+    "a1_leg_fk_jac",
 ]
 
 
@@ -76,6 +78,12 @@ def load_library():
     lib.mpc_set_torque_inputs.argtypes = [vp, vp, i32]
     lib.mpc_get_torques.argtypes = [vp, vp]
     lib.mpc_generate_torque_inputs.argtypes = [u64, u64, i32, vp]
+    lib.prep_config_default.argtypes = [C.POINTER(abi.PrepConfig)]
+    lib.mpc_prepare_states.argtypes = [vp, C.POINTER(abi.PrepConfig), vp, i32]
+    lib.mpc_get_prepared.argtypes = [vp, vp, vp, vp]
+    lib.mpc_prepare_reset.argtypes = [vp]
+    lib.mpc_generate_sensors.argtypes = [u64, u64, i32, C.c_int64, vp]
+    lib.a1_leg_fk_jac.argtypes = [vp, vp, vp, vp]
     lib.mpc_solve_warm.argtypes = [vp]
     lib.mpc_solve_warm_async.argtypes = [vp]
     lib.mpc_stream_reset.argtypes = [vp]
@@ -144,6 +152,35 @@ def generate_torque_inputs(seed, first_index, n):
     if rc:
         raise MpcError(rc, "mpc_generate_torque_inputs")
     return out
+
+
+def prep_config_default():
+    cfg = abi.PrepConfig()
+    rc = load_library().prep_config_default(C.byref(cfg))
+    if rc:
+        raise MpcError(rc, "prep_config_default")
+    return cfg
+
+
+def generate_sensors(seed, first_index, n, tick=0):
+    """Synthetic RobotSensorIn records for the robots of generate_stream_states at `tick`."""
+    out = np.zeros(n, dtype=abi.SENSOR_DTYPE)
+    rc = load_library().mpc_generate_sensors(seed, first_index, n, tick, _ptr(out))
+    if rc:
+        raise MpcError(rc, "mpc_generate_sensors")
+    return out
+
+
+def a1_leg_fk_jac(rho_fix, q):
+    """Foot position (3,) and Jacobian (3, 3) of one A1 leg, rho_fix = (ox, oy, d, lt, lc)."""
+    r = np.ascontiguousarray(rho_fix, np.float64)
+    qq = np.ascontiguousarray(q, np.float64)
+    p = np.zeros(3)
+    J = np.zeros((3, 3))
+    rc = load_library().a1_leg_fk_jac(_ptr(r), _ptr(qq), _ptr(p), _ptr(J))
+    if rc:
+        raise MpcError(rc, "a1_leg_fk_jac")
+    return p, J
 
 
 def generate_balance_states(seed, first_index, n):
@@ -280,6 +317,26 @@ class MpcEngine:
             self._check(self._lib.mpc_compute_grf_batch(self._h, _ptr(states), _ptr(out), len(states)))
         self.n = len(states)
         return out
+
+    # upstream state preparation on the device (orientation, leg kinematics, EKF, terrain pitch)
+    def prepare_states(self, sensors, prep_cfg=None):
+        """Sensor records in; afterwards the engine holds the states and torque inputs on the device."""
+        s = np.ascontiguousarray(sensors)
+        assert s.dtype == abi.SENSOR_DTYPE
+        self._keep = s
+        self._prep_cfg = prep_cfg if prep_cfg is not None else getattr(self, "_prep_cfg", None) or prep_config_default()
+        self._check(self._lib.mpc_prepare_states(self._h, C.byref(self._prep_cfg), _ptr(s), len(s)))
+        self.n = len(s)
+
+    def get_prepared(self):
+        st = np.zeros(self.n, dtype=abi.STATE_DTYPE)
+        tin = np.zeros(self.n, dtype=abi.TORQUE_IN_DTYPE)
+        ex = np.zeros(self.n, dtype=abi.PREP_OUT_DTYPE)
+        self._check(self._lib.mpc_get_prepared(self._h, _ptr(st), _ptr(tin), _ptr(ex)))
+        return st, tin, ex
+
+    def prepare_reset(self):
+        self._check(self._lib.mpc_prepare_reset(self._h))
 
     # torque map fused into the result writer (compute_joint_torques, A1RobotControl.cpp:289-319)
     def set_torque_inputs(self, torque_in):

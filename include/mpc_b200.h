@@ -129,6 +129,60 @@ typedef struct MpcTorqueOut {
   int32_t pad[3];
 } MpcTorqueOut;
 
+/* What the sensor callbacks and the joystick/gait code leave in A1CtrlStates before a control
+ * tick (GazeboA1ROS.cpp:216-308, HardwareA1ROS.cpp:270-350): the input of the on-device state
+ * preparation.  384 B. */
+typedef struct RobotSensorIn {
+  float joint_pos[12];              /* FL, FR, RL, RR x (hip, thigh, calf) */
+  float joint_vel[12];
+  float root_quat[4];               /* w, x, y, z */
+  float imu_acc[3];
+  float imu_ang_vel[3];             /* body frame */
+  float foot_force[4];              /* contact sensors, N */
+  float root_pos[3];                /* odometry; used when the estimator is off or on its first tick */
+  float root_lin_vel[3];
+  float root_euler_d[3];            /* commands */
+  float root_pos_d_z;
+  float root_lin_vel_d[3];
+  float root_ang_vel_d[3];
+  float contacts[4];                /* gait scheduler / early-contact logic, 0 or 1 */
+  float foot_pos_recent_contact[12];/* 3 per leg, filtered by the swing-leg code (A1RobotControl.cpp:271-279) */
+  float foot_forces_kin[12];        /* swing PD force, 3 per leg */
+  float movement_mode;              /* 0 stand, 1 walk (A1BasicEKF.cpp:79-86) */
+  float dt;                         /* estimator step */
+  float pad[12];
+} RobotSensorIn;
+
+/* Derived quantities of the state preparation that do not travel in MpcStateIn; 512 B. */
+typedef struct RobotPrepOut {
+  float root_euler[3];
+  float root_rot_mat[9];
+  float root_ang_vel[3];
+  float foot_pos_rel[12];           /* 3 per leg */
+  float foot_vel_rel[12];
+  float foot_pos_abs[12];
+  float foot_vel_abs[12];
+  float foot_pos_world[12];
+  float foot_vel_world[12];
+  float estimated_root_pos[3];
+  float estimated_root_vel[3];
+  float estimated_contacts[4];
+  float terrain_pitch_angle;
+  float root_euler_d_pitch;         /* root_euler_d[1] after terrain adaptation */
+  float pad[29];
+} RobotPrepOut;
+
+/* Engine-wide constants of the state preparation. */
+typedef struct PrepConfig {
+  double rho_fix[20];        /* per leg: leg_offset_x, leg_offset_y, motor_offset, upper, lower (GazeboA1ROS.cpp:76-93) */
+  double km_foot[3];         /* A1CtrlStates.h:122 */
+  double torques_gravity[12];/* A1CtrlStates.h:129 */
+  int32_t use_estimator;     /* 1: A1BasicEKF writes root_pos / root_lin_vel (A1BasicEKF.cpp:160-163) */
+  int32_t assume_flat_ground;/* A1BasicEKF.cpp:43-53 */
+  int32_t use_terrain_adapt; /* A1RobotControl.cpp:358-364 */
+  int32_t pad;
+} PrepConfig;
+
 /* OSQP settings (osqp 0.6.x names).  The reference leaves all but verbose and
  * warm_start at library defaults (A1RobotControl.cpp:523-524). */
 typedef struct MpcSolverSettings {
@@ -270,6 +324,32 @@ int mpc_get_torques(MpcEngine *e, MpcTorqueOut *host);
  * drawn joint angles (own derivation of the hip-thigh-calf chain, rho_opt = 0 as in
  * GazeboA1ROS.cpp:95), PD forces, km and gravity terms of A1CtrlStates.h:122,129. */
 int mpc_generate_torque_inputs(uint64_t seed, uint64_t first_index, int32_t n, MpcTorqueIn *out);
+
+/* ---- upstream state preparation on the device ---------- *
+ * One call turns n sensor records into the solver's input, on the device, so that the batch
+ * never goes back to the host between sensing and solving:
+ *   quaternion -> root_rot_mat, root_euler, yaw rotation       (GazeboA1ROS.cpp:262-269,
+ *                                                                Utils.cpp:7-33)
+ *   leg forward kinematics and Jacobians, foot positions and
+ *   velocities in the robot, rotated and world frames          (GazeboA1ROS.cpp:272-288,
+ *                                                                legKinematics/A1Kinematics.cpp)
+ *   root_ang_vel = R imu_ang_vel                                (GazeboA1ROS.cpp:306)
+ *   A1BasicEKF init_state / update_estimation, one persistent
+ *   filter per robot slot                                      (A1BasicEKF.cpp:54-164)
+ *   terrain plane fit + moving-window pitch, root_euler_d[1]   (A1RobotControl.cpp:335-376, :566-582)
+ * Afterwards the engine is in the state mpc_load_states + mpc_set_torque_inputs would leave it
+ * in (Jacobians from the kinematics, PD forces from the record, km / gravity from PrepConfig):
+ * call mpc_build_qp / mpc_solve(_warm) / mpc_get_results / mpc_get_torques as usual. */
+int prep_config_default(PrepConfig *cfg);
+int mpc_prepare_states(MpcEngine *e, const PrepConfig *cfg, const RobotSensorIn *host, int32_t n);
+/* Read-back of the prepared records (parity tests, logging); any pointer may be NULL. */
+int mpc_get_prepared(MpcEngine *e, MpcStateIn *states, MpcTorqueIn *torque_in, RobotPrepOut *extras);
+/* Forget every robot slot's estimator and terrain filter (next tick initialises them). */
+int mpc_prepare_reset(MpcEngine *e);
+/* Synthetic sensor records for the robots of mpc_generate_stream_states at `tick`. */
+int mpc_generate_sensors(uint64_t seed, uint64_t first_index, int32_t n, int64_t tick, RobotSensorIn *out);
+/* The A1 leg chain on the host (for tests and host-side users): p[3], J[9] row-major. */
+int a1_leg_fk_jac(const double rho_fix[5], const double q[3], double *p, double *J);
 
 /* ---- warm-started streaming: the solver the controller keeps alive --------- *
  * A1RobotControl.h:67 holds ONE OsqpEigen::Solver for the controller's life;

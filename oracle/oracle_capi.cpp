@@ -10,6 +10,7 @@
 #include <chrono>
 
 #include "mpc_oracle.hpp"
+#include "prep_oracle.hpp"
 
 using namespace oracle;
 
@@ -301,6 +302,25 @@ int oracle_torque_map(const float* state_words, int32_t state_stride, int32_t co
     for (int k = 0; k < 4; ++k) contacts[k] = state_words[size_t(i) * state_stride + contact_offset + k] != 0.0f;
     nan_mask[i] = torque_map<double>(J, contacts, grf + size_t(i) * 12, fk, km, tg, joint_torques + size_t(i) * 12);
   }
+  return 0;
+}
+
+// State preparation for n robots over `ticks` consecutive sensor batches (tick-major), one
+// persistent estimator / terrain filter per robot like the controller's members.
+int oracle_prep_stream(const PrepConfig* cfg, const RobotSensorIn* sensors, int32_t n, int32_t ticks,
+                       MpcStateIn* states, MpcTorqueIn* tin, RobotPrepOut* extras) {
+  for (int i = 0; i < n; ++i) {
+    prep_oracle::RobotSlot slot;
+    for (int t = 0; t < ticks; ++t) {
+      const size_t k = size_t(t) * n + i;
+      prep_oracle::prep_tick(*cfg, sensors[k], slot, states[k], tin[k], extras[k]);
+    }
+  }
+  return 0;
+}
+
+int oracle_leg_fk_jac(const double* rho_fix, const double* q, double* p, double* J) {
+  prep_oracle::leg_fk_jac(rho_fix, q, p, J);
   return 0;
 }
 

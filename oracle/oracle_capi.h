@@ -54,6 +54,11 @@ int oracle_mpc_stream(const MpcConfig *cfg, const MpcStateIn *states, int32_t n,
 int oracle_torque_map(const float *state_words, int32_t state_stride, int32_t contact_offset,
                       const MpcTorqueIn *tin, const double *grf, int32_t n, double *joint_torques,
                       int32_t *nan_mask);
+/* GazeboA1ROS.cpp:262-288,306 + A1BasicEKF.cpp:54-164 + A1RobotControl.cpp:335-376,566-582 over
+ * `ticks` consecutive sensor batches (tick-major), persistent estimator per robot. */
+int oracle_prep_stream(const PrepConfig *cfg, const RobotSensorIn *sensors, int32_t n, int32_t ticks,
+                       MpcStateIn *states, MpcTorqueIn *tin, RobotPrepOut *extras);
+int oracle_leg_fk_jac(const double *rho_fix, const double *q, double *p, double *J);
 int oracle_max_threads(void);
 
 #ifdef __cplusplus

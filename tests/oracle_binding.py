@@ -187,6 +187,27 @@ def torque_map(states, torque_in, grf, balance=False):
     return tau, mask
 
 
+def prep_stream(prep_cfg, sensors_tn):
+    """sensors_tn: (ticks, n) RobotSensorIn records -> (states, torque_in, extras), each (ticks, n)."""
+    s = np.ascontiguousarray(sensors_tn)
+    ticks, n = s.shape
+    st = np.zeros((ticks, n), dtype=abi.STATE_DTYPE)
+    tin = np.zeros((ticks, n), dtype=abi.TORQUE_IN_DTYPE)
+    ex = np.zeros((ticks, n), dtype=abi.PREP_OUT_DTYPE)
+    rc = lib().oracle_prep_stream(C.byref(prep_cfg), _vp(s), C.c_int32(n), C.c_int32(ticks), _vp(st), _vp(tin), _vp(ex))
+    assert rc == 0
+    return st, tin, ex
+
+
+def leg_fk_jac(rho_fix, q):
+    r = np.ascontiguousarray(rho_fix, np.float64)
+    qq = np.ascontiguousarray(q, np.float64)
+    p = np.zeros(3)
+    J = np.zeros((3, 3))
+    lib().oracle_leg_fk_jac(_p(r), _p(qq), _p(p), _p(J))
+    return p, J
+
+
 def max_threads():
     return int(lib().oracle_max_threads())
 

@@ -562,3 +562,48 @@ def test_mirror_compute_joint_torques(pkg, ob):
     ctl.compute_joint_torques(s)
     tau, mask = ob.torque_map(s.to_record(), s.to_torque_record(), grf.T.reshape(1, 12))
     assert mask[0] == 0 and np.allclose(s.joint_torques, tau[0], rtol=1e-5, atol=1e-5)
+
+
+def test_state_preparation_parity(pkg, ob):
+    """Orientation, leg kinematics, EKF and terrain pitch on the device against the oracle, tick by
+    tick with persistent per-robot filters; then the prepared batch goes straight into the solver."""
+    cfg = pkg.prep_config_default()
+    N, T = 300, 14
+    sens = np.stack([pkg.generate_sensors(1007, 0, N, 3 * t) for t in range(T)])
+    st_o, tin_o, ex_o = ob.prep_stream(cfg, sens)
+    e = pkg.MpcEngine(pkg.config_default(), 0)
+    for t in range(T):
+        e.prepare_states(sens[t], cfg)
+        st, tin, ex = e.get_prepared()
+        for rec, ref in ((st, st_o[t]), (tin, tin_o[t]), (ex, ex_o[t])):
+            for f in rec.dtype.names:
+                a, b = rec[f].astype(np.float64), ref[f].astype(np.float64)
+                tol = 2e-5 if f.startswith("estimated_root") or f in ("pos", "lin_vel", "foot_pos_world", "foot_vel_world") else 2e-6
+                assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max()), (t, f, np.abs(a - b).max())
+    # the prepared batch feeds the solver without leaving the device: same results as the host path
+    e.build_qp()
+    e.solve()
+    res, tq = e.get_results(), e.get_torques()
+    e2 = pkg.MpcEngine(pkg.config_default(), 0)
+    e2.load_states(st)
+    e2.set_torque_inputs(tin)
+    e2.build_qp()
+    e2.solve()
+    res2, tq2 = e2.get_results(), e2.get_torques()
+    assert np.array_equal(res["grf"], res2["grf"]) and np.array_equal(res["iters"], res2["iters"])
+    assert np.array_equal(tq["joint_torques"], tq2["joint_torques"])
+    assert (res["status"] == 1).all()
+    # reset forgets the filters: the next tick initialises again (root_pos = odometry)
+    e.prepare_reset()
+    e.prepare_states(sens[5], cfg)
+    st_r, _, ex_r = e.get_prepared()
+    assert np.array_equal(st_r["pos"], sens[5]["root_pos"]) and (ex_r["estimated_root_pos"] == 0).all()
+    # estimator and terrain adaptation off: odometry and commanded pitch pass through
+    off = pkg.prep_config_default()
+    off.use_estimator = 0
+    off.use_terrain_adapt = 0
+    e.prepare_states(sens[6], off)
+    st_f, _, _ = e.get_prepared()
+    assert np.array_equal(st_f["pos"], sens[6]["root_pos"]) and np.array_equal(st_f["euler_d"], sens[6]["root_euler_d"])
+    e.close()
+    e2.close()

@@ -350,3 +350,83 @@ def test_torque_input_generator(pkg):
     assert (J[:, :, 0, 0] == 0).all()                       # the hip joint does not move the foot along x
     assert (np.abs(np.linalg.det(J)) > 1e-3).all()          # drawn away from the knee singularity
     assert np.allclose(t["torques_gravity"][0], [0.8, 0, 0, -0.8, 0, 0, 0.8, 0, 0, -0.8, 0, 0])
+
+
+# ---- upstream state preparation (GazeboA1ROS.cpp:262-288, A1BasicEKF.cpp, terrain fit) -------------
+
+def test_leg_kinematics(pkg, ob):
+    cfg = pkg.prep_config_default()
+    rng = np.random.default_rng(3)
+    for leg in range(4):
+        rho = np.array(cfg.rho_fix[5 * leg:5 * leg + 5])
+        for _ in range(5):
+            q = rng.uniform([-0.4, 0.3, -2.2], [0.4, 1.3, -1.0])
+            p1, J1 = pkg.a1_leg_fk_jac(rho, q)          # product host function
+            p2, J2 = ob.leg_fk_jac(rho, q)              # oracle, written from the rotation chain
+            assert np.abs(p1 - p2).max() < 1e-15 and np.abs(J1 - J2).max() < 1e-15
+            h = 1e-6
+            Jfd = np.stack([(ob.leg_fk_jac(rho, q + h * np.eye(3)[k])[0] - ob.leg_fk_jac(rho, q - h * np.eye(3)[k])[0]) / (2 * h)
+                            for k in range(3)], axis=1)
+            assert np.abs(Jfd - J1).max() < 1e-9
+            # chain identity: |foot - hip|^2 = d^2 + lt^2 + lc^2 + 2 lt lc cos(q2)
+            hip = np.array([rho[0], rho[1], 0.0])
+            assert abs(np.sum((p1 - hip) ** 2) - (rho[2] ** 2 + rho[3] ** 2 + rho[4] ** 2 + 2 * rho[3] * rho[4] * np.cos(q[2]))) < 1e-12
+    # the standing pose of the reference's default foot position (config/gazebo_a1_mpc.yaml:17-31)
+    p, _ = pkg.a1_leg_fk_jac(np.array(cfg.rho_fix[:5]), [0.0, 0.8, -1.6])
+    assert abs(p[0] - 0.1881) < 0.02 and abs(p[1] - 0.12675) < 1e-6 and -0.32 < p[2] < -0.28
+
+
+def test_prep_oracle_orientation_and_packing(pkg, ob):
+    cfg = pkg.prep_config_default()
+    N, T = 16, 3
+    sens = np.stack([pkg.generate_sensors(1002, 0, N, t) for t in range(T)])
+    st, tin, ex = ob.prep_stream(cfg, sens)
+    ref = np.stack([pkg.generate_stream_states(1002, 0, N, t) for t in range(T)])
+    # the sensor stream is the same robots seen through quaternion / IMU: the preparation recovers them
+    assert np.abs(st["euler"] - ref["euler"]).max() < 1e-6
+    assert np.abs(st["rot_mat"] - ref["rot_mat"]).max() < 1e-6
+    assert np.abs(st["ang_vel"] - ref["ang_vel"]).max() < 1e-6
+    for f in ("pos_d_z", "lin_vel_d", "ang_vel_d", "contacts"):
+        assert np.array_equal(st[f], ref[f])
+    # first tick: the estimator only initialises, root_pos stays the odometry value (GazeboA1ROS.cpp:194-198)
+    assert np.array_equal(st["pos"][0], ref["pos"][0]) and np.array_equal(st["lin_vel"][0], ref["lin_vel"][0])
+    assert not np.array_equal(st["pos"][1], ref["pos"][1])
+    R = st["rot_mat"].reshape(T, N, 3, 3).astype(np.float64)
+    prel = ex["foot_pos_rel"].reshape(T, N, 4, 3).astype(np.float64)
+    assert np.abs(np.einsum("tnij,tnlj->tnli", R, prel).reshape(T, N, 12) - st["foot_pos_abs"]).max() < 1e-6
+    J = tin["j_foot"].reshape(T, N, 4, 3, 3).astype(np.float64)
+    qd = sens["joint_vel"].reshape(T, N, 4, 3).astype(np.float64)
+    assert np.abs(np.einsum("tnlij,tnlj->tnli", J, qd).reshape(T, N, 12) - ex["foot_vel_rel"]).max() < 1e-5
+    off = pkg.prep_config_default()
+    off.use_estimator = 0
+    off.use_terrain_adapt = 0
+    st2, _, ex2 = ob.prep_stream(off, sens)
+    assert np.array_equal(st2["pos"], ref["pos"]) and np.array_equal(st2["euler_d"], ref["euler_d"])
+
+
+def test_prep_oracle_terrain_and_ekf(pkg, ob):
+    cfg = pkg.prep_config_default()
+    N, T = 3, 130
+    base = pkg.generate_sensors(1002, 0, N, 0)
+    # a standing robot on a known slope: constant sensors, feet exactly on z = -0.3 + 0.2 x - 0.05 y
+    base["movement_mode"] = 0
+    base["joint_vel"] = 0
+    base["imu_ang_vel"] = 0
+    base["root_quat"] = [1, 0, 0, 0]
+    base["imu_acc"] = [0, 0, 9.81]
+    base["root_pos"][:, 2] = 0.3
+    frc = base["foot_pos_recent_contact"].reshape(N, 4, 3)
+    frc[:, :, 2] = -0.3 + 0.2 * frc[:, :, 0] - 0.05 * frc[:, :, 1]
+    frc[:, 0, 2] += 0.0  # FL+FR-RL-RR > 0.05 for slope 0.2 over 0.35 m
+    sens = np.stack([base] * T)
+    st, tin, ex = ob.prep_stream(cfg, sens)
+    want = np.arccos(1.0 / np.sqrt(0.2 ** 2 + 0.05 ** 2 + 1.0))
+    assert np.abs(ex["terrain_pitch_angle"][-1] - want).max() < 1e-6          # window of 100 is full
+    assert np.abs(ex["terrain_pitch_angle"][49] - 0.5 * want).max() < 1e-6   # half full: the average divides by 100
+    frd = frc[:, 0, 2] + frc[:, 1, 2] - frc[:, 2, 2] - frc[:, 3, 2]
+    sign = np.where(frd > 0.05, -1.0, 1.0)
+    assert np.abs(st["euler_d"][-1, :, 1] - sign * want).max() < 1e-6
+    # estimator: a motionless robot whose feet are on the ground converges to height = -foot z
+    h = -ex["foot_pos_rel"][-1].reshape(N, 4, 3)[:, :, 2].mean(axis=1)
+    assert np.abs(ex["estimated_root_pos"][-1, :, 2] - h).max() < 5e-3
+    assert np.abs(ex["estimated_root_vel"][-1]).max() < 5e-3
