@@ -7,7 +7,7 @@ this package is the host-side mirror of the reference interface.
 """
 from . import abi  # noqa: F401
 from .engine import (MpcEngine, MpcError, balance_config_default, config_default,  # noqa: F401
-                     config_hardware, generate_balance_states, generate_states, generate_stream_states, generate_torque_inputs, generate_sensors, prep_config_default,
+                     config_hardware, generate_balance_states, generate_states, generate_stream_states, generate_torque_inputs, generate_sensors, generate_gait_inputs, prep_config_default,
                      a1_leg_fk_jac, load_library,
                      settings_osqp_default)
 from .convex_mpc import A1CtrlStates, A1RobotControl, ConvexMpc  # noqa: F401

@@ -103,6 +103,10 @@ class MpcConfig(C.Structure):
         ("q_weights", C.c_double * 13),
         ("r_weights", C.c_double * 12),
         ("osqp", MpcSolverSettings),
+        ("exact_discretization", C.c_int32),
+        ("foot_drift", C.c_int32),
+        ("gait_aware", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 
@@ -178,6 +182,9 @@ TORQUE_IN_DTYPE = np.dtype(
 TORQUE_OUT_DTYPE = np.dtype([("joint_torques", "<f4", 12), ("nan_mask", "<i4"), ("pad", "<i4", 3)])
 assert TORQUE_IN_DTYPE.itemsize == 256 and TORQUE_OUT_DTYPE.itemsize == 64
 
+GAIT_DTYPE = np.dtype([("gait_counter", "<f4", 4), ("gait_counter_speed", "<f4", 4), ("counter_per_gait", "<f4"),
+                       ("counter_per_swing", "<f4"), ("ticks_per_step", "<f4"), ("pad", "<f4")])
+assert GAIT_DTYPE.itemsize == 48
 SENSOR_DTYPE = np.dtype(
     [
         ("joint_pos", "<f4", 12), ("joint_vel", "<f4", 12), ("root_quat", "<f4", 4), ("imu_acc", "<f4", 3),

@@ -362,6 +362,38 @@ int mpc_generate_sensors(uint64_t seed, uint64_t first_index, int32_t n, int64_t
   return MPC_OK;
 }
 
+// Gait scheduler records consistent with make_mpc_state's trot pattern: counters advance by
+// gait_counter_speed = 2 per tick through a 240-count gait with 120 counts of stance
+// (A1CtrlStates.h:24-25,103); the phase is chosen so that "counter <= counter_per_swing" agrees
+// with the state's contact flags at this tick and swaps together with them every 48 ticks...
+// except that a real gait swaps every 60 ticks: records near a swap exercise contact changes
+// INSIDE the horizon, which is what the gait-aware bounds are for.
+int mpc_generate_gait_inputs(uint64_t seed, uint64_t first_index, int32_t n, int64_t tick, MpcGaitIn* out) {
+  if (!out || n < 0 || tick < 0) return MPC_ERR_INVALID;
+  for (int32_t k = 0; k < n; ++k) {
+    const uint64_t index = first_index + uint64_t(k);
+    MpcStateIn st;
+    make_mpc_state(seed, index, tick, st);
+    SplitMix g(seed ^ 0x676169743a303031ULL, index);
+    MpcGaitIn& r = out[k];
+    std::memset(&r, 0, sizeof(r));
+    r.counter_per_gait = 240.0f;
+    r.counter_per_swing = 120.0f;
+    r.ticks_per_step = 1.0f;
+    const double into = g.uni(0.0, 118.0);  // how far the current phase (stance or swing) has progressed
+    for (int leg = 0; leg < 4; ++leg) {
+      r.gait_counter_speed[leg] = 2.0f;
+      const bool contact = st.contacts[leg] != 0.0f;
+      const bool all_four = st.contacts[0] != 0.0f && st.contacts[1] != 0.0f;
+      // stance occupies counts [0, 120], swing (120, 240); a standing robot stays deep in stance
+      double c = contact ? std::floor(into) : 121.0 + std::floor(into);
+      if (all_four) c = 10.0;
+      r.gait_counter[leg] = float(c);
+    }
+  }
+  return MPC_OK;
+}
+
 int balance_generate_states(uint64_t seed, uint64_t first_index, int32_t n, BalanceStateIn* out) {
   if (!out || n < 0) return MPC_ERR_INVALID;
   for (int32_t k = 0; k < n; ++k) {

@@ -55,6 +55,9 @@ struct MpcEngine {
   MpcTorqueOut* d_tout = nullptr;
   int torque_capacity = 0;
   bool torque_on = false;
+  MpcGaitIn* d_gait = nullptr;    // gait scheduler records of the loaded states (gait_aware engines)
+  int gait_capacity = 0;
+  bool gait_on = false;
   RobotSensorIn* d_sensors = nullptr;  // state preparation: inputs, derived quantities, per-robot
   RobotPrepOut* d_extras = nullptr;    // estimator / terrain-filter slots (kPrepSlotStride doubles)
   double* d_prep_slots = nullptr;
@@ -185,7 +188,8 @@ int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n,
                  float* l, float* u) {
   if (e->H == kH) {
     const int grid = n < e->num_sms * 8 ? n : e->num_sms * 8;
-    qp_build_kernel<<<grid, kThreads, sizeof(BuildSmem), e->stream>>>(d_states, model, n, P, q, l, u, e->bp);
+    qp_build_kernel<<<grid, kThreads, sizeof(BuildSmem), e->stream>>>(d_states, d_states ? e->d_gait : nullptr, model, n,
+                                                                      P, q, l, u, e->bp);
   } else {
     const int grid = n < e->num_sms ? n : e->num_sms;
     gen_build_kernel<30><<<grid, kGenBuildThreads, sizeof(GenBuildSmem<30>), e->stream>>>(
@@ -297,6 +301,8 @@ int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
   if (validate_settings(cfg->osqp, &why)) return fail(nullptr, MPC_ERR_INVALID, why);
   if (!(cfg->dt > 0) || !(cfg->mass > 0) || !(cfg->mu > 0))
     return fail(nullptr, MPC_ERR_INVALID, "dt/mass/mu must be positive");
+  if (cfg->horizon != kH && (cfg->exact_discretization || cfg->foot_drift || cfg->gait_aware))
+    return fail(nullptr, MPC_ERR_UNSUPPORTED, "exact_discretization / foot_drift / gait_aware are built for horizon 10 only");
   MpcEngine* e = nullptr;
   int rc = create_common(0, device, &e);
   if (rc != MPC_OK) return rc;
@@ -320,6 +326,9 @@ int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
   for (int i = 0; i < 9; ++i) e->bp.inertia[i] = cfg->inertia[i];
   for (int i = 0; i < 13; ++i) e->bp.Qd[i] = 2.0 * cfg->q_weights[i];
   for (int i = 0; i < 12; ++i) e->bp.Rd[i] = 2.0 * cfg->r_weights[i];
+  e->bp.exact_discretization = cfg->exact_discretization != 0;
+  e->bp.foot_drift = cfg->foot_drift != 0;
+  e->bp.gait_aware = cfg->gait_aware != 0;
   e->sp = make_solve_params(cfg->osqp, cfg->mu);
   *out = e;
   return MPC_OK;
@@ -352,6 +361,7 @@ void mpc_engine_destroy(MpcEngine* e) {
   cudaFree(e->d_sensors);
   cudaFree(e->d_extras);
   cudaFree(e->d_prep_slots);
+  cudaFree(e->d_gait);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -410,7 +420,8 @@ int mpc_load_states(MpcEngine* e, const MpcStateIn* host, int32_t n) {
   e->d_states = e->d_states_own;
   e->n = n;
   e->built = e->solved = false;
-  e->torque_on = false;  // torque inputs belong to one batch of states
+  e->torque_on = false;  // torque and gait inputs belong to one batch of states
+  e->gait_on = false;
   e->prepared = false;
   return MPC_OK;
 }
@@ -424,7 +435,8 @@ int mpc_set_states_device(MpcEngine* e, const MpcStateIn* dev, int32_t n) {
   e->d_states = dev;
   e->n = n;
   e->built = e->solved = false;
-  e->torque_on = false;  // torque inputs belong to one batch of states
+  e->torque_on = false;  // torque and gait inputs belong to one batch of states
+  e->gait_on = false;
   e->prepared = false;
   return MPC_OK;
 }
@@ -432,6 +444,8 @@ int mpc_set_states_device(MpcEngine* e, const MpcStateIn* dev, int32_t n) {
 int mpc_build_qp_async(MpcEngine* e) {
   if (!e || e->kind != 0) return MPC_ERR_INVALID;
   if (!e->d_states && e->n > 0) return fail(e, MPC_ERR_STATE, "mpc_build_qp before mpc_load_states");
+  if (e->bp.gait_aware && !e->gait_on && e->n > 0)
+    return fail(e, MPC_ERR_STATE, "gait_aware engine: mpc_set_gait_inputs must follow the state load");
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->n > 0) {
     ModelIn none{};
@@ -490,6 +504,32 @@ int mpc_solve(MpcEngine* e) {
   int rc = mpc_solve_async(e);
   if (rc) return rc;
   return mpc_synchronize(e);
+}
+
+// ---- gait-aware horizon -----------------------------------------------------------
+
+int mpc_set_gait_inputs(MpcEngine* e, const MpcGaitIn* host, int32_t n) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (!host) {
+    e->gait_on = false;
+    return MPC_OK;
+  }
+  if (n != e->n || (!e->d_states && n > 0))
+    return fail(e, MPC_ERR_STATE, "mpc_set_gait_inputs: load the n states first, then give n gait records");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (n > e->gait_capacity) {
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_gait);
+    e->d_gait = nullptr;
+    e->gait_capacity = 0;
+    CUDA_TRY(e, cudaMalloc(&e->d_gait, size_t(n) * sizeof(MpcGaitIn)));
+    e->gait_capacity = n;
+  }
+  if (n > 0)
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_gait, host, size_t(n) * sizeof(MpcGaitIn), cudaMemcpyHostToDevice, e->stream));
+  e->gait_on = true;
+  e->built = e->solved = false;
+  return MPC_OK;
 }
 
 // ---- torque map (compute_joint_torques) ----------------------------------------
@@ -581,6 +621,7 @@ int mpc_prepare_states(MpcEngine* e, const PrepConfig* cfg, const RobotSensorIn*
   e->n = n;
   e->built = e->solved = false;
   e->torque_on = true;
+  e->gait_on = false;
   e->prepared = true;
   return MPC_OK;
 }

@@ -56,6 +56,7 @@ struct BuildParams {
   double inertia[9];
   double Qd[13];  // 2 * q_weights (ConvexMpc.cpp:20)
   double Rd[12];  // 2 * r_weights (ConvexMpc.cpp:41)
+  int exact_discretization, foot_drift, gait_aware;  // SURVEY.md 8f row 4, all 0 = the reference
 };
 
 struct SolveParams {
@@ -109,7 +110,7 @@ struct BuildSmem {
   double tmp[kS];
   double x0[16];
   float st[48];
-  int contacts[4];
+  int contacts[kH * 4];  // per step and leg (replicated unless the horizon is gait aware)
 };
 
 // Optional caller-written model for the ConvexMpc surface (one problem each):
@@ -123,7 +124,8 @@ struct ModelIn {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, double* __restrict__ P_out,
+qp_build_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __restrict__ gait, ModelIn model, int num,
+                double* __restrict__ P_out,
                 double* __restrict__ q_out, float* __restrict__ l_out, float* __restrict__ u_out,
                 const __grid_constant__ BuildParams bp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -152,10 +154,12 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, d
         if (rr == 2 && cc == 8) a = 1.0;
         if (rr >= 3 && rr <= 5 && cc == rr + 6) a = 1.0;
         if (rr == 11 && cc == 12) a = 1.0;
+        // exact discretisation: A_c^3 = 0 and A_c^2 has the single entry (5, 12) = 1
+        if (bp.exact_discretization && rr == 5 && cc == 12) a = 0.5 * bp.dt;
         sm.Apow[tid] = (rr == cc) ? 1.0 : 0.0;
         sm.Apow[169 + tid] = ((rr == cc) ? 1.0 : 0.0) + a * bp.dt;
       } else if (tid >= 192 && tid < 192 + 156) {
-        sm.Bd[tid - 192] = 0.0;
+        for (int i = 0; i < kH; ++i) sm.Bd[i * 156 + tid - 192] = 0.0;
       } else if (tid >= 352 && tid < 352 + 13) {
         // mpc_states (A1RobotControl.cpp:452-456)
         const int k = tid - 352;
@@ -183,13 +187,22 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, d
         d[10] = vwy;
         d[11] = 0.0;
         d[12] = -9.8;
-      } else if (tid >= 416 && tid < 420) {
-        sm.contacts[tid - 416] = st[kOffContacts + tid - 416] != 0.0f;
+      } else if (tid >= 416 && tid < 416 + 4 * kH) {
+        const int i = (tid - 416) >> 2, leg = (tid - 416) & 3;
+        int c = st[kOffContacts + leg] != 0.0f;
+        if (bp.gait_aware && i > 0) {
+          // planned contact of step i from the gait counter (A1RobotControl.cpp:156-164)
+          const float* g = reinterpret_cast<const float*>(gait + p);
+          const double cnt = fmod((double)g[leg] + (double)i * (double)g[10] * (double)g[4 + leg], (double)g[8]);
+          c = cnt <= (double)g[9];
+        }
+        sm.contacts[4 * i + leg] = c;
       }
       __syncthreads();
-      // ---- B_d = dt*B_c, one thread per leg (ConvexMpc.cpp:132-143, :151) ----
-      if (tid < 4) {
-        const int leg = tid;
+      // ---- B_d = dt*B_c, one thread per (step, leg) (ConvexMpc.cpp:132-143, :151); without
+      //      foot_drift only step 0 is computed and then copied (A1RobotControl.cpp:498-514) ----
+      if (tid < (bp.foot_drift ? 4 * kH : 4)) {
+        const int leg = tid & 3, step = tid >> 2;
         double R[9], I[9], T[9], Iw[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) { R[i] = (double)st[kOffRot + i]; I[i] = bp.inertia[i]; }
@@ -226,8 +239,15 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, d
         Inv[6] = c02 * id;
         Inv[7] = (Iw[1] * Iw[6] - Iw[0] * Iw[7]) * id;
         Inv[8] = (Iw[0] * Iw[4] - Iw[1] * Iw[3]) * id;
-        const double fx = st[kOffFoot + 3 * leg], fy = st[kOffFoot + 3 * leg + 1],
-                     fz = st[kOffFoot + 3 * leg + 2];
+        double fx = st[kOffFoot + 3 * leg], fy = st[kOffFoot + 3 * leg + 1], fz = st[kOffFoot + 3 * leg + 2];
+        if (bp.foot_drift) {
+          // the body moves on with the commanded world velocity, the stance feet stay: r_i = r_0 - i dt v_d
+          const double vx = st[kOffLinVelD], vy = st[kOffLinVelD + 1], vz = st[kOffLinVelD + 2];
+          const double k = (double)step * bp.dt;
+          fx -= k * (R[0] * vx + R[1] * vy + R[2] * vz);
+          fy -= k * (R[3] * vx + R[4] * vy + R[5] * vz);
+          fz -= k * (R[6] * vx + R[7] * vy + R[8] * vz);
+        }
         // skew (Utils.cpp:35-41)
         const double sk[9] = {0.0, -fz, fy, fz, 0.0, -fx, -fy, fx, 0.0};
 #pragma unroll
@@ -237,13 +257,32 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, d
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) s += Inv[3 * i + k] * sk[3 * k + j];
-            sm.Bd[(6 + i) * 12 + 3 * leg + j] = s * bp.dt;
-            sm.Bd[(9 + i) * 12 + 3 * leg + j] = (i == j) ? (1.0 / bp.mass) * bp.dt : 0.0;
+            sm.Bd[step * 156 + (6 + i) * 12 + 3 * leg + j] = s * bp.dt;
+            sm.Bd[step * 156 + (9 + i) * 12 + 3 * leg + j] = (i == j) ? (1.0 / bp.mass) * bp.dt : 0.0;
           }
+        if (bp.exact_discretization) {
+          // B_d += dt^2/2 A_c B_c: euler rows <- Rz' (I^-1 [r]x), position rows <- I / m
+          const double yaw = (double)st[kOffEuler + 2];
+          double sy, cy;
+          sincos(yaw, &sy, &cy);
+          const double h = 0.5 * bp.dt;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double b6 = sm.Bd[step * 156 + 6 * 12 + 3 * leg + j], b7 = sm.Bd[step * 156 + 7 * 12 + 3 * leg + j],
+                         b8 = sm.Bd[step * 156 + 8 * 12 + 3 * leg + j];
+            sm.Bd[step * 156 + 0 * 12 + 3 * leg + j] = h * (cy * b6 + sy * b7);
+            sm.Bd[step * 156 + 1 * 12 + 3 * leg + j] = h * (-sy * b6 + cy * b7);
+            sm.Bd[step * 156 + 2 * 12 + 3 * leg + j] = h * b8;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              sm.Bd[step * 156 + (3 + i) * 12 + 3 * leg + j] = h * sm.Bd[step * 156 + (9 + i) * 12 + 3 * leg + j];
+          }
+        }
       }
       __syncthreads();
-      // same B_d for every step (A1RobotControl.cpp:498-514)
-      for (int idx = tid; idx < (kH - 1) * 156; idx += kThreads) sm.Bd[156 + idx] = sm.Bd[idx % 156];
+      // same B_d for every step unless the feet drift (A1RobotControl.cpp:498-514)
+      if (!bp.foot_drift)
+        for (int idx = tid; idx < (kH - 1) * 156; idx += kThreads) sm.Bd[156 + idx] = sm.Bd[idx % 156];
     } else {
       // ---- ConvexMpc surface: caller-written A_mat_d / B_mat_d_list ----
       if (tid < 169) {
@@ -255,7 +294,7 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, d
         sm.Bd[idx] = model.B_d_list[size_t(p) * kH * 156 + idx];
       if (tid < 13) sm.x0[tid] = model.x0[size_t(p) * 13 + tid];
       if (tid < kS) sm.xref[tid] = model.x_ref[size_t(p) * kS + tid];
-      if (tid < 4) sm.contacts[tid] = model.contacts[size_t(p) * 4 + tid] != 0;
+      if (tid < 4 * kH) sm.contacts[tid] = model.contacts[size_t(p) * 4 + (tid & 3)] != 0;
     }
     // zero B_qp (upper blocks stay zero, ConvexMpc.cpp:94)
     for (int idx = tid; idx < kS * kNP / 2; idx += kThreads)
@@ -352,7 +391,7 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, d
     if (tid >= 256 && tid < 256 + kM) {
       const int i = tid - 256;
       const int leg = (i % 20) / 5, t = i % 5;
-      const float cflag = sm.contacts[leg] ? 1.0f : 0.0f;
+      const float cflag = sm.contacts[4 * (i / 20) + leg] ? 1.0f : 0.0f;
       float lo, hi;
       if (t == 0 || t == 2) { lo = 0.0f; hi = (float)MPC_INFTY; }
       else if (t == 1 || t == 3) { lo = -(float)MPC_INFTY; hi = 0.0f; }

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "mpc_generate_stream_states", "mpc_solve_warm", "mpc_solve_warm_async", "mpc_stream_reset",
     "mpc_stream_step", "mpc_set_torque_inputs", "mpc_get_torques", "mpc_generate_torque_inputs",
     "prep_config_default", "mpc_prepare_states", "mpc_get_prepared", "mpc_prepare_reset", "mpc_generate_sensors",
-    "a1_leg_fk_jac",
+    "a1_leg_fk_jac", "mpc_set_gait_inputs", "mpc_generate_gait_inputs",
 ]
 
 
@@ -84,6 +84,8 @@ def load_library():
     lib.mpc_prepare_reset.argtypes = [vp]
     lib.mpc_generate_sensors.argtypes = [u64, u64, i32, C.c_int64, vp]
     lib.a1_leg_fk_jac.argtypes = [vp, vp, vp, vp]
+    lib.mpc_set_gait_inputs.argtypes = [vp, vp, i32]
+    lib.mpc_generate_gait_inputs.argtypes = [u64, u64, i32, C.c_int64, vp]
     lib.mpc_solve_warm.argtypes = [vp]
     lib.mpc_solve_warm_async.argtypes = [vp]
     lib.mpc_stream_reset.argtypes = [vp]
@@ -151,6 +153,14 @@ def generate_torque_inputs(seed, first_index, n):
     rc = load_library().mpc_generate_torque_inputs(seed, first_index, n, _ptr(out))
     if rc:
         raise MpcError(rc, "mpc_generate_torque_inputs")
+    return out
+
+
+def generate_gait_inputs(seed, first_index, n, tick=0):
+    out = np.zeros(n, dtype=abi.GAIT_DTYPE)
+    rc = load_library().mpc_generate_gait_inputs(seed, first_index, n, tick, _ptr(out))
+    if rc:
+        raise MpcError(rc, "mpc_generate_gait_inputs")
     return out
 
 
@@ -317,6 +327,16 @@ class MpcEngine:
             self._check(self._lib.mpc_compute_grf_batch(self._h, _ptr(states), _ptr(out), len(states)))
         self.n = len(states)
         return out
+
+    def set_gait_inputs(self, gait):
+        """Gait scheduler records of the loaded states (gait_aware engines)."""
+        if gait is None:
+            self._check(self._lib.mpc_set_gait_inputs(self._h, None, 0))
+            return
+        g = np.ascontiguousarray(gait)
+        assert g.dtype == abi.GAIT_DTYPE
+        self._keep_g = g
+        self._check(self._lib.mpc_set_gait_inputs(self._h, _ptr(g), len(g)))
 
     # upstream state preparation on the device (orientation, leg kinematics, EKF, terrain pitch)
     def prepare_states(self, sensors, prep_cfg=None):

@@ -215,7 +215,30 @@ typedef struct MpcConfig {
   double q_weights[13]; /* state.q_weights */
   double r_weights[12]; /* state.r_weights */
   MpcSolverSettings osqp;
+  /* behaviours the reference's authors sketched but left switched off.  Each
+   * CHANGES RESULTS, defaults 0 = the reference's behaviour; H = 10 only. */
+  int32_t exact_discretization; /* A_d, B_d from the matrix exponential the reference commented out
+                                   (ConvexMpc.cpp:149); A_c is nilpotent, so the series is exact:
+                                   A_d = I + A dt + A^2 dt^2/2, B_d = (dt I + A dt^2/2) B_c */
+  int32_t foot_drift;           /* per-step B_d: lever arms r_i = r_0 - i dt v_d (world), the update
+                                   commented out at A1RobotControl.cpp:504-507 */
+  int32_t gait_aware;           /* per-step contacts from the gait counters (mpc_set_gait_inputs)
+                                   instead of today's contacts replicated (ConvexMpc.cpp:242-245) */
+  int32_t reserved1;
 } MpcConfig;
+
+/* Gait scheduler state of one robot (A1CtrlStates.h:24-28,103; A1RobotControl.cpp:156-164),
+ * for gait_aware = 1.  Step 0 of the horizon keeps MpcStateIn.contacts; step i >= 1 is in
+ * contact iff fmod(gait_counter + i ticks_per_step gait_counter_speed, counter_per_gait)
+ * <= counter_per_swing.  48 B. */
+typedef struct MpcGaitIn {
+  float gait_counter[4];
+  float gait_counter_speed[4];
+  float counter_per_gait;
+  float counter_per_swing;
+  float ticks_per_step; /* control ticks per MPC step (mpc_dt / control dt) */
+  float pad;
+} MpcGaitIn;
 
 /* Constants of the stance-balance QP (A1RobotControl.cpp:11-15) plus the PD
  * gains it reads from A1CtrlStates (A1CtrlStates.h:429-432). */
@@ -310,6 +333,12 @@ int mpc_get_solution(MpcEngine *e, int32_t idx, float *x);
 /* The whole compute_grf MPC branch for n robots: host records in, host results
  * out (H2D + build + solve + D2H). */
 int mpc_compute_grf_batch(MpcEngine *e, const MpcStateIn *host_in, MpcResult *host_out, int32_t n);
+
+/* ---- gait-aware horizon -------------------------------- *
+ * The n gait records of the loaded states; required before mpc_build_qp when the engine was
+ * created with gait_aware = 1 (MPC_ERR_STATE otherwise), ignored when it was not. */
+int mpc_set_gait_inputs(MpcEngine *e, const MpcGaitIn *host, int32_t n);
+int mpc_generate_gait_inputs(uint64_t seed, uint64_t first_index, int32_t n, int64_t tick, MpcGaitIn *out);
 
 /* ---- torque map fused into the result writer ----------- *
  * compute_joint_torques (A1RobotControl.cpp:289-319): stance leg tau = J^T (-f_grf), swing leg

@@ -199,6 +199,34 @@ struct ConvexMpc {
     for (int i = 0; i < kStateDim * kNumDof; ++i) B_mat_d[i] = B_mat_c[i] * dt;
   }
 
+  // SURVEY.md 8f row 4 (NOT the reference's behaviour; behind MpcConfig.exact_discretization):
+  // the matrix exponential the authors left commented out (ConvexMpc.cpp:149),
+  // exp([[A_c, B_c], [0, 0]] dt) = [[A_d, B_d], [0, I]], by its Taylor series (A_c is nilpotent,
+  // the series terminates; twelve terms are summed without assuming that).
+  void state_space_discretization_exact(T dt) {
+    const int S = kStateDim, D = kNumDof, Nn = S + D;
+    std::vector<T> Mx(size_t(Nn) * Nn, T(0)), term(size_t(Nn) * Nn, T(0)), acc(size_t(Nn) * Nn, T(0)), nxt(size_t(Nn) * Nn);
+    for (int r = 0; r < S; ++r) {
+      for (int c = 0; c < S; ++c) Mx[size_t(r) * Nn + c] = A_mat_c[r * S + c] * dt;
+      for (int c = 0; c < D; ++c) Mx[size_t(r) * Nn + S + c] = B_mat_c[r * D + c] * dt;
+    }
+    for (int i = 0; i < Nn; ++i) term[size_t(i) * Nn + i] = acc[size_t(i) * Nn + i] = T(1);
+    for (int k = 1; k <= 12; ++k) {
+      for (int r = 0; r < Nn; ++r)
+        for (int c = 0; c < Nn; ++c) {
+          T s_ = 0;
+          for (int j = 0; j < Nn; ++j) s_ += term[size_t(r) * Nn + j] * Mx[size_t(j) * Nn + c];
+          nxt[size_t(r) * Nn + c] = s_ / T(k);
+        }
+      term = nxt;
+      for (size_t i = 0; i < acc.size(); ++i) acc[i] += term[i];
+    }
+    for (int r = 0; r < S; ++r) {
+      for (int c = 0; c < S; ++c) A_mat_d[r * S + c] = acc[size_t(r) * Nn + c];
+      for (int c = 0; c < D; ++c) B_mat_d[r * D + c] = acc[size_t(r) * Nn + S + c];
+    }
+  }
+
   // The caller stores B_mat_d into B_mat_d_list block i (A1RobotControl.cpp:513).
   void store_B_mat_d(int i) {
     std::copy(B_mat_d, B_mat_d + kStateDim * kNumDof,
@@ -206,7 +234,8 @@ struct ConvexMpc {
   }
 
   // ConvexMpc.cpp:158-245
-  void calculate_qp_mats(const T* mpc_states, const T* mpc_states_d, const bool* contacts) {
+  // contacts: 4 flags replicated over the horizon (the reference), or, with per_step, 4 H flags
+  void calculate_qp_mats(const T* mpc_states, const T* mpc_states_d, const bool* contacts, bool per_step = false) {
     const int S = kStateDim, D = kNumDof;
     // :184-202  A_qp block i = A_qp block (i-1) * A_d ; B_qp block (i,j)
     for (int i = 0; i < H; ++i) {
@@ -271,7 +300,7 @@ struct ConvexMpc {
     fz_max = 180;
     for (int h = 0; h < H; ++h)
       for (int i = 0; i < kNumLeg; ++i) {
-        const T c = contacts[i] ? T(1) : T(0);
+        const T c = contacts[per_step ? 4 * h + i : i] ? T(1) : T(0);
         T* l = &lb[h * kConDim + 5 * i];
         T* u = &ub[h * kConDim + 5 * i];
         l[0] = 0;               u[0] = T(kOsqpInfty);
@@ -756,6 +785,8 @@ struct MpcParams {
   double q_weights[13] = {20, 10, 1, 0, 0, 420, 0.05, 0.05, 0.05, 30, 30, 10, 0};
   double r_weights[12] = {1e-7, 1e-7, 1e-7, 1e-7, 1e-7, 1e-7, 1e-7, 1e-7, 1e-7, 1e-7, 1e-7, 1e-7};
   Settings osqp;
+  // SURVEY.md 8f row 4 extensions (change results; all false = the reference)
+  bool exact_discretization = false, foot_drift = false, gait_aware = false;
 };
 
 // Field-for-field the MpcStateIn record of include/mpc_b200.h, already widened.
@@ -782,7 +813,7 @@ struct MpcProblem {
 
 // A1RobotControl.cpp:446-518: pack x0 / reference, drive ConvexMpc.
 template <class T>
-void mpc_build(const MpcParams& p, const RobotState<T>& st, MpcProblem<T>& pb) {
+void mpc_build(const MpcParams& p, const RobotState<T>& st, MpcProblem<T>& pb, const MpcGaitIn* gait = nullptr) {
   ConvexMpc<T>& mpc = pb.mpc;
   mpc.reset();                                   // :448
   mpc.mu = T(p.mu);
@@ -820,11 +851,35 @@ void mpc_build(const MpcParams& p, const RobotState<T>& st, MpcProblem<T>& pb) {
   T inertia[9];
   for (int i = 0; i < 9; ++i) inertia[i] = T(p.inertia[i]);
   for (int i = 0; i < p.H; ++i) {                // :498-514 (same B_d every step)
-    mpc.calculate_B_mat_c(T(p.mass), inertia, st.rot_mat, st.foot_pos_abs);
-    mpc.state_space_discretization(dt);
+    T foot[12];
+    for (int k = 0; k < 12; ++k) foot[k] = st.foot_pos_abs[k];
+    if (p.foot_drift)                            // the update commented out at :504-507, in the world frame
+      for (int leg = 0; leg < kNumLeg; ++leg)
+        for (int r = 0; r < 3; ++r) foot[3 * leg + r] -= T(i) * dt * vdw[r];
+    mpc.calculate_B_mat_c(T(p.mass), inertia, st.rot_mat, foot);
+    if (p.exact_discretization) mpc.state_space_discretization_exact(dt);
+    else mpc.state_space_discretization(dt);
     mpc.store_B_mat_d(i);
   }
-  mpc.calculate_qp_mats(x0, pb.x_ref.data(), st.contacts);  // :518
+  if (p.gait_aware && gait) {
+    // planned contacts of step i >= 1 from the gait counters (A1RobotControl.cpp:156-164)
+    std::vector<char> cs(size_t(4) * p.H);
+    bool* flags = reinterpret_cast<bool*>(cs.data());
+    for (int i = 0; i < p.H; ++i)
+      for (int leg = 0; leg < kNumLeg; ++leg) {
+        bool c = st.contacts[leg];
+        if (i > 0) {
+          const double cnt = std::fmod(double(gait->gait_counter[leg]) +
+                                           double(i) * double(gait->ticks_per_step) * double(gait->gait_counter_speed[leg]),
+                                       double(gait->counter_per_gait));
+          c = cnt <= double(gait->counter_per_swing);
+        }
+        flags[4 * i + leg] = c;
+      }
+    mpc.calculate_qp_mats(x0, pb.x_ref.data(), flags, true);
+  } else {
+    mpc.calculate_qp_mats(x0, pb.x_ref.data(), st.contacts);  // :518
+  }
 }
 
 template <class T>

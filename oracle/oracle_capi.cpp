@@ -35,6 +35,9 @@ MpcParams to_params(const MpcConfig* c) {
   p.osqp.scaling = s.scaling; p.osqp.adaptive_rho = s.adaptive_rho;
   p.osqp.adaptive_rho_interval = s.adaptive_rho_interval;
   p.osqp.adaptive_rho_tolerance = s.adaptive_rho_tolerance;
+  p.exact_discretization = c->exact_discretization != 0;
+  p.foot_drift = c->foot_drift != 0;
+  p.gait_aware = c->gait_aware != 0;
   return p;
 }
 
@@ -321,6 +324,58 @@ int oracle_prep_stream(const PrepConfig* cfg, const RobotSensorIn* sensors, int3
 
 int oracle_leg_fk_jac(const double* rho_fix, const double* q, double* p, double* J) {
   prep_oracle::leg_fk_jac(rho_fix, q, p, J);
+  return 0;
+}
+
+// the flags of cfg (exact_discretization, foot_drift, gait_aware) with the
+// robots' gait records (may be NULL when gait_aware is 0).
+int oracle_mpc_build_qp_ext(const MpcConfig* cfg, const MpcStateIn* state, const MpcGaitIn* gait, double* P, double* q,
+                            double* l, double* u) {
+  const MpcParams p = to_params(cfg);
+  MpcProblem<double> pb(p);
+  RobotState<double> st = widen<double>(*state);
+  mpc_build(p, st, pb, gait);
+  const int n = pb.mpc.n, m = pb.mpc.m;
+  if (P) std::copy(pb.mpc.hessian.begin(), pb.mpc.hessian.begin() + size_t(n) * n, P);
+  if (q) std::copy(pb.mpc.gradient.begin(), pb.mpc.gradient.begin() + n, q);
+  if (l) std::copy(pb.mpc.lb.begin(), pb.mpc.lb.begin() + m, l);
+  if (u) std::copy(pb.mpc.ub.begin(), pb.mpc.ub.begin() + m, u);
+  return 0;
+}
+
+int oracle_mpc_compute_grf_ext(const MpcConfig* cfg, const MpcStateIn* states, const MpcGaitIn* gait, int32_t n,
+                               OracleResult* out, int32_t threads) {
+  const MpcParams p = to_params(cfg);
+  if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads)
+  {
+    MpcProblem<double> pb(p);
+#pragma omp for schedule(dynamic, 1)
+    for (int i = 0; i < n; ++i) {
+      RobotState<double> st = widen<double>(states[i]);
+      GrfResult<double> g;
+      mpc_build(p, st, pb, gait ? gait + i : nullptr);
+      mpc_solve(p, st, pb, g);
+      to_result(g, &out[i]);
+    }
+  }
+  return 0;
+}
+
+// the exact discretisation alone, for checking against a matrix exponential computed elsewhere
+int oracle_discretize_exact(const MpcConfig* cfg, const MpcStateIn* state, double* A_d, double* B_d) {
+  const MpcParams p = to_params(cfg);
+  MpcProblem<double> pb(p);
+  RobotState<double> st = widen<double>(*state);
+  ConvexMpc<double>& mpc = pb.mpc;
+  mpc.reset();
+  mpc.calculate_A_mat_c(st.euler);
+  double inertia[9];
+  for (int i = 0; i < 9; ++i) inertia[i] = p.inertia[i];
+  mpc.calculate_B_mat_c(p.mass, inertia, st.rot_mat, st.foot_pos_abs);
+  mpc.state_space_discretization_exact(p.dt);
+  std::copy(mpc.A_mat_d, mpc.A_mat_d + 169, A_d);
+  std::copy(mpc.B_mat_d, mpc.B_mat_d + 156, B_d);
   return 0;
 }
 

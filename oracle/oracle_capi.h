@@ -59,6 +59,12 @@ int oracle_torque_map(const float *state_words, int32_t state_stride, int32_t co
 int oracle_prep_stream(const PrepConfig *cfg, const RobotSensorIn *sensors, int32_t n, int32_t ticks,
                        MpcStateIn *states, MpcTorqueIn *tin, RobotPrepOut *extras);
 int oracle_leg_fk_jac(const double *rho_fix, const double *q, double *p, double *J);
+/* SURVEY.md 8f row 4 (flags in cfg; gait may be NULL when gait_aware = 0). */
+int oracle_mpc_build_qp_ext(const MpcConfig *cfg, const MpcStateIn *state, const MpcGaitIn *gait, double *P,
+                            double *q, double *l, double *u);
+int oracle_mpc_compute_grf_ext(const MpcConfig *cfg, const MpcStateIn *states, const MpcGaitIn *gait, int32_t n,
+                               OracleResult *out, int32_t threads);
+int oracle_discretize_exact(const MpcConfig *cfg, const MpcStateIn *state, double *A_d, double *B_d);
 int oracle_max_threads(void);
 
 #ifdef __cplusplus

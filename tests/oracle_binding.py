@@ -208,6 +208,35 @@ def leg_fk_jac(rho_fix, q):
     return p, J
 
 
+def mpc_build_qp_ext(cfg, state_rec, gait_rec=None):
+    H = cfg.horizon
+    n, m = 12 * H, 20 * H
+    st = np.ascontiguousarray(np.atleast_1d(state_rec)[:1])
+    g = None if gait_rec is None else np.ascontiguousarray(np.atleast_1d(gait_rec)[:1])
+    P = np.empty((n, n)); q = np.empty(n); l = np.empty(m); u = np.empty(m)
+    rc = lib().oracle_mpc_build_qp_ext(C.byref(cfg), _vp(st), None if g is None else _vp(g), _p(P), _p(q), _p(l), _p(u))
+    assert rc == 0
+    return P, q, l, u
+
+
+def mpc_compute_grf_ext(cfg, states, gait=None, threads=0):
+    states = np.ascontiguousarray(states)
+    g = None if gait is None else np.ascontiguousarray(gait)
+    out = np.zeros(len(states), dtype=ORACLE_RESULT_DTYPE)
+    rc = lib().oracle_mpc_compute_grf_ext(C.byref(cfg), _vp(states), None if g is None else _vp(g), C.c_int32(len(states)),
+                                          _vp(out), C.c_int32(threads))
+    assert rc == 0
+    return out
+
+
+def discretize_exact(cfg, state_rec):
+    st = np.ascontiguousarray(np.atleast_1d(state_rec)[:1])
+    A = np.empty((13, 13)); B = np.empty((13, 12))
+    rc = lib().oracle_discretize_exact(C.byref(cfg), _vp(st), _p(A), _p(B))
+    assert rc == 0
+    return A, B
+
+
 def max_threads():
     return int(lib().oracle_max_threads())
 

@@ -11,8 +11,8 @@ EXE = os.path.join(ROOT, "tests", "cpp", "test_mpc_b200")
 
 
 def _build():
-    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(
-            os.path.getmtime(SRC), os.path.getmtime(os.path.join(ROOT, "include", "convex_mpc_b200.hpp"))):
+    deps = [SRC, os.path.join(ROOT, "include", "convex_mpc_b200.hpp"), os.path.join(ROOT, "include", "mpc_b200.h")]
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), SRC,
                                "-L" + os.path.join(ROOT, "go1_qp_mpc_controller_b200"), "-lmpc_b200",
                                "-Wl,-rpath," + os.path.join(ROOT, "go1_qp_mpc_controller_b200"), "-o", EXE])

@@ -607,3 +607,49 @@ def test_state_preparation_parity(pkg, ob):
     assert np.array_equal(st_f["pos"], sens[6]["root_pos"]) and np.array_equal(st_f["euler_d"], sens[6]["root_euler_d"])
     e.close()
     e2.close()
+
+
+@pytest.mark.parametrize("flags", [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)])
+def test_horizon_extensions_parity(pkg, ob, flags):
+    """SURVEY 8f row 4 behind flags: exact discretisation, drifting feet, gait-aware contacts.
+    QP matrices and GRFs against the oracle's own restatement of the same extensions."""
+    cfg = pkg.config_default()
+    cfg.exact_discretization, cfg.foot_drift, cfg.gait_aware = flags
+    n = 384
+    st = pkg.generate_states(1002, 0, n)
+    gait = pkg.generate_gait_inputs(1002, 0, n, 0)
+    e = pkg.MpcEngine(cfg, 0)
+    e.load_states(st)
+    if cfg.gait_aware:
+        with pytest.raises(pkg.MpcError) as ei:
+            e.build_qp()                                   # gait records are mandatory for such an engine
+        assert ei.value.code == pkg.abi.MPC_ERR_STATE
+        e.set_gait_inputs(gait)
+    e.build_qp()
+    worst = 0.0
+    for i in range(0, n, 8):
+        P, q, l, u = e.get_qp(i)
+        Po, qo, lo, uo = ob.mpc_build_qp_ext(cfg, st[i], gait[i])
+        worst = max(worst, np.abs(P - Po).max() / np.abs(Po).max(), np.abs(q - qo).max() / np.abs(qo).max())
+        assert np.array_equal(l, lo.astype(np.float32)) and np.array_equal(u, uo.astype(np.float32))
+    assert worst <= TOL_QP, worst
+    e.solve()
+    res = e.get_results()
+    ref = ob.mpc_compute_grf_ext(cfg, st, gait)
+    assert (res["status"] == ref["status"]).all()
+    same = res["iters"] == ref["iters"]
+    assert same.mean() >= 0.98
+    assert grf_rel(res["grf"][same], ref["grf"][same]).max() <= TOL_GRF
+    # the flags do change the answer (otherwise this test checks nothing)
+    base = ob.mpc_compute_grf(pkg.config_default(), st)
+    assert grf_rel(res["grf"], base["grf"]).max() > 1e-4
+    e.close()
+
+
+def test_horizon_extensions_unsupported_for_h30(pkg):
+    cfg = pkg.config_default()
+    cfg.horizon = 30
+    cfg.exact_discretization = 1
+    with pytest.raises(pkg.MpcError) as ei:
+        pkg.MpcEngine(cfg, 0)
+    assert ei.value.code == pkg.abi.MPC_ERR_UNSUPPORTED

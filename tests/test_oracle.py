@@ -430,3 +430,48 @@ def test_prep_oracle_terrain_and_ekf(pkg, ob):
     h = -ex["foot_pos_rel"][-1].reshape(N, 4, 3)[:, :, 2].mean(axis=1)
     assert np.abs(ex["estimated_root_pos"][-1, :, 2] - h).max() < 5e-3
     assert np.abs(ex["estimated_root_vel"][-1]).max() < 5e-3
+
+
+# ---- exact discretisation, drifting feet, gait-aware contacts (behind flags) ------
+
+def test_exact_discretization_is_the_matrix_exponential(pkg, ob):
+    from scipy.linalg import expm
+    cfg = pkg.config_default()
+    st = pkg.generate_states(1002, 0, 6)
+    for i in range(6):
+        A, B = ob.discretize_exact(cfg, st[i])
+        inter = ob.mpc_build_intermediates(cfg, st[i])          # forward Euler: A_d = I + dt A_c, B_d = dt B_c
+        Ac, Bc = (inter["A_d"] - np.eye(13)) / cfg.dt, inter["B_d"] / cfg.dt
+        M = np.zeros((25, 25))
+        M[:13, :13], M[:13, 13:] = Ac * cfg.dt, Bc * cfg.dt
+        E = expm(M)
+        assert np.abs(E[:13, :13] - A).max() < 1e-15 and np.abs(E[:13, 13:] - B).max() < 1e-15
+        assert abs(A[5, 12] - 0.5 * cfg.dt ** 2) < 1e-18           # the one entry Euler misses in A_d
+        assert np.abs(B[3:6] - 0.5 * cfg.dt * B[9:12]).max() < 1e-18
+
+
+def test_extension_flags_off_is_the_reference_and_gait_schedule(pkg, ob):
+    cfg = pkg.config_default()
+    st = pkg.generate_states(1002, 0, 64)
+    gait = pkg.generate_gait_inputs(1002, 0, 64, 0)
+    P0, q0, l0, u0 = ob.mpc_build_qp(cfg, st[3])
+    P1, q1, l1, u1 = ob.mpc_build_qp_ext(cfg, st[3], gait[3])    # flags 0: gait records are ignored
+    assert np.array_equal(P0, P1) and np.array_equal(q0, q1) and np.array_equal(u0, u1)
+    cfg.gait_aware = 1
+    changed = 0
+    for i in range(64):
+        P, q, l, u = ob.mpc_build_qp_ext(cfg, st[i], gait[i])
+        assert np.array_equal(P, ob.mpc_build_qp(pkg.config_default(), st[i])[0])   # only the bounds move
+        # python restatement of the scheduler loop (A1RobotControl.cpp:156-164), one tick per MPC step
+        cnt = gait["gait_counter"][i].astype(np.float64).copy()
+        for h in range(10):
+            if h > 0:
+                cnt = np.fmod(cnt + gait["gait_counter_speed"][i], gait["counter_per_gait"][i])
+            want = st["contacts"][i] != 0 if h == 0 else cnt <= gait["counter_per_swing"][i]
+            assert np.array_equal(u[20 * h + 4:20 * h + 20:5] > 0, want), (i, h)
+        changed += int(not np.array_equal(u, ob.mpc_build_qp(pkg.config_default(), st[i])[3]))
+    assert changed >= 4   # some robots swap stance and swing inside the horizon
+    cfg = pkg.config_default()
+    cfg.foot_drift = 1
+    moving = int(np.argmax(np.abs(st["lin_vel_d"]).sum(axis=1)))
+    assert not np.array_equal(ob.mpc_build_qp_ext(cfg, st[moving])[0], ob.mpc_build_qp(pkg.config_default(), st[moving])[0])
