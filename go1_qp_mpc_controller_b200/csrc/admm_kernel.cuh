@@ -64,7 +64,7 @@ struct SolveSmem {
   long long fine_mark;
   int flags[8];             // 0:done 1:status 2:refactor 3:problem index 4:sweep flag wait timed out
   int pub_ready;            // blocked sweep: number of blocks published so far (monotone, release/acquire)
-  int grp_done;             // blocked sweep: warps x groups finished so far (monotone): slot recycling
+  int grp_done[2];          // blocked sweep, per slot set: (warps x groups that used the set) finished so far
 };
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -94,6 +94,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // (r < 15); lanes 30, 31 hold the padding row.  No shared memory, no warp barrier.
 struct AddOp { __device__ __forceinline__ double operator()(double a, double b) const { return a + b; } };
 struct MaxOp { __device__ __forceinline__ double operator()(double a, double b) const { return fmax(a, b); } };
+// max of NON-NEGATIVE doubles through their bit patterns (ordered like the values): integer
+// compares on the ALU instead of DSETP on the FP64 pipe; bit-identical result
+struct MaxBitsOp {
+  __device__ __forceinline__ double operator()(double a, double b) const {
+    return (__double_as_longlong(a) > __double_as_longlong(b)) ? a : b;
+  }
+};
 template <class Op>
 __device__ __forceinline__ double reduce_rows(const double (&s)[kTR], int lane, Op op) {
   static_assert(kTR == 15, "recursive halving is written for 15 (padded to 16) rows");
@@ -146,10 +153,10 @@ __device__ __forceinline__ double row_norm_pass(SolveSmem& sm, int rg, int cg) {
     load_cols(&sm.P[(kTR * rg + rr) * kNP], cg, pv);
     double mm = 0.0;
 #pragma unroll
-    for (int jj = 0; jj < kTC; ++jj) mm = fmax(mm, fabs(pv[jj]) * dcol[jj]);
+    for (int jj = 0; jj < kTC; ++jj) mm = MaxBitsOp()(mm, fabs(pv[jj]) * dcol[jj]);
     m[rr] = mm;
   }
-  return reduce_rows(m, cg, MaxOp());
+  return reduce_rows(m, cg, MaxBitsOp());
 }
 
 // Blocked symmetric sweep (Gauss-Jordan on the SPD matrix), one leg-step (3 pivots
@@ -286,7 +293,10 @@ __device__ __forceinline__ void wait_flag(SolveSmem& sm, const int* f, int want)
 //   other warps: apply the five blocks as their flags come in; warp kp + 1 updates its rows 0..2
 //     first on the last block and publishes block 0 of the next group.
 // A slot set is rewritten two groups later: the first write waits until every warp has reported
-// the old group done (grp_done counts warps x groups, monotone).
+// the set's previous group done.  The counters are PER SET: nobody can finish the set's next
+// group before its first block is published, so the count is exact.  (One counter over all groups
+// is not: seven fast warps finishing two groups outvote a slow owner still reading its slots --
+// seen on the first problem of a CTA, when the owner's code is cold in the instruction cache.)
 template <bool kProfile>
 __device__ __forceinline__ void sweep_group(SolveSmem& sm, double (&a)[kTR][kTC], int kp, int rg, int cg, int base,
                                             int done_base) {
@@ -331,7 +341,7 @@ __device__ __forceinline__ void sweep_group(SolveSmem& sm, double (&a)[kTR][kTC]
     if (rg == kp + 1) {
       update_rows<0, 3>(sm, a, set + 4, rg, cg);
       // first write into the other slot set in its new life: everyone must be done with group kp - 1
-      if (kp >= 1) wait_flag(sm, &sm.grp_done, done_base + kSolveWarps * kp);
+      if (kp >= 1) wait_flag(sm, &sm.grp_done[(kp + 1) & 1], done_base + kSolveWarps * ((kp + 1) >> 1));
       publish_block<0>(sm, a, kb0 + kLegPerWarp, cg, ((kp + 1) & 1) * kLegPerWarp, base + kb0 + kLegPerWarp + 1);
       update_rows<3, 12>(sm, a, set + 4, rg, cg);
     } else {
@@ -341,7 +351,8 @@ __device__ __forceinline__ void sweep_group(SolveSmem& sm, double (&a)[kTR][kTC]
   }
   // this warp no longer reads the slots of group kp
   __syncwarp();
-  if (cg == 0) asm volatile("red.release.cta.shared::cta.add.s32 [%0], 1;" ::"r"(smem_u32(&sm.grp_done)) : "memory");
+  if (cg == 0)
+    asm volatile("red.release.cta.shared::cta.add.s32 [%0], 1;" ::"r"(smem_u32(&sm.grp_done[kp & 1])) : "memory");
 }
 
 // Build K = c D P D + sigma I + A' diag(rho) A into the register tiles, then overwrite it
@@ -385,7 +396,7 @@ __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][k
   if (kProfile && threadIdx.x == 0) sm.fine_mark = clock64();
   for (int kp = 0; kp < kRowGroups; ++kp) sweep_group<kProfile>(sm, a, kp, rg, cg, base, done_base);
   base += kLegSteps;
-  done_base += kSolveWarps * kRowGroups;
+  done_base += kSolveWarps * (kRowGroups / 2);  // four groups per slot set and factorisation
 }
 
 template <bool kProfile, bool kWarm>
@@ -423,7 +434,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
   }
   uint32_t phase = 0;
   int sweep_base = 0, sweep_done = 0;  // blocks published / (warps x groups) finished by this CTA so far
-  if (tid == 0) { sm.pub_ready = 0; sm.grp_done = 0; }
+  if (tid == 0) { sm.pub_ready = 0; sm.grp_done[0] = 0; sm.grp_done[1] = 0; }
   if (kProfile && tid == 0) {
     for (int i = 0; i < 16; ++i) sm.fine[i] = 0;
     sm.fine_mark = clock64();
@@ -497,6 +508,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     // ---- K3a: modified Ruiz equilibration (osqp scaling.c scale_data) ----
     // scaled quantities are never materialised: P_bar = c D P D, A_bar = E A D.
     double D = 1.0, E = 1.0;  // D on variable lanes, E on row lanes
+    double c_run = 1.0;       // the cost scaling c, carried by every thread
     if (sp.scaling > 0) {
       double nP = row_norm_pass(sm, rg, cg);  // c = 1, D = 1 (valid on the variable lanes)
       __syncthreads();                        // Dp is rewritten inside the loop
@@ -522,35 +534,38 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         D = Dn;
         E = En;
         __syncthreads();
-        // cost normalisation with the new D and the old c
-        const double c_old = sm.scal[0];
+        // cost normalisation with the new D and the old c; every thread combines the eight warp
+        // partials itself (same order, same bits): one block barrier, no serial section
+        const double c_old = c_run;
         const double nP2 = c_old * D * row_norm_pass(sm, rg, cg);
         double part_sum = vown ? nP2 : 0.0;
         double part_q = vown ? fabs(c_old * D * q_scale) : 0.0;
-        part_sum = warp_sum(part_sum);
-        part_q = warp_max(part_q);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          part_sum += __shfl_xor_sync(0xffffffffu, part_sum, o);
+          part_q = fmax(part_q, __shfl_xor_sync(0xffffffffu, part_q, o));
+        }
+        double* red = sm.red + (it & 1) * (kSolveWarps * 8);  // double buffered by pass parity
         if (lane == 0) {
-          sm.red[warp * 16 + 0] = part_sum;
-          sm.red[warp * 16 + 1] = part_q;
+          red[warp * 2 + 0] = part_sum;
+          red[warp * 2 + 1] = part_q;
         }
         __syncthreads();
-        if (tid == 0) {
-          double s = 0.0, qn = 0.0;
-          for (int w = 0; w < kSolveWarps; ++w) {
-            s += sm.red[w * 16 + 0];
-            qn = fmax(qn, sm.red[w * 16 + 1]);
-          }
-          const double mean = s / (double)kN;
-          const double ct = 1.0 / limit_scaling(fmax(mean, limit_scaling(qn)));
-          sm.scal[3] = ct;
-          sm.scal[0] = c_old * ct;
+        double s = 0.0, qn = 0.0;
+#pragma unroll
+        for (int w = 0; w < kSolveWarps; ++w) {
+          s += red[w * 2 + 0];
+          qn = fmax(qn, red[w * 2 + 1]);
         }
-        __syncthreads();
-        nP = nP2 * sm.scal[3];
+        const double mean = s / (double)kN;
+        const double ct = 1.0 / limit_scaling(fmax(mean, limit_scaling(qn)));
+        c_run = c_old * ct;
+        nP = nP2 * ct;
       }
+      if (tid == 0) sm.scal[0] = c_run;
     }
     // ---- scaled data on the owning lanes (constants go to per-lane shared-memory slots) ----
-    const double c = sm.scal[0];
+    const double c = c_run;
     const double qb0 = c * D * q0;
     lb *= E;
     ub *= E;
