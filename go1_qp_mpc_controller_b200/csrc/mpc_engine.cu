@@ -188,7 +188,7 @@ int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n,
                  float* l, float* u) {
   if (e->H == kH) {
     const int grid = n < e->num_sms * 8 ? n : e->num_sms * 8;
-    qp_build_kernel<<<grid, kThreads, sizeof(BuildSmem), e->stream>>>(d_states, d_states ? e->d_gait : nullptr, model, n,
+    qp_build_kernel<<<grid, kBuildThreads, sizeof(BuildSmem), e->stream>>>(d_states, d_states ? e->d_gait : nullptr, model, n,
                                                                       P, q, l, u, e->bp);
   } else {
     const int grid = n < e->num_sms ? n : e->num_sms;
