@@ -57,6 +57,17 @@ __device__ __forceinline__ double ekf_C(int i, int j) {
   return (j == 6 + 3 * (i - 24) + 2) ? 1.0 : 0.0;
 }
 
+// (C X)_i for a length-18 column X given by an accessor: every row of C has one or two non-zeros
+template <class F>
+__device__ __forceinline__ double ekf_C_row(int i, F X) {
+  if (i < 12) {
+    const int leg = i / 3, r = i - 3 * leg;
+    return X(6 + 3 * leg + r) - X(r);
+  }
+  if (i < 24) return X(3 + (i - 12) % 3);
+  return X(6 + 3 * (i - 24) + 2);
+}
+
 __device__ __forceinline__ void leg_chain(const double* rho, const double* q, double* p, double* J) {
   const double ox = rho[0], oy = rho[1], d = rho[2], lt = rho[3], lc = rho[4];
   double s0, c0, s1, c1, s12, c12;
@@ -212,19 +223,14 @@ state_prep_kernel(const RobotSensorIn* __restrict__ sensors, int n, double* __re
       // CP = C Pbar
       for (int idx = lane; idx < M * N; idx += 32) {
         const int i = idx / N, j = idx - N * i;
-        double acc = 0.0;
-        for (int k = 0; k < N; ++k) acc += ekf_C(i, k) * sm.Pbar[k * N + j];
-        sm.CP[idx] = acc;
+        sm.CP[idx] = ekf_C_row(i, [&](int k) { return sm.Pbar[k * N + j]; });
       }
       __syncwarp();
       // S = sym(CP C' + R)
       for (int idx = lane; idx < M * M; idx += 32) {
         const int i = idx / M, j = idx - M * i;
-        double acc = 0.0, accT = 0.0;
-        for (int k = 0; k < N; ++k) {
-          acc += sm.CP[i * N + k] * ekf_C(j, k);
-          accT += sm.CP[j * N + k] * ekf_C(i, k);
-        }
+        const double acc = ekf_C_row(j, [&](int k) { return sm.CP[i * N + k]; });
+        const double accT = ekf_C_row(i, [&](int k) { return sm.CP[j * N + k]; });
         double v = 0.5 * (acc + accT);
         if (i == j) {
           double rd;
@@ -256,9 +262,7 @@ state_prep_kernel(const RobotSensorIn* __restrict__ sensors, int n, double* __re
             const int leg = i - 24;
             yv = (1.0 - estc[leg]) * (sm.x[2] + sm.prel[3 * leg + 2]);
           }
-          double yh = 0.0;
-          for (int k = 0; k < N; ++k) yh += ekf_C(i, k) * sm.xbar[k];
-          v = yv - yh;
+          v = yv - ekf_C_row(i, [&](int k) { return sm.xbar[k]; });
         }
         sm.RHS[idx] = v;
       }

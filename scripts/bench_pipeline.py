@@ -10,7 +10,17 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 eng = pkg.MpcEngine(pkg.config_default(), 0)
 pcfg = pkg.prep_config_default()
-sens = [pkg.generate_sensors(1002, 0, n, 40 + t) for t in range(ticks)]
+import torch  # pinned host buffers only (plumbing), as in bench.py's e2e leg
+def pinned(dtype, count):
+    t = torch.empty(count * dtype.itemsize, dtype=torch.uint8).pin_memory()
+    return t, t.numpy().view(dtype)
+_keep = []
+sens = []
+for t in range(ticks):
+    buf, arr = pinned(pkg.abi.SENSOR_DTYPE, n)
+    arr[:] = pkg.generate_sensors(1002, 0, n, 40 + t)
+    _keep.append(buf); sens.append(arr)
+_rb, res_buf = pinned(pkg.abi.RESULT_DTYPE, n)
 eng.prepare_states(sens[0][:296], pcfg); eng.build_qp(); eng.solve_warm(); eng.get_results()
 eng.prepare_reset(); eng.stream_reset()
 rows = []
@@ -20,7 +30,7 @@ for t in range(ticks):
     t1 = time.perf_counter()
     eng.build_qp(sync=False)
     eng.solve_warm(sync=False)
-    res = eng.get_results()
+    res = eng.get_results(res_buf)
     tq = eng.get_torques()
     t2 = time.perf_counter()
     eng.synchronize()

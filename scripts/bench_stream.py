@@ -9,10 +9,19 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 cfg = pkg.config_default()
 eng = pkg.MpcEngine(cfg, 0)
-states = [pkg.generate_stream_states(1002, 0, n, 40 + t) for t in range(ticks)]
+import torch  # pinned host buffers only (plumbing), as in bench.py's e2e leg
+def pinned(dtype, count):
+    t = torch.empty(count * dtype.itemsize, dtype=torch.uint8).pin_memory()
+    return t, t.numpy().view(dtype)
+_keep = []
+states = []
+for t in range(ticks):
+    buf, arr = pinned(pkg.abi.STATE_DTYPE, n)
+    arr[:] = pkg.generate_stream_states(1002, 0, n, 40 + t)
+    _keep.append(buf); states.append(arr)
 eng.compute_grf_batch(states[0][:296])
 eng.stream_reset()
-out = np.zeros(n, dtype=pkg.abi.RESULT_DTYPE)
+_ob, out = pinned(pkg.abi.RESULT_DTYPE, n)
 rows = []
 for t in range(ticks):
     t0 = time.perf_counter(); eng.stream_step(states[t], out); dt = time.perf_counter() - t0
