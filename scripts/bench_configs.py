@@ -1,6 +1,7 @@
 """Measures the BASELINE.json configs that are not the bench.py line (single GPU parts):
   1  single solve latency: 1000 states one at a time (seed 1001), GPU vs CPU oracle
   3  65536 states (seed 1003) on this rank's GPU(s) -- run under torchrun for 2/4/8
+  4  8192 states at H = 30 (seed 1004), sharded
   5  stance-balance QP batch (seed 1005), n per GPU given on the command line
 Prints one JSON object per config; results are kept under profiles/."""
 import json, os, sys, time
@@ -58,6 +59,21 @@ elif which == "3":
                           "solves_per_s": n / float(np.mean(times)), "batch_ms_mean": 1e3 * float(np.mean(times)),
                           "batch_ms_p99": 1e3 * float(np.max(times)), "all_solved": bool((out["status"] == 1).all()),
                           "mean_iters": float(out["iters"].mean())}))
+elif which == "4":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+    lo, hi = shard_range(n, rank, world)
+    cfg = pkg.config_default(); cfg.horizon = 30; eng = pkg.MpcEngine(cfg, local)
+    st = pkg.generate_states(1004, lo, hi - lo); out = np.zeros(hi - lo, dtype=pkg.abi.RESULT_DTYPE)
+    eng.compute_grf_batch(st[:148]); sync_all(); times = []
+    for rep in range(2):
+        sync_all(); t0 = time.perf_counter(); eng.compute_grf_batch(st, out); dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        times.append(dt)
+    if rank == 0:
+        print(json.dumps({"config": 4, "what": "long-horizon Go1 MPC H=30 (360 var), sharded, host to host", "n_gpus": world, "n": n,
+                          "solves_per_s": n / float(np.mean(times)), "batch_ms_mean": 1e3 * float(np.mean(times)),
+                          "all_solved": bool((out["status"] == 1).all()), "mean_iters": float(out["iters"].mean())}))
 elif which == "5":
     n_total = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
     lo, hi = shard_range(n_total, rank, world)
