@@ -1,33 +1,25 @@
-// Device kernels of the batched convex-MPC GRF engine (sm_100a).
+// Device kernels of the batched convex-MPC GRF engine (sm_100a): shared constants and the QP build.
 //
-//   qp_build_kernel     K0+K1+K2  state record -> A_d, B_d, A_qp powers, block-lower-triangular
-//                                 B_qp, Hessian B'QB+R, gradient, bounds
+//   qp_build_kernel     K0+K1+K2  state record -> A_d, B_d, A_d powers, condensed Hessian
+//                                 B_qp'QB_qp + R and gradient WITHOUT materialising B_qp
+//                                 (S_j / T_j / U_jl regrouping, see the kernel), bounds
 //                                 (ConvexMpc.cpp:110-245, A1RobotControl.cpp:452-518)
-//   admm_solve_kernel   K3+K4+K5  OSQP-equivalent ADMM: Ruiz scaling, K = P+sigma I+A'rho A,
-//                                 K^-1 by symmetric sweep held in REGISTERS, ADMM loop,
-//                                 residual termination, rho adaptation, unscale + R'f writer
+//   admm_solve_kernel   K3+K4+K5  (admm_kernel.cuh) OSQP-equivalent ADMM: Ruiz scaling,
+//                                 K = P+sigma I+A'rho A, K^-1 by a blocked symmetric sweep held
+//                                 in REGISTERS, ADMM loop, residual termination, rho adaptation,
+//                                 unscale + R'f writer (+ fused torque map)
 //                                 (OSQP 0.6.x as driven by A1RobotControl.cpp:522-561)
 //
 // Precision (measured on the CPU arithmetic model, see DESIGN.md "precision"):
 // the GRF parity gate (1e-3 vs the fp64 oracle at eps 1e-5) needs the Hessian
 // ACCUMULATED in fp64 and K, K^-1 and the ADMM iterates in fp64; fp32 is fine
 // for the QP as read back through mpc_get_qp.  Between the two kernels P and q
-// stay in f64 (HBM traffic is ~1 GB per 4096-state step, irrelevant next to the
+// stay in f64 (HBM traffic is ~0.5 GB per 4096-state step, irrelevant next to the
 // solve), which keeps the device iterate sequence identical to the oracle's:
 // with f32 hand-over 0.3 % of states flipped a termination check.  B200 runs
 // DFMA at half the FFMA rate (measured 17.1 T DFMA/s).
-//
-// Thread layout shared by both kernels (H = 10, n = 120): 480 threads =
-// 30 row groups x 16 column groups; thread (rg, cg) owns the 4 x 8 register
-// tile rows 4rg..4rg+3 x columns {32i + 2cg, 32i + 2cg + 1 : i = 0..3}.
-// Columns are interleaved in pairs at stride 32 so that one LDS.128 per i
-// fetches a thread's column pair and the 16 lanes of a half-warp read 256
-// contiguous bytes (no bank conflicts); the other half-warp (next row group)
-// reads the same addresses (broadcast).  Row sums are finished with a
-// reduce-scatter over the 16 lanes (5 double shuffles for 4 rows).  Matrices
-// are padded to 128 columns; columns 120..127 are structurally zero.
-// v1 of this file used a 1 x 30 tile: 4-way bank conflicts and 3x the operand
-// traffic (profiles/r01_v1_admm_solve_ncu_summary.txt).
+// P is padded to 128 columns per row (columns 120..127 exact zeros) so that one cp.async.bulk
+// moves a whole problem into the solver's shared memory.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -42,10 +34,8 @@ constexpr int kN = 12 * kH;  // 120 variables
 constexpr int kS = 13 * kH;  // 130 stacked states
 constexpr int kM = 20 * kH;  // 200 constraint rows
 constexpr int kLegSteps = 4 * kH;
-constexpr int kThreads = 480;
 constexpr int kBuildThreads = 256;  // qp_build_kernel: two CTAs per SM (114 KB shared memory, 128 registers)
 constexpr int kNP = 128;     // padded column count
-constexpr int kWarps = kThreads / 32;
 
 // float offsets inside MpcStateIn
 constexpr int kOffEuler = 0, kOffPos = 3, kOffAngVel = 6, kOffLinVel = 9, kOffEulerD = 12,
@@ -64,41 +54,6 @@ struct SolveParams {
   double rho, sigma, alpha, eps_abs, eps_rel, adaptive_rho_tolerance, mu;
   int max_iter, check_termination, scaling, adaptive_rho, adaptive_rho_interval;
 };
-
-// column owned by column group cg at tile position jj (0..7)
-__host__ __device__ constexpr int tile_col(int cg, int jj) { return 32 * (jj >> 1) + 2 * cg + (jj & 1); }
-
-// Reduce 4 per-row partials over the 16 column-group lanes of a half-warp.
-// Returns the total of row `owned_row(cg)`; lanes cg, cg+1, cg+2, cg+3 (cg%4==0)
-// all hold the same value.
-__device__ __forceinline__ int owned_row(int cg) { return 2 * ((cg >> 3) & 1) + ((cg >> 2) & 1); }
-
-__device__ __forceinline__ double reduce_scatter_sum(const double (&s)[4], int cg) {
-  const bool h8 = (cg & 8) != 0, h4 = (cg & 4) != 0;
-  double k0 = h8 ? s[2] : s[0], k1 = h8 ? s[3] : s[1];
-  const double t0 = h8 ? s[0] : s[2], t1 = h8 ? s[1] : s[3];
-  k0 += __shfl_xor_sync(0xffffffffu, t0, 8);
-  k1 += __shfl_xor_sync(0xffffffffu, t1, 8);
-  double k = h4 ? k1 : k0;
-  const double t = h4 ? k0 : k1;
-  k += __shfl_xor_sync(0xffffffffu, t, 4);
-  k += __shfl_xor_sync(0xffffffffu, k, 2);
-  k += __shfl_xor_sync(0xffffffffu, k, 1);
-  return k;
-}
-__device__ __forceinline__ double reduce_scatter_max(const double (&s)[4], int cg) {
-  const bool h8 = (cg & 8) != 0, h4 = (cg & 4) != 0;
-  double k0 = h8 ? s[2] : s[0], k1 = h8 ? s[3] : s[1];
-  const double t0 = h8 ? s[0] : s[2], t1 = h8 ? s[1] : s[3];
-  k0 = fmax(k0, __shfl_xor_sync(0xffffffffu, t0, 8));
-  k1 = fmax(k1, __shfl_xor_sync(0xffffffffu, t1, 8));
-  double k = h4 ? k1 : k0;
-  const double t = h4 ? k0 : k1;
-  k = fmax(k, __shfl_xor_sync(0xffffffffu, t, 4));
-  k = fmax(k, __shfl_xor_sync(0xffffffffu, k, 2));
-  k = fmax(k, __shfl_xor_sync(0xffffffffu, k, 1));
-  return k;
-}
 
 // ---------------------------------------------------------------------------
 // K0+K1+K2: QP build.  One CTA per problem, grid-stride over problems.
@@ -135,7 +90,6 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __restri
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BuildSmem& sm = *reinterpret_cast<BuildSmem*>(smem_raw);
   const int tid = threadIdx.x;
-  const int rg = tid >> 4, cg = tid & 15;
 
   for (int p = blockIdx.x; p < num; p += gridDim.x) {
     __syncthreads();  // smem reuse across problems
