@@ -672,3 +672,21 @@ def test_run_to_run_determinism(pkg):
         assert np.array_equal(res["iters"], first["iters"])
         e2.close()
     e.close()
+
+
+def test_stream_slots_survive_growth(pkg, ob):
+    """Growing the batch keeps the live solvers of the robots that already have a slot; the new
+    robots start cold (their first tick is an initSolver)."""
+    cfg = pkg.config_hardware()
+    n0, n1 = 96, 160
+    st = [pkg.generate_stream_states(1006, 0, n1, 44 + t) for t in range(3)]
+    e = pkg.MpcEngine(cfg, 0)
+    e.stream_step(st[0][:n0])
+    e.stream_step(st[1][:n0])
+    res = e.stream_step(st[2])                      # 160 robots: 96 warm third ticks + 64 cold first ticks
+    warm = ob.mpc_stream(cfg, np.stack([s[:n0] for s in st]))[2]
+    cold = ob.mpc_compute_grf(cfg, st[2][n0:])
+    assert np.array_equal(res["iters"][:n0], warm["iters"]) and np.array_equal(res["iters"][n0:], cold["iters"])
+    assert grf_rel(res["grf"][:n0], warm["grf"]).max() <= TOL_GRF
+    assert grf_rel(res["grf"][n0:], cold["grf"]).max() <= TOL_GRF
+    e.close()
