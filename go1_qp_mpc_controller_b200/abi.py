@@ -106,7 +106,7 @@ class MpcConfig(C.Structure):
         ("exact_discretization", C.c_int32),
         ("foot_drift", C.c_int32),
         ("gait_aware", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("structured_solver", C.c_int32),
     ]
 
 

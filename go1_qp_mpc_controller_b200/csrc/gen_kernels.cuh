@@ -40,7 +40,8 @@ struct GenBuildSmem {
 
 template <int H>
 __global__ void __launch_bounds__(kGenBuildThreads, 1)
-gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, double* __restrict__ P_out,
+gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, double* __restrict__ model_out,
+                 double* __restrict__ P_out,
                  double* __restrict__ q_out, float* __restrict__ l_out, float* __restrict__ u_out,
                  double* __restrict__ workspace, const __grid_constant__ BuildParams bp) {
   constexpr int n = 12 * H, s = 13 * H, m = 20 * H;
@@ -149,6 +150,12 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
       if (tid < 13) sm.x0[tid] = model.x0[size_t(p) * 13 + tid];
       for (int idx = tid; idx < s; idx += kGenBuildThreads) sm.xref[idx] = model.x_ref[size_t(p) * s + idx];
       if (tid < 4) sm.contacts[tid] = model.contacts[size_t(p) * 4 + tid] != 0;
+    }
+    if (model_out != nullptr) {
+      // A_d and the B_d list for the structured (Riccati) solver
+      double* mo = model_out + size_t(p) * (169 + H * 156);
+      for (int idx = tid; idx < 169 + H * 156; idx += kGenBuildThreads)
+        mo[idx] = (idx < 169) ? sm.Apow[169 + idx] : sm.Bd[idx - 169];
     }
     // zero B_qp (upper blocks stay zero)
     for (int idx = tid; idx < s * n / 2; idx += kGenBuildThreads)

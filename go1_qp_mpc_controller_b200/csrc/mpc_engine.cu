@@ -16,6 +16,7 @@
 #include "gen_kernels.cuh"
 #include "mpc_kernels.cuh"
 #include "prep_kernel.cuh"
+#include "riccati_kernel.cuh"
 #include "torque_map.cuh"
 
 using namespace mpcb200;
@@ -55,6 +56,8 @@ struct MpcEngine {
   MpcTorqueOut* d_tout = nullptr;
   int torque_capacity = 0;
   bool torque_on = false;
+  double* d_model = nullptr;      // structured solver: A_d | B_d list per problem (169 + 156 H doubles)
+  bool structured = false;        // solve through the Riccati recursion instead of the dense inverse
   MpcGaitIn* d_gait = nullptr;    // gait scheduler records of the loaded states (gait_aware engines)
   int gait_capacity = 0;
   bool gait_on = false;
@@ -142,6 +145,8 @@ void free_buffers(MpcEngine* e) {
   cudaFree(e->d_bstates);
   cudaFree(e->d_P);
   cudaFree(e->d_q);
+  cudaFree(e->d_model);
+  e->d_model = nullptr;
   cudaFree(e->d_Pb);
   cudaFree(e->d_qb);
   cudaFree(e->d_l);
@@ -172,6 +177,7 @@ int reserve(MpcEngine* e, int n) {
     CUDA_TRY(e, cudaMalloc(&e->d_l, size_t(cap) * e->ncon() * sizeof(float)));
     CUDA_TRY(e, cudaMalloc(&e->d_u, size_t(cap) * e->ncon() * sizeof(float)));
     CUDA_TRY(e, cudaMalloc(&e->d_x, size_t(cap) * e->nvar() * sizeof(float)));
+    if (e->structured) CUDA_TRY(e, cudaMalloc(&e->d_model, size_t(cap) * (169 + 156 * e->H) * sizeof(double)));
   } else {
     CUDA_TRY(e, cudaMalloc(&e->d_bstates, size_t(cap) * sizeof(BalanceStateIn)));
     CUDA_TRY(e, cudaMalloc(&e->d_Pb, size_t(cap) * 144 * sizeof(float)));
@@ -185,15 +191,15 @@ int reserve(MpcEngine* e, int n) {
 }
 
 int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n, double* P, double* q,
-                 float* l, float* u) {
+                 float* l, float* u, double* model_out = nullptr) {
   if (e->H == kH) {
     const int grid = n < e->num_sms * 8 ? n : e->num_sms * 8;
     qp_build_kernel<<<grid, kBuildThreads, sizeof(BuildSmem), e->stream>>>(d_states, d_states ? e->d_gait : nullptr, model, n,
-                                                                      P, q, l, u, e->bp);
+                                                                      model_out, P, q, l, u, e->bp);
   } else {
     const int grid = n < e->num_sms ? n : e->num_sms;
     gen_build_kernel<30><<<grid, kGenBuildThreads, sizeof(GenBuildSmem<30>), e->stream>>>(
-        d_states, model, n, P, q, l, u, e->d_workspace, e->bp);
+        d_states, model, n, model_out, P, q, l, u, e->d_workspace, e->bp);
   }
   ++e->launches;
   CUDA_TRY(e, cudaGetLastError());
@@ -206,6 +212,27 @@ int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l,
   const MpcTorqueIn* tin = (with_torque && d_states) ? e->d_tin : nullptr;
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
   const int grid = n < e->num_sms ? n : e->num_sms;
+  if (e->structured && !warm && P == e->d_P) {
+    // Riccati-structured ADMM (riccati_kernel.cuh): any horizon, one CTA of 128 threads per problem
+    if (e->H == kH) {
+      const int g = n < e->num_sms * 3 ? n : e->num_sms * 3;
+      riccati_solve_kernel<kH><<<g, kRicThreads, sizeof(RicSmem<kH>), e->stream>>>(
+          P, e->p_stride(), kNP, q, l, u, e->d_model, d_states, res, x, n, e->d_counter, e->bp, e->sp);
+    } else {
+      const int g = n < e->num_sms ? n : e->num_sms;
+      riccati_solve_kernel<30><<<g, kRicThreads, sizeof(RicSmem<30>), e->stream>>>(
+          P, e->p_stride(), e->nvar(), q, l, u, e->d_model, d_states, res, x, n, e->d_counter, e->bp, e->sp);
+    }
+    ++e->launches;
+    CUDA_TRY(e, cudaGetLastError());
+    if (tin) {
+      torque_map_kernel<<<(4 * n + 127) / 128, 128, 0, e->stream>>>(
+          res, reinterpret_cast<const float*>(d_states), int(sizeof(MpcStateIn) / 4), kOffContacts, tin, e->d_tout, n);
+      ++e->launches;
+      CUDA_TRY(e, cudaGetLastError());
+    }
+    return MPC_OK;
+  }
   if (warm)
     admm_solve_kernel<false, true><<<grid, kSolveThreads, sizeof(SolveSmem), e->stream>>>(
         P, q, l, u, d_states, res, x, n, e->d_counter, nullptr, warm, tin, e->d_tout, e->sp);
@@ -258,26 +285,22 @@ int create_common(int kind, int device, MpcEngine** out) {
   e->num_sms = num_sms;
   cudaError_t crc = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
   if (crc == cudaSuccess) crc = cudaMalloc(&e->d_counter, sizeof(int));
-  if (crc == cudaSuccess)
-    crc = cudaFuncSetAttribute(qp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(BuildSmem));
-  if (crc == cudaSuccess)
-    crc = cudaFuncSetAttribute(admm_solve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(SolveSmem));
-  if (crc == cudaSuccess)
-    crc = cudaFuncSetAttribute(admm_solve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(SolveSmem));
-  if (crc == cudaSuccess)
-    crc = cudaFuncSetAttribute(admm_solve_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(SolveSmem));
-  if (crc == cudaSuccess)
-    crc = cudaFuncSetAttribute(gen_build_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(GenBuildSmem<30>));
-  if (crc == cudaSuccess)
-    crc = cudaFuncSetAttribute(gen_solve_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(GenSolveSmem<30>));
+  const char* what = "stream / counter";
+  auto opt_in = [&](const void* fn, size_t bytes, const char* name) {
+    if (crc != cudaSuccess) return;
+    crc = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (crc != cudaSuccess) what = name;
+  };
+  opt_in((const void*)qp_build_kernel, sizeof(BuildSmem), "qp_build_kernel shared memory");
+  opt_in((const void*)admm_solve_kernel<false, false>, sizeof(SolveSmem), "admm_solve_kernel shared memory");
+  opt_in((const void*)admm_solve_kernel<true, false>, sizeof(SolveSmem), "admm_solve_kernel (profile) shared memory");
+  opt_in((const void*)admm_solve_kernel<false, true>, sizeof(SolveSmem), "admm_solve_kernel (warm) shared memory");
+  opt_in((const void*)riccati_solve_kernel<kH>, sizeof(RicSmem<kH>), "riccati_solve_kernel<10> shared memory");
+  opt_in((const void*)riccati_solve_kernel<30>, sizeof(RicSmem<30>), "riccati_solve_kernel<30> shared memory");
+  opt_in((const void*)gen_build_kernel<30>, sizeof(GenBuildSmem<30>), "gen_build_kernel<30> shared memory");
+  opt_in((const void*)gen_solve_kernel<30>, sizeof(GenSolveSmem<30>), "gen_solve_kernel<30> shared memory");
   if (crc != cudaSuccess) {
-    std::string msg = std::string("engine setup: ") + cudaGetErrorString(crc);
+    std::string msg = std::string("engine setup (") + what + "): " + cudaGetErrorString(crc);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     cudaFree(e->d_counter);
     delete e;
@@ -329,6 +352,7 @@ int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
   e->bp.exact_discretization = cfg->exact_discretization != 0;
   e->bp.foot_drift = cfg->foot_drift != 0;
   e->bp.gait_aware = cfg->gait_aware != 0;
+  e->structured = cfg->structured_solver != 0;
   e->sp = make_solve_params(cfg->osqp, cfg->mu);
   *out = e;
   return MPC_OK;
@@ -449,7 +473,7 @@ int mpc_build_qp_async(MpcEngine* e) {
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->n > 0) {
     ModelIn none{};
-    int rc = launch_build(e, e->d_states, none, e->n, e->d_P, e->d_q, e->d_l, e->d_u);
+    int rc = launch_build(e, e->d_states, none, e->n, e->d_P, e->d_q, e->d_l, e->d_u, e->structured ? e->d_model : nullptr);
     if (rc) return rc;
   }
   e->built = true;

@@ -84,7 +84,7 @@ struct ModelIn {
 
 __global__ void __launch_bounds__(kBuildThreads, 2)
 qp_build_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __restrict__ gait, ModelIn model, int num,
-                double* __restrict__ P_out,
+                double* __restrict__ model_out, double* __restrict__ P_out,
                 double* __restrict__ q_out, float* __restrict__ l_out, float* __restrict__ u_out,
                 const __grid_constant__ BuildParams bp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -269,6 +269,12 @@ qp_build_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __restri
         sm.Apow[(i + 1) * 169 + tid] = s;
       }
       __syncthreads();
+    }
+    if (model_out != nullptr) {
+      // A_d and the B_d list for the structured (Riccati) solver
+      double* mo = model_out + size_t(p) * (169 + kH * 156);
+      for (int idx = tid; idx < 169 + kH * 156; idx += kBuildThreads)
+        mo[idx] = (idx < 169) ? sm.Apow[169 + idx] : sm.Bd[idx - 169];
     }
     // ---- K2: the condensed Hessian WITHOUT materialising B_qp (ConvexMpc.cpp:185-217).
     // B_qp block (i, j) = A_d^(i-j) B_d(j) for i >= j, so with S_j = sum_{m <= H-1-j} (A^m)' Q A^m

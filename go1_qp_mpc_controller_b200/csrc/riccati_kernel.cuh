@@ -1,0 +1,601 @@
+// Structured ADMM solve of the condensed MPC QP (any horizon H): the same OSQP iteration as
+// admm_kernel.cuh (Ruiz equilibration, per-row rho, K x~ = sigma x - q + A'(rho z - y), relaxation,
+// residual termination every check_termination iterations, rho adaptation with refactorisation;
+// OSQP 0.6.x as driven by A1RobotControl.cpp:522-561), but the linear system is never formed:
+//
+//   K = c D (R + B_qp' Q B_qp) D + sigma I + A' diag(rho) A
+//
+// is the Hessian of a finite-horizon LQR problem (states X_k+1 = A_d X_k + Bs_k u_k from X_0 = 0,
+// Bs_k = B_d(k) diag(D_k), stage cost c Q on X_k+1, input cost Dk = c D R D + sigma I + G_k), so
+// K x~ = r is solved EXACTLY by a Riccati recursion:
+//   factor (once per rho):  Pi_H = cQ;  M_k = Dk + Bs' Pi_k+1 Bs,  K_k = M_k^-1 Bs' Pi_k+1 A,
+//                           L_k = A - Bs K_k,  Pi_k = cQ + A' Pi_k+1 L_k                 O(H 13^3)
+//   solve (per iteration):  p_k = L_k' p_k+1 + K_k' r_k  (backward),  g_k = -M_k^-1 (Bs' p_k+1 - r_k),
+//                           X_k+1 = L_k X_k + Bs g_k (forward),  u_k = -K_k X_k + g_k     O(H 13^2)
+// against n^3 / n^2 for the dense inverse.  For H = 30 that is 1/40 of the flops and, decisive on
+// this machine, 110 KB of per-step gains in shared memory instead of a 1.04 MB inverse streamed
+// from L2 every iteration.  P x for the residuals is the same structure without feedback.  The
+// explicit Hessian (from the build kernel, in HBM) is only read by the Ruiz passes.
+//
+// One CTA of 128 threads per problem (problems pulled from an atomic counter); the two
+// recursions run on 13 lanes of warp 0, everything else is one-output-per-thread phases.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mpc_kernels.cuh"
+
+namespace mpcb200 {
+
+constexpr int kRicThreads = 128;
+
+template <int H>
+struct RicSmem {
+  static constexpr int n = 12 * H, m = 20 * H;
+  double A[169];
+  double Bs[H][156];   // scaled input matrices Bs_k = B_d(k) diag(D_k), 13 x 12 row-major
+  double Kk[H][156];   // gains, 12 x 13
+  double Lk[H][169];   // closed loop A - Bs K, 13 x 13
+  double Mi[H][144];   // M_k^-1, 12 x 12
+  double Pi[169], W1[169], W2[169], W3[156], W4[156], Mm[144];  // factor scratch
+  double x[n], xt[n], rhs[n], qb[n], Dv[n], Px[n];  // xt doubles as the new-D scratch of the Ruiz passes
+  double z[m], y[m], rv[m], cca[m], ccz[m], Ev[m];
+  float lb[m], ub[m];  // UNSCALED bounds exactly as given; scaled by E (f64) where they are used
+  double pv[(H + 1) * 13], Xv[(H + 1) * 13], tv[H * 13], gv[H * 12], wv[H * 12];
+  double red[16 * 4];
+  double scal[8];  // 0:c 1:cinv 2:rho 4:pri_res
+  int flags[8];    // 0:done 1:status 2:refactor 3:problem index
+};
+
+__device__ __forceinline__ double ric_limit_scaling(double v) {
+  v = v < 1e-4 ? 1.0 : v;
+  return v > 1e4 ? 1e4 : v;
+}
+
+// block-wide max or sum of one value per thread (128 threads); result to every thread
+template <bool kMax>
+__device__ __forceinline__ double ric_block_reduce(double v, double* red, int slot) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = kMax ? fmax(v, t) : v + t;
+  }
+  if ((threadIdx.x & 31) == 0) red[slot * 4 + (threadIdx.x >> 5)] = v;
+  __syncthreads();
+  const double a = red[slot * 4], b = red[slot * 4 + 1], c = red[slot * 4 + 2], d = red[slot * 4 + 3];
+  return kMax ? fmax(fmax(a, b), fmax(c, d)) : (a + b) + (c + d);
+}
+
+template <int H>
+__global__ void __launch_bounds__(kRicThreads)
+riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_row_stride,
+                     const double* __restrict__ q_all, const float* __restrict__ l_all,
+                     const float* __restrict__ u_all, const double* __restrict__ model_all,
+                     const MpcStateIn* __restrict__ states, MpcResult* __restrict__ results,
+                     float* __restrict__ x_all, int num, int* __restrict__ counter,
+                     const __grid_constant__ BuildParams bp, const __grid_constant__ SolveParams sp) {
+  constexpr int n = 12 * H, m = 20 * H;
+  extern __shared__ __align__(16) unsigned char ric_smem_raw[];
+  RicSmem<H>& sm = *reinterpret_cast<RicSmem<H>*>(ric_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double sigma = sp.sigma, alpha = sp.alpha, mu = sp.mu;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sm.flags[3] = atomicAdd(counter, 1);
+    __syncthreads();
+    const int p = sm.flags[3];
+    if (p >= num) break;
+    const double* Pg = P_all + size_t(p) * p_stride;
+    const double* model = model_all + size_t(p) * (169 + H * 156);
+
+    // ---- load: A_d, bounds, gradient ----
+    for (int i = tid; i < 169; i += kRicThreads) sm.A[i] = model[i];
+    for (int i = tid; i < n; i += kRicThreads) {
+      sm.Dv[i] = 1.0;
+      sm.x[i] = 0.0;
+    }
+    for (int i = tid; i < m; i += kRicThreads) {
+      sm.Ev[i] = 1.0;
+      sm.z[i] = 0.0;
+      sm.y[i] = 0.0;
+    }
+    if (tid == 0) {
+      sm.scal[0] = 1.0;
+      sm.scal[2] = sp.rho;
+      sm.flags[0] = 0;
+      sm.flags[1] = MPC_STATUS_UNSOLVED;
+    }
+    __syncthreads();
+
+    // ---- modified Ruiz equilibration (osqp scaling.c scale_data), P read from global ----
+    double c_run = 1.0;
+    // row norms of the scaled Hessian, max_j |P_rj| D_j (its column norms, by symmetry): warp per row
+    auto p_row_norms = [&](bool accumulate, double& psum, double& qmax) {
+      for (int r = warp; r < n; r += kRicThreads / 32) {
+        const double* row = Pg + size_t(r) * p_row_stride;
+        double mx = 0.0;
+        for (int j = lane; j < n; j += 32) mx = fmax(mx, fabs(row[j]) * sm.Dv[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) {
+          const double v = c_run * sm.Dv[r] * mx;
+          sm.Px[r] = v;
+          if (accumulate) {
+            psum += v;
+            qmax = fmax(qmax, fabs(c_run * sm.Dv[r] * q_all[size_t(p) * n + r]));
+          }
+        }
+      }
+    };
+    if (sp.scaling > 0) {
+      double dummy_s = 0.0, dummy_q = 0.0;
+      p_row_norms(false, dummy_s, dummy_q);  // c = 1, D = 1
+      __syncthreads();
+      for (int it = 0; it < sp.scaling; ++it) {
+        // new D from the column norms of [P; A] (old E), new E from the row norms of A (old D)
+        for (int j = tid; j < n; j += kRicThreads) {
+          const int ls = j / 3, vc = j - 3 * ls;
+          const double* Er = &sm.Ev[5 * ls];
+          double nA;
+          if (vc == 0) nA = fmax(Er[0], Er[1]);
+          else if (vc == 1) nA = fmax(Er[2], Er[3]);
+          else nA = fmax(mu * fmax(fmax(Er[0], Er[1]), fmax(Er[2], Er[3])), Er[4]);
+          nA *= sm.Dv[j];
+          sm.xt[j] = sm.Dv[j] * rsqrt(ric_limit_scaling(fmax(sm.Px[j], nA)));
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += kRicThreads) {
+          const int ls = i / 5, pos = i - 5 * ls;
+          const double Dx = sm.Dv[3 * ls], Dy = sm.Dv[3 * ls + 1], Dz = sm.Dv[3 * ls + 2];
+          const double nrow = (pos == 4) ? Dz : fmax((pos < 2) ? Dx : Dy, mu * Dz);
+          const double E = sm.Ev[i];
+          sm.Ev[i] = E * rsqrt(ric_limit_scaling(E * nrow));
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += kRicThreads) sm.Dv[j] = sm.xt[j];
+        __syncthreads();
+        // cost normalisation with the new D and the old c
+        double psum = 0.0, qmax = 0.0;
+        p_row_norms(true, psum, qmax);
+        const double s_all = ric_block_reduce<false>(psum, sm.red, 0);
+        const double q_all_max = ric_block_reduce<true>(qmax, sm.red, 1);
+        const double ct = 1.0 / ric_limit_scaling(fmax(s_all / (double)n, ric_limit_scaling(q_all_max)));
+        c_run *= ct;
+        for (int j = tid; j < n; j += kRicThreads) sm.Px[j] *= ct;  // norms under the new c
+        __syncthreads();
+      }
+    }
+    const double c = c_run, cinv = 1.0 / c_run;
+    // ---- scaled data ----
+    for (int j = tid; j < n; j += kRicThreads) sm.qb[j] = c * sm.Dv[j] * q_all[size_t(p) * n + j];
+    for (int i = tid; i < m; i += kRicThreads) {
+      const int ls = i / 5, pos = i - 5 * ls;
+      const double E = sm.Ev[i];
+      const double lo = (double)l_all[size_t(p) * m + i] * E, hi = (double)u_all[size_t(p) * m + i] * E;
+      sm.lb[i] = l_all[size_t(p) * m + i];
+      sm.ub[i] = u_all[size_t(p) * m + i];
+      const double Dlat = sm.Dv[3 * ls + ((pos < 2) ? 0 : 1)], Dz = sm.Dv[3 * ls + 2];
+      sm.cca[i] = (pos == 4) ? 0.0 : E * Dlat;
+      sm.ccz[i] = (pos == 4) ? E * Dz : ((pos & 1) ? -mu : mu) * E * Dz;
+      int ctype = 0;
+      if (lo < -MPC_INFTY * 1e-4 && hi > MPC_INFTY * 1e-4) ctype = -1;
+      else if (hi - lo < 1e-4) ctype = 1;
+      const double rv = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * sp.rho : sp.rho;
+      sm.rv[i] = rv;
+      // the constraint type is re-derived from the bounds at every rho update (same test)
+    }
+    for (int idx = tid; idx < H * 156; idx += kRicThreads) {
+      const int k = idx / 156, e = idx - 156 * k, a = e % 12;
+      sm.Bs[k][e] = model[169 + idx] * sm.Dv[12 * k + a];
+    }
+    for (int j = tid; j < n; j += kRicThreads) sm.rhs[j] = -sm.qb[j];  // iteration 1: x = z = y = 0
+    __syncthreads();
+
+    int iter = 0, rho_updates = 0, status = MPC_STATUS_UNSOLVED;
+    double pri_res_out = 0.0;
+    int until_check = sp.check_termination > 0 ? sp.check_termination : 0x7fffffff;
+    int until_adapt = (sp.adaptive_rho && sp.adaptive_rho_interval > 0) ? sp.adaptive_rho_interval : 0x7fffffff;
+    bool need_factor = true;
+    for (iter = 1; iter <= sp.max_iter; ++iter) {
+      if (need_factor) {
+        need_factor = false;
+        // ---- Riccati factorisation ----
+        for (int i = tid; i < 169; i += kRicThreads) sm.Pi[i] = (i / 13 == i % 13) ? c * bp.Qd[i / 13] : 0.0;
+        __syncthreads();
+        for (int k = H - 1; k >= 0; --k) {
+          const double* Bk = sm.Bs[k];
+          // W3 = Bs' Pi (12 x 13)
+          for (int idx = tid; idx < 156; idx += kRicThreads) {
+            const int a = idx / 13, j = idx - 13 * a;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 13; ++i) s = fma(Bk[i * 12 + a], sm.Pi[i * 13 + j], s);
+            sm.W3[idx] = s;
+          }
+          __syncthreads();
+          // Mm = Dk + W3 Bs (12 x 12) ; W4 = W3 A (12 x 13)
+          for (int idx = tid; idx < 144 + 156; idx += kRicThreads) {
+            if (idx < 144) {
+              const int a = idx / 12, b = idx - 12 * a;
+              double s = 0.0;
+#pragma unroll
+              for (int i = 0; i < 13; ++i) s = fma(sm.W3[a * 13 + i], Bk[i * 12 + b], s);
+              // input cost block: c D R D + sigma on the diagonal, G = A' rho A per leg (3 x 3)
+              if (a / 3 == b / 3) {
+                const int ls = 4 * k + a / 3, ra = a % 3, rb = b % 3;
+                const double* r_ = &sm.rv[5 * ls];
+                const double* ca = &sm.cca[5 * ls];
+                const double* cz = &sm.ccz[5 * ls];
+                double gsum = 0.0;
+                // rows 0,1 touch (x, z); rows 2,3 touch (y, z); row 4 touches z
+#pragma unroll
+                for (int rw = 0; rw < 5; ++rw) {
+                  const double fa = (rw < 2) ? ((ra == 0) ? ca[rw] : (ra == 2) ? cz[rw] : 0.0)
+                                   : (rw < 4) ? ((ra == 1) ? ca[rw] : (ra == 2) ? cz[rw] : 0.0)
+                                              : ((ra == 2) ? cz[rw] : 0.0);
+                  const double fb = (rw < 2) ? ((rb == 0) ? ca[rw] : (rb == 2) ? cz[rw] : 0.0)
+                                   : (rw < 4) ? ((rb == 1) ? ca[rw] : (rb == 2) ? cz[rw] : 0.0)
+                                              : ((rb == 2) ? cz[rw] : 0.0);
+                  gsum = fma(r_[rw] * fa, fb, gsum);
+                }
+                s += gsum;
+                if (a == b) {
+                  const double d = sm.Dv[12 * k + a];
+                  s += c * d * bp.Rd[a] * d + sigma;
+                }
+              }
+              sm.Mm[idx] = s;
+            } else {
+              const int e = idx - 144, a = e / 13, j = e - 13 * a;
+              double s = 0.0;
+#pragma unroll
+              for (int i = 0; i < 13; ++i) s = fma(sm.W3[a * 13 + i], sm.A[i * 13 + j], s);
+              sm.W4[e] = s;
+            }
+          }
+          __syncthreads();
+          // Mi = Mm^-1: Gauss-Jordan sweep on the SPD 12 x 12 block, warp 0 (lane = row)
+          if (warp == 0) {
+            double* Mk = sm.Mi[k];
+            for (int i = lane; i < 144; i += 32) Mk[i] = sm.Mm[i];
+            __syncwarp();
+            for (int pv_ = 0; pv_ < 12; ++pv_) {
+              const double d = 1.0 / Mk[pv_ * 12 + pv_];
+              __syncwarp();
+              double rowp[12];
+              if (lane < 12) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) rowp[j] = Mk[pv_ * 12 + j];
+              }
+              __syncwarp();
+              if (lane < 12) {
+                const int r = lane;
+                if (r == pv_) {
+#pragma unroll
+                  for (int j = 0; j < 12; ++j) Mk[r * 12 + j] = (j == pv_) ? d : rowp[j] * d;
+                } else {
+                  const double f = Mk[r * 12 + pv_] * d;
+#pragma unroll
+                  for (int j = 0; j < 12; ++j) Mk[r * 12 + j] = (j == pv_) ? -f : Mk[r * 12 + j] - f * rowp[j];
+                }
+              }
+              __syncwarp();
+            }
+          }
+          __syncthreads();
+          // Kk = Mi W4 (12 x 13)
+          for (int idx = tid; idx < 156; idx += kRicThreads) {
+            const int a = idx / 13, j = idx - 13 * a;
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 12; ++b) s = fma(sm.Mi[k][a * 12 + b], sm.W4[b * 13 + j], s);
+            sm.Kk[k][idx] = s;
+          }
+          __syncthreads();
+          // Lk = A - Bs Kk (13 x 13)
+          for (int idx = tid; idx < 169; idx += kRicThreads) {
+            const int i = idx / 13, j = idx - 13 * i;
+            double s = sm.A[idx];
+#pragma unroll
+            for (int a = 0; a < 12; ++a) s = fma(-Bk[i * 12 + a], sm.Kk[k][a * 13 + j], s);
+            sm.Lk[k][idx] = s;
+          }
+          __syncthreads();
+          // W1 = Pi Lk ; then Pi <- sym(cQ + A' W1)
+          for (int idx = tid; idx < 169; idx += kRicThreads) {
+            const int i = idx / 13, j = idx - 13 * i;
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < 13; ++t) s = fma(sm.Pi[i * 13 + t], sm.Lk[k][t * 13 + j], s);
+            sm.W1[idx] = s;
+          }
+          __syncthreads();
+          for (int idx = tid; idx < 169; idx += kRicThreads) {
+            const int i = idx / 13, j = idx - 13 * i;
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < 13; ++t) s = fma(sm.A[t * 13 + i], sm.W1[t * 13 + j], s);
+            sm.W2[idx] = s;
+          }
+          __syncthreads();
+          for (int idx = tid; idx < 169; idx += kRicThreads) {
+            const int i = idx / 13, j = idx - 13 * i;
+            sm.Pi[idx] = 0.5 * (sm.W2[idx] + sm.W2[j * 13 + i]) + ((i == j) ? c * bp.Qd[i] : 0.0);
+          }
+          __syncthreads();
+        }
+      }
+      // ---- x~ = K^-1 rhs by the two recursions ----
+      for (int idx = tid; idx < H * 13; idx += kRicThreads) {  // t_k = K_k' r_k
+        const int k = idx / 13, i = idx - 13 * k;
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 12; ++a) s = fma(sm.Kk[k][a * 13 + i], sm.rhs[12 * k + a], s);
+        sm.tv[idx] = s;
+      }
+      if (tid < 13) sm.pv[H * 13 + tid] = 0.0;
+      __syncthreads();
+      if (warp == 0) {
+        for (int k = H - 1; k >= 0; --k) {  // p_k = L_k' p_k+1 + t_k
+          double s0 = 0.0, s1 = 0.0;
+          if (lane < 13) {
+            const double* L = sm.Lk[k];
+            const double* pn = &sm.pv[(k + 1) * 13];
+#pragma unroll
+            for (int j = 0; j < 12; j += 2) {
+              s0 = fma(L[j * 13 + lane], pn[j], s0);
+              s1 = fma(L[(j + 1) * 13 + lane], pn[j + 1], s1);
+            }
+            s0 = fma(L[12 * 13 + lane], pn[12], s0);
+            sm.pv[k * 13 + lane] = s0 + s1 + sm.tv[k * 13 + lane];
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < H * 12; idx += kRicThreads) {  // w_k = Bs' p_k+1 - r_k
+        const int k = idx / 12, a = idx - 12 * k;
+        double s = -sm.rhs[idx];
+#pragma unroll
+        for (int i = 0; i < 13; ++i) s = fma(sm.Bs[k][i * 12 + a], sm.pv[(k + 1) * 13 + i], s);
+        sm.wv[idx] = s;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < H * 12; idx += kRicThreads) {  // g_k = -M_k^-1 w_k
+        const int k = idx / 12, a = idx - 12 * k;
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < 12; ++b) s = fma(sm.Mi[k][a * 12 + b], sm.wv[12 * k + b], s);
+        sm.gv[idx] = -s;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < H * 13; idx += kRicThreads) {  // b_k = Bs g_k (into tv)
+        const int k = idx / 13, i = idx - 13 * k;
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 12; ++a) s = fma(sm.Bs[k][i * 12 + a], sm.gv[12 * k + a], s);
+        sm.tv[idx] = s;
+      }
+      if (tid < 13) sm.Xv[tid] = 0.0;
+      __syncthreads();
+      if (warp == 0) {
+        for (int k = 0; k < H; ++k) {  // X_k+1 = L_k X_k + b_k
+          double s0 = 0.0, s1 = 0.0;
+          if (lane < 13) {
+            const double* L = &sm.Lk[k][lane * 13];
+            const double* Xk = &sm.Xv[k * 13];
+#pragma unroll
+            for (int j = 0; j < 12; j += 2) {
+              s0 = fma(L[j], Xk[j], s0);
+              s1 = fma(L[j + 1], Xk[j + 1], s1);
+            }
+            s0 = fma(L[12], Xk[12], s0);
+            sm.Xv[(k + 1) * 13 + lane] = s0 + s1 + sm.tv[k * 13 + lane];
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      // x~_k = -K_k X_k + g_k ; x <- alpha x~ + (1 - alpha) x
+      for (int idx = tid; idx < n; idx += kRicThreads) {
+        const int k = idx / 12, a = idx - 12 * k;
+        double s = sm.gv[idx];
+#pragma unroll
+        for (int i = 0; i < 13; ++i) s = fma(-sm.Kk[k][a * 13 + i], sm.Xv[k * 13 + i], s);
+        sm.xt[idx] = s;
+        sm.x[idx] = alpha * s + (1.0 - alpha) * sm.x[idx];
+      }
+      __syncthreads();
+      // z~ = A x~ ; z, y updates
+      for (int i = tid; i < m; i += kRicThreads) {
+        const int ls = i / 5, pos = i - 5 * ls;
+        const double xl = sm.xt[3 * ls + ((pos < 2) ? 0 : 1)], xz = sm.xt[3 * ls + 2];
+        const double zt = sm.cca[i] * xl + sm.ccz[i] * xz;
+        const double zr = alpha * zt + (1.0 - alpha) * sm.z[i];
+        double zn = zr + (1.0 / sm.rv[i]) * sm.y[i];
+        const double lo = (double)sm.lb[i] * sm.Ev[i], hi = (double)sm.ub[i] * sm.Ev[i];
+        zn = (zn < lo) ? lo : zn;
+        zn = (zn > hi) ? hi : zn;
+        sm.y[i] = sm.y[i] + sm.rv[i] * (zr - zn);
+        sm.z[i] = zn;
+      }
+      __syncthreads();
+      // next rhs = sigma x - q + A'(rho z - y)
+      auto build_rhs = [&]() {
+        for (int j = tid; j < n; j += kRicThreads) {
+          const int ls = j / 3, vc = j - 3 * ls;
+          const int r0 = 5 * ls;
+          double s = 0.0;
+          if (vc == 0) {
+            s = sm.cca[r0] * (sm.rv[r0] * sm.z[r0] - sm.y[r0]) + sm.cca[r0 + 1] * (sm.rv[r0 + 1] * sm.z[r0 + 1] - sm.y[r0 + 1]);
+          } else if (vc == 1) {
+            s = sm.cca[r0 + 2] * (sm.rv[r0 + 2] * sm.z[r0 + 2] - sm.y[r0 + 2]) +
+                sm.cca[r0 + 3] * (sm.rv[r0 + 3] * sm.z[r0 + 3] - sm.y[r0 + 3]);
+          } else {
+#pragma unroll
+            for (int rw = 0; rw < 5; ++rw) s = fma(sm.ccz[r0 + rw], sm.rv[r0 + rw] * sm.z[r0 + rw] - sm.y[r0 + rw], s);
+          }
+          sm.rhs[j] = sigma * sm.x[j] - sm.qb[j] + s;
+        }
+      };
+      build_rhs();
+      const bool can_check = (--until_check == 0);
+      const bool can_adapt = (--until_adapt == 0);
+      if (can_check) until_check = sp.check_termination;
+      if (can_adapt) until_adapt = sp.adaptive_rho_interval;
+      const bool last = (iter == sp.max_iter);
+      __syncthreads();
+      if (!(can_check || can_adapt || last)) continue;
+
+      // ---- residuals: P x through the open-loop recursions ----
+      for (int idx = tid; idx < H * 13; idx += kRicThreads) {  // Bs x_k
+        const int k = idx / 13, i = idx - 13 * k;
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 12; ++a) s = fma(sm.Bs[k][i * 12 + a], sm.x[12 * k + a], s);
+        sm.tv[idx] = s;
+      }
+      if (tid < 13) { sm.Xv[tid] = 0.0; sm.pv[H * 13 + tid] = 0.0; }
+      __syncthreads();
+      if (warp == 0) {
+        for (int k = 0; k < H; ++k) {  // X_k+1 = A X_k + Bs x_k
+          double s = 0.0;
+          if (lane < 13) {
+#pragma unroll
+            for (int j = 0; j < 13; ++j) s = fma(sm.A[lane * 13 + j], sm.Xv[k * 13 + j], s);
+            sm.Xv[(k + 1) * 13 + lane] = s + sm.tv[k * 13 + lane];
+          }
+          __syncwarp();
+        }
+        for (int k = H - 1; k >= 0; --k) {  // mu_k+1 = cQ X_k+1 + A' mu_k+2  (stored in pv[k+1])
+          double s = 0.0;
+          if (lane < 13) {
+            if (k < H - 1) {
+#pragma unroll
+              for (int j = 0; j < 13; ++j) s = fma(sm.A[j * 13 + lane], sm.pv[(k + 2) * 13 + j], s);
+            }
+            sm.pv[(k + 1) * 13 + lane] = s + c * bp.Qd[lane] * sm.Xv[(k + 1) * 13 + lane];
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      double v[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) v[i] = 0.0;
+      for (int idx = tid; idx < n; idx += kRicThreads) {
+        const int k = idx / 12, a = idx - 12 * k, ls = idx / 3, vc = idx - 3 * ls, r0 = 5 * ls;
+        const double d = sm.Dv[idx];
+        double px = c * d * bp.Rd[a] * d * sm.x[idx];
+#pragma unroll
+        for (int i = 0; i < 13; ++i) px = fma(sm.Bs[k][i * 12 + a], sm.pv[(k + 1) * 13 + i], px);
+        double aty;
+        if (vc == 0) aty = sm.cca[r0] * sm.y[r0] + sm.cca[r0 + 1] * sm.y[r0 + 1];
+        else if (vc == 1) aty = sm.cca[r0 + 2] * sm.y[r0 + 2] + sm.cca[r0 + 3] * sm.y[r0 + 3];
+        else {
+          aty = 0.0;
+#pragma unroll
+          for (int rw = 0; rw < 5; ++rw) aty = fma(sm.ccz[r0 + rw], sm.y[r0 + rw], aty);
+        }
+        const double qb = sm.qb[idx], dinv = 1.0 / d;
+        const double rd = px + qb + aty;
+        v[6] = fmax(v[6], fabs(rd));
+        v[7] = fmax(v[7], fabs(dinv * rd));
+        v[8] = fmax(v[8], fmax(fmax(fabs(dinv * qb), fabs(dinv * aty)), fabs(dinv * px)));
+        v[9] = fmax(v[9], fmax(fmax(fabs(qb), fabs(aty)), fabs(px)));
+      }
+      for (int i = tid; i < m; i += kRicThreads) {
+        const int ls = i / 5, pos = i - 5 * ls;
+        const double xl = sm.x[3 * ls + ((pos < 2) ? 0 : 1)], xz = sm.x[3 * ls + 2];
+        const double Ax = sm.cca[i] * xl + sm.ccz[i] * xz, zz = sm.z[i], einv = 1.0 / sm.Ev[i];
+        const double rp = Ax - zz;
+        v[0] = fmax(v[0], fabs(rp));
+        v[1] = fmax(v[1], fabs(einv * rp));
+        v[2] = fmax(v[2], fabs(einv * zz));
+        v[3] = fmax(v[3], fabs(einv * Ax));
+        v[4] = fmax(v[4], fabs(zz));
+        v[5] = fmax(v[5], fabs(Ax));
+      }
+      double mres[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) mres[i] = ric_block_reduce<true>(v[i], sm.red, i);
+      if (tid == 0) {
+        const double pri = mres[1], dua = cinv * mres[7];
+        const double eps_pri = sp.eps_abs + sp.eps_rel * fmax(mres[2], mres[3]);
+        const double eps_dua = sp.eps_abs + sp.eps_rel * cinv * mres[8];
+        sm.scal[4] = pri;
+        int done = 0, refactor = 0;
+        if ((can_check || last) && pri < eps_pri && dua < eps_dua) {
+          done = 1;
+          sm.flags[1] = MPC_STATUS_SOLVED;
+        } else if (last) {
+          done = 1;
+          sm.flags[1] = (pri < 10.0 * eps_pri && dua < 10.0 * eps_dua) ? 2 : MPC_STATUS_MAX_ITER_REACHED;
+        } else if (can_adapt) {
+          const double rho_c = sm.scal[2];
+          const double pn = mres[0] / (fmax(mres[4], mres[5]) + 1e-10);
+          const double dn = mres[6] / (mres[9] + 1e-10);
+          double rho_new = rho_c * sqrt(pn / (dn + 1e-10));
+          rho_new = fmin(fmax(rho_new, 1e-6), 1e6);
+          if (rho_new > rho_c * sp.adaptive_rho_tolerance || rho_new < rho_c / sp.adaptive_rho_tolerance) {
+            sm.scal[2] = rho_new;
+            refactor = 1;
+          }
+        }
+        sm.flags[0] = done;
+        sm.flags[2] = refactor;
+      }
+      __syncthreads();
+      if (sm.flags[0]) {
+        status = sm.flags[1];
+        pri_res_out = sm.scal[4];
+        break;
+      }
+      if (sm.flags[2]) {
+        ++rho_updates;
+        const double rho = sm.scal[2];
+        for (int i = tid; i < m; i += kRicThreads) {
+          const double lo = (double)sm.lb[i] * sm.Ev[i], hi = (double)sm.ub[i] * sm.Ev[i];
+          int ctype = 0;
+          if (lo < -MPC_INFTY * 1e-4 && hi > MPC_INFTY * 1e-4) ctype = -1;
+          else if (hi - lo < 1e-4) ctype = 1;
+          const double rvn = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * rho : rho;
+          sm.rv[i] = rvn;
+        }
+        __syncthreads();
+        build_rhs();  // the rhs was built with the old rho vector
+        __syncthreads();
+        need_factor = true;
+      }
+    }
+    if (iter > sp.max_iter) iter = sp.max_iter;
+
+    // ---- unscale, rotate the first step to the body frame, write ----
+    if (x_all != nullptr)
+      for (int j = tid; j < n; j += kRicThreads) x_all[size_t(p) * n + j] = (float)(sm.Dv[j] * sm.x[j]);
+    if (tid < 12) {
+      const int leg = tid / 3, vc = tid - 3 * leg;
+      const double f0 = sm.Dv[3 * leg] * sm.x[3 * leg], f1 = sm.Dv[3 * leg + 1] * sm.x[3 * leg + 1],
+                   f2 = sm.Dv[3 * leg + 2] * sm.x[3 * leg + 2];
+      double g;
+      if (states != nullptr) {
+        const float* R = reinterpret_cast<const float*>(states + p) + kOffRot;
+        g = (double)R[vc] * f0 + (double)R[3 + vc] * f1 + (double)R[6 + vc] * f2;
+      } else {
+        g = (vc == 0) ? f0 : (vc == 1) ? f1 : f2;
+      }
+      const bool bad = isnan(f0) || isnan(f1) || isnan(f2);
+      results[p].grf[tid] = bad ? 0.0f : (float)g;
+    }
+    if (tid == 0) {
+      results[p].status = status;
+      results[p].iters = iter;
+      results[p].rho_updates = rho_updates;
+      results[p].pri_res = (float)pri_res_out;
+    }
+  }
+}
+
+}  // namespace mpcb200

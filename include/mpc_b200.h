@@ -224,7 +224,10 @@ typedef struct MpcConfig {
                                    commented out at A1RobotControl.cpp:504-507 */
   int32_t gait_aware;           /* per-step contacts from the gait counters (mpc_set_gait_inputs)
                                    instead of today's contacts replicated (ConvexMpc.cpp:242-245) */
-  int32_t reserved1;
+  int32_t structured_solver;    /* 0: dense K^-1 in registers (H = 10) / in an L2 workspace (H = 30);
+                                   1: the same ADMM with K x = r solved by a Riccati recursion over the
+                                   horizon (riccati_kernel.cuh) -- same iterates up to rounding; cold
+                                   solves only */
 } MpcConfig;
 
 /* Gait scheduler state of one robot (A1CtrlStates.h:24-28,103; A1RobotControl.cpp:156-164),

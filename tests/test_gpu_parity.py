@@ -690,3 +690,51 @@ def test_stream_slots_survive_growth(pkg, ob):
     assert grf_rel(res["grf"][:n0], warm["grf"]).max() <= TOL_GRF
     assert grf_rel(res["grf"][n0:], cold["grf"]).max() <= TOL_GRF
     e.close()
+
+
+@pytest.mark.parametrize("H,n,seed", [(10, 1024, 1002), (10, 512, 1003), (30, 96, 1004)])
+def test_structured_solver_parity(pkg, ob, H, n, seed):
+    """The Riccati-structured solver (riccati_kernel.cuh): the same ADMM with K x = r solved by a
+    recursion over the horizon instead of the dense inverse.  Same gates as the dense path."""
+    cfg = pkg.config_default()
+    cfg.horizon = H
+    cfg.structured_solver = 1
+    e = pkg.MpcEngine(cfg, 0)
+    st = pkg.generate_states(seed, 0, n)
+    res = e.compute_grf_batch(st)
+    ref = ob.mpc_compute_grf(cfg, st)
+    assert (res["status"] == 1).all() and (ref["status"] == 1).all()
+    assert grf_rel(res["grf"], ref["grf"]).max() <= TOL_GRF
+    assert (res["iters"] == ref["iters"]).mean() >= 0.995
+    assert (res["rho_updates"] == ref["rho_updates"]).mean() >= 0.995
+    # the full primal solution is feasible like the dense one
+    x = e.get_solution(0).astype(np.float64).reshape(-1, 3)
+    assert (np.abs(x[:, 0]) <= cfg.mu * x[:, 2] + TOL_CONE * cfg.fz_max).all()
+    # the torque map runs behind it too
+    tin = pkg.generate_torque_inputs(seed, 0, n)
+    e.load_states(st)
+    e.set_torque_inputs(tin)
+    e.build_qp()
+    e.solve()
+    _check_torques(ob, st, tin, e.get_results(), e.get_torques())
+    e.close()
+
+
+def test_structured_solver_hardware_weights_and_extensions(pkg, ob):
+    cfg = pkg.config_hardware()
+    cfg.structured_solver = 1
+    cfg.exact_discretization = cfg.foot_drift = cfg.gait_aware = 1
+    n = 256
+    st = pkg.generate_states(1002, 0, n)
+    gait = pkg.generate_gait_inputs(1002, 0, n, 0)
+    e = pkg.MpcEngine(cfg, 0)
+    e.load_states(st)
+    e.set_gait_inputs(gait)
+    e.build_qp()
+    e.solve()
+    res = e.get_results()
+    ref = ob.mpc_compute_grf_ext(cfg, st, gait)
+    assert (res["status"] == ref["status"]).all()
+    same = res["iters"] == ref["iters"]
+    assert same.mean() >= 0.98 and grf_rel(res["grf"][same], ref["grf"][same]).max() <= TOL_GRF
+    e.close()
