@@ -28,12 +28,14 @@ constexpr int kKChunk = 26;  // k rows per staged chunk (s = 13 H must be a mult
 template <int H>
 struct GenBuildSmem {
   double Apow[(H + 1) * 169];
-  double Bd[H * 156];
+  alignas(16) double Bd[H * 156];
+  double S[H * 169];   // first C_m = (A^m)' Q A^m, then their running sums
+  double T[H * 156];   // B_j' S_j
   double xref[13 * H];
   double tmp[13 * H];
+  double g[13 * H];
   double x0[16];
-  double tA[kKChunk][64];
-  double tB[kKChunk][64];
+  alignas(16) double scratch[kGenBuildThreads / 32][312];  // per warp: U (13 x 12, padded to 160) and a 12 x 12 block
   float st[48];
   int contacts[4];
 };
@@ -49,7 +51,7 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GenBuildSmem<H>& sm = *reinterpret_cast<GenBuildSmem<H>*>(smem_raw);
   const int tid = threadIdx.x;
-  double* Bq = workspace + size_t(blockIdx.x) * s * n;  // this CTA's B_qp, s x n row-major
+  (void)workspace;  // the build no longer needs scratch in global memory (B_qp is never formed)
 
   for (int p = blockIdx.x; p < num; p += gridDim.x) {
     __syncthreads();
@@ -157,9 +159,6 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
       for (int idx = tid; idx < 169 + H * 156; idx += kGenBuildThreads)
         mo[idx] = (idx < 169) ? sm.Apow[169 + idx] : sm.Bd[idx - 169];
     }
-    // zero B_qp (upper blocks stay zero)
-    for (int idx = tid; idx < s * n / 2; idx += kGenBuildThreads)
-      reinterpret_cast<double2*>(Bq)[idx] = make_double2(0.0, 0.0);
     __syncthreads();
     // A_qp powers (ConvexMpc.cpp:185-191)
     for (int i = 1; i < H; ++i) {
@@ -174,21 +173,18 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
       }
       __syncthreads();
     }
-    // B_qp block (i, j), j <= i: A_d^(i-j) B_d(j) (ConvexMpc.cpp:192-201)
-    for (int idx = tid; idx < (H * (H + 1) / 2) * 156; idx += kGenBuildThreads) {
-      const int blk = idx / 156, e = idx % 156;
-      int i = 0, rem = blk;
-      while (rem > i) { rem -= (i + 1); ++i; }
-      const int j = rem, rr = e / 12, cc = e % 12;
-      const double* Ap = &sm.Apow[(i - j) * 169];
-      const double* Bj = &sm.Bd[j * 156];
+    // Condensed Hessian and gradient WITHOUT B_qp, as in qp_build_kernel (mpc_kernels.cuh):
+    //   block (j, l), j >= l:  T_j (A^(j-l) B_l),  T_j = B_j' S_j,  S_j = sum_{m <= H-1-j} (A^m)' Q A^m
+    //   gradient block j:      B_j' g_j,  g_j = sum_{i >= j} (A^(i-j))' Q (A^(i+1) x0 - x_ref,i)
+    for (int idx = tid; idx < H * 169; idx += kGenBuildThreads) {  // C_m = (A^m)' Q A^m
+      const int mm = idx / 169, e = idx - 169 * mm, ia = e / 13, ib = e - 13 * ia;
+      const double* Am = &sm.Apow[mm * 169];
       double a = 0.0;
 #pragma unroll
-      for (int k = 0; k < 13; ++k) a += Ap[rr * 13 + k] * Bj[k * 12 + cc];
-      Bq[size_t(13 * i + rr) * n + 12 * j + cc] = a;
+      for (int k = 0; k < 13; ++k) a = fma(Am[k * 13 + ia] * bp.Qd[k], Am[k * 13 + ib], a);
+      sm.S[idx] = a;
     }
-    // tmp = Q (A_qp x0 - x_ref)
-    for (int idx = tid; idx < s; idx += kGenBuildThreads) {
+    for (int idx = tid; idx < s; idx += kGenBuildThreads) {  // tmp_i = Q (A^(i+1) x0 - x_ref,i)
       const int i = idx / 13, rr = idx % 13;
       const double* Ai = &sm.Apow[(i + 1) * 169 + rr * 13];
       double a = 0.0;
@@ -196,65 +192,87 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
       for (int k = 0; k < 13; ++k) a += Ai[k] * sm.x0[k];
       sm.tmp[idx] = bp.Qd[rr] * (a - sm.xref[idx]);
     }
-    __threadfence_block();
     __syncthreads();
-    // Hessian = B_qp' Q B_qp + R by 60 x 60 output tiles, lower triangle of tiles, f64 accumulate
-    double* Pp = P_out + size_t(p) * n * n;
-    const int ty = tid / 15, tx = tid % 15;  // 15 x 15 threads, 4 x 4 outputs each (225 of 256 active)
-    for (int ti = 0; ti < n / kTile; ++ti) {
-      for (int tj = 0; tj <= ti; ++tj) {
-        double acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-        const int kstart = 13 * ((kTile * ti) / 12);  // rows above the larger tile's step block are zero
-        for (int k0 = kstart; k0 < s; k0 += kKChunk) {
-          __syncthreads();
-          for (int idx = tid; idx < kKChunk * kTile; idx += kGenBuildThreads) {
-            const int kk = idx / kTile, cc = idx % kTile;
-            const int k = k0 + kk;  // kstart is not chunk aligned: the last chunk may run past s
-            sm.tA[kk][cc] = (k < s) ? Bq[size_t(k) * n + kTile * ti + cc] * bp.Qd[k % 13] : 0.0;
-            sm.tB[kk][cc] = (k < s) ? Bq[size_t(k) * n + kTile * tj + cc] : 0.0;
-          }
-          __syncthreads();
-          if (tid < 225) {
-#pragma unroll 2
-            for (int kk = 0; kk < kKChunk; ++kk) {
-              double av[4], bv[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) { av[i] = sm.tA[kk][4 * ty + i]; bv[i] = sm.tB[kk][4 * tx + i]; }
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-            }
-          }
-        }
-        if (tid < 225) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int row = kTile * ti + 4 * ty + i, col = kTile * tj + 4 * tx + j;
-              double v = acc[i][j];
-              if (row == col) v += bp.Rd[row % 12];
-              if (ti != tj) {
-                Pp[size_t(row) * n + col] = v;
-                Pp[size_t(col) * n + row] = v;  // mirror: the solver gets an exactly symmetric Hessian
-              } else if (col <= row) {
-                Pp[size_t(row) * n + col] = v;
-                Pp[size_t(col) * n + row] = v;
-              }
-            }
-        }
+    if (tid < 169) {  // running sums in place: S[mm] = C_0 + .. + C_mm, so S_j = S[H-1-j]
+      double acc = 0.0;
+      for (int mm = 0; mm < H; ++mm) {
+        acc += sm.S[mm * 169 + tid];
+        sm.S[mm * 169 + tid] = acc;
       }
     }
-    // gradient = B_qp' tmp
-    for (int cidx = tid; cidx < n; cidx += kGenBuildThreads) {
+    for (int idx = tid; idx < s; idx += kGenBuildThreads) {  // g_j
+      const int j = idx / 13, ia = idx - 13 * j;
       double a = 0.0;
-      for (int k = 13 * (cidx / 12); k < s; ++k) a = fma(Bq[size_t(k) * n + cidx], sm.tmp[k], a);
+      for (int i = j; i < H; ++i) {
+        const double* Am = &sm.Apow[(i - j) * 169];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) a = fma(Am[k * 13 + ia], sm.tmp[13 * i + k], a);
+      }
+      sm.g[idx] = a;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < H * 156; idx += kGenBuildThreads) {  // T_j = B_j' S_j (12 x 13)
+      const int j = idx / 156, e = idx - 156 * j, ia = e / 13, k = e - 13 * ia;
+      const double* Bj = &sm.Bd[j * 156];
+      const double* Sj = &sm.S[(H - 1 - j) * 169];
+      double a = 0.0;
+#pragma unroll
+      for (int pp = 0; pp < 13; ++pp) a = fma(Bj[pp * 12 + ia], Sj[pp * 13 + k], a);
+      sm.T[idx] = a;
+    }
+    for (int cidx = tid; cidx < n; cidx += kGenBuildThreads) {  // gradient = B_j' g_j
+      const int j = cidx / 12, ia = cidx - 12 * j;
+      const double* Bj = &sm.Bd[j * 156];
+      double a = 0.0;
+#pragma unroll
+      for (int pp = 0; pp < 13; ++pp) a = fma(Bj[pp * 12 + ia], sm.g[13 * j + pp], a);
       q_out[size_t(p) * n + cidx] = a;
+    }
+    __syncthreads();
+    // one WARP per block (j, l), l <= j: U = A^(j-l) B_l into the warp's scratch, then the 12 x 12
+    // block T_j U; the block and its mirror leave as rows of 12 contiguous doubles
+    {
+      double* Pp = P_out + size_t(p) * n * n;
+      const int warp = tid >> 5, lane = tid & 31;
+      double* U = sm.scratch[warp];        // 13 x 12
+      double* Blk = sm.scratch[warp] + 160;  // 12 x 12
+      for (int blk = warp; blk < H * (H + 1) / 2; blk += kGenBuildThreads / 32) {
+        int j = 0, rem = blk;
+        while (rem > j) { rem -= (j + 1); ++j; }
+        const int l = rem;
+        const double* Ap = &sm.Apow[(j - l) * 169];
+        const double* Bl = &sm.Bd[l * 156];
+        const double* Tj = &sm.T[j * 156];
+        __syncwarp();
+        for (int e = lane; e < 156; e += 32) {
+          const int rr = e / 12, cc = e - 12 * rr;
+          double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < 13; ++k) a = fma(Ap[rr * 13 + k], Bl[k * 12 + cc], a);
+          U[e] = a;
+        }
+        __syncwarp();
+        for (int e = lane; e < 144; e += 32) {
+          int ia = e / 12, ib = e - 12 * ia;
+          if (j == l && ib > ia) { const int t = ia; ia = ib; ib = t; }  // diagonal block: exact symmetry
+          double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < 13; ++k) a = fma(Tj[ia * 13 + k], U[k * 12 + ib], a);
+          if (j == l && ia == ib) a += bp.Rd[ia];
+          Blk[e] = a;
+        }
+        __syncwarp();
+        if (lane < 12) {
+          double2* dst = reinterpret_cast<double2*>(Pp + size_t(12 * j + lane) * n + 12 * l);
+#pragma unroll
+          for (int h = 0; h < 6; ++h) dst[h] = make_double2(Blk[lane * 12 + 2 * h], Blk[lane * 12 + 2 * h + 1]);
+        } else if (lane >= 16 && lane < 28 && j != l) {
+          const int ib = lane - 16;  // the mirrored block: row ib of block (l, j) is column ib of Blk
+          double2* dst = reinterpret_cast<double2*>(Pp + size_t(12 * l + ib) * n + 12 * j);
+#pragma unroll
+          for (int h = 0; h < 6; ++h) dst[h] = make_double2(Blk[(2 * h) * 12 + ib], Blk[(2 * h + 1) * 12 + ib]);
+        }
+      }
     }
     // bounds
     for (int i = tid; i < m; i += kGenBuildThreads) {

@@ -352,7 +352,7 @@ int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
   e->bp.exact_discretization = cfg->exact_discretization != 0;
   e->bp.foot_drift = cfg->foot_drift != 0;
   e->bp.gait_aware = cfg->gait_aware != 0;
-  e->structured = cfg->structured_solver != 0;
+  e->structured = cfg->structured_solver == 1 || (cfg->structured_solver == 0 && cfg->horizon != kH);
   e->sp = make_solve_params(cfg->osqp, cfg->mu);
   *out = e;
   return MPC_OK;

@@ -338,20 +338,34 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       if (tid < 13) sm.pv[H * 13 + tid] = 0.0;
       __syncthreads();
       if (warp == 0) {
-        for (int k = H - 1; k >= 0; --k) {  // p_k = L_k' p_k+1 + t_k
-          double s0 = 0.0, s1 = 0.0;
-          if (lane < 13) {
-            const double* L = sm.Lk[k];
-            const double* pn = &sm.pv[(k + 1) * 13];
+        // p_k = L_k' p_k+1 + t_k: the vector lives in registers (lane i < 13 holds p[i]) and moves by
+        // shuffles; the matrix column and t of the NEXT step are fetched while this one computes
+        const int li = lane < 13 ? lane : 0;
+        double pc = 0.0, Lr[13], tk;
 #pragma unroll
-            for (int j = 0; j < 12; j += 2) {
-              s0 = fma(L[j * 13 + lane], pn[j], s0);
-              s1 = fma(L[(j + 1) * 13 + lane], pn[j + 1], s1);
-            }
-            s0 = fma(L[12 * 13 + lane], pn[12], s0);
-            sm.pv[k * 13 + lane] = s0 + s1 + sm.tv[k * 13 + lane];
+        for (int j = 0; j < 13; ++j) Lr[j] = sm.Lk[H - 1][j * 13 + li];
+        tk = sm.tv[(H - 1) * 13 + li];
+        for (int k = H - 1; k >= 0; --k) {
+          double Ln[13], tn = 0.0;
+          if (k > 0) {
+#pragma unroll
+            for (int j = 0; j < 13; ++j) Ln[j] = sm.Lk[k - 1][j * 13 + li];
+            tn = sm.tv[(k - 1) * 13 + li];
           }
-          __syncwarp();
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < 12; j += 2) {
+            s0 = fma(Lr[j], __shfl_sync(0xffffffffu, pc, j), s0);
+            s1 = fma(Lr[j + 1], __shfl_sync(0xffffffffu, pc, j + 1), s1);
+          }
+          s0 = fma(Lr[12], __shfl_sync(0xffffffffu, pc, 12), s0);
+          pc = s0 + s1 + tk;
+          if (lane < 13) sm.pv[k * 13 + lane] = pc;
+          if (k > 0) {
+#pragma unroll
+            for (int j = 0; j < 13; ++j) Lr[j] = Ln[j];
+            tk = tn;
+          }
         }
       }
       __syncthreads();
@@ -381,20 +395,36 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       if (tid < 13) sm.Xv[tid] = 0.0;
       __syncthreads();
       if (warp == 0) {
-        for (int k = 0; k < H; ++k) {  // X_k+1 = L_k X_k + b_k
-          double s0 = 0.0, s1 = 0.0;
-          if (lane < 13) {
-            const double* L = &sm.Lk[k][lane * 13];
-            const double* Xk = &sm.Xv[k * 13];
+        // X_k+1 = L_k X_k + b_k, same scheme (X_1 = b_0 because X_0 = 0)
+        const int li = lane < 13 ? lane : 0;
+        double xc = sm.tv[li], Lr[13], bk = 0.0;
+        if (lane < 13) sm.Xv[13 + lane] = xc;
+        if (H > 1) {
 #pragma unroll
-            for (int j = 0; j < 12; j += 2) {
-              s0 = fma(L[j], Xk[j], s0);
-              s1 = fma(L[j + 1], Xk[j + 1], s1);
-            }
-            s0 = fma(L[12], Xk[12], s0);
-            sm.Xv[(k + 1) * 13 + lane] = s0 + s1 + sm.tv[k * 13 + lane];
+          for (int j = 0; j < 13; ++j) Lr[j] = sm.Lk[1][li * 13 + j];
+          bk = sm.tv[13 + li];
+        }
+        for (int k = 1; k < H; ++k) {
+          double Ln[13], bn = 0.0;
+          if (k + 1 < H) {
+#pragma unroll
+            for (int j = 0; j < 13; ++j) Ln[j] = sm.Lk[k + 1][li * 13 + j];
+            bn = sm.tv[(k + 1) * 13 + li];
           }
-          __syncwarp();
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < 12; j += 2) {
+            s0 = fma(Lr[j], __shfl_sync(0xffffffffu, xc, j), s0);
+            s1 = fma(Lr[j + 1], __shfl_sync(0xffffffffu, xc, j + 1), s1);
+          }
+          s0 = fma(Lr[12], __shfl_sync(0xffffffffu, xc, 12), s0);
+          xc = s0 + s1 + bk;
+          if (lane < 13) sm.Xv[(k + 1) * 13 + lane] = xc;
+          if (k + 1 < H) {
+#pragma unroll
+            for (int j = 0; j < 13; ++j) Lr[j] = Ln[j];
+            bk = bn;
+          }
         }
       }
       __syncthreads();

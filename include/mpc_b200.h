@@ -224,10 +224,11 @@ typedef struct MpcConfig {
                                    commented out at A1RobotControl.cpp:504-507 */
   int32_t gait_aware;           /* per-step contacts from the gait counters (mpc_set_gait_inputs)
                                    instead of today's contacts replicated (ConvexMpc.cpp:242-245) */
-  int32_t structured_solver;    /* 0: dense K^-1 in registers (H = 10) / in an L2 workspace (H = 30);
-                                   1: the same ADMM with K x = r solved by a Riccati recursion over the
-                                   horizon (riccati_kernel.cuh) -- same iterates up to rounding; cold
-                                   solves only */
+  int32_t structured_solver;    /* how K x = r is solved inside the ADMM (same iterates up to rounding):
+                                   0 automatic: dense K^-1 in registers for H = 10, Riccati recursion
+                                     over the horizon (riccati_kernel.cuh) for H = 30;
+                                   1 Riccati recursion (cold solves; warm-started solves stay dense);
+                                   2 dense (for H = 30: K^-1 in a per-CTA L2 workspace, 7x slower) */
 } MpcConfig;
 
 /* Gait scheduler state of one robot (A1CtrlStates.h:24-28,103; A1RobotControl.cpp:156-164),

@@ -738,3 +738,18 @@ def test_structured_solver_hardware_weights_and_extensions(pkg, ob):
     same = res["iters"] == ref["iters"]
     assert same.mean() >= 0.98 and grf_rel(res["grf"][same], ref["grf"][same]).max() <= TOL_GRF
     e.close()
+
+
+def test_long_horizon_dense_workspace_path(pkg, ob):
+    """H = 30 through the dense K^-1-in-L2-workspace kernels (structured_solver = 2), kept as the
+    independent second implementation of the long horizon."""
+    cfg = pkg.config_default()
+    cfg.horizon = 30
+    cfg.structured_solver = 2
+    e = pkg.MpcEngine(cfg, 0)
+    st = pkg.generate_states(1004, 0, 24)
+    res = e.compute_grf_batch(st)
+    ref = ob.mpc_compute_grf(cfg, st)
+    assert (res["status"] == 1).all()
+    assert np.array_equal(res["iters"], ref["iters"]) and grf_rel(res["grf"], ref["grf"]).max() <= TOL_GRF
+    e.close()
