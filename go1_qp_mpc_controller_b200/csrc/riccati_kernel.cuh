@@ -29,6 +29,7 @@
 namespace mpcb200 {
 
 constexpr int kRicThreads = 128;
+constexpr int kVS = 14;  // row stride of the recursion vectors in shared memory
 
 template <int H>
 struct RicSmem {
@@ -42,7 +43,9 @@ struct RicSmem {
   double x[n], xt[n], rhs[n], qb[n], Dv[n], Px[n];  // xt doubles as the new-D scratch of the Ruiz passes
   double z[m], y[m], rv[m], cca[m], ccz[m], Ev[m];
   float lb[m], ub[m];  // UNSCALED bounds exactly as given; scaled by E (f64) where they are used
-  double pv[(H + 1) * 13], Xv[(H + 1) * 13], tv[H * 13], gv[H * 12], wv[H * 12];
+  alignas(16) double pv[(H + 1) * kVS];  // costates, one row of kVS = 14 doubles per step (16 B aligned)
+  alignas(16) double Xv[(H + 1) * kVS];  // states
+  double tv[H * 13], gv[H * 12], wv[H * 12];
   double red[16 * 4];
   double scal[8];  // 0:c 1:cinv 2:rho 4:pri_res
   int flags[8];    // 0:done 1:status 2:refactor 3:problem index
@@ -81,12 +84,21 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double sigma = sp.sigma, alpha = sp.alpha, mu = sp.mu;
 
+#ifdef RIC_PROF
+  long long pc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pm_ = 0;
+#define RP(i) do { if (tid == 0) { const long long t_ = clock64(); pc_[i] += t_ - pm_; pm_ = t_; } } while (0)
+#else
+#define RP(i) do {} while (0)
+#endif
   for (;;) {
     __syncthreads();
     if (tid == 0) sm.flags[3] = atomicAdd(counter, 1);
     __syncthreads();
     const int p = sm.flags[3];
     if (p >= num) break;
+#ifdef RIC_PROF
+    if (tid == 0) pm_ = clock64();
+#endif
     const double* Pg = P_all + size_t(p) * p_stride;
     const double* model = model_all + size_t(p) * (169 + H * 156);
 
@@ -167,6 +179,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         __syncthreads();
       }
     }
+    RP(0);  // load + Ruiz
     const double c = c_run, cinv = 1.0 / c_run;
     // ---- scaled data ----
     for (int j = tid; j < n; j += kRicThreads) sm.qb[j] = c * sm.Dv[j] * q_all[size_t(p) * n + j];
@@ -327,6 +340,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
           __syncthreads();
         }
       }
+      RP(1);  // (factor when it ran, else loop overhead)
       // ---- x~ = K^-1 rhs by the two recursions ----
       for (int idx = tid; idx < H * 13; idx += kRicThreads) {  // t_k = K_k' r_k
         const int k = idx / 13, i = idx - 13 * k;
@@ -335,45 +349,50 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         for (int a = 0; a < 12; ++a) s = fma(sm.Kk[k][a * 13 + i], sm.rhs[12 * k + a], s);
         sm.tv[idx] = s;
       }
-      if (tid < 13) sm.pv[H * 13 + tid] = 0.0;
+      if (tid < 13) sm.pv[H * kVS + tid] = 0.0;
       __syncthreads();
+      RP(2);  // t phase
       if (warp == 0) {
-        // p_k = L_k' p_k+1 + t_k: the vector lives in registers (lane i < 13 holds p[i]) and moves by
-        // shuffles; the matrix column and t of the NEXT step are fetched while this one computes
+        // p_k = L_k' p_k+1 + t_k on 13 lanes: the vector is read back from shared memory with seven
+        // 16-byte loads, the matrix column and t of the NEXT step are fetched while this one computes
+        // (two register sets, the loop is unrolled by two so that nothing is copied)
         const int li = lane < 13 ? lane : 0;
-        double pc = 0.0, Lr[13], tk;
+        auto fetch = [&](int k, double (&Lr)[13], double& tk) {
 #pragma unroll
-        for (int j = 0; j < 13; ++j) Lr[j] = sm.Lk[H - 1][j * 13 + li];
-        tk = sm.tv[(H - 1) * 13 + li];
-        for (int k = H - 1; k >= 0; --k) {
-          double Ln[13], tn = 0.0;
-          if (k > 0) {
+          for (int j = 0; j < 13; ++j) Lr[j] = sm.Lk[k][j * 13 + li];
+          tk = sm.tv[k * 13 + li];
+        };
+        auto step = [&](int k, const double (&Lr)[13], double tk) {
+          const double2* pn = reinterpret_cast<const double2*>(&sm.pv[(k + 1) * kVS]);
+          double v[14];
 #pragma unroll
-            for (int j = 0; j < 13; ++j) Ln[j] = sm.Lk[k - 1][j * 13 + li];
-            tn = sm.tv[(k - 1) * 13 + li];
-          }
+          for (int h = 0; h < 7; ++h) { const double2 t = pn[h]; v[2 * h] = t.x; v[2 * h + 1] = t.y; }
           double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-          for (int j = 0; j < 12; j += 2) {
-            s0 = fma(Lr[j], __shfl_sync(0xffffffffu, pc, j), s0);
-            s1 = fma(Lr[j + 1], __shfl_sync(0xffffffffu, pc, j + 1), s1);
-          }
-          s0 = fma(Lr[12], __shfl_sync(0xffffffffu, pc, 12), s0);
-          pc = s0 + s1 + tk;
-          if (lane < 13) sm.pv[k * 13 + lane] = pc;
-          if (k > 0) {
-#pragma unroll
-            for (int j = 0; j < 13; ++j) Lr[j] = Ln[j];
-            tk = tn;
-          }
+          for (int j = 0; j < 12; j += 2) { s0 = fma(Lr[j], v[j], s0); s1 = fma(Lr[j + 1], v[j + 1], s1); }
+          s0 = fma(Lr[12], v[12], s0);
+          if (lane < 13) sm.pv[k * kVS + lane] = s0 + s1 + tk;
+          __syncwarp();
+        };
+        double LA[13], LB[13], tA = 0.0, tB = 0.0;
+        fetch(H - 1, LA, tA);
+        int k = H - 1;
+#pragma unroll 1
+        for (; k >= 1; k -= 2) {
+          fetch(k - 1, LB, tB);
+          step(k, LA, tA);
+          if (k >= 2) fetch(k - 2, LA, tA);
+          step(k - 1, LB, tB);
         }
+        if (k == 0) step(0, LA, tA);
       }
+      RP(3);  // backward chain
       __syncthreads();
       for (int idx = tid; idx < H * 12; idx += kRicThreads) {  // w_k = Bs' p_k+1 - r_k
         const int k = idx / 12, a = idx - 12 * k;
         double s = -sm.rhs[idx];
 #pragma unroll
-        for (int i = 0; i < 13; ++i) s = fma(sm.Bs[k][i * 12 + a], sm.pv[(k + 1) * 13 + i], s);
+        for (int i = 0; i < 13; ++i) s = fma(sm.Bs[k][i * 12 + a], sm.pv[(k + 1) * kVS + i], s);
         sm.wv[idx] = s;
       }
       __syncthreads();
@@ -394,46 +413,47 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       }
       if (tid < 13) sm.Xv[tid] = 0.0;
       __syncthreads();
+      RP(4);  // w, g, b phases
       if (warp == 0) {
-        // X_k+1 = L_k X_k + b_k, same scheme (X_1 = b_0 because X_0 = 0)
+        // X_k+1 = L_k X_k + b_k, same scheme (X_0 = 0)
         const int li = lane < 13 ? lane : 0;
-        double xc = sm.tv[li], Lr[13], bk = 0.0;
-        if (lane < 13) sm.Xv[13 + lane] = xc;
-        if (H > 1) {
+        auto fetch = [&](int k, double (&Lr)[13], double& bk) {
 #pragma unroll
-          for (int j = 0; j < 13; ++j) Lr[j] = sm.Lk[1][li * 13 + j];
-          bk = sm.tv[13 + li];
-        }
-        for (int k = 1; k < H; ++k) {
-          double Ln[13], bn = 0.0;
-          if (k + 1 < H) {
+          for (int j = 0; j < 13; ++j) Lr[j] = sm.Lk[k][li * 13 + j];
+          bk = sm.tv[k * 13 + li];
+        };
+        auto step = [&](int k, const double (&Lr)[13], double bk) {
+          const double2* xk = reinterpret_cast<const double2*>(&sm.Xv[k * kVS]);
+          double v[14];
 #pragma unroll
-            for (int j = 0; j < 13; ++j) Ln[j] = sm.Lk[k + 1][li * 13 + j];
-            bn = sm.tv[(k + 1) * 13 + li];
-          }
+          for (int h = 0; h < 7; ++h) { const double2 t = xk[h]; v[2 * h] = t.x; v[2 * h + 1] = t.y; }
           double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-          for (int j = 0; j < 12; j += 2) {
-            s0 = fma(Lr[j], __shfl_sync(0xffffffffu, xc, j), s0);
-            s1 = fma(Lr[j + 1], __shfl_sync(0xffffffffu, xc, j + 1), s1);
-          }
-          s0 = fma(Lr[12], __shfl_sync(0xffffffffu, xc, 12), s0);
-          xc = s0 + s1 + bk;
-          if (lane < 13) sm.Xv[(k + 1) * 13 + lane] = xc;
-          if (k + 1 < H) {
-#pragma unroll
-            for (int j = 0; j < 13; ++j) Lr[j] = Ln[j];
-            bk = bn;
-          }
+          for (int j = 0; j < 12; j += 2) { s0 = fma(Lr[j], v[j], s0); s1 = fma(Lr[j + 1], v[j + 1], s1); }
+          s0 = fma(Lr[12], v[12], s0);
+          if (lane < 13) sm.Xv[(k + 1) * kVS + lane] = s0 + s1 + bk;
+          __syncwarp();
+        };
+        double LA[13], LB[13], bA = 0.0, bB = 0.0;
+        fetch(0, LA, bA);
+        int k = 0;
+#pragma unroll 1
+        for (; k + 1 < H; k += 2) {
+          fetch(k + 1, LB, bB);
+          step(k, LA, bA);
+          if (k + 2 < H) fetch(k + 2, LA, bA);
+          step(k + 1, LB, bB);
         }
+        if (k < H) step(k, LA, bA);
       }
+      RP(5);  // forward chain
       __syncthreads();
       // x~_k = -K_k X_k + g_k ; x <- alpha x~ + (1 - alpha) x
       for (int idx = tid; idx < n; idx += kRicThreads) {
         const int k = idx / 12, a = idx - 12 * k;
         double s = sm.gv[idx];
 #pragma unroll
-        for (int i = 0; i < 13; ++i) s = fma(-sm.Kk[k][a * 13 + i], sm.Xv[k * 13 + i], s);
+        for (int i = 0; i < 13; ++i) s = fma(-sm.Kk[k][a * 13 + i], sm.Xv[k * kVS + i], s);
         sm.xt[idx] = s;
         sm.x[idx] = alpha * s + (1.0 - alpha) * sm.x[idx];
       }
@@ -477,6 +497,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       if (can_adapt) until_adapt = sp.adaptive_rho_interval;
       const bool last = (iter == sp.max_iter);
       __syncthreads();
+      RP(6);  // x~, z/y, rhs phases
       if (!(can_check || can_adapt || last)) continue;
 
       // ---- residuals: P x through the open-loop recursions ----
@@ -487,15 +508,15 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         for (int a = 0; a < 12; ++a) s = fma(sm.Bs[k][i * 12 + a], sm.x[12 * k + a], s);
         sm.tv[idx] = s;
       }
-      if (tid < 13) { sm.Xv[tid] = 0.0; sm.pv[H * 13 + tid] = 0.0; }
+      if (tid < 13) { sm.Xv[tid] = 0.0; sm.pv[H * kVS + tid] = 0.0; }
       __syncthreads();
       if (warp == 0) {
         for (int k = 0; k < H; ++k) {  // X_k+1 = A X_k + Bs x_k
           double s = 0.0;
           if (lane < 13) {
 #pragma unroll
-            for (int j = 0; j < 13; ++j) s = fma(sm.A[lane * 13 + j], sm.Xv[k * 13 + j], s);
-            sm.Xv[(k + 1) * 13 + lane] = s + sm.tv[k * 13 + lane];
+            for (int j = 0; j < 13; ++j) s = fma(sm.A[lane * 13 + j], sm.Xv[k * kVS + j], s);
+            sm.Xv[(k + 1) * kVS + lane] = s + sm.tv[k * 13 + lane];
           }
           __syncwarp();
         }
@@ -504,9 +525,9 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
           if (lane < 13) {
             if (k < H - 1) {
 #pragma unroll
-              for (int j = 0; j < 13; ++j) s = fma(sm.A[j * 13 + lane], sm.pv[(k + 2) * 13 + j], s);
+              for (int j = 0; j < 13; ++j) s = fma(sm.A[j * 13 + lane], sm.pv[(k + 2) * kVS + j], s);
             }
-            sm.pv[(k + 1) * 13 + lane] = s + c * bp.Qd[lane] * sm.Xv[(k + 1) * 13 + lane];
+            sm.pv[(k + 1) * kVS + lane] = s + c * bp.Qd[lane] * sm.Xv[(k + 1) * kVS + lane];
           }
           __syncwarp();
         }
@@ -520,7 +541,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         const double d = sm.Dv[idx];
         double px = c * d * bp.Rd[a] * d * sm.x[idx];
 #pragma unroll
-        for (int i = 0; i < 13; ++i) px = fma(sm.Bs[k][i * 12 + a], sm.pv[(k + 1) * 13 + i], px);
+        for (int i = 0; i < 13; ++i) px = fma(sm.Bs[k][i * 12 + a], sm.pv[(k + 1) * kVS + i], px);
         double aty;
         if (vc == 0) aty = sm.cca[r0] * sm.y[r0] + sm.cca[r0 + 1] * sm.y[r0 + 1];
         else if (vc == 1) aty = sm.cca[r0 + 2] * sm.y[r0 + 2] + sm.cca[r0 + 3] * sm.y[r0 + 3];
@@ -578,6 +599,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         sm.flags[2] = refactor;
       }
       __syncthreads();
+      RP(7);  // residual check
       if (sm.flags[0]) {
         status = sm.flags[1];
         pri_res_out = sm.scal[4];
@@ -619,6 +641,11 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       const bool bad = isnan(f0) || isnan(f1) || isnan(f2);
       results[p].grf[tid] = bad ? 0.0f : (float)g;
     }
+#ifdef RIC_PROF
+    if (tid == 0 && p < 2)
+      printf("RICPROF p %d iters %d: ruiz %lld factor+ %lld t %lld bwd %lld wgb %lld fwd %lld xzy %lld check %lld\n", p, iter,
+             pc_[0], pc_[1], pc_[2], pc_[3], pc_[4], pc_[5], pc_[6], pc_[7]);
+#endif
     if (tid == 0) {
       results[p].status = status;
       results[p].iters = iter;
