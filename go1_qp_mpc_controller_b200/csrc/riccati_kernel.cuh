@@ -28,8 +28,10 @@
 
 namespace mpcb200 {
 
-constexpr int kRicThreads = 128;
+constexpr int kRicThreads = 256;
+constexpr int kRicWarps = kRicThreads / 32;
 constexpr int kVS = 14;  // row stride of the recursion vectors in shared memory
+constexpr int kRicGroup = 5;  // steps per recursion group (H must be a multiple)
 
 template <int H>
 struct RicSmem {
@@ -39,14 +41,18 @@ struct RicSmem {
   double Kk[H][156];   // gains, 12 x 13
   double Lk[H][169];   // closed loop A - Bs K, 13 x 13
   double Mi[H][144];   // M_k^-1, 12 x 12
-  double Pi[169], W1[169], W2[169], W3[156], W4[156], Mm[144];  // factor scratch
+  double Pi[169];
+  // factor scratch W1|W2|W3|W4|Mm (794 doubles) while the recursion is being factored; afterwards the
+  // group transition matrices Phi_j = L_(5j+4) ... L_(5j), 13 x 13 each, used by every iteration
+  static constexpr int kFs = (H / 5) * 169 > 794 ? (H / 5) * 169 : 794;
+  double fs[kFs];
   double x[n], xt[n], rhs[n], qb[n], Dv[n], Px[n];  // xt doubles as the new-D scratch of the Ruiz passes
   double z[m], y[m], rv[m], cca[m], ccz[m], Ev[m];
   float lb[m], ub[m];  // UNSCALED bounds exactly as given; scaled by E (f64) where they are used
   alignas(16) double pv[(H + 1) * kVS];  // costates, one row of kVS = 14 doubles per step (16 B aligned)
   alignas(16) double Xv[(H + 1) * kVS];  // states
   double tv[H * 13], gv[H * 12], wv[H * 12];
-  double red[16 * 4];
+  double red[16 * kRicWarps];
   double scal[8];  // 0:c 1:cinv 2:rho 4:pri_res
   int flags[8];    // 0:done 1:status 2:refactor 3:problem index
 };
@@ -56,7 +62,7 @@ __device__ __forceinline__ double ric_limit_scaling(double v) {
   return v > 1e4 ? 1e4 : v;
 }
 
-// block-wide max or sum of one value per thread (128 threads); result to every thread
+// block-wide max or sum of one value per thread; result to every thread
 template <bool kMax>
 __device__ __forceinline__ double ric_block_reduce(double v, double* red, int slot) {
 #pragma unroll
@@ -64,10 +70,58 @@ __device__ __forceinline__ double ric_block_reduce(double v, double* red, int sl
     const double t = __shfl_xor_sync(0xffffffffu, v, o);
     v = kMax ? fmax(v, t) : v + t;
   }
-  if ((threadIdx.x & 31) == 0) red[slot * 4 + (threadIdx.x >> 5)] = v;
+  if ((threadIdx.x & 31) == 0) red[slot * kRicWarps + (threadIdx.x >> 5)] = v;
   __syncthreads();
-  const double a = red[slot * 4], b = red[slot * 4 + 1], c = red[slot * 4 + 2], d = red[slot * 4 + 3];
-  return kMax ? fmax(fmax(a, b), fmax(c, d)) : (a + b) + (c + d);
+  double r[kRicWarps];
+#pragma unroll
+  for (int w = 0; w < kRicWarps; ++w) r[w] = red[slot * kRicWarps + w];
+#pragma unroll
+  for (int st = 1; st < kRicWarps; st *= 2)
+#pragma unroll
+    for (int w = 0; w + st < kRicWarps; w += 2 * st) r[w] = kMax ? fmax(r[w], r[w + st]) : r[w] + r[w + st];
+  return r[0];
+}
+
+// One 13-lane recursion  out_s = M_s in_s + add_s,  s = 0 .. nsteps-1, on a half warp.  Every pointer
+// is per lane:  Mp + s m_step + j sj  is element j of this lane's row (or column, for M') of M_s;
+// vin + s v_step  the 13-vector in_s (a 16-byte aligned row of kVS doubles; out_(s-1) for s > 0);
+// vout + s o_step  this lane's element of out_s;  addp + s a_step  its addend.  The vector comes back
+// from shared memory with seven 16-byte loads; the matrix elements and addend of the NEXT step are
+// fetched while this one computes (two register sets, loop unrolled by two so nothing is copied).
+// One shared body for all six recursion phases keeps the iteration loop inside the instruction cache.
+__device__ __noinline__ void ric_chain(const double* Mp, int m_step, int sj, const double* vin, int v_step,
+                                       double* vout, int o_step, const double* addp, int a_step,
+                                       int nsteps, bool wr) {
+  auto fetch = [&](int s_, double (&Lr)[13], double& ad) {
+    const double* q = Mp + s_ * m_step;
+#pragma unroll
+    for (int j = 0; j < 13; ++j) Lr[j] = q[j * sj];
+    ad = addp[s_ * a_step];
+  };
+  auto step = [&](int s_, const double (&Lr)[13], double ad) {
+    const double2* pn = reinterpret_cast<const double2*>(vin + s_ * v_step);
+    double v[14];
+#pragma unroll
+    for (int h = 0; h < 7; ++h) { const double2 t = pn[h]; v[2 * h] = t.x; v[2 * h + 1] = t.y; }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 12; j += 2) { s0 = fma(Lr[j], v[j], s0); s1 = fma(Lr[j + 1], v[j + 1], s1); }
+    s0 = fma(Lr[12], v[12], s0);
+    if (wr) vout[s_ * o_step] = s0 + s1 + ad;
+    __syncwarp();
+  };
+  double LA[13], LB[13], aA = 0.0, aB = 0.0;
+  __syncwarp();
+  fetch(0, LA, aA);
+  int s_ = 0;
+#pragma unroll 1
+  for (; s_ + 1 < nsteps; s_ += 2) {
+    fetch(s_ + 1, LB, aB);
+    step(s_, LA, aA);
+    if (s_ + 2 < nsteps) fetch(s_ + 2, LA, aA);
+    step(s_ + 1, LB, aB);
+  }
+  if (s_ < nsteps) step(s_, LA, aA);
 }
 
 template <int H>
@@ -83,6 +137,17 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
   RicSmem<H>& sm = *reinterpret_cast<RicSmem<H>*>(ric_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double sigma = sp.sigma, alpha = sp.alpha, mu = sp.mu;
+  double* const W1 = sm.fs;
+  double* const W2 = sm.fs + 169;
+  double* const W3 = sm.fs + 338;
+  double* const W4 = sm.fs + 494;
+  double* const Mm = sm.fs + 650;
+  double (*const Phi)[169] = reinterpret_cast<double (*)[169]>(sm.fs);
+  constexpr int kG = H / kRicGroup;  // groups of kRicGroup consecutive steps
+  // recursion slots: two per warp (lanes 0-12 and 16-28); slot q works on group q
+  const int hl = lane & 15, slot = 2 * warp + (lane >> 4);
+  const bool slot_on = hl < 13 && slot < kG;
+  const int sl = hl < 13 ? hl : 0, sg = slot < kG ? slot : 0;
 
 #ifdef RIC_PROF
   long long pc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pm_ = 0;
@@ -125,14 +190,37 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
     double c_run = 1.0;
     // row norms of the scaled Hessian, max_j |P_rj| D_j (its column norms, by symmetry): warp per row
     auto p_row_norms = [&](bool accumulate, double& psum, double& qmax) {
-      for (int r = warp; r < n; r += kRicThreads / 32) {
-        const double* row = Pg + size_t(r) * p_row_stride;
-        double mx = 0.0;
-        for (int j = lane; j < n; j += 32) mx = fmax(mx, fabs(row[j]) * sm.Dv[j]);
+      constexpr int kNJ = (n + 31) / 32, kRows = 2;
+      for (int r0 = kRows * warp; r0 < n; r0 += kRows * kRicWarps) {
+        // all the loads of kRows rows are in flight before the first is used (the pass is latency bound)
+        double e[kRows][kNJ];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) {
-          const double v = c_run * sm.Dv[r] * mx;
+        for (int rr = 0; rr < kRows; ++rr) {
+          const double* row = Pg + size_t(r0 + rr < n ? r0 + rr : r0) * p_row_stride;
+#pragma unroll
+          for (int t = 0; t < kNJ; ++t) {
+            const int j = lane + 32 * t;
+            e[rr][t] = (j < n) ? row[j] : 0.0;
+          }
+        }
+        double mx[kRows];
+#pragma unroll
+        for (int rr = 0; rr < kRows; ++rr) mx[rr] = 0.0;
+#pragma unroll
+        for (int t = 0; t < kNJ; ++t) {
+          const int j = lane + 32 * t;
+          const double d = (j < n) ? sm.Dv[j] : 0.0;
+#pragma unroll
+          for (int rr = 0; rr < kRows; ++rr) mx[rr] = fmax(mx[rr], fabs(e[rr][t]) * d);
+        }
+#pragma unroll
+        for (int rr = 0; rr < kRows; ++rr) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mx[rr] = fmax(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], o));
+        }
+        if (lane < kRows && r0 + lane < n) {
+          const int r = r0 + lane;
+          const double v = c_run * sm.Dv[r] * (lane == 0 ? mx[0] : mx[kRows - 1]);
           sm.Px[r] = v;
           if (accumulate) {
             psum += v;
@@ -211,6 +299,8 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
     int until_check = sp.check_termination > 0 ? sp.check_termination : 0x7fffffff;
     int until_adapt = (sp.adaptive_rho && sp.adaptive_rho_interval > 0) ? sp.adaptive_rho_interval : 0x7fffffff;
     bool need_factor = true;
+    double rho_cur = sp.rho, rinv_in = 1.0 / sp.rho, rinv_eq = 1.0 / (1e3 * sp.rho);
+    const double rinv_free = 1.0 / 1e-6;
     for (iter = 1; iter <= sp.max_iter; ++iter) {
       if (need_factor) {
         need_factor = false;
@@ -225,7 +315,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
             double s = 0.0;
 #pragma unroll
             for (int i = 0; i < 13; ++i) s = fma(Bk[i * 12 + a], sm.Pi[i * 13 + j], s);
-            sm.W3[idx] = s;
+            W3[idx] = s;
           }
           __syncthreads();
           // Mm = Dk + W3 Bs (12 x 12) ; W4 = W3 A (12 x 13)
@@ -234,7 +324,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
               const int a = idx / 12, b = idx - 12 * a;
               double s = 0.0;
 #pragma unroll
-              for (int i = 0; i < 13; ++i) s = fma(sm.W3[a * 13 + i], Bk[i * 12 + b], s);
+              for (int i = 0; i < 13; ++i) s = fma(W3[a * 13 + i], Bk[i * 12 + b], s);
               // input cost block: c D R D + sigma on the diagonal, G = A' rho A per leg (3 x 3)
               if (a / 3 == b / 3) {
                 const int ls = 4 * k + a / 3, ra = a % 3, rb = b % 3;
@@ -259,20 +349,20 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
                   s += c * d * bp.Rd[a] * d + sigma;
                 }
               }
-              sm.Mm[idx] = s;
+              Mm[idx] = s;
             } else {
               const int e = idx - 144, a = e / 13, j = e - 13 * a;
               double s = 0.0;
 #pragma unroll
-              for (int i = 0; i < 13; ++i) s = fma(sm.W3[a * 13 + i], sm.A[i * 13 + j], s);
-              sm.W4[e] = s;
+              for (int i = 0; i < 13; ++i) s = fma(W3[a * 13 + i], sm.A[i * 13 + j], s);
+              W4[e] = s;
             }
           }
           __syncthreads();
           // Mi = Mm^-1: Gauss-Jordan sweep on the SPD 12 x 12 block, warp 0 (lane = row)
           if (warp == 0) {
             double* Mk = sm.Mi[k];
-            for (int i = lane; i < 144; i += 32) Mk[i] = sm.Mm[i];
+            for (int i = lane; i < 144; i += 32) Mk[i] = Mm[i];
             __syncwarp();
             for (int pv_ = 0; pv_ < 12; ++pv_) {
               const double d = 1.0 / Mk[pv_ * 12 + pv_];
@@ -303,7 +393,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
             const int a = idx / 13, j = idx - 13 * a;
             double s = 0.0;
 #pragma unroll
-            for (int b = 0; b < 12; ++b) s = fma(sm.Mi[k][a * 12 + b], sm.W4[b * 13 + j], s);
+            for (int b = 0; b < 12; ++b) s = fma(sm.Mi[k][a * 12 + b], W4[b * 13 + j], s);
             sm.Kk[k][idx] = s;
           }
           __syncthreads();
@@ -322,23 +412,46 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
             double s = 0.0;
 #pragma unroll
             for (int t = 0; t < 13; ++t) s = fma(sm.Pi[i * 13 + t], sm.Lk[k][t * 13 + j], s);
-            sm.W1[idx] = s;
+            W1[idx] = s;
           }
           __syncthreads();
           for (int idx = tid; idx < 169; idx += kRicThreads) {
             const int i = idx / 13, j = idx - 13 * i;
             double s = 0.0;
 #pragma unroll
-            for (int t = 0; t < 13; ++t) s = fma(sm.A[t * 13 + i], sm.W1[t * 13 + j], s);
-            sm.W2[idx] = s;
+            for (int t = 0; t < 13; ++t) s = fma(sm.A[t * 13 + i], W1[t * 13 + j], s);
+            W2[idx] = s;
           }
           __syncthreads();
           for (int idx = tid; idx < 169; idx += kRicThreads) {
             const int i = idx / 13, j = idx - 13 * i;
-            sm.Pi[idx] = 0.5 * (sm.W2[idx] + sm.W2[j * 13 + i]) + ((i == j) ? c * bp.Qd[i] : 0.0);
+            sm.Pi[idx] = 0.5 * (W2[idx] + W2[j * 13 + i]) + ((i == j) ? c * bp.Qd[i] : 0.0);
           }
           __syncthreads();
         }
+        // group transitions Phi_j = L_(gj+g-1) ... L_(gj): one thread per column, the column in registers
+        if (tid < kG * 13) {
+          const int gj = tid / 13, col = tid - 13 * gj;
+          double T[13], Tn[13];
+#pragma unroll
+          for (int i = 0; i < 13; ++i) T[i] = sm.Lk[kRicGroup * gj][i * 13 + col];
+#pragma unroll 1
+          for (int s_ = 1; s_ < kRicGroup; ++s_) {
+            const double* Ls = sm.Lk[kRicGroup * gj + s_];
+#pragma unroll
+            for (int r = 0; r < 13; ++r) {
+              double acc = 0.0;
+#pragma unroll
+              for (int i = 0; i < 13; ++i) acc = fma(Ls[r * 13 + i], T[i], acc);
+              Tn[r] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < 13; ++i) T[i] = Tn[i];
+          }
+#pragma unroll
+          for (int r = 0; r < 13; ++r) Phi[gj][r * 13 + col] = T[r];
+        }
+        __syncthreads();
       }
       RP(1);  // (factor when it ran, else loop overhead)
       // ---- x~ = K^-1 rhs by the two recursions ----
@@ -352,39 +465,26 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       if (tid < 13) sm.pv[H * kVS + tid] = 0.0;
       __syncthreads();
       RP(2);  // t phase
-      if (warp == 0) {
-        // p_k = L_k' p_k+1 + t_k on 13 lanes: the vector is read back from shared memory with seven
-        // 16-byte loads, the matrix column and t of the NEXT step are fetched while this one computes
-        // (two register sets, the loop is unrolled by two so that nothing is copied)
-        const int li = lane < 13 ? lane : 0;
-        auto fetch = [&](int k, double (&Lr)[13], double& tk) {
-#pragma unroll
-          for (int j = 0; j < 13; ++j) Lr[j] = sm.Lk[k][j * 13 + li];
-          tk = sm.tv[k * 13 + li];
-        };
-        auto step = [&](int k, const double (&Lr)[13], double tk) {
-          const double2* pn = reinterpret_cast<const double2*>(&sm.pv[(k + 1) * kVS]);
-          double v[14];
-#pragma unroll
-          for (int h = 0; h < 7; ++h) { const double2 t = pn[h]; v[2 * h] = t.x; v[2 * h + 1] = t.y; }
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int j = 0; j < 12; j += 2) { s0 = fma(Lr[j], v[j], s0); s1 = fma(Lr[j + 1], v[j + 1], s1); }
-          s0 = fma(Lr[12], v[12], s0);
-          if (lane < 13) sm.pv[k * kVS + lane] = s0 + s1 + tk;
-          __syncwarp();
-        };
-        double LA[13], LB[13], tA = 0.0, tB = 0.0;
-        fetch(H - 1, LA, tA);
-        int k = H - 1;
-#pragma unroll 1
-        for (; k >= 1; k -= 2) {
-          fetch(k - 1, LB, tB);
-          step(k, LA, tA);
-          if (k >= 2) fetch(k - 2, LA, tA);
-          step(k - 1, LB, tB);
+      {
+        // p_k = L_k' p_k+1 + t_k (p_H = 0) in three sweeps of 4 + (kG - 1) + 4 dependent steps instead of
+        // H: (1) every group runs its own recursion from a zero terminal costate, all groups at once on
+        // the half-warp slots; (2) warp 0 carries the group boundaries, p_gj = Phi_j' p_g(j+1) + (1);
+        // (3) the groups redo their interior steps from the true boundary value.
+        constexpr int g = kRicGroup;
+        const int kl = g * sg + g - 1;  // last step of this slot's group
+        if (slot_on) sm.pv[kl * kVS + sl] = sm.tv[kl * 13 + sl];
+        ric_chain(&sm.Lk[kl - 1][sl], -169, 13, &sm.pv[kl * kVS], -kVS, &sm.pv[(kl - 1) * kVS + sl], -kVS,
+                  &sm.tv[(kl - 1) * 13 + sl], -13, g - 1, slot_on);
+        __syncthreads();
+        if (warp == 0 && kG > 1) {
+          const int l0 = lane < 13 ? lane : 0;
+          ric_chain(&Phi[kG - 2][l0], -169, 13, &sm.pv[g * (kG - 1) * kVS], -g * kVS,
+                    &sm.pv[g * (kG - 2) * kVS + l0], -g * kVS, &sm.pv[g * (kG - 2) * kVS + l0], -g * kVS,
+                    kG - 1, lane < 13);
         }
-        if (k == 0) step(0, LA, tA);
+        __syncthreads();
+        ric_chain(&sm.Lk[kl][sl], -169, 13, &sm.pv[(kl + 1) * kVS], -kVS, &sm.pv[kl * kVS + sl], -kVS,
+                  &sm.tv[kl * 13 + sl], -13, g - 1, slot_on);
       }
       RP(3);  // backward chain
       __syncthreads();
@@ -414,37 +514,22 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       if (tid < 13) sm.Xv[tid] = 0.0;
       __syncthreads();
       RP(4);  // w, g, b phases
-      if (warp == 0) {
-        // X_k+1 = L_k X_k + b_k, same scheme (X_0 = 0)
-        const int li = lane < 13 ? lane : 0;
-        auto fetch = [&](int k, double (&Lr)[13], double& bk) {
-#pragma unroll
-          for (int j = 0; j < 13; ++j) Lr[j] = sm.Lk[k][li * 13 + j];
-          bk = sm.tv[k * 13 + li];
-        };
-        auto step = [&](int k, const double (&Lr)[13], double bk) {
-          const double2* xk = reinterpret_cast<const double2*>(&sm.Xv[k * kVS]);
-          double v[14];
-#pragma unroll
-          for (int h = 0; h < 7; ++h) { const double2 t = xk[h]; v[2 * h] = t.x; v[2 * h + 1] = t.y; }
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int j = 0; j < 12; j += 2) { s0 = fma(Lr[j], v[j], s0); s1 = fma(Lr[j + 1], v[j + 1], s1); }
-          s0 = fma(Lr[12], v[12], s0);
-          if (lane < 13) sm.Xv[(k + 1) * kVS + lane] = s0 + s1 + bk;
-          __syncwarp();
-        };
-        double LA[13], LB[13], bA = 0.0, bB = 0.0;
-        fetch(0, LA, bA);
-        int k = 0;
-#pragma unroll 1
-        for (; k + 1 < H; k += 2) {
-          fetch(k + 1, LB, bB);
-          step(k, LA, bA);
-          if (k + 2 < H) fetch(k + 2, LA, bA);
-          step(k + 1, LB, bB);
+      {
+        // X_k+1 = L_k X_k + b_k (X_0 = 0), same three sweeps forwards
+        constexpr int g = kRicGroup;
+        const int k0 = g * sg;  // first step of this slot's group
+        if (slot_on) sm.Xv[(k0 + 1) * kVS + sl] = sm.tv[k0 * 13 + sl];
+        ric_chain(&sm.Lk[k0 + 1][sl * 13], 169, 1, &sm.Xv[(k0 + 1) * kVS], kVS, &sm.Xv[(k0 + 2) * kVS + sl], kVS,
+                  &sm.tv[(k0 + 1) * 13 + sl], 13, g - 1, slot_on);
+        __syncthreads();
+        if (warp == 0 && kG > 1) {
+          const int l0 = lane < 13 ? lane : 0;
+          ric_chain(&Phi[1][l0 * 13], 169, 1, &sm.Xv[g * kVS], g * kVS, &sm.Xv[2 * g * kVS + l0], g * kVS,
+                    &sm.Xv[2 * g * kVS + l0], g * kVS, kG - 1, lane < 13);
         }
-        if (k < H) step(k, LA, bA);
+        __syncthreads();
+        ric_chain(&sm.Lk[k0][sl * 13], 169, 1, &sm.Xv[k0 * kVS], kVS, &sm.Xv[(k0 + 1) * kVS + sl], kVS,
+                  &sm.tv[k0 * 13 + sl], 13, g - 1, slot_on);
       }
       RP(5);  // forward chain
       __syncthreads();
@@ -464,11 +549,14 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         const double xl = sm.xt[3 * ls + ((pos < 2) ? 0 : 1)], xz = sm.xt[3 * ls + 2];
         const double zt = sm.cca[i] * xl + sm.ccz[i] * xz;
         const double zr = alpha * zt + (1.0 - alpha) * sm.z[i];
-        double zn = zr + (1.0 / sm.rv[i]) * sm.y[i];
+        // 1 / rho_i without a division: rho_i is one of three values (auxil.c set_rho_vec)
+        const double rvi = sm.rv[i];
+        const double rinv = (rvi == rho_cur) ? rinv_in : (rvi == 1e-6) ? rinv_free : rinv_eq;
+        double zn = zr + rinv * sm.y[i];
         const double lo = (double)sm.lb[i] * sm.Ev[i], hi = (double)sm.ub[i] * sm.Ev[i];
         zn = (zn < lo) ? lo : zn;
         zn = (zn > hi) ? hi : zn;
-        sm.y[i] = sm.y[i] + sm.rv[i] * (zr - zn);
+        sm.y[i] = sm.y[i] + rvi * (zr - zn);
         sm.z[i] = zn;
       }
       __syncthreads();
@@ -608,6 +696,9 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       if (sm.flags[2]) {
         ++rho_updates;
         const double rho = sm.scal[2];
+        rho_cur = rho;
+        rinv_in = 1.0 / rho;
+        rinv_eq = 1.0 / (1e3 * rho);
         for (int i = tid; i < m; i += kRicThreads) {
           const double lo = (double)sm.lb[i] * sm.Ev[i], hi = (double)sm.ub[i] * sm.Ev[i];
           int ctype = 0;
