@@ -92,36 +92,47 @@ __device__ __forceinline__ double ric_block_reduce(double v, double* red, int sl
 __device__ __noinline__ void ric_chain(const double* Mp, int m_step, int sj, const double* vin, int v_step,
                                        double* vout, int o_step, const double* addp, int a_step,
                                        int nsteps, bool wr) {
-  auto fetch = [&](int s_, double (&Lr)[13], double& ad) {
-    const double* q = Mp + s_ * m_step;
-#pragma unroll
-    for (int j = 0; j < 13; ++j) Lr[j] = q[j * sj];
-    ad = addp[s_ * a_step];
-  };
-  auto step = [&](int s_, const double (&Lr)[13], double ad) {
-    const double2* pn = reinterpret_cast<const double2*>(vin + s_ * v_step);
+  // one step: the vector loads go first (they are the critical path after the previous step's store),
+  // the next step's matrix elements and addend are requested behind them, then 13 FMAs on four
+  // accumulators (the addend seeds one of them)
+  auto step = [&](const double (&Lr)[13], double ad, bool more, double (&Ln)[13], double& adn) {
+    const double2* pn = reinterpret_cast<const double2*>(vin);
     double v[14];
 #pragma unroll
     for (int h = 0; h < 7; ++h) { const double2 t = pn[h]; v[2 * h] = t.x; v[2 * h + 1] = t.y; }
-    double s0 = 0.0, s1 = 0.0;
+    vin += v_step;
+    if (more) {
+      Mp += m_step;
+      addp += a_step;
 #pragma unroll
-    for (int j = 0; j < 12; j += 2) { s0 = fma(Lr[j], v[j], s0); s1 = fma(Lr[j + 1], v[j + 1], s1); }
-    s0 = fma(Lr[12], v[12], s0);
-    if (wr) vout[s_ * o_step] = s0 + s1 + ad;
+      for (int j = 0; j < 13; ++j) Ln[j] = Mp[j * sj];
+      adn = *addp;
+    }
+    double s0 = ad, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 12; j += 4) {
+      s0 = fma(Lr[j], v[j], s0);
+      s1 = fma(Lr[j + 1], v[j + 1], s1);
+      s2 = fma(Lr[j + 2], v[j + 2], s2);
+      s3 = fma(Lr[j + 3], v[j + 3], s3);
+    }
+    s1 = fma(Lr[12], v[12], s1);
+    if (wr) *vout = (s0 + s1) + (s2 + s3);
+    vout += o_step;
     __syncwarp();
   };
-  double LA[13], LB[13], aA = 0.0, aB = 0.0;
+  double LA[13], LB[13], aA, aB = 0.0;
+#pragma unroll
+  for (int j = 0; j < 13; ++j) LA[j] = Mp[j * sj];
+  aA = *addp;
   __syncwarp();
-  fetch(0, LA, aA);
-  int s_ = 0;
+  int left = nsteps;
 #pragma unroll 1
-  for (; s_ + 1 < nsteps; s_ += 2) {
-    fetch(s_ + 1, LB, aB);
-    step(s_, LA, aA);
-    if (s_ + 2 < nsteps) fetch(s_ + 2, LA, aA);
-    step(s_ + 1, LB, aB);
+  for (; left >= 2; left -= 2) {
+    step(LA, aA, true, LB, aB);
+    step(LB, aB, left > 2, LA, aA);
   }
-  if (s_ < nsteps) step(s_, LA, aA);
+  if (left == 1) step(LA, aA, false, LB, aB);
 }
 
 template <int H>
@@ -359,32 +370,31 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
             }
           }
           __syncthreads();
-          // Mi = Mm^-1: Gauss-Jordan sweep on the SPD 12 x 12 block, warp 0 (lane = row)
+          // Mi = Mm^-1: Gauss-Jordan sweep on the SPD 12 x 12 block, warp 0, lane r holds row r in
+          // registers; the pivot row travels by shuffle (no shared-memory round trips between pivots)
           if (warp == 0) {
-            double* Mk = sm.Mi[k];
-            for (int i = lane; i < 144; i += 32) Mk[i] = Mm[i];
-            __syncwarp();
+            const int r = lane < 12 ? lane : 0;
+            double row[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) row[j] = Mm[r * 12 + j];
+#pragma unroll
             for (int pv_ = 0; pv_ < 12; ++pv_) {
-              const double d = 1.0 / Mk[pv_ * 12 + pv_];
-              __syncwarp();
               double rowp[12];
-              if (lane < 12) {
 #pragma unroll
-                for (int j = 0; j < 12; ++j) rowp[j] = Mk[pv_ * 12 + j];
+              for (int j = 0; j < 12; ++j) rowp[j] = __shfl_sync(0xffffffffu, row[j], pv_);
+              const double d = 1.0 / rowp[pv_];
+              const bool piv = (lane == pv_);
+              const double f = row[pv_] * d;
+#pragma unroll
+              for (int j = 0; j < 12; ++j) {
+                const double upd = (j == pv_) ? -f : row[j] - f * rowp[j];
+                const double prw = (j == pv_) ? d : rowp[j] * d;
+                row[j] = piv ? prw : upd;
               }
-              __syncwarp();
-              if (lane < 12) {
-                const int r = lane;
-                if (r == pv_) {
+            }
+            if (lane < 12) {
 #pragma unroll
-                  for (int j = 0; j < 12; ++j) Mk[r * 12 + j] = (j == pv_) ? d : rowp[j] * d;
-                } else {
-                  const double f = Mk[r * 12 + pv_] * d;
-#pragma unroll
-                  for (int j = 0; j < 12; ++j) Mk[r * 12 + j] = (j == pv_) ? -f : Mk[r * 12 + j] - f * rowp[j];
-                }
-              }
-              __syncwarp();
+              for (int j = 0; j < 12; ++j) sm.Mi[k][lane * 12 + j] = row[j];
             }
           }
           __syncthreads();
@@ -473,8 +483,9 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         constexpr int g = kRicGroup;
         const int kl = g * sg + g - 1;  // last step of this slot's group
         if (slot_on) sm.pv[kl * kVS + sl] = sm.tv[kl * 13 + sl];
-        ric_chain(&sm.Lk[kl - 1][sl], -169, 13, &sm.pv[kl * kVS], -kVS, &sm.pv[(kl - 1) * kVS + sl], -kVS,
-                  &sm.tv[(kl - 1) * 13 + sl], -13, g - 1, slot_on);
+        if (2 * warp < kG)
+          ric_chain(&sm.Lk[kl - 1][sl], -169, 13, &sm.pv[kl * kVS], -kVS, &sm.pv[(kl - 1) * kVS + sl], -kVS,
+                    &sm.tv[(kl - 1) * 13 + sl], -13, g - 1, slot_on);
         __syncthreads();
         if (warp == 0 && kG > 1) {
           const int l0 = lane < 13 ? lane : 0;
@@ -483,8 +494,9 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
                     kG - 1, lane < 13);
         }
         __syncthreads();
-        ric_chain(&sm.Lk[kl][sl], -169, 13, &sm.pv[(kl + 1) * kVS], -kVS, &sm.pv[kl * kVS + sl], -kVS,
-                  &sm.tv[kl * 13 + sl], -13, g - 1, slot_on);
+        if (2 * warp < kG)
+          ric_chain(&sm.Lk[kl][sl], -169, 13, &sm.pv[(kl + 1) * kVS], -kVS, &sm.pv[kl * kVS + sl], -kVS,
+                    &sm.tv[kl * 13 + sl], -13, g - 1, slot_on);
       }
       RP(3);  // backward chain
       __syncthreads();
@@ -519,8 +531,9 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         constexpr int g = kRicGroup;
         const int k0 = g * sg;  // first step of this slot's group
         if (slot_on) sm.Xv[(k0 + 1) * kVS + sl] = sm.tv[k0 * 13 + sl];
-        ric_chain(&sm.Lk[k0 + 1][sl * 13], 169, 1, &sm.Xv[(k0 + 1) * kVS], kVS, &sm.Xv[(k0 + 2) * kVS + sl], kVS,
-                  &sm.tv[(k0 + 1) * 13 + sl], 13, g - 1, slot_on);
+        if (2 * warp < kG)
+          ric_chain(&sm.Lk[k0 + 1][sl * 13], 169, 1, &sm.Xv[(k0 + 1) * kVS], kVS, &sm.Xv[(k0 + 2) * kVS + sl], kVS,
+                    &sm.tv[(k0 + 1) * 13 + sl], 13, g - 1, slot_on);
         __syncthreads();
         if (warp == 0 && kG > 1) {
           const int l0 = lane < 13 ? lane : 0;
@@ -528,8 +541,9 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
                     &sm.Xv[2 * g * kVS + l0], g * kVS, kG - 1, lane < 13);
         }
         __syncthreads();
-        ric_chain(&sm.Lk[k0][sl * 13], 169, 1, &sm.Xv[k0 * kVS], kVS, &sm.Xv[(k0 + 1) * kVS + sl], kVS,
-                  &sm.tv[k0 * 13 + sl], 13, g - 1, slot_on);
+        if (2 * warp < kG)
+          ric_chain(&sm.Lk[k0][sl * 13], 169, 1, &sm.Xv[k0 * kVS], kVS, &sm.Xv[(k0 + 1) * kVS + sl], kVS,
+                    &sm.tv[k0 * 13 + sl], 13, g - 1, slot_on);
       }
       RP(5);  // forward chain
       __syncthreads();
