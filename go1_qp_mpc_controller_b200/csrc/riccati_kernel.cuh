@@ -37,21 +37,26 @@ template <int H>
 struct RicSmem {
   static constexpr int n = 12 * H, m = 20 * H;
   double A[169];
-  double Bs[H][156];   // scaled input matrices Bs_k = B_d(k) diag(D_k), 13 x 12 row-major
-  double Kk[H][156];   // gains, 12 x 13
+  alignas(16) double Bs[H][156];   // scaled input matrices Bs_k = B_d(k) diag(D_k), 13 x 12 row-major
+  alignas(16) double Kk[H][156];   // gains K_k (12 x 13) stored TRANSPOSED, 13 rows of 12: Kk[i * 12 + a] = K[a][i]
   double Lk[H][169];   // closed loop A - Bs K, 13 x 13
-  double Mi[H][144];   // M_k^-1, 12 x 12
+  alignas(16) double Mi[H][144];   // M_k^-1, 12 x 12
   double Pi[169];
   // factor scratch W1|W2|W3|W4|Mm (794 doubles) while the recursion is being factored; afterwards the
   // group transition matrices Phi_j = L_(5j+4) ... L_(5j), 13 x 13 each, used by every iteration
   static constexpr int kFs = (H / 5) * 169 > 794 ? (H / 5) * 169 : 794;
   double fs[kFs];
-  double x[n], xt[n], rhs[n], qb[n], Dv[n], Px[n];  // xt doubles as the new-D scratch of the Ruiz passes
+  alignas(16) double x[n];
+  alignas(16) double xt[n];
+  alignas(16) double rhs[n];
+  double qb[n], Dv[n], Px[n];  // xt doubles as the new-D scratch of the Ruiz passes
   double z[m], y[m], rv[m], cca[m], ccz[m], Ev[m];
   float lb[m], ub[m];  // UNSCALED bounds exactly as given; scaled by E (f64) where they are used
   alignas(16) double pv[(H + 1) * kVS];  // costates, one row of kVS = 14 doubles per step (16 B aligned)
   alignas(16) double Xv[(H + 1) * kVS];  // states
-  double tv[H * 13], gv[H * 12], wv[H * 12];
+  double tv[H * 13];
+  alignas(16) double gv[H * 12];
+  alignas(16) double wv[H * 12];
   double red[16 * kRicWarps];
   double scal[8];  // 0:c 1:cinv 2:rho 4:pri_res
   int flags[8];    // 0:done 1:status 2:refactor 3:problem index
@@ -80,6 +85,44 @@ __device__ __forceinline__ double ric_block_reduce(double v, double* red, int sl
 #pragma unroll
     for (int w = 0; w + st < kRicWarps; w += 2 * st) r[w] = kMax ? fmax(r[w], r[w + st]) : r[w] + r[w + st];
   return r[0];
+}
+
+// dot product of two 16-byte aligned runs of 12 doubles: six 16-byte loads each, two accumulators
+__device__ __forceinline__ double ric_dot12(const double* a, const double* b) {
+  const double2* a2 = reinterpret_cast<const double2*>(a);
+  const double2* b2 = reinterpret_cast<const double2*>(b);
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int h = 0; h < 6; ++h) {
+    const double2 x = a2[h], y = b2[h];
+    s0 = fma(x.x, y.x, s0);
+    s1 = fma(x.y, y.y, s1);
+  }
+  return s0 + s1;
+}
+
+// two adjacent outputs  (o0, o1) = sum_i M[i * 12 + a .. a + 1] v[i],  i < 13:  M 13 x 12 row-major with a
+// even (16-byte loads of the pair), v a 16-byte aligned row of kVS = 14 doubles
+__device__ __forceinline__ void ric_pair13(const double* Mcol, const double* vrow, double& o0, double& o1) {
+  const double2* v2 = reinterpret_cast<const double2*>(vrow);
+  double v[14];
+#pragma unroll
+  for (int h = 0; h < 7; ++h) { const double2 t = v2[h]; v[2 * h] = t.x; v[2 * h + 1] = t.y; }
+  double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 12; i += 2) {
+    const double2 ma = *reinterpret_cast<const double2*>(Mcol + i * 12);
+    const double2 mb = *reinterpret_cast<const double2*>(Mcol + (i + 1) * 12);
+    s0 = fma(ma.x, v[i], s0);
+    s1 = fma(ma.y, v[i], s1);
+    t0 = fma(mb.x, v[i + 1], t0);
+    t1 = fma(mb.y, v[i + 1], t1);
+  }
+  const double2 mc = *reinterpret_cast<const double2*>(Mcol + 12 * 12);
+  s0 = fma(mc.x, v[12], s0);
+  s1 = fma(mc.y, v[12], s1);
+  o0 = s0 + t0;
+  o1 = s1 + t1;
 }
 
 // One 13-lane recursion  out_s = M_s in_s + add_s,  s = 0 .. nsteps-1, on a half warp.  Every pointer
@@ -404,16 +447,13 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
             double s = 0.0;
 #pragma unroll
             for (int b = 0; b < 12; ++b) s = fma(sm.Mi[k][a * 12 + b], W4[b * 13 + j], s);
-            sm.Kk[k][idx] = s;
+            sm.Kk[k][j * 12 + a] = s;
           }
           __syncthreads();
           // Lk = A - Bs Kk (13 x 13)
           for (int idx = tid; idx < 169; idx += kRicThreads) {
             const int i = idx / 13, j = idx - 13 * i;
-            double s = sm.A[idx];
-#pragma unroll
-            for (int a = 0; a < 12; ++a) s = fma(-Bk[i * 12 + a], sm.Kk[k][a * 13 + j], s);
-            sm.Lk[k][idx] = s;
+            sm.Lk[k][idx] = sm.A[idx] - ric_dot12(&Bk[i * 12], &sm.Kk[k][j * 12]);
           }
           __syncthreads();
           // W1 = Pi Lk ; then Pi <- sym(cQ + A' W1)
@@ -467,10 +507,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       // ---- x~ = K^-1 rhs by the two recursions ----
       for (int idx = tid; idx < H * 13; idx += kRicThreads) {  // t_k = K_k' r_k
         const int k = idx / 13, i = idx - 13 * k;
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < 12; ++a) s = fma(sm.Kk[k][a * 13 + i], sm.rhs[12 * k + a], s);
-        sm.tv[idx] = s;
+        sm.tv[idx] = ric_dot12(&sm.Kk[k][i * 12], &sm.rhs[12 * k]);
       }
       if (tid < 13) sm.pv[H * kVS + tid] = 0.0;
       __syncthreads();
@@ -500,28 +537,22 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       }
       RP(3);  // backward chain
       __syncthreads();
-      for (int idx = tid; idx < H * 12; idx += kRicThreads) {  // w_k = Bs' p_k+1 - r_k
-        const int k = idx / 12, a = idx - 12 * k;
-        double s = -sm.rhs[idx];
-#pragma unroll
-        for (int i = 0; i < 13; ++i) s = fma(sm.Bs[k][i * 12 + a], sm.pv[(k + 1) * kVS + i], s);
-        sm.wv[idx] = s;
+      for (int idx = tid; idx < H * 6; idx += kRicThreads) {  // w_k = Bs' p_k+1 - r_k, two outputs per thread
+        const int k = idx / 6, a = 2 * (idx - 6 * k);
+        double o0, o1;
+        ric_pair13(&sm.Bs[k][a], &sm.pv[(k + 1) * kVS], o0, o1);
+        const double2 r2 = *reinterpret_cast<const double2*>(&sm.rhs[12 * k + a]);
+        *reinterpret_cast<double2*>(&sm.wv[12 * k + a]) = make_double2(o0 - r2.x, o1 - r2.y);
       }
       __syncthreads();
       for (int idx = tid; idx < H * 12; idx += kRicThreads) {  // g_k = -M_k^-1 w_k
         const int k = idx / 12, a = idx - 12 * k;
-        double s = 0.0;
-#pragma unroll
-        for (int b = 0; b < 12; ++b) s = fma(sm.Mi[k][a * 12 + b], sm.wv[12 * k + b], s);
-        sm.gv[idx] = -s;
+        sm.gv[idx] = -ric_dot12(&sm.Mi[k][a * 12], &sm.wv[12 * k]);
       }
       __syncthreads();
       for (int idx = tid; idx < H * 13; idx += kRicThreads) {  // b_k = Bs g_k (into tv)
         const int k = idx / 13, i = idx - 13 * k;
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < 12; ++a) s = fma(sm.Bs[k][i * 12 + a], sm.gv[12 * k + a], s);
-        sm.tv[idx] = s;
+        sm.tv[idx] = ric_dot12(&sm.Bs[k][i * 12], &sm.gv[12 * k]);
       }
       if (tid < 13) sm.Xv[tid] = 0.0;
       __syncthreads();
@@ -548,13 +579,16 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       RP(5);  // forward chain
       __syncthreads();
       // x~_k = -K_k X_k + g_k ; x <- alpha x~ + (1 - alpha) x
-      for (int idx = tid; idx < n; idx += kRicThreads) {
-        const int k = idx / 12, a = idx - 12 * k;
-        double s = sm.gv[idx];
-#pragma unroll
-        for (int i = 0; i < 13; ++i) s = fma(-sm.Kk[k][a * 13 + i], sm.Xv[k * kVS + i], s);
-        sm.xt[idx] = s;
-        sm.x[idx] = alpha * s + (1.0 - alpha) * sm.x[idx];
+      for (int idx = tid; idx < H * 6; idx += kRicThreads) {  // two outputs per thread
+        const int k = idx / 6, a = 2 * (idx - 6 * k);
+        double o0, o1;
+        ric_pair13(&sm.Kk[k][a], &sm.Xv[k * kVS], o0, o1);
+        const double2 g2 = *reinterpret_cast<const double2*>(&sm.gv[12 * k + a]);
+        const double2 xo = *reinterpret_cast<const double2*>(&sm.x[12 * k + a]);
+        const double xa = g2.x - o0, xb = g2.y - o1;
+        *reinterpret_cast<double2*>(&sm.xt[12 * k + a]) = make_double2(xa, xb);
+        *reinterpret_cast<double2*>(&sm.x[12 * k + a]) =
+            make_double2(alpha * xa + (1.0 - alpha) * xo.x, alpha * xb + (1.0 - alpha) * xo.y);
       }
       __syncthreads();
       // z~ = A x~ ; z, y updates
