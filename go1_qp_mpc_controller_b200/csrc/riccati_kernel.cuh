@@ -87,14 +87,18 @@ __device__ __forceinline__ double ric_block_reduce(double v, double* red, int sl
   return r[0];
 }
 
-// dot product of two 16-byte aligned runs of 12 doubles: six 16-byte loads each, two accumulators
-__device__ __forceinline__ double ric_dot12(const double* a, const double* b) {
+// dot product of two 16-byte aligned runs of 12 doubles: six 16-byte loads each, two accumulators.
+// Matrix rows are 96 bytes apart, so rows r and r + 4 start in the same bank group; `rot` (0 or 1,
+// bit 2 of the linear row index) makes the second of each such pair walk its chunks one position
+// ahead, which keeps the eight lanes of a quarter warp on eight different 16-byte bank groups.
+__device__ __forceinline__ double ric_dot12(const double* a, const double* b, int rot) {
   const double2* a2 = reinterpret_cast<const double2*>(a);
   const double2* b2 = reinterpret_cast<const double2*>(b);
   double s0 = 0.0, s1 = 0.0;
 #pragma unroll
   for (int h = 0; h < 6; ++h) {
-    const double2 x = a2[h], y = b2[h];
+    const int c = (h == 5) ? (rot ? 0 : 5) : h + rot;
+    const double2 x = a2[c], y = b2[c];
     s0 = fma(x.x, y.x, s0);
     s1 = fma(x.y, y.y, s1);
   }
@@ -453,7 +457,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
           // Lk = A - Bs Kk (13 x 13)
           for (int idx = tid; idx < 169; idx += kRicThreads) {
             const int i = idx / 13, j = idx - 13 * i;
-            sm.Lk[k][idx] = sm.A[idx] - ric_dot12(&Bk[i * 12], &sm.Kk[k][j * 12]);
+            sm.Lk[k][idx] = sm.A[idx] - ric_dot12(&Bk[i * 12], &sm.Kk[k][j * 12], 0);
           }
           __syncthreads();
           // W1 = Pi Lk ; then Pi <- sym(cQ + A' W1)
@@ -507,7 +511,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       // ---- x~ = K^-1 rhs by the two recursions ----
       for (int idx = tid; idx < H * 13; idx += kRicThreads) {  // t_k = K_k' r_k
         const int k = idx / 13, i = idx - 13 * k;
-        sm.tv[idx] = ric_dot12(&sm.Kk[k][i * 12], &sm.rhs[12 * k]);
+        sm.tv[idx] = ric_dot12(&sm.Kk[k][i * 12], &sm.rhs[12 * k], (idx >> 2) & 1);
       }
       if (tid < 13) sm.pv[H * kVS + tid] = 0.0;
       __syncthreads();
@@ -547,12 +551,12 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       __syncthreads();
       for (int idx = tid; idx < H * 12; idx += kRicThreads) {  // g_k = -M_k^-1 w_k
         const int k = idx / 12, a = idx - 12 * k;
-        sm.gv[idx] = -ric_dot12(&sm.Mi[k][a * 12], &sm.wv[12 * k]);
+        sm.gv[idx] = -ric_dot12(&sm.Mi[k][a * 12], &sm.wv[12 * k], (idx >> 2) & 1);
       }
       __syncthreads();
       for (int idx = tid; idx < H * 13; idx += kRicThreads) {  // b_k = Bs g_k (into tv)
         const int k = idx / 13, i = idx - 13 * k;
-        sm.tv[idx] = ric_dot12(&sm.Bs[k][i * 12], &sm.gv[12 * k]);
+        sm.tv[idx] = ric_dot12(&sm.Bs[k][i * 12], &sm.gv[12 * k], (idx >> 2) & 1);
       }
       if (tid < 13) sm.Xv[tid] = 0.0;
       __syncthreads();
