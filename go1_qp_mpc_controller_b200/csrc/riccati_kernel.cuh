@@ -247,43 +247,61 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
     // ---- modified Ruiz equilibration (osqp scaling.c scale_data), P read from global ----
     double c_run = 1.0;
     // row norms of the scaled Hessian, max_j |P_rj| D_j (its column norms, by symmetry): warp per row
+    // Only the upper triangle is read: element (r, j), j > r, serves row r (times D_j) and, by symmetry,
+    // row j (times D_r), so a pass moves half the bytes and the 148 resident Hessians (74 MB of upper
+    // triangles) stay in L2 between passes.  Row maxima by shuffle, column maxima in registers per
+    // warp; both are merged in shared memory as integer maxima of the (non-negative) bit patterns.
     auto p_row_norms = [&](bool accumulate, double& psum, double& qmax) {
-      constexpr int kNJ = (n + 31) / 32, kRows = 2;
-      for (int r0 = kRows * warp; r0 < n; r0 += kRows * kRicWarps) {
-        // all the loads of kRows rows are in flight before the first is used (the pass is latency bound)
-        double e[kRows][kNJ];
+      constexpr int kNJ = (n + 31) / 32;
+      unsigned long long* pxb = reinterpret_cast<unsigned long long*>(sm.Px);
+      for (int j = tid; j < n; j += kRicThreads) pxb[j] = 0ull;
+      __syncthreads();
+      double cm[kNJ];
 #pragma unroll
-        for (int rr = 0; rr < kRows; ++rr) {
-          const double* row = Pg + size_t(r0 + rr < n ? r0 + rr : r0) * p_row_stride;
+      for (int t = 0; t < kNJ; ++t) cm[t] = 0.0;
+      for (int rp = warp; rp < n / 2; rp += kRicWarps) {  // rows rp and n - 1 - rp: n + 1 elements together
+        const int ra = rp, rb = n - 1 - rp;
+        const double* rowa = Pg + size_t(ra) * p_row_stride;
+        const double* rowb = Pg + size_t(rb) * p_row_stride;
+        double ea[kNJ], eb[kNJ];
 #pragma unroll
-          for (int t = 0; t < kNJ; ++t) {
-            const int j = lane + 32 * t;
-            e[rr][t] = (j < n) ? row[j] : 0.0;
-          }
+        for (int t = 0; t < kNJ; ++t) {
+          const int j = lane + 32 * t;
+          ea[t] = (j >= ra && j < n) ? rowa[j] : 0.0;
+          eb[t] = (j >= rb && j < n) ? rowb[j] : 0.0;
         }
-        double mx[kRows];
-#pragma unroll
-        for (int rr = 0; rr < kRows; ++rr) mx[rr] = 0.0;
+        const double da = sm.Dv[ra], db = sm.Dv[rb];
+        double ma = 0.0, mb = 0.0;
 #pragma unroll
         for (int t = 0; t < kNJ; ++t) {
           const int j = lane + 32 * t;
           const double d = (j < n) ? sm.Dv[j] : 0.0;
-#pragma unroll
-          for (int rr = 0; rr < kRows; ++rr) mx[rr] = fmax(mx[rr], fabs(e[rr][t]) * d);
+          const double fa = fabs(ea[t]), fb = fabs(eb[t]);
+          ma = fmax(ma, fa * d);
+          mb = fmax(mb, fb * d);
+          // the diagonal element belongs to its row only
+          cm[t] = fmax(cm[t], fmax((j > ra) ? fa * da : 0.0, (j > rb) ? fb * db : 0.0));
         }
 #pragma unroll
-        for (int rr = 0; rr < kRows; ++rr) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) mx[rr] = fmax(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], o));
+        for (int o = 16; o > 0; o >>= 1) {
+          ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+          mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, o));
         }
-        if (lane < kRows && r0 + lane < n) {
-          const int r = r0 + lane;
-          const double v = c_run * sm.Dv[r] * (lane == 0 ? mx[0] : mx[kRows - 1]);
-          sm.Px[r] = v;
-          if (accumulate) {
-            psum += v;
-            qmax = fmax(qmax, fabs(c_run * sm.Dv[r] * q_all[size_t(p) * n + r]));
-          }
+        if (lane == 0) atomicMax(&pxb[ra], (unsigned long long)__double_as_longlong(ma));
+        if (lane == 1) atomicMax(&pxb[rb], (unsigned long long)__double_as_longlong(mb));
+      }
+#pragma unroll
+      for (int t = 0; t < kNJ; ++t) {
+        const int j = lane + 32 * t;
+        if (j < n && cm[t] > 0.0) atomicMax(&pxb[j], (unsigned long long)__double_as_longlong(cm[t]));
+      }
+      __syncthreads();
+      for (int r = tid; r < n; r += kRicThreads) {
+        const double v = c_run * sm.Dv[r] * sm.Px[r];
+        sm.Px[r] = v;
+        if (accumulate) {
+          psum += v;
+          qmax = fmax(qmax, fabs(c_run * sm.Dv[r] * q_all[size_t(p) * n + r]));
         }
       }
     };
@@ -595,23 +613,42 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
             make_double2(alpha * xa + (1.0 - alpha) * xo.x, alpha * xb + (1.0 - alpha) * xo.y);
       }
       __syncthreads();
-      // z~ = A x~ ; z, y updates
-      for (int i = tid; i < m; i += kRicThreads) {
-        const int ls = i / 5, pos = i - 5 * ls;
-        const double xl = sm.xt[3 * ls + ((pos < 2) ? 0 : 1)], xz = sm.xt[3 * ls + 2];
-        const double zt = sm.cca[i] * xl + sm.ccz[i] * xz;
-        const double zr = alpha * zt + (1.0 - alpha) * sm.z[i];
-        // 1 / rho_i without a division: rho_i is one of three values (auxil.c set_rho_vec)
-        const double rvi = sm.rv[i];
-        const double rinv = (rvi == rho_cur) ? rinv_in : (rvi == 1e-6) ? rinv_free : rinv_eq;
-        double zn = zr + rinv * sm.y[i];
-        const double lo = (double)sm.lb[i] * sm.Ev[i], hi = (double)sm.ub[i] * sm.Ev[i];
-        zn = (zn < lo) ? lo : zn;
-        zn = (zn > hi) ? hi : zn;
-        sm.y[i] = sm.y[i] + rvi * (zr - zn);
-        sm.z[i] = zn;
+      // z~ = A x~, z / y updates and the next rhs = sigma x - q + A'(rho z - y), fused: one thread per
+      // leg-step owns its five constraint rows and three variables, so no barrier separates the two
+      for (int ls = tid; ls < n / 3; ls += kRicThreads) {
+        const int r0 = 5 * ls, j0 = 3 * ls;
+        const double xtx = sm.xt[j0], xty = sm.xt[j0 + 1], xtz = sm.xt[j0 + 2];
+        double wgt[5], ca[5], cz[5];
+#pragma unroll
+        for (int rw = 0; rw < 5; ++rw) {
+          const int i = r0 + rw;
+          ca[rw] = sm.cca[i];
+          cz[rw] = sm.ccz[i];
+          const double zt = ca[rw] * ((rw < 2) ? xtx : xty) + cz[rw] * xtz;
+          const double zr = alpha * zt + (1.0 - alpha) * sm.z[i];
+          // 1 / rho_i without a division: rho_i is one of three values (auxil.c set_rho_vec)
+          const double rvi = sm.rv[i];
+          const double rinv = (rvi == rho_cur) ? rinv_in : (rvi == 1e-6) ? rinv_free : rinv_eq;
+          const double yi = sm.y[i];
+          double zn = zr + rinv * yi;
+          const double E = sm.Ev[i];
+          const double lo = (double)sm.lb[i] * E, hi = (double)sm.ub[i] * E;
+          zn = (zn < lo) ? lo : zn;
+          zn = (zn > hi) ? hi : zn;
+          const double yn = yi + rvi * (zr - zn);
+          sm.y[i] = yn;
+          sm.z[i] = zn;
+          wgt[rw] = rvi * zn - yn;
+        }
+        const double sx = ca[0] * wgt[0] + ca[1] * wgt[1];
+        const double sy = ca[2] * wgt[2] + ca[3] * wgt[3];
+        double sz = 0.0;
+#pragma unroll
+        for (int rw = 0; rw < 5; ++rw) sz = fma(cz[rw], wgt[rw], sz);
+        sm.rhs[j0] = sigma * sm.x[j0] - sm.qb[j0] + sx;
+        sm.rhs[j0 + 1] = sigma * sm.x[j0 + 1] - sm.qb[j0 + 1] + sy;
+        sm.rhs[j0 + 2] = sigma * sm.x[j0 + 2] - sm.qb[j0 + 2] + sz;
       }
-      __syncthreads();
       // next rhs = sigma x - q + A'(rho z - y)
       auto build_rhs = [&]() {
         for (int j = tid; j < n; j += kRicThreads) {
@@ -630,7 +667,6 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
           sm.rhs[j] = sigma * sm.x[j] - sm.qb[j] + s;
         }
       };
-      build_rhs();
       const bool can_check = (--until_check == 0);
       const bool can_adapt = (--until_adapt == 0);
       if (can_check) until_check = sp.check_termination;
