@@ -129,32 +129,45 @@ __device__ __forceinline__ void ric_pair13(const double* Mcol, const double* vro
   o1 = s1 + t1;
 }
 
+__device__ __forceinline__ double ric_lds(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 ric_lds2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
 // One 13-lane recursion  out_s = M_s in_s + add_s,  s = 0 .. nsteps-1, on a half warp.  Every pointer
-// is per lane:  Mp + s m_step + j sj  is element j of this lane's row (or column, for M') of M_s;
-// vin + s v_step  the 13-vector in_s (a 16-byte aligned row of kVS doubles; out_(s-1) for s > 0);
-// vout + s o_step  this lane's element of out_s;  addp + s a_step  its addend.  The vector comes back
-// from shared memory with seven 16-byte loads; the matrix elements and addend of the NEXT step are
-// fetched while this one computes (two register sets, loop unrolled by two so nothing is copied).
-// One shared body for all six recursion phases keeps the iteration loop inside the instruction cache.
-__device__ __noinline__ void ric_chain(const double* Mp, int m_step, int sj, const double* vin, int v_step,
+// is per lane:  Mp + s m_step + j SJ  is element j of this lane's row (SJ = 1) or column (SJ = 13, for
+// M') of M_s;  vin + s v_step  the 13-vector in_s (a 16-byte aligned row of kVS doubles; out_(s-1) for
+// s > 0);  vout + s o_step  this lane's element of out_s;  addp + s a_step  its addend.
+// A step issues, IN THIS ORDER (the loads are volatile asm so that the order survives scheduling):
+// the seven 16-byte loads of the vector, which are the critical path behind the previous step's
+// store; the matrix elements and addend of the NEXT step into the other register set (always -- one
+// step past the end reads shared memory that is allocated and ignores it, which keeps the step free
+// of branches); 13 FMAs on four accumulators, the addend seeding one; the store; the warp barrier.
+// One shared body per direction keeps the iteration loop inside the instruction cache.
+template <int SJ>
+__device__ __noinline__ void ric_chain(const double* Mp, int m_step, const double* vin, int v_step,
                                        double* vout, int o_step, const double* addp, int a_step,
                                        int nsteps, bool wr) {
-  // one step: the vector loads go first (they are the critical path after the previous step's store),
-  // the next step's matrix elements and addend are requested behind them, then 13 FMAs on four
-  // accumulators (the addend seeds one of them)
-  auto step = [&](const double (&Lr)[13], double ad, bool more, double (&Ln)[13], double& adn) {
-    const double2* pn = reinterpret_cast<const double2*>(vin);
+  uint32_t m_a = (uint32_t)__cvta_generic_to_shared(Mp);
+  uint32_t v_a = (uint32_t)__cvta_generic_to_shared(vin);
+  uint32_t d_a = (uint32_t)__cvta_generic_to_shared(addp);
+  const int m_b = m_step * 8, v_b = v_step * 8, d_b = a_step * 8;
+  auto step = [&](const double (&Lr)[13], double ad, double (&Ln)[13], double& adn) {
     double v[14];
 #pragma unroll
-    for (int h = 0; h < 7; ++h) { const double2 t = pn[h]; v[2 * h] = t.x; v[2 * h + 1] = t.y; }
-    vin += v_step;
-    if (more) {
-      Mp += m_step;
-      addp += a_step;
+    for (int h = 0; h < 7; ++h) { const double2 t = ric_lds2(v_a + 16 * h); v[2 * h] = t.x; v[2 * h + 1] = t.y; }
+    v_a += v_b;
+    m_a += m_b;
+    d_a += d_b;
 #pragma unroll
-      for (int j = 0; j < 13; ++j) Ln[j] = Mp[j * sj];
-      adn = *addp;
-    }
+    for (int j = 0; j < 13; ++j) Ln[j] = ric_lds(m_a + 8 * SJ * j);
+    adn = ric_lds(d_a);
     double s0 = ad, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int j = 0; j < 12; j += 4) {
@@ -168,18 +181,18 @@ __device__ __noinline__ void ric_chain(const double* Mp, int m_step, int sj, con
     vout += o_step;
     __syncwarp();
   };
-  double LA[13], LB[13], aA, aB = 0.0;
+  double LA[13], LB[13], aA, aB;
 #pragma unroll
-  for (int j = 0; j < 13; ++j) LA[j] = Mp[j * sj];
-  aA = *addp;
+  for (int j = 0; j < 13; ++j) LA[j] = ric_lds(m_a + 8 * SJ * j);
+  aA = ric_lds(d_a);
   __syncwarp();
   int left = nsteps;
 #pragma unroll 1
   for (; left >= 2; left -= 2) {
-    step(LA, aA, true, LB, aB);
-    step(LB, aB, left > 2, LA, aA);
+    step(LA, aA, LB, aB);
+    step(LB, aB, LA, aA);
   }
-  if (left == 1) step(LA, aA, false, LB, aB);
+  if (left == 1) step(LA, aA, LB, aB);
 }
 
 template <int H>
@@ -259,17 +272,24 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       double cm[kNJ];
 #pragma unroll
       for (int t = 0; t < kNJ; ++t) cm[t] = 0.0;
-      for (int rp = warp; rp < n / 2; rp += kRicWarps) {  // rows rp and n - 1 - rp: n + 1 elements together
-        const int ra = rp, rb = n - 1 - rp;
+      // rows rp and n - 1 - rp together hold n + 1 upper-triangle elements: every warp iteration does
+      // the same work.  The loads of the NEXT pair are in flight while this one is reduced (two
+      // register sets, loop unrolled by two): a pass is bound by the latency of one pair otherwise.
+      auto load_pair = [&](int rp, double (&ea)[kNJ], double (&eb)[kNJ]) {
+        const bool on = rp < n / 2;
+        const int ra = on ? rp : 0, rb = n - 1 - ra;
         const double* rowa = Pg + size_t(ra) * p_row_stride;
         const double* rowb = Pg + size_t(rb) * p_row_stride;
-        double ea[kNJ], eb[kNJ];
 #pragma unroll
         for (int t = 0; t < kNJ; ++t) {
           const int j = lane + 32 * t;
-          ea[t] = (j >= ra && j < n) ? rowa[j] : 0.0;
-          eb[t] = (j >= rb && j < n) ? rowb[j] : 0.0;
+          ea[t] = (on && j >= ra && j < n) ? rowa[j] : 0.0;
+          eb[t] = (on && j >= rb && j < n) ? rowb[j] : 0.0;
         }
+      };
+      auto reduce_pair = [&](int rp, const double (&ea)[kNJ], const double (&eb)[kNJ]) {
+        if (rp >= n / 2) return;
+        const int ra = rp, rb = n - 1 - rp;
         const double da = sm.Dv[ra], db = sm.Dv[rb];
         double ma = 0.0, mb = 0.0;
 #pragma unroll
@@ -289,6 +309,17 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         }
         if (lane == 0) atomicMax(&pxb[ra], (unsigned long long)__double_as_longlong(ma));
         if (lane == 1) atomicMax(&pxb[rb], (unsigned long long)__double_as_longlong(mb));
+      };
+      {
+        double eA[kNJ], fA[kNJ], eB[kNJ], fB[kNJ];
+        load_pair(warp, eA, fA);
+#pragma unroll 1
+        for (int rp = warp; rp < n / 2; rp += 2 * kRicWarps) {
+          load_pair(rp + kRicWarps, eB, fB);
+          reduce_pair(rp, eA, fA);
+          load_pair(rp + 2 * kRicWarps, eA, fA);
+          reduce_pair(rp + kRicWarps, eB, fB);
+        }
       }
 #pragma unroll
       for (int t = 0; t < kNJ; ++t) {
@@ -543,18 +574,18 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         const int kl = g * sg + g - 1;  // last step of this slot's group
         if (slot_on) sm.pv[kl * kVS + sl] = sm.tv[kl * 13 + sl];
         if (2 * warp < kG)
-          ric_chain(&sm.Lk[kl - 1][sl], -169, 13, &sm.pv[kl * kVS], -kVS, &sm.pv[(kl - 1) * kVS + sl], -kVS,
+          ric_chain<13>(&sm.Lk[kl - 1][sl], -169, &sm.pv[kl * kVS], -kVS, &sm.pv[(kl - 1) * kVS + sl], -kVS,
                     &sm.tv[(kl - 1) * 13 + sl], -13, g - 1, slot_on);
         __syncthreads();
         if (warp == 0 && kG > 1) {
           const int l0 = lane < 13 ? lane : 0;
-          ric_chain(&Phi[kG - 2][l0], -169, 13, &sm.pv[g * (kG - 1) * kVS], -g * kVS,
+          ric_chain<13>(&Phi[kG - 2][l0], -169, &sm.pv[g * (kG - 1) * kVS], -g * kVS,
                     &sm.pv[g * (kG - 2) * kVS + l0], -g * kVS, &sm.pv[g * (kG - 2) * kVS + l0], -g * kVS,
                     kG - 1, lane < 13);
         }
         __syncthreads();
         if (2 * warp < kG)
-          ric_chain(&sm.Lk[kl][sl], -169, 13, &sm.pv[(kl + 1) * kVS], -kVS, &sm.pv[kl * kVS + sl], -kVS,
+          ric_chain<13>(&sm.Lk[kl][sl], -169, &sm.pv[(kl + 1) * kVS], -kVS, &sm.pv[kl * kVS + sl], -kVS,
                     &sm.tv[kl * 13 + sl], -13, g - 1, slot_on);
       }
       RP(3);  // backward chain
@@ -585,17 +616,17 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         const int k0 = g * sg;  // first step of this slot's group
         if (slot_on) sm.Xv[(k0 + 1) * kVS + sl] = sm.tv[k0 * 13 + sl];
         if (2 * warp < kG)
-          ric_chain(&sm.Lk[k0 + 1][sl * 13], 169, 1, &sm.Xv[(k0 + 1) * kVS], kVS, &sm.Xv[(k0 + 2) * kVS + sl], kVS,
+          ric_chain<1>(&sm.Lk[k0 + 1][sl * 13], 169, &sm.Xv[(k0 + 1) * kVS], kVS, &sm.Xv[(k0 + 2) * kVS + sl], kVS,
                     &sm.tv[(k0 + 1) * 13 + sl], 13, g - 1, slot_on);
         __syncthreads();
         if (warp == 0 && kG > 1) {
           const int l0 = lane < 13 ? lane : 0;
-          ric_chain(&Phi[1][l0 * 13], 169, 1, &sm.Xv[g * kVS], g * kVS, &sm.Xv[2 * g * kVS + l0], g * kVS,
+          ric_chain<1>(&Phi[1][l0 * 13], 169, &sm.Xv[g * kVS], g * kVS, &sm.Xv[2 * g * kVS + l0], g * kVS,
                     &sm.Xv[2 * g * kVS + l0], g * kVS, kG - 1, lane < 13);
         }
         __syncthreads();
         if (2 * warp < kG)
-          ric_chain(&sm.Lk[k0][sl * 13], 169, 1, &sm.Xv[k0 * kVS], kVS, &sm.Xv[(k0 + 1) * kVS + sl], kVS,
+          ric_chain<1>(&sm.Lk[k0][sl * 13], 169, &sm.Xv[k0 * kVS], kVS, &sm.Xv[(k0 + 1) * kVS + sl], kVS,
                     &sm.tv[k0 * 13 + sl], 13, g - 1, slot_on);
       }
       RP(5);  // forward chain
