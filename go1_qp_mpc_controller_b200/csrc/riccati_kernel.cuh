@@ -37,6 +37,7 @@ template <int H>
 struct RicSmem {
   static constexpr int n = 12 * H, m = 20 * H;
   double A[169];
+  double A5[169];  // A_d^5: group transition of the open-loop recursions of the residual check
   alignas(16) double Bs[H][156];   // scaled input matrices Bs_k = B_d(k) diag(D_k), 13 x 12 row-major
   alignas(16) double Kk[H][156];   // gains K_k (12 x 13) stored TRANSPOSED, 13 rows of 12: Kk[i * 12 + a] = K[a][i]
   double Lk[H][169];   // closed loop A - Bs K, 13 x 13
@@ -52,7 +53,7 @@ struct RicSmem {
   double qb[n], Dv[n], Px[n];  // xt doubles as the new-D scratch of the Ruiz passes
   double z[m], y[m], rv[m], cca[m], ccz[m], Ev[m];
   float lb[m], ub[m];  // UNSCALED bounds exactly as given; scaled by E (f64) where they are used
-  alignas(16) double pv[(H + 1) * kVS];  // costates, one row of kVS = 14 doubles per step (16 B aligned)
+  alignas(16) double pv[(H + 2) * kVS];  // costates, one row of kVS = 14 doubles per step (16 B aligned)
   alignas(16) double Xv[(H + 1) * kVS];  // states
   double tv[H * 13];
   alignas(16) double gv[H * 12];
@@ -256,6 +257,22 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       sm.flags[1] = MPC_STATUS_UNSOLVED;
     }
     __syncthreads();
+    {  // A_d^kRicGroup by repeated products through the (still unused) factor scratch
+      const double* src = sm.A;
+#pragma unroll 1
+      for (int s_ = 1; s_ < kRicGroup; ++s_) {
+        double* dst = (s_ == kRicGroup - 1) ? sm.A5 : ((s_ & 1) ? W1 : W2);
+        if (tid < 169) {
+          const int r = tid / 13, cc = tid - 13 * r;
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < 13; ++i) acc = fma(sm.A[r * 13 + i], src[i * 13 + cc], acc);
+          dst[tid] = acc;
+        }
+        __syncthreads();
+        src = dst;
+      }
+    }
 
     // ---- modified Ruiz equilibration (osqp scaling.c scale_data), P read from global ----
     double c_run = 1.0;
@@ -715,29 +732,45 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         for (int a = 0; a < 12; ++a) s = fma(sm.Bs[k][i * 12 + a], sm.x[12 * k + a], s);
         sm.tv[idx] = s;
       }
-      if (tid < 13) { sm.Xv[tid] = 0.0; sm.pv[H * kVS + tid] = 0.0; }
+      if (tid < kVS) { sm.Xv[tid] = 0.0; sm.pv[(H + 1) * kVS + tid] = 0.0; }
       __syncthreads();
-      if (warp == 0) {
-        for (int k = 0; k < H; ++k) {  // X_k+1 = A X_k + Bs x_k
-          double s = 0.0;
-          if (lane < 13) {
-#pragma unroll
-            for (int j = 0; j < 13; ++j) s = fma(sm.A[lane * 13 + j], sm.Xv[k * kVS + j], s);
-            sm.Xv[(k + 1) * kVS + lane] = s + sm.tv[k * 13 + lane];
-          }
-          __syncwarp();
+      {
+        // X_k+1 = A X_k + (Bs x)_k from X_0 = 0, then mu_i = A' mu_i+1 + c Q X_i for i = H .. 1 (mu_H+1 = 0,
+        // stored in pv[i]): the same three sweeps as the closed-loop recursions, with A and A^5
+        constexpr int g = kRicGroup;
+        const int k0 = g * sg, l0 = lane < 13 ? lane : 0;
+        if (slot_on) sm.Xv[(k0 + 1) * kVS + sl] = sm.tv[k0 * 13 + sl];
+        if (2 * warp < kG)
+          ric_chain<1>(&sm.A[sl * 13], 0, &sm.Xv[(k0 + 1) * kVS], kVS, &sm.Xv[(k0 + 2) * kVS + sl], kVS,
+                       &sm.tv[(k0 + 1) * 13 + sl], 13, g - 1, slot_on);
+        __syncthreads();
+        if (warp == 0 && kG > 1)
+          ric_chain<1>(&sm.A5[l0 * 13], 0, &sm.Xv[g * kVS], g * kVS, &sm.Xv[2 * g * kVS + l0], g * kVS,
+                       &sm.Xv[2 * g * kVS + l0], g * kVS, kG - 1, lane < 13);
+        __syncthreads();
+        if (2 * warp < kG)
+          ric_chain<1>(&sm.A[sl * 13], 0, &sm.Xv[k0 * kVS], kVS, &sm.Xv[(k0 + 1) * kVS + sl], kVS,
+                       &sm.tv[k0 * 13 + sl], 13, g - 1, slot_on);
+        __syncthreads();
+        for (int idx = tid; idx < H * 13; idx += kRicThreads) {  // addends c Q X_i, i = 1 .. H, at tv[13 (i - 1)]
+          const int k = idx / 13, i = idx - 13 * k;
+          sm.tv[idx] = c * bp.Qd[i] * sm.Xv[(k + 1) * kVS + i];
         }
-        for (int k = H - 1; k >= 0; --k) {  // mu_k+1 = cQ X_k+1 + A' mu_k+2  (stored in pv[k+1])
-          double s = 0.0;
-          if (lane < 13) {
-            if (k < H - 1) {
-#pragma unroll
-              for (int j = 0; j < 13; ++j) s = fma(sm.A[j * 13 + lane], sm.pv[(k + 2) * kVS + j], s);
-            }
-            sm.pv[(k + 1) * kVS + lane] = s + c * bp.Qd[lane] * sm.Xv[(k + 1) * kVS + lane];
-          }
-          __syncwarp();
-        }
+        __syncthreads();
+        const int il = k0 + g;  // last index of this slot's group
+        if (slot_on) sm.pv[il * kVS + sl] = sm.tv[(il - 1) * 13 + sl];
+        if (2 * warp < kG)
+          ric_chain<13>(&sm.A[sl], 0, &sm.pv[il * kVS], -kVS, &sm.pv[(il - 1) * kVS + sl], -kVS,
+                        &sm.tv[(il - 2) * 13 + sl], -13, g - 1, slot_on);
+        __syncthreads();
+        if (warp == 0 && kG > 1)
+          ric_chain<13>(&sm.A5[l0], 0, &sm.pv[(g * (kG - 1) + 1) * kVS], -g * kVS,
+                        &sm.pv[(g * (kG - 2) + 1) * kVS + l0], -g * kVS, &sm.pv[(g * (kG - 2) + 1) * kVS + l0],
+                        -g * kVS, kG - 1, lane < 13);
+        __syncthreads();
+        if (2 * warp < kG)
+          ric_chain<13>(&sm.A[sl], 0, &sm.pv[(il + 1) * kVS], -kVS, &sm.pv[il * kVS + sl], -kVS,
+                        &sm.tv[(il - 1) * 13 + sl], -13, g - 1, slot_on);
       }
       __syncthreads();
       double v[10];
