@@ -17,8 +17,12 @@
 // from L2 every iteration.  P x for the residuals is the same structure without feedback.  The
 // explicit Hessian (from the build kernel, in HBM) is only read by the Ruiz passes.
 //
-// One CTA of 128 threads per problem (problems pulled from an atomic counter); the two
-// recursions run on 13 lanes of warp 0, everything else is one-output-per-thread phases.
+// One CTA of 256 threads per problem (problems pulled from an atomic counter).  The recursions are
+// the serial part: steps are grouped by kRicGroup = 5 and the factorisation also forms the group
+// transitions Phi_j = L_(5j+4) ... L_(5j), so that each recursion runs as three sweeps -- all groups at
+// once from a zero boundary (one group per half warp), the true group boundaries on one warp through
+// Phi_j, the groups again from their true boundary -- 4 + 5 + 4 dependent steps at H = 30 instead of
+// 30 (ric_chain).  Everything else is one- or two-outputs-per-thread phases over the horizon.
 #pragma once
 
 #include <cuda_runtime.h>
