@@ -72,6 +72,11 @@ __device__ __forceinline__ double ric_limit_scaling(double v) {
   return v > 1e4 ? 1e4 : v;
 }
 
+// max of NON-NEGATIVE doubles through their bit patterns (ordered like the values); bit-identical
+__device__ __forceinline__ double ric_max_nn(double a, double b) {
+  return (__double_as_longlong(a) > __double_as_longlong(b)) ? a : b;
+}
+
 // block-wide max or sum of one value per thread; result to every thread
 template <bool kMax>
 __device__ __forceinline__ double ric_block_reduce(double v, double* red, int slot) {
@@ -318,15 +323,16 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
           const int j = lane + 32 * t;
           const double d = (j < n) ? sm.Dv[j] : 0.0;
           const double fa = fabs(ea[t]), fb = fabs(eb[t]);
-          ma = fmax(ma, fa * d);
-          mb = fmax(mb, fb * d);
+          // maxima of non-negative doubles through their bit patterns (integer compares, not DSETP)
+          ma = ric_max_nn(ma, fa * d);
+          mb = ric_max_nn(mb, fb * d);
           // the diagonal element belongs to its row only
-          cm[t] = fmax(cm[t], fmax((j > ra) ? fa * da : 0.0, (j > rb) ? fb * db : 0.0));
+          cm[t] = ric_max_nn(cm[t], ric_max_nn((j > ra) ? fa * da : 0.0, (j > rb) ? fb * db : 0.0));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, o));
-          mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+          ma = ric_max_nn(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+          mb = ric_max_nn(mb, __shfl_xor_sync(0xffffffffu, mb, o));
         }
         if (lane == 0) atomicMax(&pxb[ra], (unsigned long long)__double_as_longlong(ma));
         if (lane == 1) atomicMax(&pxb[rb], (unsigned long long)__double_as_longlong(mb));
