@@ -46,7 +46,9 @@ constexpr int kPBytes = kN * kNP * 8;  // 122,880
 
 struct SolveSmem {
   double P[kN * kNP];       // unscaled Hessian, row stride 128, pad columns zero (TMA destination)
-  double rhs[2][kNP];       // operand of the K^-1 matvec, double buffered by iteration parity (pad = 0)
+  double rloc[kSolveWarps][16];         // right-hand side, each warp's own 15 entries (16-byte aligned, pad = 0)
+  double part[2][kSolveWarps][kNP];     // K^-1 matvec: per-warp partial sums of every output, double
+                                        //   buffered by iteration parity
   double xD[kNP];           // D .* x for P x (pad = 0)
   double Dp[kNP];           // D (pad = 0)
   double Vb[10][3][kNP];    // blocked sweep, ten slots: published pivot rows V' = A_S,: with A_SS - I
@@ -474,8 +476,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     const double rho0 = live ? ws[kWarmRho] : sp.rho;
     if (tid < kNP) {
       sm.Dp[tid] = (tid < kN) ? 1.0 : 0.0;
-      sm.rhs[0][tid] = 0.0;
-      sm.rhs[1][tid] = 0.0;
+      sm.rloc[tid >> 4][tid & 15] = 0.0;
       sm.xD[tid] = 0.0;
     }
     if (tid == 0) {
@@ -604,9 +605,9 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       if (rown) { z = ws[kWarmZ + ri]; y = ws[kWarmY + ri]; }
       const double w = rown ? (rv0 * z - y) : 0.0;
       const LegSums s = leg_reduce(cca * w, ccz * w, lbase);
-      if (vown) sm.rhs[1][vj] = sigma * x - qb0 + ((vc == 2) ? s.z : s.lat);
+      if (vown) sm.rloc[rg][vj - kTR * rg] = sigma * x - qb0 + ((vc == 2) ? s.z : s.lat);
     } else {
-      if (vown) sm.rhs[1][vj] = -qb0;  // rhs of iteration 1: x = z = y = 0
+      if (vown) sm.rloc[rg][vj - kTR * rg] = -qb0;  // rhs of iteration 1: x = z = y = 0
     }
     __syncthreads();
 
@@ -626,22 +627,54 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         PHASE_MARK(1);
       }
       if (kProfile && tid == 0) sm.fine_mark = clock64();
-      __syncthreads();  // rhs[iter & 1] is complete; rhs[(iter + 1) & 1] is free to rewrite
-      FINE_PROBE(sm, 8);  // iteration: barrier
-      // x~ = K^-1 rhs
+      // x~ = K^-1 rhs.  K^-1 is symmetric, so the 15 x 4 tile of rows R_w is also the tile of COLUMNS R_w
+      // of this lane's four outputs: the warp multiplies by ITS OWN 15 right-hand-side entries (which
+      // it wrote itself: a warp barrier, no block barrier, no operand exchange) and obtains one partial
+      // sum of all 128 outputs, four per lane, with no reduction across lanes.  The eight partial
+      // vectors meet in shared memory behind the iteration's one block barrier; lanes 2r, 2r+1 then
+      // add the eight terms of tile row r.  (This replaces a 16-shuffle transpose-reduction per warp.)
+      __syncwarp();
       double xt;
       {
-        double v[kTC];
-        load_cols(sm.rhs[iter & 1], cg, v);
-        double s[kTR];
+        double rv15[16];
+        const double2* rp = reinterpret_cast<const double2*>(sm.rloc[rg]);
 #pragma unroll
-        for (int rr = 0; rr < kTR; ++rr)
-          s[rr] = fma(a[rr][3], v[3], fma(a[rr][2], v[2], fma(a[rr][1], v[1], a[rr][0] * v[0])));
-        if (kProfile) { double chk = 0.0; for (int rr = 0; rr < kTR; ++rr) chk += s[rr]; if (chk == 1.2345e300) sm.fine[15] += 1; }
-        FINE_PROBE(sm, 9);  // iteration: rhs load + 60 FMA
-        xt = -reduce_rows(s, lane, AddOp());  // lanes 2r, 2r+1: x~ of tile row r
+        for (int h = 0; h < 8; ++h) {
+          const double2 t = rp[h];
+          rv15[2 * h] = t.x;
+          rv15[2 * h + 1] = t.y;
+        }
+        double s[kTC], u[kTC];
+#pragma unroll
+        for (int jj = 0; jj < kTC; ++jj) {
+          s[jj] = a[0][jj] * rv15[0];
+          u[jj] = a[1][jj] * rv15[1];
+        }
+#pragma unroll
+        for (int rr = 2; rr + 1 < kTR; rr += 2) {
+#pragma unroll
+          for (int jj = 0; jj < kTC; ++jj) {
+            s[jj] = fma(a[rr][jj], rv15[rr], s[jj]);
+            u[jj] = fma(a[rr + 1][jj], rv15[rr + 1], u[jj]);
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < kTC; ++jj) s[jj] = fma(a[kTR - 1][jj], rv15[kTR - 1], s[jj]) + u[jj];
+        double2* outp = reinterpret_cast<double2*>(&sm.part[iter & 1][rg][2 * cg]);
+        outp[0] = make_double2(s[0], s[1]);
+        outp[32] = make_double2(s[2], s[3]);
+        if (kProfile && s[0] == 1.2345e300) sm.fine[15] += 1;
+        FINE_PROBE(sm, 9);  // iteration: rhs load + 60 FMA + partial store
+        __syncthreads();
+        FINE_PROBE(sm, 8);  // iteration: barrier
+        const int r = (lane >> 1) < kTR ? (lane >> 1) : 0;
+        const double* pp = &sm.part[iter & 1][0][kTR * rg + r];
+        double p8[kSolveWarps];
+#pragma unroll
+        for (int w = 0; w < kSolveWarps; ++w) p8[w] = pp[w * kNP];
+        xt = -(((p8[0] + p8[1]) + (p8[2] + p8[3])) + ((p8[4] + p8[5]) + (p8[6] + p8[7])));
         if (kProfile && xt == 1.2345e300) sm.fine[15] += 1;
-        FINE_PROBE(sm, 10);  // iteration: row reduction
+        FINE_PROBE(sm, 10);  // iteration: gather of the eight partial sums
       }
       // x <- alpha x~ + (1 - alpha) x
       x = alpha * xt + (1.0 - alpha) * x;
@@ -667,7 +700,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       {
         const double w = rown ? (rvv * z - y) : 0.0;
         const LegSums s = leg_reduce(cca * w, ccz * w, lbase);
-        if (vown) sm.rhs[(iter + 1) & 1][vj] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
+        if (vown) sm.rloc[rg][vj - kTR * rg] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
       }
       FINE_PROBE(sm, 12);  // iteration: next rhs
       const bool can_check = (--until_check == 0);
@@ -790,7 +823,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         {
           const double w = rown ? (rvn * z - y) : 0.0;
           const LegSums s = leg_reduce(cca * w, ccz * w, lbase);
-          if (vown) sm.rhs[(iter + 1) & 1][vj] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
+          if (vown) sm.rloc[rg][vj - kTR * rg] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
         }
         build_G();
         __syncthreads();
