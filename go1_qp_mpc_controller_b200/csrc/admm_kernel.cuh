@@ -757,10 +757,13 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
           v[9] = fmax(fmax(fabs(qb), fabs(Aty)), fabs(Px));
         }
       }
+      {
+        // ten non-negative maxima per warp in one transpose-reduction (16 shuffles instead of 50)
+        double v15[kTR];
 #pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        const double m = warp_max(v[i]);
-        if (lane == 0) sm.red[warp * 16 + i] = m;
+        for (int i = 0; i < kTR; ++i) v15[i] = (i < 10) ? v[i] : 0.0;
+        const double m = reduce_rows(v15, lane, MaxBitsOp());  // lanes 2i, 2i+1: quantity i
+        if (!(lane & 1) && (lane >> 1) < 10) sm.red[warp * 16 + (lane >> 1)] = m;
       }
       __syncthreads();
       if (warp == 0) {
