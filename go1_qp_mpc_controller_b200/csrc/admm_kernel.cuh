@@ -4,17 +4,20 @@
 // K = P + sigma I + A' diag(rho) A, ADMM with alpha-relaxation, residual termination
 // every check_termination iterations, rho adaptation with refactorisation.
 //
-// Layout (history and measurements of v1..v12 in profiles/ and DESIGN.md):
+// Layout (history and measurements of v1..v15 in profiles/ and DESIGN.md):
 //   256 threads = 8 warps; WARP w holds rows 15w..15w+14 of -K^-1 (five leg-steps), lane cg
 //   holds the 15 x 4 register tile of columns {64i + 2cg, 64i + 2cg + 1 : i < 2}
 //   (120 registers of the 255 per thread).
 //   8 warps = 2 per SM sub-partition: the FP64-bound phases are balanced (10 warps were
 //   3:3:2:2 and left a third of the sweep at the barrier, profiles/r01_v5_*).
-//   Row sums are a recursive-halving shuffle transpose-reduction (16 shuffles per warp):
-//   afterwards lanes (2r, 2r+1) hold x~ of tile row r, i.e. leg-step g of the warp has fx/fy/fz
-//   on lanes 6g, 6g+2, 6g+4, and lanes 6g..6g+4 own its five constraint rows: the z/y update and
-//   the next right-hand side run through shuffles, ONE block barrier per ADMM iteration, x/z/y
-//   in registers.
+//   The K^-1 mat-vec of an iteration uses the SYMMETRY of the tile: warp w multiplies the columns
+//   R_w of its lanes' outputs by its own 15 right-hand-side entries, the eight partial vectors
+//   meet in shared memory behind the ONE block barrier of the iteration, and lanes (2r, 2r+1)
+//   add the eight terms of tile row r.  (Row sums by a recursive-halving shuffle transpose-
+//   reduction, 16 shuffles per warp, remain for the Ruiz norms, P x and the residual maxima.)
+//   Leg-step g of the warp has fx/fy/fz on lanes 6g, 6g+2, 6g+4, and lanes 6g..6g+4 own its five
+//   constraint rows: the z/y update and the next right-hand side run through shuffles, x/z/y in
+//   registers.
 //   K^-1 comes from a BLOCKED symmetric sweep (Gauss-Jordan on the SPD matrix) over the register
 //   tiles: 40 rank-3 blocks, synchronised by release/acquire flags instead of block barriers
 //   (owner panel runs ahead, consumers stream; see sweep_group).
