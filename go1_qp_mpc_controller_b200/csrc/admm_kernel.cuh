@@ -373,24 +373,23 @@ __device__ __forceinline__ void factor_inverse(SolveSmem& sm, double (&a)[kTR][k
     for (int rr = 0; rr < kTR; ++rr) {
       const int row = kTR * rg + rr;
       const int ls = kLegPerWarp * rg + rr / 3, rc = rr % 3;  // leg-step and component of this row (static rc)
+      // G = [[xx, 0, xz], [0, yy, yz], [xz, yz, zz]] of the row's leg-step: row rc of it, loaded
+      // unconditionally so that the column test below is three selects and no branch
       const double* g = &sm.G[ls * 6];
+      const double gr0 = (rc == 0) ? g[0] : (rc == 1) ? 0.0 : g[1];
+      const double gr1 = (rc == 0) ? 0.0 : (rc == 1) ? g[2] : g[3];
+      const double gr2 = (rc == 0) ? g[1] : (rc == 1) ? g[3] : g[4];
       const double cDr = c * sm.Dp[row];
       double pv[kTC];
       load_cols(&sm.P[row * kNP], cg, pv);
 #pragma unroll
       for (int jj = 0; jj < kTC; ++jj) {
         const int col = solve_col(cg, jj);
-        double val = cDr * pv[jj] * dcol[jj];
-        if (col == row) val += sigma;
         const int cc = col - 3 * ls;
-        if (cc >= 0 && cc < 3) {
-          // G = [[xx, 0, xz], [0, yy, yz], [xz, yz, zz]]
-          double gv;
-          if (rc == 0) gv = (cc == 0) ? g[0] : (cc == 1) ? 0.0 : g[1];
-          else if (rc == 1) gv = (cc == 0) ? 0.0 : (cc == 1) ? g[2] : g[3];
-          else gv = (cc == 0) ? g[1] : (cc == 1) ? g[3] : g[4];
-          val += gv;
-        }
+        // same order of additions as the branching form (adding 0.0 is exact)
+        double val = cDr * pv[jj] * dcol[jj];
+        val += (col == row) ? sigma : 0.0;
+        val += (cc == 0) ? gr0 : (cc == 1) ? gr1 : (cc == 2) ? gr2 : 0.0;
         a[rr][jj] = val;
       }
     }
