@@ -333,6 +333,10 @@ __device__ __forceinline__ void sweep_group(SolveSmem& sm, double (&a)[kTR][kTC]
     update_rows<0, 12>(sm, a, set + 4, rg, cg);
     FINE_PROBE(sm, 3);  // deferred part
   } else {
+    // The owner's sub-partition partner (warp kp ^ 4 shares its FP64 pipe) stays out of the way until
+    // the panel -- the serial chain every other warp waits for -- has published its last block, and
+    // applies the five blocks afterwards with the pipe to itself.
+    if (rg == (kp ^ 4)) wait_flag(sm, &sm.pub_ready, base + kb0 + kLegPerWarp);
 #pragma unroll 1
     for (int sub = 0; sub < kLegPerWarp - 1; ++sub) {
       wait_flag(sm, &sm.pub_ready, base + kb0 + sub + 1);
