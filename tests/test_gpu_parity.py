@@ -753,3 +753,36 @@ def test_long_horizon_dense_workspace_path(pkg, ob):
     assert (res["status"] == 1).all()
     assert np.array_equal(res["iters"], ref["iters"]) and grf_rel(res["grf"], ref["grf"]).max() <= TOL_GRF
     e.close()
+
+
+def test_two_engines_two_host_threads(pkg):
+    """The double-buffered use INTEGRATION.md recommends: two engines, one host thread each, batches
+    alternating between them while the kernels of both share the SMs.  Results must be the bits of a
+    single engine working through the same batches alone."""
+    import threading
+    cfg = pkg.config_default()
+    batches = [pkg.generate_states(1002, 700 * b, 700) for b in range(6)]
+    solo = pkg.MpcEngine(cfg, 0)
+    want = [solo.compute_grf_batch(b).copy() for b in batches]
+    solo.close()
+    engs = [pkg.MpcEngine(cfg, 0), pkg.MpcEngine(cfg, 0)]
+    got = [None] * len(batches)
+    errs = []
+
+    def worker(i):
+        try:
+            for b in range(i, len(batches), 2):
+                got[b] = engs[i].compute_grf_batch(batches[b]).copy()
+        except Exception as ex:  # surfaced below: an exception in a thread must fail the test
+            errs.append(ex)
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in engs:
+        e.close()
+    assert not errs, errs
+    for b in range(len(batches)):
+        assert got[b].tobytes() == want[b].tobytes()
