@@ -625,13 +625,22 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     int until_check = sp.check_termination > 0 ? sp.check_termination : 0x7fffffff;
     int until_adapt = (sp.adaptive_rho && sp.adaptive_rho_interval > 0) ? sp.adaptive_rho_interval : 0x7fffffff;
     bool need_factor = true;
-    for (iter = 1; iter <= sp.max_iter; ++iter) {
+    int par = 0;  // buffer parity of the partial sums
+    // Outer loop = one stretch of iterations up to the next event (termination check, rho adaptation,
+    // iteration limit); the inner loop runs on a plain counter, so an ordinary iteration carries no
+    // bookkeeping of the three countdowns.
+    for (;;) {
       if (need_factor) {
         // ---- K3b: factor (explicit inverse in registers); ONE call site keeps the code small ----
         need_factor = false;
         factor_inverse<kProfile>(sm, a, rg, cg, sigma, sweep_base, sweep_done);
         PHASE_MARK(1);
       }
+      int run = until_check < until_adapt ? until_check : until_adapt;
+      run = run < sp.max_iter - iter ? run : sp.max_iter - iter;
+#pragma unroll 1
+      for (int q = 0; q < run; ++q) {
+      par ^= 1;
       if (kProfile && tid == 0) sm.fine_mark = clock64();
       // x~ = K^-1 rhs.  K^-1 is symmetric, so the 15 x 4 tile of rows R_w is also the tile of COLUMNS R_w
       // of this lane's four outputs: the warp multiplies by ITS OWN 15 right-hand-side entries (which
@@ -666,7 +675,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         }
 #pragma unroll
         for (int jj = 0; jj < kTC; ++jj) s[jj] = fma(a[kTR - 1][jj], rv15[kTR - 1], s[jj]) + u[jj];
-        double2* outp = reinterpret_cast<double2*>(&sm.part[iter & 1][rg][2 * cg]);
+        double2* outp = reinterpret_cast<double2*>(&sm.part[par][rg][2 * cg]);
         outp[0] = make_double2(s[0], s[1]);
         outp[32] = make_double2(s[2], s[3]);
         if (kProfile && s[0] == 1.2345e300) sm.fine[15] += 1;
@@ -674,7 +683,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         __syncthreads();
         FINE_PROBE(sm, 8);  // iteration: barrier
         const int r = (lane >> 1) < kTR ? (lane >> 1) : 0;
-        const double* pp = &sm.part[iter & 1][0][kTR * rg + r];
+        const double* pp = &sm.part[par][0][kTR * rg + r];
         double p8[kSolveWarps];
 #pragma unroll
         for (int w = 0; w < kSolveWarps; ++w) p8[w] = pp[w * kNP];
@@ -709,12 +718,15 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         if (vown) sm.rloc[rg][vj - kTR * rg] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
       }
       FINE_PROBE(sm, 12);  // iteration: next rhs
-      const bool can_check = (--until_check == 0);
-      const bool can_adapt = (--until_adapt == 0);
+      }  // stretch of ordinary iterations
+      iter += run;
+      until_check -= run;
+      until_adapt -= run;
+      const bool can_check = (until_check == 0);
+      const bool can_adapt = (until_adapt == 0);
       if (can_check) until_check = sp.check_termination;
       if (can_adapt) until_adapt = sp.adaptive_rho_interval;
       const bool last = (iter == sp.max_iter);
-      if (!(can_check || can_adapt || last)) continue;
       PHASE_MARK(2);
 
       // ---- residuals (auxil.c compute_pri_res / compute_dua_res / tolerances) ----
