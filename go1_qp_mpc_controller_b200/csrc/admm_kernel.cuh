@@ -90,6 +90,12 @@ __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// shared-memory load that stays where it is written (the scheduler may not sink it to its first use)
+__device__ __forceinline__ double lds_f64(const double* p) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(p)));
+  return v;
+}
 
 // Reduce fifteen per-row partials over the 32 lanes of a warp by recursive halving: at the stage
 // with lane mask m a lane keeps the half of its rows whose index bit matches its own lane bit and
@@ -649,7 +655,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       // vectors meet in shared memory behind the iteration's one block barrier; lanes 2r, 2r+1 then
       // add the eight terms of tile row r.  (This replaces a 16-shuffle transpose-reduction per warp.)
       __syncwarp();
-      double xt;
+      double xt, lc_rv, lc_rinv, lc_lo, lc_hi, lc_qb;
       {
         double rv15[16];
         const double2* rp = reinterpret_cast<const double2*>(sm.rloc[rg]);
@@ -682,6 +688,13 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
         FINE_PROBE(sm, 9);  // iteration: rhs load + 60 FMA + partial store
         __syncthreads();
         FINE_PROBE(sm, 8);  // iteration: barrier
+        // the five per-lane constants of the z / y / rhs chain are requested here, behind the barrier
+        // and ahead of the gather (volatile asm keeps them from sinking to their first use)
+        lc_rv = lds_f64(&sm.lane_rv[tid]);
+        lc_rinv = lds_f64(&sm.lane_rinv[tid]);
+        lc_lo = lds_f64(&sm.lane_lb[tid]);
+        lc_hi = lds_f64(&sm.lane_ub[tid]);
+        lc_qb = lds_f64(&sm.lane_qb[tid]);
         const int r = (lane >> 1) < kTR ? (lane >> 1) : 0;
         const double* pp = &sm.part[par][0][kTR * rg + r];
         double p8[kSolveWarps];
@@ -694,15 +707,15 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       // x <- alpha x~ + (1 - alpha) x
       x = alpha * xt + (1.0 - alpha) * x;
       // z~ = A x~ ; z, y update on the row lanes
-      const double rvv = sm.lane_rv[tid];
+      const double rvv = lc_rv;
       {
         const double xt_lat = shfl(xt, latsrc), xt_z = shfl(xt, zsrc);
         const double zt = cca * xt_lat + ccz * xt_z;
         const double zr = alpha * zt + (1.0 - alpha) * z;
-        double zn = zr + sm.lane_rinv[tid] * y;
+        double zn = zr + lc_rinv * y;
         {
           // box projection; plain compare-selects (double fmin/fmax cost ~25 cycles each here)
-          const double lo = sm.lane_lb[tid], hi = sm.lane_ub[tid];
+          const double lo = lc_lo, hi = lc_hi;
           zn = (zn < lo) ? lo : zn;
           zn = (zn > hi) ? hi : zn;
         }
@@ -715,7 +728,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       {
         const double w = rown ? (rvv * z - y) : 0.0;
         const LegSums s = leg_reduce(cca * w, ccz * w, lbase);
-        if (vown) sm.rloc[rg][vj - kTR * rg] = sigma * x - sm.lane_qb[tid] + ((vc == 2) ? s.z : s.lat);
+        if (vown) sm.rloc[rg][vj - kTR * rg] = sigma * x - lc_qb + ((vc == 2) ? s.z : s.lat);
       }
       FINE_PROBE(sm, 12);  // iteration: next rhs
       }  // stretch of ordinary iterations
