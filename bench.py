@@ -47,7 +47,7 @@ FP64_PEAK_TFLOPS = 34.1
 # ncu --set full capture (profiles/r01_v13_ncu_summary.txt: 37.30 MB read, 0 written, 296 solves):
 # the padded f64 Hessian (122,880 B) + q, l, u, state.  P is an intermediate of the path, not
 # algorithmic input, hence the much smaller hbm_algorithmic_bytes_per_solve.
-NCU_DRAM_BYTES_PER_SOLVE = 37.295616e6 / 296
+NCU_DRAM_BYTES_PER_SOLVE = 37.295872e6 / 296
 
 
 def measured_hbm_peak_gbs():
@@ -395,7 +395,7 @@ def run_ours(args):
                          "kernel": "admm_solve_kernel", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
                          "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
                          "traffic": NCU_DRAM_BYTES_PER_SOLVE * BATCH,
-                         "traffic_source": "ncu --set full, profiles/r01_v17_ncu_summary.txt, scaled to this launch's solves",
+                         "traffic_source": "ncu --set full, profiles/r01_v19_ncu_summary.txt, scaled to this launch's solves",
                          "hbm": {"achieved": NCU_DRAM_BYTES_PER_SOLVE * BATCH / (solve_ms * 1e-3) / 1e9,
                                  "peak": measured_hbm_peak_gbs()[0], "unit": "GB/s",
                                  "frac": NCU_DRAM_BYTES_PER_SOLVE * BATCH / (solve_ms * 1e-3) / 1e9 / measured_hbm_peak_gbs()[0],
