@@ -706,6 +706,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       }
       // x <- alpha x~ + (1 - alpha) x
       x = alpha * xt + (1.0 - alpha) * x;
+      const double sxq = sigma * x - lc_qb;  // off the z / y chain: only the leg sums are added at its end
       // z~ = A x~ ; z, y update on the row lanes
       const double rvv = lc_rv;
       {
@@ -728,7 +729,7 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
       {
         const double w = rown ? (rvv * z - y) : 0.0;
         const LegSums s = leg_reduce(cca * w, ccz * w, lbase);
-        if (vown) sm.rloc[rg][vj - kTR * rg] = sigma * x - lc_qb + ((vc == 2) ? s.z : s.lat);
+        if (vown) sm.rloc[rg][vj - kTR * rg] = sxq + ((vc == 2) ? s.z : s.lat);
       }
       FINE_PROBE(sm, 12);  // iteration: next rhs
       }  // stretch of ordinary iterations
