@@ -230,6 +230,9 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
   const bool slot_on = hl < 13 && slot < kG;
   const int sl = hl < 13 ? hl : 0, sg = slot < kG ? slot : 0;
 
+  // Profiling build only (-DRIC_PROF, or `#define RIC_PROF 1` above; run scripts/prof_ric.py): thread 0
+  // accumulates clock64 per phase and prints the totals of the first two problems.  Compiled out
+  // otherwise: RP(i) is empty.
 #ifdef RIC_PROF
   long long pc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pm_ = 0;
 #define RP(i) do { if (tid == 0) { const long long t_ = clock64(); pc_[i] += t_ - pm_; pm_ = t_; } } while (0)
