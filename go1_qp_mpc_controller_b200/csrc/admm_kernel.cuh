@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // shared-memory load that stays where it is written (the scheduler may not sink it to its first use)
 __device__ __forceinline__ double lds_f64(const double* p) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(p)));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(p)) : "memory");
   return v;
 }
 
