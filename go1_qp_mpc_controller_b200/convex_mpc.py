@@ -203,14 +203,23 @@ class A1RobotControl:
         self._device = device
         self._engine = None
         self._balance = None
+        self._balance_key = None
+        self.last_status = None
+        self.last_iters = None
         self.mpc_init_counter = 0
         self._torques = None
 
     def _mpc_engine(self, state, mpc_dt):
+        """The engine whose slot 0 is this controller's member solver (A1RobotControl.h:67).  The
+        reference re-reads mass, inertia and weights from the state on every call into a fresh
+        ConvexMpc (A1RobotControl.cpp:447) while the OsqpEigen solver lives on: a change of those is
+        one more Hessian update, not a new solver -- so the engine's model is updated in place."""
         cfg = self._cfg
-        same = (self._engine is not None and abs(cfg.dt - mpc_dt) == 0.0 and cfg.mass == state.robot_mass
-                and list(cfg.q_weights) == list(state.q_weights) and list(cfg.r_weights) == list(state.r_weights)
-                and list(cfg.inertia) == list(np.asarray(state.a1_trunk_inertia).reshape(9)))
+        inertia = [float(v) for v in np.asarray(state.a1_trunk_inertia).reshape(9)]
+        same = (abs(cfg.dt - mpc_dt) == 0.0 and cfg.mass == state.robot_mass
+                and list(cfg.q_weights) == [float(v) for v in state.q_weights]
+                and list(cfg.r_weights) == [float(v) for v in state.r_weights]
+                and list(cfg.inertia) == inertia)
         if not same:
             cfg.dt = mpc_dt
             cfg.mass = state.robot_mass
@@ -218,16 +227,40 @@ class A1RobotControl:
                 cfg.q_weights[i] = state.q_weights[i]
             for i in range(12):
                 cfg.r_weights[i] = state.r_weights[i]
-            inertia = np.asarray(state.a1_trunk_inertia).reshape(9)
             for i in range(9):
                 cfg.inertia[i] = inertia[i]
             if self._engine is not None:
-                self._engine.close()
+                self._engine.update_model(cfg)
+        if self._engine is None:
             self._engine = MpcEngine(cfg, self._device)
         return self._engine
 
+    def _balance_engine(self, state):
+        """Gains and mass are read from the state on every tick (A1RobotControl.cpp:380-391): a change
+        rebuilds the engine (this branch's solver is a per-call local in the reference, :416-432)."""
+        from .engine import balance_config_default
+        key = (float(state.robot_mass),) + tuple(float(v) for f in ("kp_linear", "kd_linear", "kp_angular", "kd_angular")
+                                                 for v in getattr(state, f))
+        if self._balance is None or key != self._balance_key:
+            bcfg = balance_config_default()
+            bcfg.mass = state.robot_mass
+            for i in range(3):
+                bcfg.kp_linear[i] = state.kp_linear[i]
+                bcfg.kd_linear[i] = state.kd_linear[i]
+                bcfg.kp_angular[i] = state.kp_angular[i]
+                bcfg.kd_angular[i] = state.kd_angular[i]
+            if self._balance is not None:
+                self._balance.close()
+            self._balance = MpcEngine(bcfg, self._device, balance=True)
+            self._balance_key = key
+        return self._balance
+
     def compute_grf(self, state, dt):
-        """Returns the 3x4 body-frame GRF like the reference; also writes mpc_states(_d)."""
+        """Returns the 3x4 body-frame GRF like the reference; also writes mpc_states(_d).
+
+        MPC branch: ONE persistent, warm-started solver like the reference's member
+        (A1RobotControl.cpp:522-540): the first call is initSolver (cold), every later call is
+        updateHessianMatrix / updateGradient / updateBounds + a warm solve()."""
         if state.stance_leg_control_type == 1:
             mpc_dt = dt if self.use_sim_time == "true" else 0.0025  # :462-467
             eng = self._mpc_engine(state, mpc_dt)
@@ -237,26 +270,24 @@ class A1RobotControl:
             eng.load_states(state.to_record())
             eng.set_torque_inputs(state.to_torque_record())
             eng.build_qp(sync=False)
-            eng.solve(sync=False)
+            eng.solve_warm(sync=False)
             res = eng.get_results()
             self._torques = eng.get_torques()[0]
         else:
-            if self._balance is None:
-                from .engine import balance_config_default
-                bcfg = balance_config_default()
-                bcfg.mass = state.robot_mass
-                for i in range(3):
-                    bcfg.kp_linear[i] = state.kp_linear[i]
-                    bcfg.kd_linear[i] = state.kd_linear[i]
-                    bcfg.kp_angular[i] = state.kp_angular[i]
-                    bcfg.kd_angular[i] = state.kd_angular[i]
-                self._balance = MpcEngine(bcfg, self._device, balance=True)
-            self._balance.load_states(state.to_balance_record())
-            self._balance.set_torque_inputs(state.to_torque_record())
-            self._balance.solve(sync=False)
-            res = self._balance.get_results()
-            self._torques = self._balance.get_torques()[0]
+            bal = self._balance_engine(state)
+            bal.load_states(state.to_balance_record())
+            bal.set_torque_inputs(state.to_torque_record())
+            bal.solve(sync=False)
+            res = bal.get_results()
+            self._torques = bal.get_torques()[0]
+        self.last_status = int(res["status"][0])
+        self.last_iters = int(res["iters"][0])
         return np.asarray(res["grf"][0], dtype=np.float64).reshape(4, 3).T
+
+    def reset_solver(self):
+        """Forget the member solver (the next MPC call is an initSolver again)."""
+        if self._engine is not None:
+            self._engine.stream_reset()
 
     def compute_joint_torques(self, state):
         """A1RobotControl.cpp:289-319 with the torques the device wrote next to the last GRF:

@@ -868,10 +868,17 @@ admm_solve_kernel(const double* __restrict__ P_all, const double* __restrict__ q
     if (iter > sp.max_iter) iter = sp.max_iter;
 
     if (kWarm) {
-      // keep the solver alive for the next tick
+      // keep the solver alive for the next tick -- unless this solve went wrong (non-finite iterates
+      // from one bad record, or the sweep's flag wait timed out): a poisoned slot would warm-start
+      // every later tick of this robot from NaN, so it is left dead and the next tick is an initSolver
+      const bool own_ok = (!vown || isfinite(x)) && (!rown || (isfinite(z) && isfinite(y)));
+      const int all_ok = __syncthreads_and(own_ok);
       if (vown) { ws[kWarmX + vj] = x; ws[kWarmQ + vj] = q0; }
       if (rown) { ws[kWarmZ + ri] = z; ws[kWarmY + ri] = y; }
-      if (tid == 0) { ws[kWarmRho] = sm.scal[2]; ws[kWarmLive] = 1.0; }
+      if (tid == 0) {
+        ws[kWarmRho] = sm.scal[2];
+        ws[kWarmLive] = (all_ok && !sm.flags[4] && isfinite(sm.scal[2])) ? 1.0 : 0.0;
+      }
     }
     // ---- K5: unscale, rotate the first step to the body frame, write ----
     const double xo = sm.lane_D[tid] * x;

@@ -18,6 +18,7 @@
 #include "prep_kernel.cuh"
 #include "riccati_kernel.cuh"
 #include "torque_map.cuh"
+#include "wrench_kernel.cuh"
 
 using namespace mpcb200;
 
@@ -58,6 +59,9 @@ struct MpcEngine {
   bool torque_on = false;
   double* d_model = nullptr;      // structured solver: A_d | B_d list per problem (169 + 156 H doubles)
   bool structured = false;        // solve through the Riccati recursion instead of the dense inverse
+  bool wrench = false;            // H = 10 default: fused build + wrench-space ADMM (wrench_kernel.cuh), no Hessian in HBM
+  bool dense_ready = false;       // wrench engines: the dense QP (P, q, l, u) of the loaded states has been built for mpc_get_qp
+  int dense_capacity = 0;         // problems the dense QP buffers can hold
   MpcGaitIn* d_gait = nullptr;    // gait scheduler records of the loaded states (gait_aware engines)
   int gait_capacity = 0;
   bool gait_on = false;
@@ -107,6 +111,20 @@ SolveParams make_solve_params(const MpcSolverSettings& s, double mu) {
   sp.adaptive_rho = s.adaptive_rho;
   sp.adaptive_rho_interval = s.adaptive_rho_interval;
   return sp;
+}
+
+void fill_model(MpcEngine* e, const MpcConfig* cfg) {
+  e->bp.dt = cfg->dt;
+  e->bp.mu = cfg->mu;
+  e->bp.fz_min = cfg->fz_min;
+  e->bp.fz_max = cfg->fz_max;
+  e->bp.mass = cfg->mass;
+  for (int i = 0; i < 9; ++i) e->bp.inertia[i] = cfg->inertia[i];
+  for (int i = 0; i < 13; ++i) e->bp.Qd[i] = 2.0 * cfg->q_weights[i];  // ConvexMpc.cpp:20
+  for (int i = 0; i < 12; ++i) e->bp.Rd[i] = 2.0 * cfg->r_weights[i];  // ConvexMpc.cpp:41
+  e->bp.exact_discretization = cfg->exact_discretization != 0;
+  e->bp.foot_drift = cfg->foot_drift != 0;
+  e->bp.gait_aware = cfg->gait_aware != 0;
 }
 
 int validate_settings(const MpcSolverSettings& s, std::string* why) {
@@ -172,10 +190,15 @@ int reserve(MpcEngine* e, int n) {
   if (e->kind == 0 && e->H != kH && cap > n) cap = n < 64 ? 64 : n;  // 1 MB per problem: no slack
   if (e->kind == 0) {
     CUDA_TRY(e, cudaMalloc(&e->d_states_own, size_t(cap) * sizeof(MpcStateIn)));
-    CUDA_TRY(e, cudaMalloc(&e->d_P, size_t(cap) * e->p_stride() * sizeof(double)));
-    CUDA_TRY(e, cudaMalloc(&e->d_q, size_t(cap) * e->nvar() * sizeof(double)));
-    CUDA_TRY(e, cudaMalloc(&e->d_l, size_t(cap) * e->ncon() * sizeof(float)));
-    CUDA_TRY(e, cudaMalloc(&e->d_u, size_t(cap) * e->ncon() * sizeof(float)));
+    e->dense_capacity = 0;
+    if (!e->wrench) {
+      // the wrench-space engine never writes the QP to memory; mpc_get_qp builds it on demand
+      CUDA_TRY(e, cudaMalloc(&e->d_P, size_t(cap) * e->p_stride() * sizeof(double)));
+      CUDA_TRY(e, cudaMalloc(&e->d_q, size_t(cap) * e->nvar() * sizeof(double)));
+      CUDA_TRY(e, cudaMalloc(&e->d_l, size_t(cap) * e->ncon() * sizeof(float)));
+      CUDA_TRY(e, cudaMalloc(&e->d_u, size_t(cap) * e->ncon() * sizeof(float)));
+      e->dense_capacity = cap;
+    }
     CUDA_TRY(e, cudaMalloc(&e->d_x, size_t(cap) * e->nvar() * sizeof(float)));
     if (e->structured) CUDA_TRY(e, cudaMalloc(&e->d_model, size_t(cap) * (169 + 156 * e->H) * sizeof(double)));
   } else {
@@ -257,6 +280,36 @@ int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l,
   return MPC_OK;
 }
 
+// H = 10 default path: one fused kernel from the state records to the results
+int launch_wrench(MpcEngine* e, int n, double* warm, bool with_torque) {
+  const MpcTorqueIn* tin = with_torque ? e->d_tin : nullptr;
+  CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
+  const int full = e->num_sms * kWrCtasPerSm;
+  const int grid = n < full ? n : full;
+  wrench_solve_kernel<<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
+      e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
+  ++e->launches;
+  CUDA_TRY(e, cudaGetLastError());
+  return MPC_OK;
+}
+
+// wrench engines: dense QP buffers for the parity / debug read-back
+int ensure_dense(MpcEngine* e) {
+  if (e->dense_capacity >= e->n && e->d_P) return MPC_OK;
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  cudaFree(e->d_P); cudaFree(e->d_q); cudaFree(e->d_l); cudaFree(e->d_u);
+  e->d_P = e->d_q = nullptr;
+  e->d_l = e->d_u = nullptr;
+  e->dense_capacity = 0;
+  const size_t cap = size_t(e->n < 64 ? 64 : e->n);
+  CUDA_TRY(e, cudaMalloc(&e->d_P, cap * e->p_stride() * sizeof(double)));
+  CUDA_TRY(e, cudaMalloc(&e->d_q, cap * e->nvar() * sizeof(double)));
+  CUDA_TRY(e, cudaMalloc(&e->d_l, cap * e->ncon() * sizeof(float)));
+  CUDA_TRY(e, cudaMalloc(&e->d_u, cap * e->ncon() * sizeof(float)));
+  e->dense_capacity = int(cap);
+  return MPC_OK;
+}
+
 int reserve_torque(MpcEngine* e, int n) {
   if (n <= e->torque_capacity) return MPC_OK;
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -299,6 +352,7 @@ int create_common(int kind, int device, MpcEngine** out) {
   opt_in((const void*)riccati_solve_kernel<30>, sizeof(RicSmem<30>), "riccati_solve_kernel<30> shared memory");
   opt_in((const void*)gen_build_kernel<30>, sizeof(GenBuildSmem<30>), "gen_build_kernel<30> shared memory");
   opt_in((const void*)gen_solve_kernel<30>, sizeof(GenSolveSmem<30>), "gen_solve_kernel<30> shared memory");
+  opt_in((const void*)wrench_solve_kernel, sizeof(WrenchSmem), "wrench_solve_kernel shared memory");
   if (crc != cudaSuccess) {
     std::string msg = std::string("engine setup (") + what + "): " + cudaGetErrorString(crc);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -341,18 +395,13 @@ int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
       return fail(nullptr, MPC_ERR_CUDA, msg);
     }
   }
-  e->bp.dt = cfg->dt;
-  e->bp.mu = cfg->mu;
-  e->bp.fz_min = cfg->fz_min;
-  e->bp.fz_max = cfg->fz_max;
-  e->bp.mass = cfg->mass;
-  for (int i = 0; i < 9; ++i) e->bp.inertia[i] = cfg->inertia[i];
-  for (int i = 0; i < 13; ++i) e->bp.Qd[i] = 2.0 * cfg->q_weights[i];
-  for (int i = 0; i < 12; ++i) e->bp.Rd[i] = 2.0 * cfg->r_weights[i];
-  e->bp.exact_discretization = cfg->exact_discretization != 0;
-  e->bp.foot_drift = cfg->foot_drift != 0;
-  e->bp.gait_aware = cfg->gait_aware != 0;
+  fill_model(e, cfg);
+  if (cfg->structured_solver < 0 || cfg->structured_solver > 3 || (cfg->structured_solver == 3 && cfg->horizon != kH)) {
+    mpc_engine_destroy(e);
+    return fail(nullptr, MPC_ERR_INVALID, "structured_solver must be 0..3 (3 = wrench-space, horizon 10 only)");
+  }
   e->structured = cfg->structured_solver == 1 || (cfg->structured_solver == 0 && cfg->horizon != kH);
+  e->wrench = cfg->horizon == kH && (cfg->structured_solver == 0 || cfg->structured_solver == 3);
   e->sp = make_solve_params(cfg->osqp, cfg->mu);
   *out = e;
   return MPC_OK;
@@ -471,7 +520,9 @@ int mpc_build_qp_async(MpcEngine* e) {
   if (e->bp.gait_aware && !e->gait_on && e->n > 0)
     return fail(e, MPC_ERR_STATE, "gait_aware engine: mpc_set_gait_inputs must follow the state load");
   CUDA_TRY(e, cudaSetDevice(e->device));
-  if (e->n > 0) {
+  e->dense_ready = false;
+  if (e->n > 0 && !e->wrench) {
+    // (wrench engines build inside the solve kernel; mpc_get_qp builds the dense QP on demand)
     ModelIn none{};
     int rc = launch_build(e, e->d_states, none, e->n, e->d_P, e->d_q, e->d_l, e->d_u, e->structured ? e->d_model : nullptr);
     if (rc) return rc;
@@ -492,6 +543,14 @@ int mpc_get_qp(MpcEngine* e, int32_t idx, float* P, float* q, float* l, float* u
   if (!e->built) return fail(e, MPC_ERR_STATE, "mpc_get_qp before mpc_build_qp");
   if (idx < 0 || idx >= e->n) return fail(e, MPC_ERR_INVALID, "problem index out of range");
   CUDA_TRY(e, cudaSetDevice(e->device));
+  if (e->wrench && !e->dense_ready) {
+    int rc = ensure_dense(e);
+    if (rc) return rc;
+    ModelIn none{};
+    rc = launch_build(e, e->d_states, none, e->n, e->d_P, e->d_q, e->d_l, e->d_u, nullptr);
+    if (rc) return rc;
+    e->dense_ready = true;
+  }
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   const int nv = e->nvar(), nc = e->ncon();
   const size_t stride = e->H == kH ? size_t(kNP) : size_t(nv);
@@ -516,8 +575,9 @@ int mpc_solve_async(MpcEngine* e) {
   if (!e->built) return fail(e, MPC_ERR_STATE, "mpc_solve before mpc_build_qp");
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->n > 0) {
-    int rc = launch_solve(e, e->d_P, e->d_q, e->d_l, e->d_u, e->d_states, e->d_results, e->d_x, e->n, nullptr,
-                          e->torque_on);
+    int rc = e->wrench ? launch_wrench(e, e->n, nullptr, e->torque_on)
+                       : launch_solve(e, e->d_P, e->d_q, e->d_l, e->d_u, e->d_states, e->d_results, e->d_x, e->n, nullptr,
+                                      e->torque_on);
     if (rc) return rc;
   }
   e->solved = true;
@@ -683,6 +743,36 @@ int mpc_stream_reset(MpcEngine* e) {
   return MPC_OK;
 }
 
+int mpc_stream_reset_slots(MpcEngine* e, const int32_t* idx, int32_t k) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (k < 0 || (k > 0 && !idx)) return fail(e, MPC_ERR_INVALID, "bad slot list");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  for (int i = 0; i < k; ++i) {
+    if (idx[i] < 0) return fail(e, MPC_ERR_INVALID, "negative slot index");
+    if (idx[i] >= e->warm_capacity) continue;  // a slot that never solved is not live
+    CUDA_TRY(e, cudaMemsetAsync(e->d_warm + size_t(idx[i]) * kWarmStride + kWarmLive, 0, sizeof(double), e->stream));
+  }
+  return MPC_OK;
+}
+
+int mpc_engine_update_model(MpcEngine* e, const MpcConfig* cfg) {
+  if (!e || e->kind != 0) return MPC_ERR_INVALID;
+  if (!cfg) return fail(e, MPC_ERR_INVALID, "cfg is NULL");
+  if (cfg->horizon != e->cfg.horizon || cfg->structured_solver != e->cfg.structured_solver ||
+      (cfg->exact_discretization != 0) != (e->cfg.exact_discretization != 0) ||
+      (cfg->foot_drift != 0) != (e->cfg.foot_drift != 0) || (cfg->gait_aware != 0) != (e->cfg.gait_aware != 0))
+    return fail(e, MPC_ERR_INVALID, "mpc_engine_update_model: horizon, extension flags and structured_solver are fixed at creation");
+  std::string why;
+  if (validate_settings(cfg->osqp, &why)) return fail(e, MPC_ERR_INVALID, why);
+  if (!(cfg->dt > 0) || !(cfg->mass > 0) || !(cfg->mu > 0)) return fail(e, MPC_ERR_INVALID, "dt/mass/mu must be positive");
+  e->cfg = *cfg;
+  fill_model(e, cfg);
+  e->sp = make_solve_params(cfg->osqp, cfg->mu);
+  e->built = e->solved = false;  // the loaded states must be rebuilt with the new constants
+  e->dense_ready = false;
+  return MPC_OK;
+}
+
 int mpc_solve_warm_async(MpcEngine* e) {
   if (!e || e->kind != 0) return MPC_ERR_INVALID;
   if (e->H != kH) return fail(e, MPC_ERR_UNSUPPORTED, "warm-started streaming is built for horizon 10 only");
@@ -706,8 +796,9 @@ int mpc_solve_warm_async(MpcEngine* e) {
     e->warm_capacity = e->n;
   }
   if (e->n > 0) {
-    int rc = launch_solve(e, e->d_P, e->d_q, e->d_l, e->d_u, e->d_states, e->d_results, e->d_x, e->n, e->d_warm,
-                          e->torque_on);
+    int rc = e->wrench ? launch_wrench(e, e->n, e->d_warm, e->torque_on)
+                       : launch_solve(e, e->d_P, e->d_q, e->d_l, e->d_u, e->d_states, e->d_results, e->d_x, e->n, e->d_warm,
+                                      e->torque_on);
     if (rc) return rc;
   }
   e->solved = true;

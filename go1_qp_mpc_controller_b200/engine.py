@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "mpc_stream_step", "mpc_set_torque_inputs", "mpc_get_torques", "mpc_generate_torque_inputs",
     "prep_config_default", "mpc_prepare_states", "mpc_get_prepared", "mpc_prepare_reset", "mpc_generate_sensors",
     "a1_leg_fk_jac", "mpc_set_gait_inputs", "mpc_generate_gait_inputs",
+    "mpc_stream_reset_slots", "mpc_engine_update_model",
 ]
 
 
@@ -90,6 +91,8 @@ def load_library():
     lib.mpc_solve_warm_async.argtypes = [vp]
     lib.mpc_stream_reset.argtypes = [vp]
     lib.mpc_stream_step.argtypes = [vp, vp, vp, i32]
+    lib.mpc_stream_reset_slots.argtypes = [vp, vp, i32]
+    lib.mpc_engine_update_model.argtypes = [vp, C.POINTER(abi.MpcConfig)]
     lib.mpc_qp_mats_from_model.argtypes = [vp] + [vp] * 9
     lib.mpc_solve_qp.argtypes = [vp] + [vp] * 7
     lib.balance_qp_solve.argtypes = [vp, vp, vp, i32]
@@ -381,6 +384,17 @@ class MpcEngine:
 
     def stream_reset(self):
         self._check(self._lib.mpc_stream_reset(self._h))
+
+    def stream_reset_slots(self, idx):
+        """Forget the live solvers of the robot slots `idx` only (their next tick is an initSolver)."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        self._check(self._lib.mpc_stream_reset_slots(self._h, _ptr(idx), len(idx)))
+
+    def update_model(self, cfg):
+        """New model constants (mass, inertia, weights, dt, solver settings) on a live engine: the warm
+        solvers stay alive, like the reference's member solver across weight changes."""
+        self._check(self._lib.mpc_engine_update_model(self._h, C.byref(cfg)))
+        self.cfg = cfg
 
     def stream_step(self, states, out=None):
         """One control tick for every robot: host in, host out, warm-started solve."""

@@ -101,6 +101,18 @@ class ConvexMpc {
  public:
   ConvexMpc(const std::array<double, 13>& q_weights_, const std::array<double, 12>& r_weights_, int device = 0) {
     mu = 0.3; fz_min = 0.0; fz_max = 0.0;                       // ConvexMpc.cpp:8-10
+    // linear_constraints (ConvexMpc.cpp:46-58), dense row-major (20 H) x (12 H): per leg-step the rows
+    // fx + mu fz, fx - mu fz, fy + mu fz, fy - mu fz, fz.  The reference's callers read it when they
+    // set up their solver (A1RobotControl.cpp:527, test/test_mpc.cpp:143).
+    linear_constraints.assign(size_t(20 * PLAN_HORIZON) * 12 * PLAN_HORIZON, 0.0);
+    for (int i = 0; i < NUM_LEG * PLAN_HORIZON; ++i) {
+      auto lc = [&](int r, int c) -> double& { return linear_constraints[size_t(r) * 12 * PLAN_HORIZON + c]; };
+      lc(0 + 5 * i, 0 + 3 * i) = 1; lc(1 + 5 * i, 0 + 3 * i) = 1;
+      lc(2 + 5 * i, 1 + 3 * i) = 1; lc(3 + 5 * i, 1 + 3 * i) = 1;
+      lc(4 + 5 * i, 2 + 3 * i) = 1;
+      lc(0 + 5 * i, 2 + 3 * i) = mu; lc(1 + 5 * i, 2 + 3 * i) = -mu;
+      lc(2 + 5 * i, 2 + 3 * i) = mu; lc(3 + 5 * i, 2 + 3 * i) = -mu;
+    }
     MpcConfig cfg;
     mpc_config_default(&cfg);
     for (int i = 0; i < 13; ++i) cfg.q_weights[i] = q_weights_[i];
@@ -193,6 +205,7 @@ class ConvexMpc {
   std::array<double, 13 * 12> B_mat_c, B_mat_d;
   std::vector<double> B_mat_d_list;  // (13 H) x 12, written by the caller (A1RobotControl.cpp:513)
   std::vector<double> hessian, gradient, lb, ub;
+  std::vector<double> linear_constraints;  // (20 H) x (12 H) row-major, constant (ConvexMpc.h:84)
 
  private:
   MpcEngine* engine_ = nullptr;
@@ -220,7 +233,9 @@ class A1RobotControl {
       check(mpc_load_states(mpc_, &rec, 1), mpc_);
       check(mpc_set_torque_inputs(mpc_, &tin, 1), mpc_);
       check(mpc_build_qp_async(mpc_), mpc_);
-      check(mpc_solve_async(mpc_), mpc_);
+      // slot 0 of the engine is the member solver of A1RobotControl.h:67: initSolver on the first
+      // tick, update* + warm solve() on every later one (A1RobotControl.cpp:522-540)
+      check(mpc_solve_warm_async(mpc_), mpc_);
       check(mpc_get_results(mpc_, &res), mpc_);
       check(mpc_get_torques(mpc_, &torques_), mpc_);
     } else {
@@ -234,6 +249,8 @@ class A1RobotControl {
       check(mpc_get_torques(qp_, &torques_), qp_);
     }
     have_torques_ = true;
+    last_status = res.status;
+    last_iters = res.iters;
     std::array<double, 12> grf;
     for (int leg = 0; leg < 4; ++leg)
       for (int k = 0; k < 3; ++k) grf[4 * k + leg] = res.grf[3 * leg + k];
@@ -251,6 +268,9 @@ class A1RobotControl {
       if (!((torques_.nan_mask >> i) & 1)) state.joint_torques[i] = torques_.joint_torques[i];
   }
   int mpc_init_counter = 0;
+  int last_status = 0, last_iters = 0;  // OSQP status / iteration count of the last compute_grf (the reference drops them)
+  // forget the member solver: the next MPC call is an initSolver again
+  void reset_solver() { if (mpc_) check(mpc_stream_reset(mpc_), mpc_); }
   // the MPC branch for n robots sharing the engine-wide constants of `cfg`
   void compute_grf_batch(const MpcConfig& cfg, const MpcStateIn* states, MpcResult* out, int n) {
     if (!mpc_) check(mpc_engine_create(&cfg, device_, &mpc_), nullptr);
@@ -267,13 +287,17 @@ class A1RobotControl {
     for (int i = 0; i < 13; ++i) cfg.q_weights[i] = s.q_weights[i];
     for (int i = 0; i < 12; ++i) cfg.r_weights[i] = s.r_weights[i];
     if (mpc_ && std::memcmp(&cfg, &cfg_, sizeof(cfg)) == 0) return;
-    mpc_engine_destroy(mpc_);
-    mpc_ = nullptr;
-    check(mpc_engine_create(&cfg, device_, &mpc_), nullptr);
+    if (mpc_) {
+      // the reference re-reads these fields into a fresh ConvexMpc on every call while its solver lives
+      // on (A1RobotControl.cpp:447, A1RobotControl.h:67): new constants, same warm solver
+      check(mpc_engine_update_model(mpc_, &cfg), mpc_);
+    } else {
+      check(mpc_engine_create(&cfg, device_, &mpc_), nullptr);
+    }
     cfg_ = cfg;
   }
   void ensure_qp(const A1CtrlStates& s) {
-    if (qp_) return;
+    // gains and mass are read from the state on every tick (A1RobotControl.cpp:380-391)
     BalanceConfig b;
     balance_config_default(&b);
     b.mass = s.robot_mass;
@@ -281,12 +305,17 @@ class A1RobotControl {
       b.kp_linear[i] = s.kp_linear[i]; b.kd_linear[i] = s.kd_linear[i];
       b.kp_angular[i] = s.kp_angular[i]; b.kd_angular[i] = s.kd_angular[i];
     }
+    if (qp_ && std::memcmp(&b, &bcfg_, sizeof(b)) == 0) return;
+    mpc_engine_destroy(qp_);
+    qp_ = nullptr;
     check(balance_engine_create(&b, device_, &qp_), nullptr);
+    bcfg_ = b;
   }
   int device_;
   MpcEngine* mpc_ = nullptr;
   MpcEngine* qp_ = nullptr;
   MpcConfig cfg_{};
+  BalanceConfig bcfg_{};
   MpcTorqueOut torques_{};
   bool have_torques_ = false;
 };

@@ -23,7 +23,13 @@
  *   - 3x3 matrices are row-major float[9]; foot positions are leg-major xyz.
  *   - caller owns all host buffers; the engine owns its device memory.
  *   - one engine per host thread; one CUDA stream per engine.
- *   - functions are synchronous unless suffixed _async.
+ *   - functions are synchronous unless suffixed _async.  Exception, stated here once: the loaders
+ *     (mpc_load_states, mpc_set_torque_inputs, mpc_set_gait_inputs, mpc_prepare_states,
+ *     balance_load_states) ENQUEUE their host-to-device copy on the engine stream and return; with a
+ *     pinned host buffer that copy is truly asynchronous, so the caller must not rewrite the buffer
+ *     before the next synchronising call on the engine (mpc_get_results, mpc_get_torques,
+ *     mpc_synchronize, any non-_async solve).  The one-call paths (mpc_compute_grf_batch,
+ *     mpc_stream_step, balance_qp_solve) end in such a call.
  */
 #ifndef MPC_B200_H
 #define MPC_B200_H
@@ -225,10 +231,13 @@ typedef struct MpcConfig {
   int32_t gait_aware;           /* per-step contacts from the gait counters (mpc_set_gait_inputs)
                                    instead of today's contacts replicated (ConvexMpc.cpp:242-245) */
   int32_t structured_solver;    /* how K x = r is solved inside the ADMM (same iterates up to rounding):
-                                   0 automatic: dense K^-1 in registers for H = 10, Riccati recursion
-                                     over the horizon (riccati_kernel.cuh) for H = 30;
+                                   0 automatic: wrench-space solver for H = 10 (wrench_kernel.cuh: build and
+                                     solve fused, 60 x 60 Woodbury core, no Hessian in memory), Riccati
+                                     recursion over the horizon (riccati_kernel.cuh) for H = 30;
                                    1 Riccati recursion (cold solves; warm-started solves stay dense);
-                                   2 dense (for H = 30: K^-1 in a per-CTA L2 workspace, 7x slower) */
+                                   2 dense: qp_build_kernel + admm_solve_kernel, K^-1 (120 x 120) in registers
+                                     (for H = 30: K^-1 in a per-CTA L2 workspace, 7x slower);
+                                   3 wrench-space, explicitly (horizon 10 only) */
 } MpcConfig;
 
 /* Gait scheduler state of one robot (A1CtrlStates.h:24-28,103; A1RobotControl.cpp:156-164),
@@ -400,6 +409,17 @@ int mpc_solve_warm(MpcEngine *e);
 int mpc_solve_warm_async(MpcEngine *e);
 /* Forget every live solver (the next warm solve of each slot is an initSolver). */
 int mpc_stream_reset(MpcEngine *e);
+/* Forget the live solvers of the k robot slots idx[0..k) only (a robot was re-spawned, its state
+ * estimate jumped, ...).  The kernels contain faults per slot on their own: a solve that ends with
+ * non-finite iterates (one bad sensor record) or an internal error leaves ITS slot dead, so that
+ * robot's next tick is an initSolver instead of a warm start from NaN; other robots are untouched. */
+int mpc_stream_reset_slots(MpcEngine *e, const int32_t *idx, int32_t k);
+/* Replace the model constants of a live engine -- dt, mu, fz bounds, mass, inertia, q / r weights and
+ * the solver settings -- WITHOUT touching the live solvers.  The reference re-reads these
+ * A1CtrlStates fields on every compute_grf call into a fresh ConvexMpc (A1RobotControl.cpp:447) while
+ * its OsqpEigen member solver lives on (A1RobotControl.h:67): a weight change is just another Hessian
+ * update.  horizon, the extension flags and structured_solver must match the engine's (MPC_ERR_INVALID). */
+int mpc_engine_update_model(MpcEngine *e, const MpcConfig *cfg);
 /* One control tick for n robots: load + build + warm solve + results. */
 int mpc_stream_step(MpcEngine *e, const MpcStateIn *host_in, MpcResult *host_out, int32_t n);
 

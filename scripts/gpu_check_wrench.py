@@ -1,0 +1,110 @@
+"""GPU check of the wrench-space engine (wrench_kernel.cuh): parity against the oracle and against the
+dense engine (structured_solver = 2), warm stream, flags, timing.  Run under gpurun."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+import go1_qp_mpc_controller_b200 as pkg  # noqa: E402
+import oracle_binding as ob  # noqa: E402
+
+small = "--small" in sys.argv
+N = 64 if small else 1024
+
+
+def rel(a, b):
+    return np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1.0)
+
+
+for name in ("gazebo", "hardware"):
+    cfg = pkg.config_default() if name == "gazebo" else pkg.config_hardware()
+    states = pkg.generate_states(1002, 0, N)
+    e = pkg.MpcEngine(cfg, 0)
+    res = e.compute_grf_batch(states).copy()
+    ref = ob.mpc_compute_grf(cfg, states)
+    print(f"[{name}] status", np.unique(res["status"], return_counts=True), flush=True)
+    print(f"[{name}] same iters {(res['iters'] == ref['iters']).mean():.4f} same rho_updates "
+          f"{(res['rho_updates'] == ref['rho_updates']).mean():.4f} max GRF rel {rel(res['grf'], ref['grf']).max():.2e}",
+          flush=True)
+    rr_ = rel(res["grf"], ref["grf"])
+    four = states["contacts"].sum(axis=1) == 4
+    print(f"[{name}] all-four-stance states {int(four.sum())}: max rel {rr_[four].max():.2e} median {np.median(rr_[four]):.2e}; "
+          f"others max {rr_[~four].max():.2e}", flush=True)
+    bad = np.argsort(-rel(res["grf"], ref["grf"]))[:3]
+    for i in bad:
+        print("   worst", i, res["iters"][i], ref["iters"][i], res["rho_updates"][i], ref["rho_updates"][i],
+              res["grf"][i][:3], ref["grf"][i][:3])
+    if not small:
+        cfg2 = pkg.config_default() if name == "gazebo" else pkg.config_hardware()
+        cfg2.structured_solver = 2
+        d = pkg.MpcEngine(cfg2, 0)
+        rd = d.compute_grf_batch(states).copy()
+        print(f"[{name}] vs dense GPU engine: same iters {(res['iters'] == rd['iters']).mean():.4f} "
+              f"max GRF diff {np.abs(res['grf'] - rd['grf']).max():.3e}", flush=True)
+        d.close()
+    # full primal solution + get_qp on a wrench engine
+    x = e.get_solution(0)
+    P, q, l, u = e.get_qp(0)
+    Po, qo, lo, uo = ob.mpc_build_qp(cfg, states[0])
+    print(f"[{name}] get_qp on demand: P rel {np.abs(P - Po).max() / np.abs(Po).max():.2e}, solution finite {np.isfinite(x).all()}")
+    # warm stream
+    T = 4 if small else 8
+    n = 32 if small else 256
+    st = np.stack([pkg.generate_stream_states(1006, 0, n, 44 + t) for t in range(T)])
+    sref = ob.mpc_stream(cfg, st)
+    for t in range(T):
+        r = e.stream_step(st[t])
+        print(f"[{name}] warm tick {t}: same iters {(r['iters'] == sref['iters'][t]).mean():.4f} mean iters {r['iters'].mean():.1f} "
+              f"max GRF rel {rel(r['grf'], sref['grf'][t]).max():.2e}", flush=True)
+    e.close()
+
+if not small:
+    # extension flags
+    for flags in ((1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)):
+        cfg = pkg.config_default()
+        cfg.exact_discretization, cfg.foot_drift, cfg.gait_aware = flags
+        n = 256
+        st = pkg.generate_states(1002, 0, n)
+        gait = pkg.generate_gait_inputs(1002, 0, n, 0)
+        e = pkg.MpcEngine(cfg, 0)
+        e.load_states(st)
+        if cfg.gait_aware:
+            e.set_gait_inputs(gait)
+        e.build_qp()
+        e.solve()
+        r = e.get_results()
+        ref = ob.mpc_compute_grf_ext(cfg, st, gait)
+        print(f"[flags {flags}] same iters {(r['iters'] == ref['iters']).mean():.4f} max GRF rel {rel(r['grf'], ref['grf']).max():.2e}",
+              flush=True)
+        e.close()
+    # timing, device-resident states
+    import ctypes
+    for mode, label in ((0, "wrench"), (2, "dense")):
+        cfg = pkg.config_default()
+        cfg.structured_solver = mode
+        e = pkg.MpcEngine(cfg, 0)
+        for n in (4096, 16384):
+            st = pkg.generate_states(1002, 0, n)
+            e.compute_grf_batch(st)
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                e.compute_grf_batch(st)
+            dt = (time.perf_counter() - t0) / reps
+            print(f"[time] {label} n={n}: {dt * 1e3:.3f} ms per batch host-to-host -> {n / dt / 1e3:.1f} k solves/s", flush=True)
+        # warm ticks
+        n = 4096
+        sts = [pkg.generate_stream_states(1002, 0, n, 40 + t) for t in range(10)]
+        e.stream_reset()
+        e.stream_step(sts[0]); e.stream_step(sts[1])
+        t0 = time.perf_counter()
+        for t in range(2, 10):
+            r = e.stream_step(sts[t])
+        dt = (time.perf_counter() - t0) / 8
+        print(f"[time] {label} warm tick n={n}: {dt * 1e3:.3f} ms -> {n / dt / 1e3:.1f} k ticks/s, mean iters {r['iters'].mean():.1f}", flush=True)
+        e.close()
+print("done")
