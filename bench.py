@@ -12,9 +12,10 @@ collective, one final gather).  One JSON line on rank 0:
 
   value      whole-job solves/s with the state records already resident in HBM
   e2e        the same metric through the reference-facing C ABI call with HOST buffers
-             (mpc_compute_grf_batch: H2D + build + solve + D2H inside the timed region)
-  roofline   dominant kernel (admm_solve_kernel): algorithmic flops / CUDA-event duration
-             against this box's measured FP64 FMA peak
+             (mpc_compute_grf_batch: H2D + fused build/solve + D2H inside the timed region; at N > 1
+             also the gather of every rank's results into one host array on rank 0, every step)
+  roofline   the one kernel of the step (wrench_solve_kernel): algorithmic flops / CUDA-event
+             duration against this GPU's FP64 FMA rate measured in the same run
   cpu_baseline  the oracle (CPU port of the reference path) timed on the host cores
 
 --impl reference times the reference's own CPU algorithm (the oracle port: the real
@@ -40,14 +41,14 @@ WORKLOAD = "batched Go1 MPC H=10, 4096 synthetic robot states per GPU (BASELINE 
 F_BUILD = 4.00e6
 F_FACTOR = 0.576e6
 F_ITER = 33.0e3
-# FP64 FMA peak of this pool's B200, measured with scripts/fp64_bench.cu
-# (profiles/r01_fp64_peak.txt): 17.07 T DFMA/s = 34.1 TFLOP/s
+# FP64 FMA peak: measured live by mpc_measure_fp64_peak in every run; this constant (round 1,
+# scripts/fp64_bench.cu, profiles/r01_fp64_peak.txt) is only the fallback if the probe fails
 FP64_PEAK_TFLOPS = 34.1
-# dram__bytes_read.sum + dram__bytes_write.sum of admm_solve_kernel per solve, from the committed
-# ncu --set full capture (profiles/r01_v13_ncu_summary.txt: 37.30 MB read, 0 written, 296 solves):
-# the padded f64 Hessian (122,880 B) + q, l, u, state.  P is an intermediate of the path, not
-# algorithmic input, hence the much smaller hbm_algorithmic_bytes_per_solve.
-NCU_DRAM_BYTES_PER_SOLVE = 37.295872e6 / 296
+# dram__bytes_read.sum + dram__bytes_write.sum of wrench_solve_kernel per solve, from the committed
+# ncu --set full capture (profiles/r02_wrench_v1_ncu_summary.txt: 958.7 KB read + 695.0 KB written by
+# one launch of 4096 solves): the 192 B record in, the 64 B result and the 480 B primal solution out.
+# (Round 1's two-kernel path moved 126 KB per solve through HBM for the padded f64 Hessian.)
+NCU_DRAM_BYTES_PER_SOLVE = (958.72e3 + 695.04e3) / 4096
 
 
 def measured_hbm_peak_gbs():
@@ -144,36 +145,71 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
+# --------------------------------------------------------------------------------------------
+# host-only access to configuration defaults and the synthetic generator (libmpc_hostgen.so is
+# host_config.cpp compiled alone): the reference arm never maps the product library
+# --------------------------------------------------------------------------------------------
+class HostGen:
+    def __init__(self):
+        import ctypes as C
+        import __graft_entry__ as g
+        from go1_qp_mpc_controller_b200 import abi     # ctypes / numpy record layouts only, loads nothing
+        if not os.path.exists(g.HOSTGEN):
+            g.build()
+        self.C, self.abi = C, abi
+        self.lib = C.CDLL(g.HOSTGEN)
+        self.lib.mpc_generate_states.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]
+
+    def config_default(self):
+        cfg = self.abi.MpcConfig()
+        self.lib.mpc_config_default(self.C.byref(cfg))
+        return cfg
+
+    def generate_states(self, seed, first, n):
+        out = np.zeros(n, dtype=self.abi.STATE_DTYPE)
+        rc = self.lib.mpc_generate_states(seed, first, n, out.ctypes.data_as(self.C.c_void_p))
+        assert rc == 0
+        return out
+
+
 def run_reference(args):
-    """The reference's CPU algorithm (oracle port) on the host cores, same config and metric."""
+    """The reference's CPU algorithm (oracle port; the real Eigen/OsqpEigen/OSQP stack cannot be built
+    here) on ALL host cores, on exactly the batches rank 0 of the GPU arm solves: the full
+    4096-state batch of every step, same stream indices, same settings."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import go1_qp_mpc_controller_b200 as pkg
     import oracle_binding as ob
-    cfg = pkg.config_default()
+    hg = HostGen()
+    cfg = hg.config_default()
+    flags = ob.use_native()
     threads = host_cores()  # torchrun exports OMP_NUM_THREADS=1; num_threads() overrides it
-    sample = 1024  # bounded sample of the 4096-state batch per step
+    world = max(1, args.gpus)
     times = []
     for step in range(args.warmup + args.steps):
-        states = pkg.generate_states(SEED, step * BATCH, sample)
+        states = hg.generate_states(SEED, (step * world + 0) * BATCH, BATCH)   # rank 0's batch of this step
         t0 = time.perf_counter()
         res = ob.mpc_compute_grf(cfg, states, threads=threads)
         dt = time.perf_counter() - t0
         if step >= args.warmup:
             times.append(dt)
     total = float(np.sum(times))
-    value = sample * args.steps / total
+    value = BATCH * args.steps / total
     line = {
         "impl": "reference", "metric": "batched MPC QP solves/sec (H=10)", "value": value,
         "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "horizon": 10, "eps_abs": 1e-5, "eps_rel": 1e-5,
-                   "sample_per_step": sample},
+        "config": {"workload": WORKLOAD, "horizon": 10, "states_per_gpu": BATCH,
+                   "weights": "config/gazebo_a1_mpc.yaml", "eps_abs": 1e-5, "eps_rel": 1e-5,
+                   "max_iter": 4000, "adaptive_rho_interval": 50, "cold_start": True,
+                   "sample_per_step": BATCH, "stream_indices": "rank 0's batches of the GPU arm"},
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} states of the 4096-state batch per step, OpenMP one problem per thread"},
+                         "sample": f"all {BATCH} states of every step, OpenMP one problem per thread, fp64",
+                         "compiler_flags": flags,
+                         "p50_batch_ms": 1e3 * float(np.percentile(times, 50)),
+                         "p99_batch_ms": 1e3 * float(np.percentile(times, 99))},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mean_iters": float(res["iters"].mean()),
     }
@@ -181,12 +217,19 @@ def run_reference(args):
     return 0
 
 
+class DevBuf:
+    """A device pointer as a __cuda_array_interface__ object, so that torch can view the engine's result
+    buffer without a copy (the device-side gather reads it in place)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import go1_qp_mpc_controller_b200 as pkg
-    from go1_qp_mpc_controller_b200.sharding import gather_results
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -224,6 +267,7 @@ def run_ours(args):
 
     nsteps = args.warmup + args.steps
     rec = pkg.abi.STATE_DTYPE.itemsize
+    rsz = pkg.abi.RESULT_DTYPE.itemsize
     # fresh batch per step and per rank: global state index = (step * world + rank) * BATCH + i
     host_batches = [pkg.generate_states(SEED, (s * world + rank) * BATCH, BATCH) for s in range(nsteps)]
     pinned_in = torch.empty(nsteps * BATCH * rec, dtype=torch.uint8).pin_memory()
@@ -231,13 +275,24 @@ def run_ours(args):
     for s in range(nsteps):
         pin_np[s * BATCH:(s + 1) * BATCH] = host_batches[s]
     dev_in = pinned_in.cuda()
-    pinned_out = torch.empty(BATCH * pkg.abi.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    pinned_out = torch.empty(BATCH * rsz, dtype=torch.uint8).pin_memory()
     out_np = pinned_out.numpy().view(pkg.abi.RESULT_DTYPE)
 
     def step_device(s):
         eng.set_states_device(dev_in.data_ptr() + s * BATCH * rec, BATCH)
-        eng.build_qp(sync=False)
+        eng.build_qp(sync=False)     # no launch: the wrench-space engine builds inside the solve kernel
         eng.solve(sync=False)
+
+    # ---------------- FP64 roofline denominator, measured now, with the clocks it ran at ----------------
+    peak_sampler = ClockSampler(local_rank)
+    fp64_peak = None
+    if rank == 0:
+        peak_sampler.start()
+        pkg.measure_fp64_peak(local_rank, 2.0)       # warm-up; NVML comes up meanwhile
+        peak_sampler.begin()
+        fp64_peak = pkg.measure_fp64_peak(local_rank, 60.0)
+        peak_clocks = peak_sampler.stop()
+    barrier()
 
     # ---------------- value: inputs resident in HBM, device-timed ----------------
     sampler = ClockSampler(local_rank)
@@ -249,62 +304,79 @@ def run_ours(args):
     barrier()
     sampler.begin()
     launches0 = eng.kernel_launches()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record()
         for k in range(args.steps):
             s = args.warmup + k
             eng.set_states_device(dev_in.data_ptr() + s * BATCH * rec, BATCH)
-            ev[k][0].record()
             eng.build_qp(sync=False)
-            ev[k][1].record()
+            ev[k][0].record()
             eng.solve(sync=False)
-            ev[k][2].record()
+            ev[k][1].record()
         e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.kernel_launches() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    build_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]))
-    solve_ms = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)]))
+    solve_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]))
     last = eng.get_results()
     ok = bool((last["status"] == 1).all())
     mean_iters = sum_over_ranks(float(last["iters"].mean())) / world
     mean_fac = 1.0 + sum_over_ranks(float(last["rho_updates"].mean())) / world
     value = world * BATCH * args.steps / (ms_total * 1e-3)
 
-    # ---------------- e2e: host buffers through the C ABI, H2D and D2H inside ----------------
+    # ---------------- e2e: host buffers through the C ABI, H2D and D2H inside; at N > 1 the fleet's ----------------
+    # results are ALSO gathered into one host array on rank 0 inside the timed region, every step:
+    # NCCL gather of the 64 B records straight from each engine's device result buffer, then one D2H copy
+    gather_out = gather_list = None
+    if world > 1:
+        res_view = None
+        if rank == 0:
+            gather_list = [torch.empty(BATCH * rsz, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            gather_out = torch.empty(world * BATCH * rsz, dtype=torch.uint8).pin_memory()
+
+    def e2e_step(s):
+        eng.compute_grf_batch(pin_np[s * BATCH:(s + 1) * BATCH], out_np)
+        if world > 1:
+            view = torch.as_tensor(DevBuf(eng.results_device_ptr(), BATCH * rsz), device="cuda")
+            dist.gather(view, gather_list, dst=0)
+            if rank == 0:
+                for r in range(world):
+                    gather_out[r * BATCH * rsz:(r + 1) * BATCH * rsz].copy_(gather_list[r], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
     lat = []
     for s in range(args.warmup):
-        eng.compute_grf_batch(pin_np[s * BATCH:(s + 1) * BATCH], out_np)
+        e2e_step(s)
     barrier()
     t_start = time.perf_counter()
     for k in range(args.steps):
-        s = args.warmup + k
         t0 = time.perf_counter()
-        eng.compute_grf_batch(pin_np[s * BATCH:(s + 1) * BATCH], out_np)
+        e2e_step(args.warmup + k)
         lat.append(time.perf_counter() - t0)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t_start)
     barrier()
     e2e_value = world * BATCH * args.steps / e2e_s
     last_out = out_np.copy()  # results of the last timed batch: the CPU baseline checks parity on these
-    # the single exchange of the path: final gather of the 64 B records (outside the step loop)
-    if world > 1:
-        g0 = time.perf_counter()
-        full = gather_results(out_np.copy(), BATCH * world)
-        torch.cuda.synchronize()
-        gather_ms = 1e3 * (time.perf_counter() - g0)
-        assert rank != 0 or len(full) == BATCH * world
-    else:
-        gather_ms = 0.0
+    gather_ok = None
+    if world > 1 and rank == 0:
+        full = gather_out.numpy().view(pkg.abi.RESULT_DTYPE)
+        gather_ok = bool(np.array_equal(full[:BATCH]["grf"], last_out["grf"]) and (full["status"] == 1).all())
+
+    extras = {}
+
+    def extra(name, fn):
+        try:
+            extras[name] = fn()
+        except Exception as ex:  # the headline line must not depend on an extra
+            extras[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        barrier()
 
     # ---------------- extra: the widened path, warm-started streaming ticks ----------------
-    # one persistent solver per robot slot, consecutive control ticks of the same robots, host
-    # buffers in and out every tick; every rank streams its own BATCH robots
-    stream_warm = None
-    try:
+    def x_stream():
         ticks = 12
         sbuf = torch.empty(ticks * BATCH * rec, dtype=torch.uint8).pin_memory()
         s_np = sbuf.numpy().view(pkg.abi.STATE_DTYPE)
@@ -321,21 +393,39 @@ def run_ours(args):
             it_sum += float(out_np["iters"].mean())
         torch.cuda.synchronize()
         sdt = max_over_ranks(time.perf_counter() - t0)
-        stream_warm = {"metric": "warm-started MPC robot-ticks/sec (H=10)", "value": world * BATCH * (ticks - 2) / sdt,
-                  "unit": "robot-ticks/s", "ticks_timed": ticks - 2, "ms_per_tick": 1e3 * sdt / (ticks - 2),
-                  "mean_iters": it_sum / (ticks - 2), "all_solved": bool((out_np["status"] == 1).all())}
-    except Exception as ex:  # the headline line must not depend on the extra
-        stream_warm = {"error": str(ex)}
-    barrier()
+        return {"metric": "warm-started MPC robot-ticks/sec (H=10)", "value": world * BATCH * (ticks - 2) / sdt,
+                "unit": "robot-ticks/s", "ticks_timed": ticks - 2, "ms_per_tick": 1e3 * sdt / (ticks - 2),
+                "mean_iters": it_sum / (ticks - 2), "all_solved": bool((out_np["status"] == 1).all())}
+    extra("stream_warm", x_stream)
+
+    # ---------------- extra: BASELINE configs[2], 65536 states over the N GPUs (strong scaling) ----------------
+    def x_strong():
+        total = 65536
+        lo, hi = pkg.fleet_shard_range(total, world, rank)
+        st = pkg.generate_states(1003, lo, hi - lo)
+        buf = torch.empty((hi - lo) * rec, dtype=torch.uint8).pin_memory()
+        b_np = buf.numpy().view(pkg.abi.STATE_DTYPE)
+        b_np[:] = st
+        o = torch.empty((hi - lo) * rsz, dtype=torch.uint8).pin_memory().numpy().view(pkg.abi.RESULT_DTYPE)
+        eng.compute_grf_batch(b_np, o)
+        barrier()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eng.compute_grf_batch(b_np, o)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        return {"metric": "batched MPC QP solves/sec (H=10), 65536 states sharded over the GPUs", "scaling": "strong",
+                "value": total * reps / dt, "unit": "solves/s", "states_total": total, "states_per_gpu": hi - lo,
+                "ms_per_batch": 1e3 * dt / reps, "all_solved": bool((o["status"] == 1).all())}
+    extra("config3_65536_sharded", x_strong)
 
     # ---------------- extra: BASELINE configs[3], long horizon H = 30 (360 variables) ----------------
-    # Riccati-structured solver, 2048 synthetic states per GPU (seed 1004), host buffers in and out
-    long_horizon = None
-    try:
+    def x_h30():
         cfg30 = pkg.config_default()
         cfg30.horizon = 30
         eng30 = pkg.MpcEngine(cfg30, local_rank)
-        n30 = 2048
+        n30 = 8192 // world if world > 1 else 2048
         st30 = pkg.generate_states(1004, rank * n30, n30)
         eng30.compute_grf_batch(st30)  # full-size warm-up: the engine sizes its buffers on first use
         barrier()
@@ -345,35 +435,123 @@ def run_ours(args):
             out30 = eng30.compute_grf_batch(st30)
         torch.cuda.synchronize()
         dt30 = max_over_ranks(time.perf_counter() - t0)
-        long_horizon = {"metric": "batched MPC QP solves/sec (H=30)", "value": world * n30 * reps30 / dt30,
-                        "unit": "solves/s", "states_per_gpu": n30, "ms_per_batch": 1e3 * dt30 / reps30,
-                        "mean_iters": float(out30["iters"].mean()),
-                        "all_solved": bool((out30["status"] == 1).all())}
+        r = {"metric": "batched MPC QP solves/sec (H=30)", "value": world * n30 * reps30 / dt30,
+             "unit": "solves/s", "states_per_gpu": n30, "ms_per_batch": 1e3 * dt30 / reps30,
+             "mean_iters": float(out30["iters"].mean()), "all_solved": bool((out30["status"] == 1).all())}
         eng30.close()
-    except Exception as ex:  # the headline line must not depend on the extra
-        long_horizon = {"error": str(ex)}
-    barrier()
+        return r
+    extra("long_horizon_h30", x_h30)
+
+    # ---------------- extra: BASELINE configs[4], stance-balance QP, 1 M problems over 8 GPUs ----------------
+    def x_balance():
+        bcfg = pkg.balance_config_default()
+        be = pkg.MpcEngine(bcfg, local_rank, balance=True)
+        nb = 125000                                       # the per-GPU share of 1 M problems on 8 GPUs
+        stb = pkg.generate_balance_states(1005, rank * nb, nb)
+        be.compute_grf_batch(stb)
+        barrier()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            ob_ = be.compute_grf_batch(stb)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        # SURVEY.md 8d flop model of the 12-variable QP: 2.3 k (build + factor) + 0.6 k per iteration
+        it = float(ob_["iters"].mean())
+        fl = 2.3e3 + 0.6e3 * it
+        r = {"metric": "stance-balance QP solves/sec (12 var / 20 con)", "value": world * nb * reps / dt,
+             "unit": "solves/s", "problems_per_gpu": nb, "ms_per_batch": 1e3 * dt / reps, "mean_iters": it,
+             "max_iters": int(ob_["iters"].max()), "all_solved": bool((ob_["status"] == 1).all()),
+             "roofline": {"bound": "fp64-fma", "achieved": nb * reps * fl / dt / 1e12, "unit": "TFLOP/s",
+                          "algorithmic_flops_per_solve": fl, "note": "host to host, per GPU"}}
+        be.close()
+        return r
+    extra("balance_qp", x_balance)
+
+    # ---------------- extra: BASELINE configs[0], single-solve latency, GPU and CPU (N = 1, rank 0) ----------------
+    def x_latency():
+        if world > 1:
+            return {"skipped": "replicas only at N > 1 (DESIGN.md 6)"}
+        one = pkg.generate_states(1001, 0, 300)
+        o1 = np.zeros(1, dtype=pkg.abi.RESULT_DTYPE)
+        for i in range(20):
+            eng.compute_grf_batch(one[i:i + 1], o1)
+        g = []
+        for i in range(200):
+            t0 = time.perf_counter()
+            eng.compute_grf_batch(one[i:i + 1], o1)
+            g.append(time.perf_counter() - t0)
+        r = {"metric": "single Go1 MPC solve latency (H=10), host to host", "unit": "ms", "solves": 200,
+             "gpu_p50_ms": 1e3 * float(np.percentile(g, 50)), "gpu_p99_ms": 1e3 * float(np.percentile(g, 99))}
+        if not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_binding as ob
+            ob.use_native()
+            c = []
+            for i in range(100):
+                t0 = time.perf_counter()
+                ob.mpc_compute_grf(cfg, one[i:i + 1], threads=1)
+                c.append(time.perf_counter() - t0)
+            r.update({"cpu_p50_ms": 1e3 * float(np.percentile(c, 50)), "cpu_p99_ms": 1e3 * float(np.percentile(c, 99)),
+                      "cpu_kind": "port, one thread"})
+        return r
+    extra("latency_single", x_latency)
+
+    # ---------------- extra: every GPU of the box through ONE C-ABI call from ONE process (rank 0) ----------------
+    def x_fleet():
+        ndev = torch.cuda.device_count() if world == 1 else world
+        if rank != 0:
+            return None
+        fl = pkg.MpcFleet(cfg, list(range(ndev)))
+        n = BATCH * ndev
+        stf = pkg.generate_states(SEED, 0, n)
+        fin = torch.empty(n * rec, dtype=torch.uint8).pin_memory()
+        f_np = fin.numpy().view(pkg.abi.STATE_DTYPE)
+        f_np[:] = stf
+        fo = torch.empty(n * rsz, dtype=torch.uint8).pin_memory().numpy().view(pkg.abi.RESULT_DTYPE)
+        fl.compute_grf_batch(f_np, fo)
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fl.compute_grf_batch(f_np, fo)
+        dt = time.perf_counter() - t0
+        r = {"metric": "batched MPC QP solves/sec (H=10) through mpc_fleet_compute_grf_batch, one process",
+             "value": n * reps / dt, "unit": "solves/s", "devices": ndev, "states_total": n,
+             "ms_per_batch": 1e3 * dt / reps, "all_solved": bool((fo["status"] == 1).all()),
+             "note": "host array in, ONE host array out; per-GPU cudaMemcpyAsync is the gather, no NCCL"}
+        fl.close()
+        return r
+    extra("fleet_c_abi", x_fleet)
 
     # ---------------- CPU baseline: the oracle on the host cores (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_binding as ob
+        flags = ob.use_native()
         threads = host_cores()
-        sample = 2048
-        t0 = time.perf_counter()
-        ref = ob.mpc_compute_grf(cfg, host_batches[nsteps - 1][:sample], threads=threads)
-        cdt = time.perf_counter() - t0
-        den = np.maximum(np.linalg.norm(ref["grf"], axis=1), 1.0)
-        rel = np.linalg.norm(last_out["grf"][:sample].astype(np.float64) - ref["grf"], axis=1) / den
-        cpu = {"value": sample / cdt, "unit": "solves/s", "cores": threads, "kind": "port",
-               "sample": f"first {sample} states of the last timed batch, OpenMP one problem per thread, fp64",
+        ct = []
+        for b in range(3):                                # three whole batches: a CPU batch latency beside the GPU's
+            t0 = time.perf_counter()
+            ref = ob.mpc_compute_grf(cfg, host_batches[nsteps - 1 - b], threads=threads)
+            ct.append(time.perf_counter() - t0)
+            if b == 0:
+                ref_last = ref
+        den = np.maximum(np.linalg.norm(ref_last["grf"], axis=1), 1.0)
+        rel = np.linalg.norm(last_out["grf"].astype(np.float64) - ref_last["grf"], axis=1) / den
+        cpu = {"value": 3 * BATCH / float(np.sum(ct)), "unit": "solves/s", "cores": threads, "kind": "port",
+               "sample": f"the last three timed batches ({3 * BATCH} states), OpenMP one problem per thread, fp64",
+               "compiler_flags": flags,
+               "p50_batch_ms": 1e3 * float(np.percentile(ct, 50)), "p99_batch_ms": 1e3 * float(np.max(ct)),
                "parity_max_rel_grf_err": float(rel.max()),
-               "parity_same_iters": float((ref["iters"] == last_out["iters"][:sample]).mean())}
+               "parity_same_iters": float((ref_last["iters"] == last_out["iters"]).mean())}
 
     if rank == 0:
-        flops_solve = mean_fac * F_FACTOR + mean_iters * F_ITER          # admm_solve_kernel, per solve
+        flops_solve = F_BUILD + mean_fac * F_FACTOR + mean_iters * F_ITER   # build is inside the kernel now
         achieved = BATCH * flops_solve / (solve_ms * 1e-3) / 1e12
+        peak = fp64_peak if fp64_peak else FP64_PEAK_TFLOPS
+        hbm_peak, hbm_src = measured_hbm_peak_gbs()
+        traffic = NCU_DRAM_BYTES_PER_SOLVE * BATCH
         line = {
             "metric": "batched MPC QP solves/sec (H=10)", "value": value, "unit": "solves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -382,33 +560,39 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "horizon": 10, "states_per_gpu": BATCH,
                        "weights": "config/gazebo_a1_mpc.yaml", "eps_abs": 1e-5, "eps_rel": 1e-5,
                        "max_iter": 4000, "adaptive_rho_interval": 50, "cold_start": True,
-                       "l2": "fresh state batch per step; per-step working set (P, 236 MB) exceeds the 126 MB L2",
+                       "l2": "fresh state batch per step; the path keeps no Hessian in memory (0.4 KB of HBM traffic "
+                             "per solve), so there is nothing for the L2 to retain between steps",
                        "parallelism": f"shard{world}"},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": BATCH * rec,
-                    "d2h_bytes_per_step": BATCH * pkg.abi.RESULT_DTYPE.itemsize,
+                    "d2h_bytes_per_step": BATCH * rsz * (1 + (world if world > 1 else 0)),
                     "p50_batch_ms": 1e3 * float(np.percentile(lat, 50)),
-                    "p99_batch_ms": 1e3 * float(np.percentile(lat, 99))},
+                    "p99_batch_ms": 1e3 * float(np.percentile(lat, 99)),
+                    "gather": (None if world == 1 else
+                               {"inside_timed_region": True, "how": "NCCL gather of the 64 B records from every engine's device "
+                                "result buffer to rank 0, then one D2H copy into one pinned host array, every step",
+                                "verified": gather_ok})},
             "gpu_launches": int(launches),
-            "kernels": {"qp_build_kernel_ms": build_ms, "admm_solve_kernel_ms": solve_ms,
-                        "final_gather_ms": gather_ms},
+            "kernels": {"wrench_solve_kernel_ms": solve_ms, "launches_per_step": launches / max(1, args.steps)},
             "roofline": {"bound": "fp64-fma (compute/latency; neither hbm nor tensor, SURVEY.md 8d)",
-                         "kernel": "admm_solve_kernel", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
-                         "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
-                         "traffic": NCU_DRAM_BYTES_PER_SOLVE * BATCH,
-                         "traffic_source": "ncu --set full, profiles/r01_v19_ncu_summary.txt, scaled to this launch's solves",
-                         "hbm": {"achieved": NCU_DRAM_BYTES_PER_SOLVE * BATCH / (solve_ms * 1e-3) / 1e9,
-                                 "peak": measured_hbm_peak_gbs()[0], "unit": "GB/s",
-                                 "frac": NCU_DRAM_BYTES_PER_SOLVE * BATCH / (solve_ms * 1e-3) / 1e9 / measured_hbm_peak_gbs()[0],
-                                 "peak_source": measured_hbm_peak_gbs()[1]},
-                         "peak_source": "measured on this pool: scripts/fp64_bench.cu, profiles/r01_fp64_peak.txt",
+                         "kernel": "wrench_solve_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": ("mpc_measure_fp64_peak on this GPU in this run (register-only DFMA kernel, all SMs)"
+                                         if fp64_peak else "profiles/r01_fp64_peak.txt (live probe failed)"),
+                         "peak_clocks": (peak_clocks if fp64_peak else None),
+                         "traffic": traffic,
+                         "traffic_source": "ncu --set full, profiles/r02_wrench_v1_ncu_summary.txt (dram read + write of one "
+                                           "4096-solve launch), scaled to this launch's solves",
+                         "hbm": {"achieved": traffic / (solve_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": traffic / (solve_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
                          "algorithmic_flops_per_solve": flops_solve,
+                         "algorithmic_flop_model": "SURVEY.md 8d dense formulation: 4.00 M (build) + n_fac 0.576 M + n_iter 33 k; "
+                                                   "the kernel executes about a third of that (rank-60 structure)",
                          "hbm_algorithmic_bytes_per_solve": 256},
             "solver": {"mean_iters": mean_iters, "mean_factorisations": mean_fac, "all_solved": ok},
-            "stream_warm": stream_warm,
-            "long_horizon_h30": long_horizon,
             "clocks": clocks,
             "cpu_baseline": cpu,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -284,10 +285,22 @@ int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l,
 int launch_wrench(MpcEngine* e, int n, double* warm, bool with_torque) {
   const MpcTorqueIn* tin = with_torque ? e->d_tin : nullptr;
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
-  const int full = e->num_sms * kWrCtasPerSm;
+  // MPC_WRENCH_CTAS=5 selects the 96-register instantiation (five CTAs per SM), a tuning experiment
+  static const int ctas = [] {
+    const char* v = std::getenv("MPC_WRENCH_CTAS");
+    return (v && v[0] == '5') ? 5 : (v && v[0] == '3') ? 3 : kWrCtasPerSm;
+  }();
+  const int full = e->num_sms * ctas;
   const int grid = n < full ? n : full;
-  wrench_solve_kernel<<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
-      e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
+  if (ctas == 3)
+    wrench_solve_kernel<3><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
+        e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
+  else if (ctas == 5)
+    wrench_solve_kernel<5><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
+        e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
+  else
+    wrench_solve_kernel<kWrCtasPerSm><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
+        e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
   ++e->launches;
   CUDA_TRY(e, cudaGetLastError());
   return MPC_OK;
@@ -352,7 +365,9 @@ int create_common(int kind, int device, MpcEngine** out) {
   opt_in((const void*)riccati_solve_kernel<30>, sizeof(RicSmem<30>), "riccati_solve_kernel<30> shared memory");
   opt_in((const void*)gen_build_kernel<30>, sizeof(GenBuildSmem<30>), "gen_build_kernel<30> shared memory");
   opt_in((const void*)gen_solve_kernel<30>, sizeof(GenSolveSmem<30>), "gen_solve_kernel<30> shared memory");
-  opt_in((const void*)wrench_solve_kernel, sizeof(WrenchSmem), "wrench_solve_kernel shared memory");
+  opt_in((const void*)wrench_solve_kernel<kWrCtasPerSm>, sizeof(WrenchSmem), "wrench_solve_kernel shared memory");
+  opt_in((const void*)wrench_solve_kernel<5>, sizeof(WrenchSmem), "wrench_solve_kernel<5> shared memory");
+  opt_in((const void*)wrench_solve_kernel<3>, sizeof(WrenchSmem), "wrench_solve_kernel<3> shared memory");
   if (crc != cudaSuccess) {
     std::string msg = std::string("engine setup (") + what + "): " + cudaGetErrorString(crc);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -367,7 +382,60 @@ int create_common(int kind, int device, MpcEngine** out) {
 
 }  // namespace
 
+// register-only DFMA chains, eight independent accumulators per thread (scripts/fp64_bench.cu)
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = double(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 extern "C" {
+
+int mpc_measure_fp64_peak(int32_t device, double ms_target, double* tflops) {
+  if (!tflops) return MPC_ERR_INVALID;
+  std::string why;
+  int num_sms = 0;
+  int rc = open_device(device, &num_sms, &why);
+  if (rc != MPC_OK) return fail(nullptr, rc, why);
+  const int blocks = num_sms * 4, threads = 512;
+  double* out = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (cudaMalloc(&out, size_t(blocks) * threads * sizeof(double)) != cudaSuccess ||
+      cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+    cudaFree(out);
+    return fail(nullptr, MPC_ERR_CUDA, "fp64 peak probe: allocation failed");
+  }
+  int iters = 2000;
+  float ms = 0.f;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { rc = MPC_ERR_CUDA; break; }
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * double(blocks) * threads * double(iters) * 8.0 / (double(ms) * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+    // size the next launch for the requested duration
+    if (ms > 0.f) iters = int(double(iters) * (ms_target > 0 ? ms_target : 3.0) / double(ms));
+    if (iters < 1000) iters = 1000;
+    if (iters > 4000000) iters = 4000000;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (rc != MPC_OK) return fail(nullptr, rc, "fp64 peak probe failed");
+  *tflops = best;
+  return MPC_OK;
+}
 
 int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
   if (!cfg) return fail(nullptr, MPC_ERR_INVALID, "cfg is NULL");
@@ -860,6 +928,169 @@ int mpc_compute_grf_batch(MpcEngine* e, const MpcStateIn* host_in, MpcResult* ho
   return mpc_get_results(e, host_out);
 }
 
+// ---- fleet: one box, several GPUs, results into one host array ------------------
+
+}  // extern "C"
+
+struct MpcFleet {
+  std::vector<MpcEngine*> eng;
+  std::vector<MpcStateIn*> pin_in;   // pinned staging per shard (pageable caller buffers only)
+  std::vector<MpcResult*> pin_out;
+  std::vector<int> pin_cap;
+  std::string err;
+};
+
+namespace {
+
+bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int fleet_fail(MpcFleet* f, int code, const std::string& msg) {
+  if (f) f->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+void shard_range(int n, int g, int i, int* b, int* e) {
+  *b = int((int64_t(n) * i + g - 1) / g);
+  *e = int((int64_t(n) * (i + 1) + g - 1) / g);
+}
+
+int fleet_run(MpcFleet* f, const MpcStateIn* host_in, MpcResult* host_out, int n, bool warm) {
+  if (!f) return MPC_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!host_in || !host_out))) return fleet_fail(f, MPC_ERR_INVALID, "bad host buffers");
+  const int G = int(f->eng.size());
+  const bool in_pinned = n > 0 && host_ptr_is_pinned(host_in);
+  const bool out_pinned = n > 0 && host_ptr_is_pinned(host_out);
+  // enqueue every shard, then wait: the GPUs work and copy concurrently
+  for (int i = 0; i < G; ++i) {
+    int b, e2;
+    shard_range(n, G, i, &b, &e2);
+    const int m = e2 - b;
+    MpcEngine* e = f->eng[i];
+    if (m > f->pin_cap[i] && (!in_pinned || !out_pinned)) {
+      if (cudaSetDevice(e->device) != cudaSuccess) return fleet_fail(f, MPC_ERR_CUDA, "cudaSetDevice");
+      cudaStreamSynchronize(e->stream);
+      cudaFreeHost(f->pin_in[i]);
+      cudaFreeHost(f->pin_out[i]);
+      f->pin_in[i] = nullptr;
+      f->pin_out[i] = nullptr;
+      f->pin_cap[i] = 0;
+      if (cudaMallocHost(&f->pin_in[i], size_t(m) * sizeof(MpcStateIn)) != cudaSuccess ||
+          cudaMallocHost(&f->pin_out[i], size_t(m) * sizeof(MpcResult)) != cudaSuccess)
+        return fleet_fail(f, MPC_ERR_CUDA, "pinned staging allocation failed");
+      f->pin_cap[i] = m;
+    }
+    const MpcStateIn* src = host_in + b;
+    if (!in_pinned && m > 0) {
+      std::memcpy(f->pin_in[i], src, size_t(m) * sizeof(MpcStateIn));
+      src = f->pin_in[i];
+    }
+    int rc = mpc_load_states(e, src, m);
+    if (rc == MPC_OK) rc = mpc_build_qp_async(e);
+    if (rc == MPC_OK) rc = warm ? mpc_solve_warm_async(e) : mpc_solve_async(e);
+    if (rc == MPC_OK && m > 0) {
+      MpcResult* dst = out_pinned ? host_out + b : f->pin_out[i];
+      if (cudaMemcpyAsync(dst, e->d_results, size_t(m) * sizeof(MpcResult), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess)
+        rc = fleet_fail(f, MPC_ERR_CUDA, "result copy");
+    }
+    if (rc != MPC_OK) {
+      if (f->err.empty() || rc != MPC_ERR_CUDA) f->err = "shard " + std::to_string(i) + ": " + e->err;
+      return rc;
+    }
+  }
+  for (int i = 0; i < G; ++i) {
+    int b, e2;
+    shard_range(n, G, i, &b, &e2);
+    MpcEngine* e = f->eng[i];
+    if (cudaSetDevice(e->device) != cudaSuccess || cudaStreamSynchronize(e->stream) != cudaSuccess)
+      return fleet_fail(f, MPC_ERR_CUDA, "shard " + std::to_string(i) + ": synchronise failed");
+    if (!out_pinned && e2 > b) std::memcpy(host_out + b, f->pin_out[i], size_t(e2 - b) * sizeof(MpcResult));
+  }
+  return MPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpc_fleet_create(const MpcConfig* cfg, const int32_t* devices, int32_t ndev, MpcFleet** out) {
+  if (!out) return fleet_fail(nullptr, MPC_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!cfg || !devices || ndev <= 0 || ndev > 64) return fleet_fail(nullptr, MPC_ERR_INVALID, "bad device list");
+  MpcFleet* f = new (std::nothrow) MpcFleet();
+  if (!f) return fleet_fail(nullptr, MPC_ERR_INVALID, "out of host memory");
+  for (int i = 0; i < ndev; ++i) {
+    MpcEngine* e = nullptr;
+    const int rc = mpc_engine_create(cfg, devices[i], &e);
+    if (rc != MPC_OK) {
+      const std::string msg = "device " + std::to_string(devices[i]) + ": " + g_create_error;
+      mpc_fleet_destroy(f);
+      return fleet_fail(nullptr, rc, msg);
+    }
+    f->eng.push_back(e);
+    f->pin_in.push_back(nullptr);
+    f->pin_out.push_back(nullptr);
+    f->pin_cap.push_back(0);
+  }
+  *out = f;
+  return MPC_OK;
+}
+
+void mpc_fleet_destroy(MpcFleet* f) {
+  if (!f) return;
+  for (size_t i = 0; i < f->eng.size(); ++i) {
+    if (f->eng[i]) cudaSetDevice(f->eng[i]->device);
+    if (f->eng[i] && f->eng[i]->stream) cudaStreamSynchronize(f->eng[i]->stream);
+    cudaFreeHost(f->pin_in[i]);
+    cudaFreeHost(f->pin_out[i]);
+    mpc_engine_destroy(f->eng[i]);
+  }
+  delete f;
+}
+
+const char* mpc_fleet_last_error(const MpcFleet* f) { return f ? f->err.c_str() : g_create_error.c_str(); }
+
+int32_t mpc_fleet_size(const MpcFleet* f) { return f ? int32_t(f->eng.size()) : 0; }
+
+int mpc_fleet_shard_range(int32_t n, int32_t ndev, int32_t i, int32_t* begin, int32_t* end) {
+  if (n < 0 || ndev <= 0 || i < 0 || i >= ndev || !begin || !end) return MPC_ERR_INVALID;
+  int b, e;
+  shard_range(n, ndev, i, &b, &e);
+  *begin = b;
+  *end = e;
+  return MPC_OK;
+}
+
+int mpc_fleet_compute_grf_batch(MpcFleet* f, const MpcStateIn* host_in, MpcResult* host_out, int32_t n) {
+  return fleet_run(f, host_in, host_out, n, false);
+}
+
+int mpc_fleet_stream_step(MpcFleet* f, const MpcStateIn* host_in, MpcResult* host_out, int32_t n) {
+  return fleet_run(f, host_in, host_out, n, true);
+}
+
+int mpc_fleet_stream_reset(MpcFleet* f) {
+  if (!f) return MPC_ERR_INVALID;
+  for (MpcEngine* e : f->eng) {
+    const int rc = mpc_stream_reset(e);
+    if (rc) return fleet_fail(f, rc, e->err);
+  }
+  return MPC_OK;
+}
+
+int64_t mpc_fleet_kernel_launches(const MpcFleet* f) {
+  int64_t s = 0;
+  if (f) for (const MpcEngine* e : f->eng) s += e->launches;
+  return s;
+}
+
 // ---- ConvexMpc surface, one problem -----------------------------------------
 
 int mpc_qp_mats_from_model(MpcEngine* e, const double* A_mat_d, const double* B_mat_d_list,
@@ -999,9 +1230,11 @@ int balance_solve(MpcEngine* e) {
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->n > 0) {
     const int warps_per_cta = kBalanceThreads / 32;
-    const int grid = (e->n + warps_per_cta - 1) / warps_per_cta;
-    balance_qp_kernel<<<grid, kBalanceThreads, 0, e->stream>>>(e->d_bstates, e->n, e->d_Pb, e->d_qb, e->d_l,
-                                                               e->d_u, e->d_results, e->bal);
+    const int need = (e->n + warps_per_cta - 1) / warps_per_cta, full = e->num_sms * kBalanceCtasPerSm;
+    const int grid = need < full ? need : full;
+    CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
+    balance_qp_kernel<<<grid, kBalanceThreads, 0, e->stream>>>(e->d_bstates, e->n, e->d_counter, e->d_Pb, e->d_qb,
+                                                               e->d_l, e->d_u, e->d_results, e->bal);
     ++e->launches;
     CUDA_TRY(e, cudaGetLastError());
     if (e->torque_on) {

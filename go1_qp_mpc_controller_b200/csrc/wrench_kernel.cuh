@@ -46,22 +46,21 @@ constexpr int kW6 = 6 * kH;  // wrench dimension
 
 struct WrenchSmem {
   alignas(16) double B6[kH][6][12];   // B6c per step (identical unless foot_drift)
-  alignas(16) double Gh[kN][6];       // G^ : slot 2r+h holds row r, columns 12 (r/6) + 6h .. +5
-  alignas(16) double Mh[kN][6];       // M^': slot j holds column j (first M1 = G_ Delta^-1 during a factorisation)
+  alignas(16) double Mr[kN][6];       // M^ by rows: slot 2r+h holds row r, columns 12 (r/6) + 6h .. +5
+  alignas(16) double Mh[kN][6];       // M^ by columns: slot j holds column j (first M1 = G_ Delta^-1 during a factorisation)
   alignas(16) double L[kH][36];       // N_k, then its Cholesky factor (row-major, zeros above the diagonal)
   double Linvd[kH][6];                // 1 / L_cc (0 for a zero pivot)
   double al[kH * kH], be[kH * kH];    // alpha_kl, beta_kl
   double Th[4];                       // Theta = Rz diag(Q0..2) Rz': 00, 01, 11, 22
   double Qe[kH][14];                  // Q (A^(i+1) x0 - x_ref,i)
   alignas(16) double gam[kW6 + 4];
-  alignas(16) double va[kWrThreads];  // a = Delta^-1 rhs          (variable order)
-  alignas(16) double vt[kW6 + 4];     // tau = G^ a                (wrench order)
+  alignas(16) double va[kWrThreads];  // rhs of the linear system   (variable order)
+  alignas(16) double vt[kW6 + 4];     // tau = G^ a = M^ rhs       (wrench order)
   alignas(16) double vo[kW6 + 4];     // omega = Y' tau
   alignas(16) double xD[kWrThreads];  // D x for the residual check
   alignas(16) double Dp[kWrThreads];  // D
-  alignas(16) double prow[2][kW6 + 4];  // published pivot row of the sweep, double buffered
-  double loA[kWrThreads], hiA[kWrThreads], loB[kWrThreads], hiB[kWrThreads];  // scaled bounds of the owned rows
-  double EinvA[kWrThreads], EinvB[kWrThreads];
+  alignas(16) double prow[2][2][kW6 + 4];  // published pivot rows of the sweep (two per block), double buffered
+  double loA[kWrThreads], hiA[kWrThreads];  // normalised bounds of row A (row B is (-inf, 0] or absent)
   double red[kWrWarps * 16];
   double scal[16];                    // 0:c 1:1/c 2:rho 4:pri_res 6:rho 7:1000 rho 8:1/rho 9:1/(1000 rho)
   float st[48];
@@ -84,37 +83,62 @@ __device__ __forceinline__ double max_bits(double a, double b) {  // max of non-
 
 // max_i |(G' S G)_ij| D_i over all 120 rows i, for column j of horizon step kj, component comp:
 // (G' S G)_ij = top_i . v + [comp_i == comp] vbm,  v = alpha u1 + beta u2 (3-vector), per block row k.
-__device__ __forceinline__ double wr_colnorm(const WrenchSmem& sm, int kj, int comp, const double (&u1)[3],
-                                             const double (&u2)[3], double vb1, double vb2) {
+// Without foot_drift every step has the same B6c: the top rows of two legs (18 doubles) are loaded once
+// and the block rows are walked twice (legs 0-1, then 2-3) -- a quarter of the shared-memory loads of the
+// generic form (hoisting all 36 at once spills).  Same products, same maxima.
+template <bool kDrift>
+__device__ __forceinline__ double wr_colnorm_t(const WrenchSmem& sm, int kj, int comp, const double (&u1)[3],
+                                               const double (&u2)[3], double vb1, double vb2) {
   double mx = 0.0;
-#pragma unroll 2
-  for (int k = 0; k < kH; ++k) {
-    const double a = sm.al[kH * k + kj], b = sm.be[kH * k + kj];
-    const double v0 = fma(b, u2[0], a * u1[0]), v1 = fma(b, u2[1], a * u1[1]), v2 = fma(b, u2[2], a * u1[2]);
-    const double vbm = fma(b, vb2, a * vb1);
-    const double2* t0 = reinterpret_cast<const double2*>(&sm.B6[k][0][0]);
-    const double2* t1 = reinterpret_cast<const double2*>(&sm.B6[k][1][0]);
-    const double2* t2 = reinterpret_cast<const double2*>(&sm.B6[k][2][0]);
-    const double2* dk = reinterpret_cast<const double2*>(&sm.Dp[12 * k]);
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    double tp[3][6];
+    if (!kDrift) {
 #pragma unroll
-    for (int h2 = 0; h2 < 6; ++h2) {
-      const double2 b0 = t0[h2], b1 = t1[h2], b2 = t2[h2], dd = dk[h2];
-      const int i0 = 2 * h2, i1 = 2 * h2 + 1;
-      double e0 = ((i0 % 3) == comp) ? vbm : 0.0;
-      double e1 = ((i1 % 3) == comp) ? vbm : 0.0;
-      e0 = fma(b0.x, v0, e0); e0 = fma(b1.x, v1, e0); e0 = fma(b2.x, v2, e0);
-      e1 = fma(b0.y, v0, e1); e1 = fma(b1.y, v1, e1); e1 = fma(b2.y, v2, e1);
-      mx = max_bits(mx, fabs(e0) * dd.x);
-      mx = max_bits(mx, fabs(e1) * dd.y);
+      for (int c3 = 0; c3 < 3; ++c3) {
+        const double2* t = reinterpret_cast<const double2*>(&sm.B6[0][c3][6 * half]);
+        const double2 q0 = t[0], q1 = t[1], q2 = t[2];
+        tp[c3][0] = q0.x; tp[c3][1] = q0.y; tp[c3][2] = q1.x; tp[c3][3] = q1.y; tp[c3][4] = q2.x; tp[c3][5] = q2.y;
+      }
+    }
+#pragma unroll 2
+    for (int k = 0; k < kH; ++k) {
+      const double a = sm.al[kH * k + kj], b = sm.be[kH * k + kj];
+      const double v0 = fma(b, u2[0], a * u1[0]), v1 = fma(b, u2[1], a * u1[1]), v2 = fma(b, u2[2], a * u1[2]);
+      const double vbm = fma(b, vb2, a * vb1);
+      if (kDrift) {
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) {
+          const double2* t = reinterpret_cast<const double2*>(&sm.B6[k][c3][6 * half]);
+          const double2 q0 = t[0], q1 = t[1], q2 = t[2];
+          tp[c3][0] = q0.x; tp[c3][1] = q0.y; tp[c3][2] = q1.x; tp[c3][3] = q1.y; tp[c3][4] = q2.x; tp[c3][5] = q2.y;
+        }
+      }
+      const double2* dk = reinterpret_cast<const double2*>(&sm.Dp[12 * k + 6 * half]);
+      const double2 d01 = dk[0], d23 = dk[1], d45 = dk[2];
+      const double dd[6] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y};
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double e = ((i % 3) == comp) ? vbm : 0.0;   // (6 half + i) % 3 == i % 3
+        e = fma(tp[0][i], v0, e);
+        e = fma(tp[1][i], v1, e);
+        e = fma(tp[2][i], v2, e);
+        mx = max_bits(mx, fabs(e) * dd[i]);
+      }
     }
   }
   return mx;
+}
+__device__ __forceinline__ double wr_colnorm(const WrenchSmem& sm, bool drift, int kj, int comp, const double (&u1)[3],
+                                             const double (&u2)[3], double vb1, double vb2) {
+  return drift ? wr_colnorm_t<true>(sm, kj, comp, u1, u2, vb1, vb2) : wr_colnorm_t<false>(sm, kj, comp, u1, u2, vb1, vb2);
 }
 
 // `warm` == nullptr: cold solves.  ONE instantiation serves both, so a fresh warm slot takes the cold
 // path instruction for instruction (bit-identical results: the all-four-stance states amplify even a
 // different FMA contraction of two template instances into the last float32 bits).
-__global__ void __launch_bounds__(kWrThreads, kWrCtasPerSm)
+template <int kCtas>
+__global__ void __launch_bounds__(kWrThreads, kCtas)
 wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __restrict__ gait,
                     MpcResult* __restrict__ results, float* __restrict__ x_all, int num, int* __restrict__ counter,
                     double* __restrict__ warm, const MpcTorqueIn* __restrict__ tin, MpcTorqueOut* __restrict__ tout,
@@ -130,9 +154,14 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
   const int leg = jj / 3;
   const int lb = active ? lane - comp : 0;        // first lane of the leg-step
   const int r = j >> 1, h = j & 1;                // wrench role: row, half
-  const int kr = r / 6, rr = r - 6 * kr;
+  const int kr = k, rr = r - 6 * k;               // r / 6 = j / 12: the row's step is the variable's step
   const bool zlane = comp == 2;
   const bool kWarm = warm != nullptr;
+  // element offsets used in every iteration
+  const int offRowIn = 12 * kr + 6 * h;  // first rhs entry of this thread's half row
+  const int offTau = 30 * h;
+  const int offOm = 6 * k;
+  const int jpin = j, rpin = r;
   const double mu = sp.mu, sigma = sp.sigma, alpha = sp.alpha;
   const double dt = bp.dt, inv_m = 1.0 / bp.mass;
   const double r2 = bp.Rd[jj];                    // 2 r_weights of this variable (ConvexMpc.cpp:41)
@@ -333,7 +362,7 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
     // ---- K3a: modified Ruiz equilibration (osqp scaling.c scale_data), nothing materialised ----
     double D = 1.0, EA = 1.0, EB = 1.0, c_run = 1.0;
     if (sp.scaling > 0) {
-      double nP = max_bits(wr_colnorm(sm, k, comp, u1, u2, vb1, vb2), pjj);
+      double nP = max_bits(wr_colnorm(sm, bp.foot_drift != 0, k, comp, u1, u2, vb1, vb2), pjj);
       __syncthreads();  // Dp is rewritten inside the loop
       for (int it = 0; it < sp.scaling; ++it) {
         // column norms of [P; A] and row norms of A from the current D, E
@@ -350,7 +379,7 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
         __syncthreads();
         // cost normalisation with the new D and the old c
         const double c_old = c_run;
-        const double nP2 = c_old * D * max_bits(wr_colnorm(sm, k, comp, u1, u2, vb1, vb2), pjj * D);
+        const double nP2 = c_old * D * max_bits(wr_colnorm(sm, bp.foot_drift != 0, k, comp, u1, u2, vb1, vb2), pjj * D);
         double part_sum = active ? nP2 : 0.0;
         double part_q = active ? fabs(c_old * D * q_scale) : 0.0;
 #pragma unroll
@@ -386,40 +415,51 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
     };
     const int ctA = ctype_of(lbA, ubA);
     const int ctB = zlane ? 0 : ctype_of(lbB, ubB);
-    // scaled constraint coefficients: z~_row = cca x~_own + ccz x~_fz
-    double ccaA, cczA, ccaB, cczB;
+    // Rows in normalised form.  A row of a leg-step is  E (D_own x_own +- mu D_fz x_fz)  (fx / fy lanes) or
+    // E D_fz x_fz (fz lane) = cca (x_own + s t x_fz) with cca = E D_own, t = mu D_fz / D_own (0 on the fz lane),
+    // s = +1 for row A, -1 for row B.  The kernel iterates on  zh = z / cca  and  uh = y / (rho cca):
+    //   zh~ = x~_own + s t x~_fz,  zh <- clip(alpha zh~ + (1 - alpha) zh + uh),  uh <- uh + (relaxed - zh),
+    //   (A_'(rho z - y))_own = kapA (zhA - uhA) + kapB (zhB - uhB),   kap = rho cca^2,
+    //   fz lane additionally receives  t (kapA (zhA - uhA) - kapB (zhB - uhB))  from the fx and fy lanes.
+    // Same iterates as OSQP's (z, y) up to rounding, with five per-lane constants instead of ten (the ten
+    // spilled out of the register file in the inner loop) and fewer multiplications.  The unscaled row
+    // value E^-1 z is simply D_own zh.
+    double ccaA, ccaB, tz;
     {
       const double Dz = shfl(D, lb + 2);
-      if (zlane) { ccaA = 0.0; cczA = EA * D; ccaB = 0.0; cczB = 0.0; }
-      else { ccaA = EA * D; cczA = mu * EA * Dz; ccaB = EB * D; cczB = -mu * EB * Dz; }
+      ccaA = EA * D;
+      ccaB = zlane ? 1.0 : EB * D;
+      tz = zlane ? 0.0 : mu * Dz / D;
     }
-    // per-thread slots (idle lanes fill theirs with the shadowed lane's finite values)
-    sm.loA[tid] = lbA; sm.hiA[tid] = ubA; sm.loB[tid] = lbB; sm.hiB[tid] = ubB;
-    sm.EinvA[tid] = 1.0 / EA; sm.EinvB[tid] = 1.0 / EB;
     auto rho_of = [](int ct, double rho) { return (ct == -1) ? 1e-6 : (ct == 1) ? 1e3 * rho : rho; };
-    double rvA = rho_of(ctA, rho0), rvB = zlane ? 0.0 : rho_of(ctB, rho0);
-    double riA = 1.0 / rvA, riB = zlane ? 0.0 : 1.0 / rvB;
+    double rvA = rho_of(ctA, rho0), rvB = rho_of(ctB, rho0);
+    double kapA = rvA * ccaA * ccaA, kapB = zlane ? 0.0 : rvB * ccaB * ccaB;
+    // per-thread slots (idle lanes fill theirs with the shadowed lane's finite values)
+    sm.loA[tid] = lbA / ccaA; sm.hiA[tid] = ubA / ccaA;
 
-    // iterates: x on the variable lane, z / y of the owned rows
-    double x = 0.0, zA = 0.0, yA = 0.0, zB = 0.0, yB = 0.0;
+    // iterates: x on the variable lane, zh / uh of the owned rows
+    double x = 0.0, zA = 0.0, uA = 0.0, zB = 0.0, uB = 0.0;
     if (live) {
       x = ws[kWarmX + j];
-      zA = ws[kWarmZ + rowA]; yA = ws[kWarmY + rowA];
-      if (!zlane) { zB = ws[kWarmZ + rowB]; yB = ws[kWarmY + rowB]; }
+      zA = ws[kWarmZ + rowA] / ccaA; uA = ws[kWarmY + rowA] / (rvA * ccaA);
+      if (!zlane) { zB = ws[kWarmZ + rowB] / ccaB; uB = ws[kWarmY + rowB] / (rvB * ccaB); }
     }
     double di0 = 0.0, di1 = 0.0, di2 = 0.0;  // row `comp` of Delta_g^-1
 
-    // rhs_j = sigma x_j - q_j + (A_'(rho z - y))_j ;  a = Delta^-1 rhs  -> sm.va
-    auto publish_a = [&]() {
-      const double wA = rvA * zA - yA, wB = rvB * zB - yB;
-      const double own = ccaA * wA + ccaB * wB, sz = cczA * wA + cczB * wB;
-      const Leg3 s3 = leg3(sz, lb);
-      const double atw = zlane ? (s3.a + s3.b + s3.c) : own;
+    // rhs_j = sigma x_j - q_j + (A_'(rho z - y))_j  -> sm.va.  tau = G^ Delta^-1 rhs = M^ rhs needs only rhs, so
+    // a = Delta^-1 rhs (three shuffles) is formed behind the barrier, off the critical path.
+    auto publish_rhs = [&]() {
+      const double eA = kapA * (zA - uA), eB = kapB * (zB - uB);
+      const double own = eA + eB, sz = tz * (eA - eB);
+      const double sx = shfl(sz, lb), sy = shfl(sz, lb + 1);
+      const double atw = zlane ? (own + (sx + sy)) : own;
       const double rhs = sigma * x - qb + atw;
+      if (active) sm.va[jpin] = rhs;
+      return rhs;
+    };
+    auto delta_inv = [&](double rhs) {
       const Leg3 r3 = leg3(rhs, lb);
-      const double a = di0 * r3.a + di1 * r3.b + di2 * r3.c;
-      if (active) sm.va[j] = a;
-      return a;
+      return di0 * r3.a + di1 * r3.b + di2 * r3.c;
     };
 
     int iter = 0, rho_updates = 0, status = MPC_STATUS_UNSOLVED;
@@ -427,7 +467,7 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
     int until_check = sp.check_termination > 0 ? sp.check_termination : 0x7fffffff;
     int until_adapt = (sp.adaptive_rho && sp.adaptive_rho_interval > 0) ? sp.adaptive_rho_interval : 0x7fffffff;
     bool need_factor = true;
-    double a_own = 0.0;
+    double a_own = 0.0, rhs_own = 0.0;
 
     for (;;) {
       if (need_factor) {
@@ -435,9 +475,10 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
         // ---- K3b: factorisation ----
         // Delta_g = diag(c D^2 r2 + sigma) + A_g' rho A_g  (3 x 3, zero xy entry), inverse by cofactors
         {
-          const double pd = c * D * D * r2 + sigma + rvA * ccaA * ccaA + rvB * ccaB * ccaB;
-          const double pc = rvA * ccaA * cczA + rvB * ccaB * cczB;
-          const double pz = rvA * cczA * cczA + rvB * cczB * cczB;
+          // own diagonal; fx / fy lanes also carry the cross term with fz and their share of the fz diagonal
+          const double pd = c * D * D * r2 + sigma + kapA + kapB;
+          const double pc = tz * (kapA - kapB);
+          const double pz = tz * tz * (kapA + kapB);
           const Leg3 d3 = leg3(pd, lb), c3 = leg3(pc, lb), z3 = leg3(pz, lb);
           const double dxx = d3.a, dyy = d3.b, dzz = d3.c + z3.a + z3.b + z3.c, dxz = c3.a, dyz = c3.b;
           const double m00 = dyy * dzz - dyz * dyz, m11 = dxx * dzz - dxz * dxz, m22 = dxx * dyy;
@@ -502,27 +543,24 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
             for (int b = 0; b < 6; ++b) sm.L[k][6 * a + b] = (b <= a) ? Lm[a][b] : 0.0;
         }
         __syncthreads();
-        // G^ = L^-1 G_ and M^ = L^-1 M1, column j of each by forward substitution
+        // M^ = L^-1 M1 (= G^ Delta^-1 with G^ = L^-1 G_), column j by forward substitution; stored by
+        // columns (x~ = a - M^' omega) and by half rows (tau = M^ rhs)
         {
           const double* Lk = sm.L[k];
           const double* li = sm.Linvd[k];
-          double gcol[6], mcol[6];
+          double mcol[6];
 #pragma unroll
           for (int cc = 0; cc < 6; ++cc) {
-            double sg = sm.B6[k][cc][jj] * D, smm = sm.Mh[j][cc];
+            double smm = sm.Mh[j][cc];
 #pragma unroll
-            for (int q = 0; q < cc; ++q) {
-              sg -= Lk[6 * cc + q] * gcol[q];
-              smm -= Lk[6 * cc + q] * mcol[q];
-            }
-            gcol[cc] = sg * li[cc];
+            for (int q = 0; q < cc; ++q) smm -= Lk[6 * cc + q] * mcol[q];
             mcol[cc] = smm * li[cc];
           }
           if (active) {
 #pragma unroll
             for (int cc = 0; cc < 6; ++cc) {
               sm.Mh[j][cc] = mcol[cc];
-              sm.Gh[2 * (6 * k + cc) + jj / 6][jj % 6] = gcol[cc];
+              sm.Mr[2 * (6 * k + cc) + jj / 6][jj % 6] = mcol[cc];
             }
           }
         }
@@ -554,66 +592,79 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
             }
           }
         }
-        // Symmetric sweep of A = I + W, one pivot per block barrier.  Sweep of pivot p with d = A_pp:
-        //   A_pp <- -1/d,  A_rp <- A_rp / d,  A_pc <- A_pc / d,  A_rc <- A_rc - A_rp A_pc / d  (r, c != p);
-        // after all pivots the matrix is -A^-1.  A swept diagonal entry is stored PLUS ONE (1 - 1/d, then
+        // Symmetric sweep of A = I + W by 2 x 2 pivot blocks S = {p, p+1}, one block per barrier.  With
+        // M = A_SS^-1:   A_SS <- -M,  A_rS <- A_rS M,  A_Sc <- M A_Sc,  A_rc <- A_rc - A_rS M A_Sc  (r, c not in S);
+        // after all blocks the matrix is -A^-1.  A swept diagonal entry is stored PLUS ONE (1 - M_ss, then
         // updated like any other entry: it is a pivot only once), so the registers end up holding
-        // I - A^-1 = Y' directly.  The pivot column is written explicitly (A_rp / d): producing it with the
-        // uniform update, A_rp - (A_rp / d)(d - 1), cancels catastrophically when d is large -- after rho
-        // has adapted to its 1e-6 floor the pivots reach 1e6 and ten digits were lost there, enough to
-        // push all-four-stance states past the GRF gate (profiles/experiments/r02_wrench_sweep_cancellation.md).
-        // The pivot index is static (loop over halves, unrolled inside) so no register is indexed dynamically.
-        if (active && r == 0) {
+        // I - A^-1 = Y' directly.  The block columns are written explicitly (A_rS M): producing them with
+        // the uniform update cancels catastrophically when the pivots are large -- after rho has adapted
+        // to its 1e-6 floor they reach 1e6 and ten digits were lost there, enough to push all-four-stance
+        // states past the GRF gate (profiles/experiments/r02_wrench_sweep_cancellation.md).
+        // Pivot indices are static (loop over halves, unrolled inside): no dynamic register index.
+        if (active && r < 2) {
 #pragma unroll
-          for (int cc = 0; cc < 30; ++cc) sm.prow[0][30 * h + cc] = y[cc];
+          for (int cc = 0; cc < 30; ++cc) sm.prow[0][r][30 * h + cc] = y[cc];
         }
         __syncthreads();
 #pragma unroll 1
         for (int ph = 0; ph < 2; ++ph) {
 #pragma unroll
-          for (int pc = 0; pc < 30; ++pc) {
+          for (int pc = 0; pc < 30; pc += 2) {
             const int pv = 30 * ph + pc;
-            const double* pr = sm.prow[pc & 1];  // = pv & 1
-            const double dinv = 1.0 / pr[pv];
-            const bool isrow = (r == pv);
-            const double f = pr[r] * dinv;
-            const double2* p2v = reinterpret_cast<const double2*>(pr + 30 * h);
+            const int buf = ((pc >> 1) + ph) & 1;  // block index 15 ph + pc / 2, parity
+            const double* r1 = sm.prow[buf][0];
+            const double* r2 = sm.prow[buf][1];
+            const double d1 = r1[pv], e12 = r1[pv + 1], d2 = r2[pv + 1];
+            const double idet = 1.0 / (d1 * d2 - e12 * e12);
+            const double m11 = d2 * idet, m12 = -e12 * idet, m22 = d1 * idet;
+            const double a1 = r1[rpin], a2 = r2[rpin];  // A_rp, A_r,p+1 by symmetry
+            const bool isrow1 = (r == pv), isrow2 = (r == pv + 1);
+            const bool isrow = isrow1 || isrow2;
+            const double g1 = isrow ? (isrow1 ? m11 : m12) : -(a1 * m11 + a2 * m12);
+            const double g2 = isrow ? (isrow1 ? m12 : m22) : -(a1 * m12 + a2 * m22);
+            const double2* v1p = reinterpret_cast<const double2*>(r1 + offTau);
+            const double2* v2p = reinterpret_cast<const double2*>(r2 + offTau);
             if (isrow) {
 #pragma unroll
               for (int hh = 0; hh < 15; ++hh) {
-                const double2 v = p2v[hh];
-                y[2 * hh] = v.x * dinv;
-                y[2 * hh + 1] = v.y * dinv;
+                const double2 v1 = v1p[hh], v2 = v2p[hh];
+                y[2 * hh] = fma(g2, v2.x, g1 * v1.x);
+                y[2 * hh + 1] = fma(g2, v2.y, g1 * v1.y);
               }
             } else {
 #pragma unroll
               for (int hh = 0; hh < 15; ++hh) {
-                const double2 v = p2v[hh];
-                y[2 * hh] = fma(-f, v.x, y[2 * hh]);
-                y[2 * hh + 1] = fma(-f, v.y, y[2 * hh + 1]);
+                const double2 v1 = v1p[hh], v2 = v2p[hh];
+                y[2 * hh] = fma(g2, v2.x, fma(g1, v1.x, y[2 * hh]));
+                y[2 * hh + 1] = fma(g2, v2.y, fma(g1, v1.y, y[2 * hh + 1]));
               }
             }
-            if (h == ph) y[pc] = isrow ? (1.0 - dinv) : f;
-            if (pv + 1 < kW6 && active && r == pv + 1) {
-              double* nx = sm.prow[(pc + 1) & 1];
+            if (h == ph) {
+              y[pc] = isrow1 ? (1.0 - m11) : isrow2 ? -m12 : -g1;
+              y[pc + 1] = isrow1 ? -m12 : isrow2 ? (1.0 - m22) : -g2;
+            }
+            if (pv + 2 < kW6 && active && (r == pv + 2 || r == pv + 3)) {
+              double* nx = sm.prow[buf ^ 1][r - (pv + 2)];
 #pragma unroll
               for (int cc = 0; cc < 30; ++cc) nx[30 * h + cc] = y[cc];
             }
             __syncthreads();
           }
         }
-        a_own = publish_a();
+        rhs_own = publish_rhs();
         __syncthreads();
       }
       int run = until_check < until_adapt ? until_check : until_adapt;
       run = run < sp.max_iter - iter ? run : sp.max_iter - iter;
-      const double loA = sm.loA[tid], hiA = sm.hiA[tid], loB = sm.loB[tid], hiB = sm.hiB[tid];
+      // row B is (-INFTY E, 0] on fx / fy lanes (the lower bound can never bind) and absent on the fz lane
+      // (all its coefficients are zero, z_B stays 0): one upper clamp at 0 serves both
+      const double loA = sm.loA[tid], hiA = sm.hiA[tid];
 #pragma unroll 1
       for (int q = 0; q < run; ++q) {
-        // tau = G^ a (half a row per thread, halves meet by one shuffle)
+        // tau = M^ rhs (half a row per thread, halves meet by one shuffle)
         {
-          const double2* gp = reinterpret_cast<const double2*>(sm.Gh[j]);
-          const double2* ap = reinterpret_cast<const double2*>(&sm.va[12 * kr + 6 * h]);
+          const double2* gp = reinterpret_cast<const double2*>(sm.Mr[jpin]);
+          const double2* ap = reinterpret_cast<const double2*>(&sm.va[offRowIn]);
           const double2 g0 = gp[0], g1 = gp[1], g2 = gp[2], a0 = ap[0], a1 = ap[1], a2 = ap[2];
           double s = g0.x * a0.x;
           double s2 = g0.y * a0.y;
@@ -621,12 +672,13 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
           s = fma(g2.x, a2.x, s); s2 = fma(g2.y, a2.y, s2);
           s += s2;
           s += shfl_xor(s, 1);
-          if (active && h == 0) sm.vt[r] = s;
+          if (active && h == 0) sm.vt[rpin] = s;
+          a_own = delta_inv(rhs_own);  // not needed before x~: overlaps the barrier
         }
         __syncthreads();
         // omega = Y' tau
         {
-          const double2* tp = reinterpret_cast<const double2*>(&sm.vt[30 * h]);
+          const double2* tp = reinterpret_cast<const double2*>(&sm.vt[offTau]);
           double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
           for (int hh = 0; hh < 15; hh += 3) {
@@ -637,13 +689,13 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
           }
           double s = (s0 + s1) + s2;
           s += shfl_xor(s, 1);
-          if (active && h == 0) sm.vo[r] = s;
+          if (active && h == 0) sm.vo[rpin] = s;
         }
         __syncthreads();
-        // x~ = a - M^' omega ; x, z, y updates of the owned rows ; next rhs and a
+        // x~ = a - M^' omega ; x, z, y updates of the owned rows ; next rhs
         {
-          const double2* mp = reinterpret_cast<const double2*>(sm.Mh[j]);
-          const double2* op = reinterpret_cast<const double2*>(&sm.vo[6 * k]);
+          const double2* mp = reinterpret_cast<const double2*>(sm.Mh[jpin]);
+          const double2* op = reinterpret_cast<const double2*>(&sm.vo[offOm]);
           const double2 m0 = mp[0], m1 = mp[1], m2 = mp[2], o0 = op[0], o1 = op[1], o2 = op[2];
           double s = fma(m0.x, o0.x, m0.y * o0.y);
           double s2 = fma(m1.x, o1.x, m1.y * o1.y);
@@ -651,15 +703,15 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
           const double xt = a_own - (s + s2);
           x = alpha * xt + (1.0 - alpha) * x;
           const double xtz = shfl(xt, lb + 2);
-          const double ztA = ccaA * xt + cczA * xtz, ztB = ccaB * xt + cczB * xtz;
+          const double ztA = fma(tz, xtz, xt), ztB = fma(-tz, xtz, xt);
           const double zrA = alpha * ztA + (1.0 - alpha) * zA, zrB = alpha * ztB + (1.0 - alpha) * zB;
-          double znA = zrA + riA * yA, znB = zrB + riB * yB;
+          double znA = zrA + uA, znB = zrB + uB;
           znA = (znA < loA) ? loA : znA; znA = (znA > hiA) ? hiA : znA;
-          znB = (znB < loB) ? loB : znB; znB = (znB > hiB) ? hiB : znB;
-          yA = yA + rvA * (zrA - znA);
-          yB = yB + rvB * (zrB - znB);
+          znB = (znB > 0.0) ? 0.0 : znB;
+          uA = uA + (zrA - znA);
+          uB = uB + (zrB - znB);
           zA = znA; zB = znB;
-          a_own = publish_a();
+          rhs_own = publish_rhs();
         }
         __syncthreads();
       }
@@ -714,24 +766,25 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
       for (int i = 0; i < 10; ++i) v[i] = 0.0;
       {
         const double xz = shfl(x, lb + 2);
-        const double AxA = ccaA * x + cczA * xz, AxB = ccaB * x + cczB * xz;
-        const double eiA = sm.EinvA[tid], eiB = zlane ? 0.0 : sm.EinvB[tid];
-        const double rpA = AxA - zA, rpB = zlane ? 0.0 : AxB - zB;
+        const double AhA = fma(tz, xz, x), AhB = fma(-tz, xz, x);      // normalised A x of the owned rows
+        const double rpA = AhA - zA, rpB = zlane ? 0.0 : AhB - zB;
         if (active) {
-          v[0] = fmax(fabs(rpA), fabs(rpB));
-          v[1] = fmax(fabs(eiA * rpA), fabs(eiB * rpB));
-          v[2] = fmax(fabs(eiA * zA), fabs(eiB * zB));
-          v[3] = fmax(fabs(eiA * AxA), fabs(eiB * AxB));
-          v[4] = fmax(fabs(zA), zlane ? 0.0 : fabs(zB));
-          v[5] = fmax(fabs(AxA), zlane ? 0.0 : fabs(AxB));
+          const double cB = zlane ? 0.0 : ccaB, DB = zlane ? 0.0 : D;
+          v[0] = fmax(fabs(ccaA * rpA), fabs(cB * rpB));               // scaled primal residual
+          v[1] = D * fmax(fabs(rpA), fabs(rpB));                       // unscaled: E^-1 cca = D
+          v[2] = fmax(fabs(D * zA), fabs(DB * zB));
+          v[3] = fmax(fabs(D * AhA), fabs(DB * AhB));
+          v[4] = fmax(fabs(ccaA * zA), fabs(cB * zB));
+          v[5] = fmax(fabs(ccaA * AhA), fabs(cB * AhB));
         }
         // P_ x = c D (R2 D x + G' w) ; A_' y
         const double* wv = &sm.vo[6 * k];
         const double gtw = top0 * wv[0] + top1 * wv[1] + top2 * wv[2] + inv_m * wv[3 + comp];
         const double Px = c * D * (r2 * (D * x) + gtw);
-        const double own = ccaA * yA + ccaB * yB, sz = cczA * yA + cczB * yB;
-        const Leg3 s3 = leg3(sz, lb);
-        const double Aty = zlane ? (s3.a + s3.b + s3.c) : own;
+        const double fA = kapA * uA, fB = kapB * uB;                   // cca y of the owned rows
+        const double own = fA + fB, sz = tz * (fA - fB);
+        const double sx = shfl(sz, lb), sy = shfl(sz, lb + 1);
+        const double Aty = zlane ? (own + (sx + sy)) : own;
         if (active) {
           const double Dinv = 1.0 / D;
           const double rd = Px + qb + Aty;
@@ -792,11 +845,13 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
       if (sm.flags[2]) {
         ++rho_updates;
         const double rho = sm.scal[2];
-        rvA = rho_of(ctA, rho);
-        rvB = zlane ? 0.0 : rho_of(ctB, rho);
-        riA = 1.0 / rvA;
-        riB = zlane ? 0.0 : 1.0 / rvB;
-        need_factor = true;  // the factorisation ends by rebuilding a with the new rho vector
+        const double rnA = rho_of(ctA, rho), rnB = rho_of(ctB, rho);
+        uA *= rvA / rnA;   // y stays, uh = y / (rho cca) follows the new rho
+        uB *= rvB / rnB;
+        rvA = rnA; rvB = rnB;
+        kapA = rvA * ccaA * ccaA;
+        kapB = zlane ? 0.0 : rvB * ccaB * ccaB;
+        need_factor = true;  // the factorisation ends by rebuilding the right-hand side with the new rho vector
       }
     }
     if (iter > sp.max_iter) iter = sp.max_iter;
@@ -806,13 +861,13 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
     if (kWarm) {
       // keep the solver alive for the next tick -- unless this solve went wrong: a poisoned slot would
       // warm-start every later tick from NaN; it is marked dead instead (next tick = initSolver)
-      const bool finite_own = isfinite(x) && isfinite(zA) && isfinite(yA) && isfinite(zB) && isfinite(yB);
+      const bool finite_own = isfinite(x) && isfinite(zA) && isfinite(uA) && isfinite(zB) && isfinite(uB);
       const int all_ok = __syncthreads_and(finite_own || !active);
       if (active) {
         ws[kWarmX + j] = x;
         ws[kWarmQ + j] = q0;
-        ws[kWarmZ + rowA] = zA; ws[kWarmY + rowA] = yA;
-        if (!zlane) { ws[kWarmZ + rowB] = zB; ws[kWarmY + rowB] = yB; }
+        ws[kWarmZ + rowA] = ccaA * zA; ws[kWarmY + rowA] = rvA * ccaA * uA;   // OSQP's scaled z, y
+        if (!zlane) { ws[kWarmZ + rowB] = ccaB * zB; ws[kWarmY + rowB] = rvB * ccaB * uB; }
       }
       if (tid == 0) {
         ws[kWarmRho] = sm.scal[2];

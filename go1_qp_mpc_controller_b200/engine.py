@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = [
     "prep_config_default", "mpc_prepare_states", "mpc_get_prepared", "mpc_prepare_reset", "mpc_generate_sensors",
     "a1_leg_fk_jac", "mpc_set_gait_inputs", "mpc_generate_gait_inputs",
     "mpc_stream_reset_slots", "mpc_engine_update_model",
+    "mpc_fleet_create", "mpc_fleet_destroy", "mpc_fleet_last_error", "mpc_fleet_size", "mpc_fleet_shard_range",
+    "mpc_measure_fp64_peak", "mpc_fleet_compute_grf_batch", "mpc_fleet_stream_step", "mpc_fleet_stream_reset", "mpc_fleet_kernel_launches",
 ]
 
 
@@ -93,6 +95,19 @@ def load_library():
     lib.mpc_stream_step.argtypes = [vp, vp, vp, i32]
     lib.mpc_stream_reset_slots.argtypes = [vp, vp, i32]
     lib.mpc_engine_update_model.argtypes = [vp, C.POINTER(abi.MpcConfig)]
+    lib.mpc_measure_fp64_peak.argtypes = [i32, C.c_double, C.POINTER(C.c_double)]
+    lib.mpc_fleet_create.argtypes = [C.POINTER(abi.MpcConfig), vp, i32, C.POINTER(vp)]
+    lib.mpc_fleet_destroy.restype = None
+    lib.mpc_fleet_destroy.argtypes = [vp]
+    lib.mpc_fleet_last_error.restype = C.c_char_p
+    lib.mpc_fleet_last_error.argtypes = [vp]
+    lib.mpc_fleet_size.argtypes = [vp]
+    lib.mpc_fleet_shard_range.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    lib.mpc_fleet_compute_grf_batch.argtypes = [vp, vp, vp, i32]
+    lib.mpc_fleet_stream_step.argtypes = [vp, vp, vp, i32]
+    lib.mpc_fleet_stream_reset.argtypes = [vp]
+    lib.mpc_fleet_kernel_launches.restype = C.c_int64
+    lib.mpc_fleet_kernel_launches.argtypes = [vp]
     lib.mpc_qp_mats_from_model.argtypes = [vp] + [vp] * 9
     lib.mpc_solve_qp.argtypes = [vp] + [vp] * 7
     lib.balance_qp_solve.argtypes = [vp, vp, vp, i32]
@@ -436,3 +451,75 @@ class MpcEngine:
                                            C.cast(C.byref(status), C.c_void_p),
                                            C.cast(C.byref(iters), C.c_void_p)))
         return x, status.value, iters.value
+
+
+def measure_fp64_peak(device=0, ms_target=3.0):
+    """This GPU's FP64 FMA rate in TFLOP/s, measured now (register-only DFMA kernel on every SM)."""
+    v = C.c_double()
+    lib = load_library()
+    rc = lib.mpc_measure_fp64_peak(device, ms_target, C.byref(v))
+    if rc:
+        raise MpcError(rc, lib.mpc_last_error(None).decode())
+    return v.value
+
+
+def fleet_shard_range(n, ndev, i):
+    """[begin, end) of shard i of ndev: ceil(n i / G) .. ceil(n (i + 1) / G) (host only)."""
+    b, e = C.c_int32(), C.c_int32()
+    rc = load_library().mpc_fleet_shard_range(n, ndev, i, C.byref(b), C.byref(e))
+    if rc:
+        raise MpcError(rc, "mpc_fleet_shard_range")
+    return b.value, e.value
+
+
+class MpcFleet:
+    """Several GPUs of one box behind one call (mpc_fleet_* of the C ABI): contiguous shards, one
+    stream and one pinned staging pair per GPU, results into ONE host array.  No NCCL, no torch."""
+
+    def __init__(self, cfg=None, devices=(0,)):
+        self._lib = load_library()
+        self.cfg = cfg if cfg is not None else config_default()
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        self._h = C.c_void_p()
+        rc = self._lib.mpc_fleet_create(C.byref(self.cfg), _ptr(dev), len(dev), C.byref(self._h))
+        if rc:
+            raise MpcError(rc, self._lib.mpc_fleet_last_error(None).decode())
+        self.devices = list(int(d) for d in dev)
+
+    def _check(self, rc):
+        if rc:
+            raise MpcError(rc, self._lib.mpc_fleet_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.mpc_fleet_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self._lib.mpc_fleet_size(self._h))
+
+    def compute_grf_batch(self, states, out=None):
+        states = np.ascontiguousarray(states)
+        if out is None:
+            out = np.zeros(len(states), dtype=abi.RESULT_DTYPE)
+        self._check(self._lib.mpc_fleet_compute_grf_batch(self._h, _ptr(states), _ptr(out), len(states)))
+        return out
+
+    def stream_step(self, states, out=None):
+        states = np.ascontiguousarray(states)
+        if out is None:
+            out = np.zeros(len(states), dtype=abi.RESULT_DTYPE)
+        self._check(self._lib.mpc_fleet_stream_step(self._h, _ptr(states), _ptr(out), len(states)))
+        return out
+
+    def stream_reset(self):
+        self._check(self._lib.mpc_fleet_stream_reset(self._h))
+
+    def kernel_launches(self):
+        return int(self._lib.mpc_fleet_kernel_launches(self._h))

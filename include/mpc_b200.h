@@ -309,6 +309,11 @@ const char *mpc_last_error(const MpcEngine *e);
  * stream) instead of the engine's own stream. */
 int mpc_set_stream(MpcEngine *e, void *cuda_stream);
 int mpc_synchronize(MpcEngine *e);
+/* Measures this GPU's FP64 FMA issue rate (the roofline denominator of the solvers: B200's tensor
+ * cores have no f64 mode worth the name and the path is f64 by its parity bar): a register-only DFMA
+ * kernel on every SM for about `ms_target` milliseconds.  Returns TFLOP/s (2 flops per FMA).  bench.py
+ * records it next to the clock sample taken while it ran instead of quoting a constant. */
+int mpc_measure_fp64_peak(int32_t device, double ms_target, double *tflops);
 /* Number of kernels this engine has launched since creation. */
 int64_t mpc_kernel_launches(const MpcEngine *e);
 /* Developer aid: per-phase SM cycle counters of admm_solve_kernel, summed over CTAs since the
@@ -422,6 +427,33 @@ int mpc_stream_reset_slots(MpcEngine *e, const int32_t *idx, int32_t k);
 int mpc_engine_update_model(MpcEngine *e, const MpcConfig *cfg);
 /* One control tick for n robots: load + build + warm solve + results. */
 int mpc_stream_step(MpcEngine *e, const MpcStateIn *host_in, MpcResult *host_out, int32_t n);
+
+/* ---- one box, several GPUs: the fleet (SURVEY.md 8b "device list", 8e) -------- *
+ * Every QP is independent, so the batch shards with no exchange during build or solve: shard i of G
+ * gets the contiguous range [ceil(n i / G), ceil(n (i + 1) / G)) of the caller's arrays.  A fleet owns
+ * one engine, one stream and one pinned staging pair per entry of `devices` (a device may be listed
+ * more than once: two shards share that GPU).  One call enqueues, for every shard, host-to-device copy,
+ * build + solve and the device-to-host copy of the results, then waits for all of them: the results
+ * land in ONE caller-owned host array (the "final gather" is these per-GPU copies; no NCCL, no
+ * collective).  Caller buffers that are already page-locked are used in place; pageable ones go through
+ * the fleet's pinned staging so that the shards' copies overlap.  No CPU fallback: MPC_ERR_NO_DEVICE. */
+typedef struct MpcFleet MpcFleet;
+int mpc_fleet_create(const MpcConfig *cfg, const int32_t *devices, int32_t ndev, MpcFleet **out);
+void mpc_fleet_destroy(MpcFleet *f);
+/* Text of the last error on this fleet (of the last create failure when f == NULL).  Never NULL. */
+const char *mpc_fleet_last_error(const MpcFleet *f);
+int32_t mpc_fleet_size(const MpcFleet *f);
+/* Host-only helper: the range of shard i (also what sharding.py uses for torch.distributed ranks). */
+int mpc_fleet_shard_range(int32_t n, int32_t ndev, int32_t i, int32_t *begin, int32_t *end);
+/* The whole compute_grf MPC branch for n robots over all GPUs of the fleet: host records in, host
+ * results out (mpc_compute_grf_batch, sharded). */
+int mpc_fleet_compute_grf_batch(MpcFleet *f, const MpcStateIn *host_in, MpcResult *host_out, int32_t n);
+/* One warm-started control tick for n robots (mpc_stream_step, sharded; robot i keeps its shard as long
+ * as n does not change). */
+int mpc_fleet_stream_step(MpcFleet *f, const MpcStateIn *host_in, MpcResult *host_out, int32_t n);
+int mpc_fleet_stream_reset(MpcFleet *f);
+/* Kernels launched by all engines of the fleet since creation. */
+int64_t mpc_fleet_kernel_launches(const MpcFleet *f);
 
 /* ---- ConvexMpc surface, one problem (ConvexMpc.h:22-35) -------------------- */
 

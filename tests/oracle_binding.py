@@ -56,6 +56,22 @@ def lib():
     return _lib
 
 
+def use_native():
+    """bench.py's CPU legs: rebuild the oracle with -march=native ON this box and use that build from now
+    on (the portable x86-64-v3 build travels with the snapshot and forgoes AVX-512).  Returns the flag
+    string actually in use."""
+    global _lib
+    native = os.path.join(_ROOT, "oracle", "liboracle_native.so")
+    try:
+        subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(_ROOT, "oracle"), "native"],   # -B: never reuse a build from another box
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+        _lib = C.CDLL(native)
+        return "-O3 -march=native (built on this box)"
+    except Exception:
+        lib()
+        return "-O3 -march=x86-64-v3 (portable build; native rebuild failed)"
+
+
 def _p(a, t=C.c_double):
     return None if a is None else a.ctypes.data_as(C.POINTER(t))
 

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_functions():
     src = open(os.path.join(ROOT, "include", "mpc_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b(?:int|void|int64_t|const char \*)\s*\*?\s*((?:mpc|balance|prep|a1)_[a-z_0-9]+)\s*\(", src)
+    names = re.findall(r"\b(?:int|void|int32_t|int64_t|const char \*)\s*\*?\s*((?:mpc|balance|prep|a1)_[a-z_0-9]+)\s*\(", src)
     return sorted(set(names))
 
 

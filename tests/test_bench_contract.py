@@ -32,6 +32,20 @@ def test_reference_arm_prints_the_contract_line(pkg, ob):
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"]
     assert e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    # the CPU arm solves the GPU arm's own batches (full 4096 states per step) and never maps the product
+    # library: its states and config come from the host-only generator library
+    assert d["config"]["states_per_gpu"] == 4096 and d["config"]["sample_per_step"] == 4096
+    assert cb["p50_batch_ms"] > 0 and "march" in cb["compiler_flags"]
+
+
+def test_reference_arm_never_maps_the_product_library(pkg):
+    code = ("import sys, os; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','3'];"
+            "import runpy\n"
+            "try:\n runpy.run_path('bench.py', run_name='__main__')\nexcept SystemExit: pass\n"
+            "maps=open('/proc/self/maps').read(); print('PRODUCT_MAPPED' if 'libmpc_b200.so' in maps else 'CLEAN');"
+            "print('HOSTGEN' if 'libmpc_hostgen.so' in maps else 'NOHOSTGEN')")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert "CLEAN" in p.stdout and "HOSTGEN" in p.stdout, p.stdout[-500:] + p.stderr[-1500:]
 
 
 def test_product_arm_needs_a_gpu():

@@ -20,9 +20,32 @@ TOL_GRF = 1e-3
 TOL_CONE = 1e-4
 
 
+# A state whose termination check flipped (rounding moved a residual across its tolerance) stops one
+# check interval earlier or later than the oracle.  Both results are eps-solutions of the same QP, but at
+# eps 1e-5 the first-step force is only determined to ~1e-2 in the weakly curved directions (P has 6 H
+# eigenvalues equal to 2 r, SURVEY.md 7 hard part 1), so such a state is gated at TOL_GRF_FLIPPED, and
+# the FRACTION of such states is gated separately (zero wherever that is what is measured).
+TOL_GRF_FLIPPED = 5e-2
+
+
 def grf_rel(gpu, ref):
     den = np.maximum(np.linalg.norm(ref, axis=1), 1.0)
     return np.linalg.norm(gpu.astype(np.float64) - ref, axis=1) / den
+
+
+def assert_same_iterates(res, ref, max_flipped=0.0, what=""):
+    """EVERY state is checked: identical iteration count -> GRF inside TOL_GRF; a flipped termination
+    check (at most the fraction max_flipped of the states) -> counts one interval apart, GRF inside
+    TOL_GRF_FLIPPED."""
+    assert np.array_equal(res["status"], ref["status"]), what
+    same = res["iters"] == ref["iters"]
+    assert (~same).mean() <= max_flipped, (what, float((~same).mean()))
+    rel = grf_rel(res["grf"], ref["grf"])
+    assert rel[same].max(initial=0.0) <= TOL_GRF, (what, float(rel[same].max(initial=0.0)))
+    assert (res["rho_updates"][same] == ref["rho_updates"][same]).all(), what
+    if (~same).any():
+        assert np.abs(res["iters"][~same] - ref["iters"][~same]).max() <= 50, what
+        assert rel[~same].max() <= TOL_GRF_FLIPPED, (what, float(rel[~same].max()))
 
 
 @pytest.fixture(scope="module")
@@ -238,10 +261,7 @@ def test_edge_cases(pkg, ob, eng):
         states["contacts"][:] = pat
         res = eng.compute_grf_batch(states)
         ref = ob.mpc_compute_grf(cfg, states)
-        assert np.array_equal(res["status"], ref["status"])
-        assert (res["iters"] == ref["iters"]).mean() >= 0.9
-        ok = res["iters"] == ref["iters"]
-        assert grf_rel(res["grf"][ok], ref["grf"][ok]).max() <= TOL_GRF
+        assert_same_iterates(res, ref, max_flipped=0.07, what=str(pat))   # at most one state of the 16
 
 
 def test_max_iter_status(pkg, ob):
@@ -349,10 +369,7 @@ def test_balance_qp_parity(pkg, ob):
     states = pkg.generate_balance_states(1005, 0, 8192)
     res = be.compute_grf_batch(states)
     ref = ob.balance_compute_grf(bcfg, states)
-    assert np.array_equal(res["status"], ref["status"])
-    assert (res["iters"] == ref["iters"]).mean() >= 0.995
-    ok = res["iters"] == ref["iters"]
-    assert grf_rel(res["grf"][ok], ref["grf"][ok]).max() <= TOL_GRF
+    assert_same_iterates(res, ref, max_flipped=0.005, what="balance 8192")
     # ragged / empty
     assert len(be.compute_grf_batch(np.zeros(0, dtype=pkg.abi.BALANCE_DTYPE))) == 0
     r1 = be.compute_grf_batch(states[:5])
@@ -379,11 +396,8 @@ def test_long_horizon_h30(pkg, ob):
     e.solve()
     res = e.get_results()
     ref = ob.mpc_compute_grf(cfg, states)
-    assert np.array_equal(res["status"], ref["status"]) and (res["status"] == 1).all()
-    assert (res["iters"] == ref["iters"]).mean() >= 0.99
-    assert (res["rho_updates"] == ref["rho_updates"]).mean() >= 0.99
-    ok = res["iters"] == ref["iters"]
-    assert grf_rel(res["grf"][ok], ref["grf"][ok]).max() <= TOL_GRF
+    assert (res["status"] == 1).all()
+    assert_same_iterates(res, ref, max_flipped=0.0, what="H=30")
     x = e.get_solution(3).astype(np.float64).reshape(30, 4, 3)
     c = states["contacts"][3].astype(np.float64)
     assert np.maximum(np.abs(x[..., :2]).max(-1) - 0.3 * x[..., 2], 0).max() <= TOL_CONE * 180.0
@@ -412,12 +426,7 @@ def test_warm_started_stream_parity(pkg, ob, which):
     cold = e.compute_grf_batch(st[1]).copy()
     for t in range(T):
         res = e.stream_step(st[t])
-        assert (res["status"] == ref["status"][t]).all()
-        same = (res["iters"] == ref["iters"][t]).mean()
-        assert same >= 0.98, (t, same)
-        ok = res["iters"] == ref["iters"][t]
-        assert grf_rel(res["grf"][ok], ref["grf"][t][ok]).max() <= TOL_GRF, t
-        assert (res["rho_updates"][ok] == ref["rho_updates"][t][ok]).all()
+        assert_same_iterates(res, ref[t], max_flipped=0.0, what=f"warm tick {t}")
         if t == 0:
             first = res.copy()
     # a warm tick is cheaper than the cold solve of the same problem
@@ -442,9 +451,8 @@ def test_warm_stream_golden(pkg, name):
     e = pkg.MpcEngine(cfg, 0)
     for t in range(g["states"].shape[0]):
         res = e.stream_step(g["states"][t])
-        ok = res["iters"] == g["iters"][t]
-        assert ok.mean() >= 0.95, t
-        assert grf_rel(res["grf"][ok], g["grf"][t][ok]).max() <= TOL_GRF
+        assert np.array_equal(res["iters"], g["iters"][t]), t
+        assert grf_rel(res["grf"], g["grf"][t]).max() <= TOL_GRF, t
     e.close()
 
 
@@ -503,8 +511,8 @@ def test_torque_map_parity(pkg, ob, path):
         _check_torques(ob, st, tin, res, tq)
         tau_ref, _ = ob.torque_map(st, tin, ref["grf"])
     # (b) end to end against the oracle's GRF -> oracle map: the GRF gate carried through J
-    same = res["iters"] == ref["iters"]
-    err = np.abs(tq["joint_torques"][same] - tau_ref[same]).max(axis=1) / np.maximum(np.abs(tau_ref[same]).max(axis=1), 1.0)
+    assert np.array_equal(res["iters"], ref["iters"])
+    err = np.abs(tq["joint_torques"] - tau_ref).max(axis=1) / np.maximum(np.abs(tau_ref).max(axis=1), 1.0)
     assert err.max() <= TOL_GRF, err.max()
     e.close()
 
@@ -636,10 +644,7 @@ def test_horizon_extensions_parity(pkg, ob, flags):
     e.solve()
     res = e.get_results()
     ref = ob.mpc_compute_grf_ext(cfg, st, gait)
-    assert (res["status"] == ref["status"]).all()
-    same = res["iters"] == ref["iters"]
-    assert same.mean() >= 0.98
-    assert grf_rel(res["grf"][same], ref["grf"][same]).max() <= TOL_GRF
+    assert_same_iterates(res, ref, max_flipped=0.0, what=str(flags))
     # the flags do change the answer (otherwise this test checks nothing)
     base = ob.mpc_compute_grf(pkg.config_default(), st)
     assert grf_rel(res["grf"], base["grf"]).max() > 1e-4
@@ -734,9 +739,7 @@ def test_structured_solver_hardware_weights_and_extensions(pkg, ob):
     e.solve()
     res = e.get_results()
     ref = ob.mpc_compute_grf_ext(cfg, st, gait)
-    assert (res["status"] == ref["status"]).all()
-    same = res["iters"] == ref["iters"]
-    assert same.mean() >= 0.98 and grf_rel(res["grf"][same], ref["grf"][same]).max() <= TOL_GRF
+    assert_same_iterates(res, ref, max_flipped=0.0, what="riccati + extensions")
     e.close()
 
 
@@ -786,3 +789,117 @@ def test_two_engines_two_host_threads(pkg):
     assert not errs, errs
     for b in range(len(batches)):
         assert got[b].tobytes() == want[b].tobytes()
+
+
+def test_config4_full_size_h30(pkg, ob):
+    """BASELINE configs[3] at its full size: 8192 states, H = 30.  Every state: solved, plausible iteration
+    count, feasible first-step force; a 1/64 sample against the oracle; a repeat is bit-identical."""
+    cfg = pkg.config_default()
+    cfg.horizon = 30
+    e = pkg.MpcEngine(cfg, 0)
+    st = pkg.generate_states(1004, 0, 8192)
+    res = e.compute_grf_batch(st).copy()
+    assert (res["status"] == 1).all()
+    assert res["iters"].min() >= 50 and res["iters"].max() <= 2000 and (res["iters"] % 25 == 0).all()
+    Rm = st["rot_mat"].reshape(-1, 3, 3).astype(np.float64)
+    fw = np.einsum("nij,nlj->nli", Rm, res["grf"].reshape(-1, 4, 3).astype(np.float64))
+    cmask = st["contacts"].astype(np.float64)
+    assert (fw[..., 2] >= -TOL_CONE * 180).all() and (fw[..., 2] <= 180.0 * cmask + TOL_CONE * 180 + 2e-3).all()
+    assert (np.abs(fw[..., :2]).max(-1) <= 0.3 * fw[..., 2] + TOL_CONE * 180 + 2e-3).all()
+    idx = np.arange(0, 8192, 64)
+    ref = ob.mpc_compute_grf(cfg, st[idx])
+    assert_same_iterates(res[idx], ref, max_flipped=0.0, what="config 4 sample")
+    assert e.compute_grf_batch(st).tobytes() == res.tobytes()
+    e.close()
+
+
+def test_config5_full_size_balance(pkg, ob):
+    """BASELINE configs[4] at its full size: 1 000 000 stance-balance QPs (on one GPU here; bench.py times
+    the per-GPU share).  Status / iteration histogram on all of them, the oracle on a 1/1024 sample."""
+    bcfg = pkg.balance_config_default()
+    be = pkg.MpcEngine(bcfg, 0, balance=True)
+    n = 1_000_000
+    st = pkg.generate_balance_states(1005, 0, n)
+    res = be.compute_grf_batch(st)
+    codes, counts = np.unique(res["status"], return_counts=True)
+    assert set(codes.tolist()) <= {1, 2, -2} and counts[codes == 1][0] >= 0.999 * n, dict(zip(codes.tolist(), counts.tolist()))
+    assert (res["iters"] % 25 == 0).all() and res["iters"].min() >= 25 and res["iters"].max() <= bcfg.osqp.max_iter
+    assert 100 <= res["iters"].mean() <= 400
+    idx = np.arange(0, n, 1024)
+    ref = ob.balance_compute_grf(bcfg, st[idx])
+    assert_same_iterates(res[idx], ref, max_flipped=0.005, what="config 5 sample")
+    # contact-gated: a swing leg carries no force in the body frame
+    sw = st["contacts"] == 0
+    assert np.abs(res["grf"].reshape(-1, 4, 3)[sw]).max() < 2e-2
+    be.close()
+
+
+def test_mirror_compute_grf_keeps_one_warm_solver(pkg, ob):
+    """The Python mirror's A1RobotControl.compute_grf: one persistent solver (A1RobotControl.h:67), 20
+    ticks of one robot across a trot swap against the oracle's MpcStream; a weight change in the state
+    is one more Hessian update of the SAME solver (A1RobotControl.cpp:447 re-reads the weights)."""
+    cfg = pkg.config_default()
+    T, robot = 20, 3
+    st = np.stack([pkg.generate_stream_states(1006, robot, 1, 38 + t) for t in range(T)])
+    ref = ob.mpc_stream(cfg, st)
+    ctl = pkg.A1RobotControl(pkg.config_default())
+    s = pkg.A1CtrlStates()
+    s.robot_mass = cfg.mass
+    s.q_weights = np.array(cfg.q_weights[:])
+    s.r_weights = np.array(cfg.r_weights[:])
+    s.a1_trunk_inertia = np.array(cfg.inertia[:]).reshape(3, 3)
+    iters = []
+    for t in range(T):
+        rec = st[t, 0]
+        s.root_euler, s.root_pos = rec["euler"].astype(float), rec["pos"].astype(float)
+        s.root_ang_vel, s.root_lin_vel = rec["ang_vel"].astype(float), rec["lin_vel"].astype(float)
+        s.root_euler_d = rec["euler_d"].astype(float)
+        s.root_pos_d = np.array([0.0, 0.0, float(rec["pos_d_z"])])
+        s.root_lin_vel_d, s.root_ang_vel_d = rec["lin_vel_d"].astype(float), rec["ang_vel_d"].astype(float)
+        s.root_rot_mat = rec["rot_mat"].astype(float).reshape(3, 3)
+        s.foot_pos_abs = rec["foot_pos_abs"].astype(float).reshape(4, 3).T
+        s.contacts = [bool(c) for c in rec["contacts"]]
+        grf = ctl.compute_grf(s, 0.0025)
+        assert ctl.last_status == 1 and ctl.last_iters == ref["iters"][t, 0], (t, ctl.last_iters, ref["iters"][t, 0])
+        want = ref["grf"][t, 0].reshape(4, 3).T
+        assert np.linalg.norm(grf - want) / max(np.linalg.norm(want), 1.0) <= TOL_GRF, t
+        iters.append(ctl.last_iters)
+    assert np.mean(iters[1:9]) < 0.7 * iters[0]
+    # new weights: same engine, same live solver (no cold restart)
+    eng_before = ctl._engine
+    s.q_weights = s.q_weights * 1.5
+    ctl.compute_grf(s, 0.0025)
+    assert ctl._engine is eng_before and ctl.last_iters < iters[0]
+    ctl.reset_solver()
+    ctl.compute_grf(s, 0.0025)
+    assert ctl.last_iters >= 100                                   # cold again
+
+
+def test_warm_slot_fault_containment_and_slot_reset(pkg, ob):
+    """One bad record (NaN) poisons only its own robot slot, and only for that tick: the kernel leaves the
+    slot dead, so the robot's next tick is an initSolver; every other robot keeps its warm solver.
+    mpc_stream_reset_slots forgets chosen robots only."""
+    cfg = pkg.config_hardware()
+    N = 96
+    st = [pkg.generate_stream_states(1006, 0, N, 44 + t) for t in range(4)]
+    ref = ob.mpc_stream(cfg, np.stack(st))
+    e = pkg.MpcEngine(cfg, 0)
+    e.stream_step(st[0])
+    bad = st[1].copy()
+    bad["pos"][5] = np.nan
+    r1 = e.stream_step(bad)
+    assert (r1["grf"][5] == 0).all() and r1["status"][5] != 1      # NaN guard: zero force, not solved
+    ok = np.arange(N) != 5
+    assert np.array_equal(r1["iters"][ok], ref["iters"][1][ok])
+    r2 = e.stream_step(st[2])
+    cold2 = ob.mpc_compute_grf(cfg, st[2][5:6])
+    assert r2["status"][5] == 1 and r2["iters"][5] == cold2["iters"][0]          # recovered by a cold start
+    assert np.array_equal(r2["iters"][ok], ref["iters"][2][ok])                   # nobody else noticed
+    # per-slot reset
+    e.stream_reset_slots([7, 9])
+    r3 = e.stream_step(st[3])
+    cold3 = ob.mpc_compute_grf(cfg, st[3][[7, 9]])
+    assert np.array_equal(r3["iters"][[7, 9]], cold3["iters"])
+    keep = ok & (np.arange(N) != 7) & (np.arange(N) != 9)
+    assert np.array_equal(r3["iters"][keep], ref["iters"][3][keep])
+    e.close()
