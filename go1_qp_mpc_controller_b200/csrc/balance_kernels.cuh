@@ -292,27 +292,46 @@ balance_qp_kernel(const BalanceStateIn* __restrict__ states, int num, int* __res
   double x = 0.0, z = 0.0, y = 0.0;
   int iter = 0, status = MPC_STATUS_UNSOLVED, rho_updates = 0;
   double pri_out = 0.0;
-  for (iter = 1; iter <= bp.max_iter; ++iter) {
-    // rhs_j = sigma x - q + A'(rho z - y)
-    const double w = rv * z - y;
-    double rhs = bp.sigma * x - qb;
+  // iterations run in stretches up to the next event (termination check, rho adaptation, iteration
+  // limit) on a plain counter: the two runtime `%` of the straightforward loop were a third of its
+  // instructions (ncu r02_balance_v2: 320 warp instructions per iteration of a 12-variable problem)
+  const int chk = bp.check_termination > 0 ? bp.check_termination : 0x7fffffff;
+  const int adp = (bp.adaptive_rho && bp.adaptive_rho_interval > 0) ? bp.adaptive_rho_interval : 0x7fffffff;
+  int until_check = chk, until_adapt = adp;
+  iter = 0;
+  for (;;) {
+    int run = until_check < until_adapt ? until_check : until_adapt;
+    run = run < bp.max_iter - iter ? run : bp.max_iter - iter;
+#pragma unroll 1
+    for (int qq = 0; qq < run; ++qq) {
+      // rhs_j = sigma x - q + A'(rho z - y)
+      const double w = rv * z - y;
+      double rhs = bp.sigma * x - qb;
 #pragma unroll
-    for (int t = 0; t < 5; ++t) rhs = fma(rcs[t], bshfl(w, ridx[t]), rhs);
-    double xt = 0.0;
+      for (int t = 0; t < 5; ++t) rhs = fma(rcs[t], bshfl(w, ridx[t]), rhs);
+      double xt0 = 0.0, xt1 = 0.0;
 #pragma unroll
-    for (int b = 0; b < 12; ++b) xt = fma(a[b], bshfl(rhs, b), xt);
-    xt = -xt;
-    x = bp.alpha * xt + (1.0 - bp.alpha) * x;
-    const double zt = ca * bshfl(xt, ja) + cz * bshfl(xt, jz);
-    const double zr = bp.alpha * zt + (1.0 - bp.alpha) * z;
-    double zn = fmin(fmax(zr + rinv * y, lb), ub);
-    y += rv * (zr - zn);
-    z = zn;
-    const bool can_check = bp.check_termination > 0 && (iter % bp.check_termination == 0);
-    const bool can_adapt = bp.adaptive_rho && bp.adaptive_rho_interval > 0 &&
-                           (iter % bp.adaptive_rho_interval == 0);
+      for (int b = 0; b < 12; b += 2) {
+        xt0 = fma(a[b], bshfl(rhs, b), xt0);
+        xt1 = fma(a[b + 1], bshfl(rhs, b + 1), xt1);
+      }
+      const double xt = -(xt0 + xt1);
+      x = bp.alpha * xt + (1.0 - bp.alpha) * x;
+      const double zt = ca * bshfl(xt, ja) + cz * bshfl(xt, jz);
+      const double zr = bp.alpha * zt + (1.0 - bp.alpha) * z;
+      double zn = zr + rinv * y;
+      zn = (zn < lb) ? lb : zn;
+      zn = (zn > ub) ? ub : zn;
+      y += rv * (zr - zn);
+      z = zn;
+    }
+    iter += run;
+    until_check -= run;
+    until_adapt -= run;
+    const bool can_check = until_check == 0, can_adapt = until_adapt == 0;
+    if (can_check) until_check = chk;
+    if (can_adapt) until_adapt = adp;
     const bool last = iter == bp.max_iter;
-    if (!(can_check || can_adapt || last)) continue;
     // residuals
     const double Ax = ca * bshfl(x, ja) + cz * bshfl(x, jz);
     const double rp = is_row ? (Ax - z) : 0.0;
@@ -358,7 +377,6 @@ balance_qp_kernel(const BalanceStateIn* __restrict__ states, int num, int* __res
       }
     }
   }
-  if (iter > bp.max_iter) iter = bp.max_iter;
 
   // ---- unscale and rotate every leg to the body frame (:439-444) ----
   const double xo = D * x;

@@ -37,12 +37,12 @@ struct GenBuildSmem {
   double x0[16];
   alignas(16) double scratch[kGenBuildThreads / 32][312];  // per warp: U (13 x 12, padded to 160) and a 12 x 12 block
   float st[48];
-  int contacts[4];
+  int contacts[4 * H];  // per step and leg (replicated unless the horizon is gait aware)
 };
 
 template <int H>
 __global__ void __launch_bounds__(kGenBuildThreads, 1)
-gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, double* __restrict__ model_out,
+gen_build_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __restrict__ gait, ModelIn model, int num, double* __restrict__ model_out,
                  double* __restrict__ P_out,
                  double* __restrict__ q_out, float* __restrict__ l_out, float* __restrict__ u_out,
                  double* __restrict__ workspace, const __grid_constant__ BuildParams bp) {
@@ -71,12 +71,24 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
         if (rr == 2 && cc == 8) a = 1.0;
         if (rr >= 3 && rr <= 5 && cc == rr + 6) a = 1.0;
         if (rr == 11 && cc == 12) a = 1.0;
+        // exact discretisation: A_c^3 = 0 and A_c^2 has the single entry (5, 12) = 1 (see qp_build_kernel)
+        if (bp.exact_discretization && rr == 5 && cc == 12) a = 0.5 * bp.dt;
         sm.Apow[tid] = (rr == cc) ? 1.0 : 0.0;
         sm.Apow[169 + tid] = ((rr == cc) ? 1.0 : 0.0) + a * bp.dt;
       }
-      if (tid < 156) sm.Bd[tid] = 0.0;
+      for (int idx = tid; idx < H * 156; idx += kGenBuildThreads) sm.Bd[idx] = 0.0;
       if (tid >= 192 && tid < 192 + 13) sm.x0[tid - 192] = (tid - 192 < 12) ? (double)st[tid - 192] : -9.8;
-      if (tid >= 208 && tid < 212) sm.contacts[tid - 208] = st[kOffContacts + tid - 208] != 0.0f;
+      for (int idx = tid; idx < 4 * H; idx += kGenBuildThreads) {
+        const int i = idx >> 2, leg = idx & 3;
+        int c = st[kOffContacts + leg] != 0.0f;
+        if (bp.gait_aware && i > 0) {
+          // planned contact of step i from the gait counter (A1RobotControl.cpp:156-164)
+          const float* gg = reinterpret_cast<const float*>(gait + p);
+          const double cnt = fmod((double)gg[leg] + (double)i * (double)gg[10] * (double)gg[4 + leg], (double)gg[8]);
+          c = cnt <= (double)gg[9];
+        }
+        sm.contacts[idx] = c;
+      }
       for (int i = tid; i < H; i += kGenBuildThreads) {  // mpc_states_d (A1RobotControl.cpp:470-488)
         const double R0 = st[kOffRot + 0], R1 = st[kOffRot + 1], R2 = st[kOffRot + 2];
         const double R3 = st[kOffRot + 3], R4 = st[kOffRot + 4], R5 = st[kOffRot + 5];
@@ -98,8 +110,10 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
         d[12] = -9.8;
       }
       __syncthreads();
-      if (tid < 4) {  // B_d = dt B_c, one thread per leg (ConvexMpc.cpp:132-143, :151)
-        const int leg = tid;
+      // B_d = dt B_c, one thread per leg (ConvexMpc.cpp:132-143, :151) -- per (step, leg) when the feet drift
+      if (tid < (bp.foot_drift ? 4 * H : 4)) {
+        const int leg = tid & 3, step = tid >> 2;
+        double* Bs_ = &sm.Bd[step * 156];
         double R[9], T[9], Iw[9], Inv[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = (double)st[kOffRot + i];
@@ -127,7 +141,15 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
         Inv[0] = c00 * id; Inv[1] = (Iw[2] * Iw[7] - Iw[1] * Iw[8]) * id; Inv[2] = (Iw[1] * Iw[5] - Iw[2] * Iw[4]) * id;
         Inv[3] = c01 * id; Inv[4] = (Iw[0] * Iw[8] - Iw[2] * Iw[6]) * id; Inv[5] = (Iw[2] * Iw[3] - Iw[0] * Iw[5]) * id;
         Inv[6] = c02 * id; Inv[7] = (Iw[1] * Iw[6] - Iw[0] * Iw[7]) * id; Inv[8] = (Iw[0] * Iw[4] - Iw[1] * Iw[3]) * id;
-        const double fx = st[kOffFoot + 3 * leg], fy = st[kOffFoot + 3 * leg + 1], fz = st[kOffFoot + 3 * leg + 2];
+        double fx = st[kOffFoot + 3 * leg], fy = st[kOffFoot + 3 * leg + 1], fz = st[kOffFoot + 3 * leg + 2];
+        if (bp.foot_drift) {
+          // the body moves on with the commanded world velocity, the stance feet stay: r_i = r_0 - i dt v_d
+          const double vx = st[kOffLinVelD], vy = st[kOffLinVelD + 1], vz = st[kOffLinVelD + 2];
+          const double kd = (double)step * bp.dt;
+          fx -= kd * (R[0] * vx + R[1] * vy + R[2] * vz);
+          fy -= kd * (R[3] * vx + R[4] * vy + R[5] * vz);
+          fz -= kd * (R[6] * vx + R[7] * vy + R[8] * vz);
+        }
         const double sk[9] = {0.0, -fz, fy, fz, 0.0, -fx, -fy, fx, 0.0};
 #pragma unroll
         for (int i = 0; i < 3; ++i)
@@ -136,12 +158,28 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
             double a = 0.0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) a += Inv[3 * i + k] * sk[3 * k + j];
-            sm.Bd[(6 + i) * 12 + 3 * leg + j] = a * bp.dt;
-            sm.Bd[(9 + i) * 12 + 3 * leg + j] = (i == j) ? (1.0 / bp.mass) * bp.dt : 0.0;
+            Bs_[(6 + i) * 12 + 3 * leg + j] = a * bp.dt;
+            Bs_[(9 + i) * 12 + 3 * leg + j] = (i == j) ? (1.0 / bp.mass) * bp.dt : 0.0;
           }
+        if (bp.exact_discretization) {
+          // B_d += dt^2/2 A_c B_c: euler rows <- Rz' (I^-1 [r]x), position rows <- I / m
+          double sy, cy;
+          sincos((double)st[kOffEuler + 2], &sy, &cy);
+          const double hh = 0.5 * bp.dt;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double b6 = Bs_[6 * 12 + 3 * leg + j], b7 = Bs_[7 * 12 + 3 * leg + j], b8 = Bs_[8 * 12 + 3 * leg + j];
+            Bs_[0 * 12 + 3 * leg + j] = hh * (cy * b6 + sy * b7);
+            Bs_[1 * 12 + 3 * leg + j] = hh * (-sy * b6 + cy * b7);
+            Bs_[2 * 12 + 3 * leg + j] = hh * b8;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Bs_[(3 + i) * 12 + 3 * leg + j] = hh * Bs_[(9 + i) * 12 + 3 * leg + j];
+          }
+        }
       }
       __syncthreads();
-      for (int idx = tid; idx < (H - 1) * 156; idx += kGenBuildThreads) sm.Bd[156 + idx] = sm.Bd[idx % 156];
+      if (!bp.foot_drift)
+        for (int idx = tid; idx < (H - 1) * 156; idx += kGenBuildThreads) sm.Bd[156 + idx] = sm.Bd[idx % 156];
     } else {
       if (tid < 169) {
         const int rr = tid / 13, cc = tid % 13;
@@ -151,7 +189,7 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
       for (int idx = tid; idx < H * 156; idx += kGenBuildThreads) sm.Bd[idx] = model.B_d_list[size_t(p) * H * 156 + idx];
       if (tid < 13) sm.x0[tid] = model.x0[size_t(p) * 13 + tid];
       for (int idx = tid; idx < s; idx += kGenBuildThreads) sm.xref[idx] = model.x_ref[size_t(p) * s + idx];
-      if (tid < 4) sm.contacts[tid] = model.contacts[size_t(p) * 4 + tid] != 0;
+      for (int idx = tid; idx < 4 * H; idx += kGenBuildThreads) sm.contacts[idx] = model.contacts[size_t(p) * 4 + (idx & 3)] != 0;
     }
     if (model_out != nullptr) {
       // A_d and the B_d list for the structured (Riccati) solver
@@ -277,7 +315,7 @@ gen_build_kernel(const MpcStateIn* __restrict__ states, ModelIn model, int num, 
     // bounds
     for (int i = tid; i < m; i += kGenBuildThreads) {
       const int leg = (i % 20) / 5, t = i % 5;
-      const float cflag = sm.contacts[leg] ? 1.0f : 0.0f;
+      const float cflag = sm.contacts[4 * (i / 20) + leg] ? 1.0f : 0.0f;
       float lo, hi;
       if (t == 0 || t == 2) { lo = 0.0f; hi = (float)MPC_INFTY; }
       else if (t == 1 || t == 3) { lo = -(float)MPC_INFTY; hi = 0.0f; }

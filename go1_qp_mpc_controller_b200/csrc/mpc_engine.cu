@@ -52,6 +52,9 @@ struct MpcEngine {
   double* d_workspace = nullptr;  // long-horizon path: per-CTA B_qp / -K^-1 scratch
   int H = kH;                     // horizon
   int nvar() const { return 12 * H; }
+  // doubles per warm-start slot: x | q | z | y | rho | live, padded (648 for H = 10, the layout of admm_kernel.cuh)
+  int warm_stride() const { return H == kH ? kWarmStride : ((2 * nvar() + 2 * ncon() + 2 + 7) / 8) * 8; }
+  int warm_live_offset() const { return 2 * nvar() + 2 * ncon() + 1; }
   int ncon() const { return 20 * H; }
   size_t p_stride() const { return H == kH ? size_t(kN) * kNP : size_t(nvar()) * nvar(); }  // doubles per problem
   MpcTorqueIn* d_tin = nullptr;   // optional torque-map inputs (compute_joint_torques), n records
@@ -223,7 +226,7 @@ int launch_build(MpcEngine* e, const MpcStateIn* d_states, ModelIn model, int n,
   } else {
     const int grid = n < e->num_sms ? n : e->num_sms;
     gen_build_kernel<30><<<grid, kGenBuildThreads, sizeof(GenBuildSmem<30>), e->stream>>>(
-        d_states, model, n, model_out, P, q, l, u, e->d_workspace, e->bp);
+        d_states, d_states ? e->d_gait : nullptr, model, n, model_out, P, q, l, u, e->d_workspace, e->bp);
   }
   ++e->launches;
   CUDA_TRY(e, cudaGetLastError());
@@ -236,16 +239,17 @@ int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l,
   const MpcTorqueIn* tin = (with_torque && d_states) ? e->d_tin : nullptr;
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
   const int grid = n < e->num_sms ? n : e->num_sms;
-  if (e->structured && !warm && P == e->d_P) {
+  if (e->structured && (!warm || e->H != kH) && P == e->d_P) {
     // Riccati-structured ADMM (riccati_kernel.cuh): any horizon, one CTA of 128 threads per problem
     if (e->H == kH) {
       const int g = n < e->num_sms * 3 ? n : e->num_sms * 3;
       riccati_solve_kernel<kH><<<g, kRicThreads, sizeof(RicSmem<kH>), e->stream>>>(
-          P, e->p_stride(), kNP, q, l, u, e->d_model, d_states, res, x, n, e->d_counter, e->bp, e->sp);
+          P, e->p_stride(), kNP, q, l, u, e->d_model, d_states, res, x, n, e->d_counter, nullptr, 0, e->bp, e->sp);
     } else {
       const int g = n < e->num_sms ? n : e->num_sms;
       riccati_solve_kernel<30><<<g, kRicThreads, sizeof(RicSmem<30>), e->stream>>>(
-          P, e->p_stride(), e->nvar(), q, l, u, e->d_model, d_states, res, x, n, e->d_counter, e->bp, e->sp);
+          P, e->p_stride(), e->nvar(), q, l, u, e->d_model, d_states, res, x, n, e->d_counter, warm, e->warm_stride(),
+          e->bp, e->sp);
     }
     ++e->launches;
     CUDA_TRY(e, cudaGetLastError());
@@ -446,8 +450,6 @@ int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
   if (validate_settings(cfg->osqp, &why)) return fail(nullptr, MPC_ERR_INVALID, why);
   if (!(cfg->dt > 0) || !(cfg->mass > 0) || !(cfg->mu > 0))
     return fail(nullptr, MPC_ERR_INVALID, "dt/mass/mu must be positive");
-  if (cfg->horizon != kH && (cfg->exact_discretization || cfg->foot_drift || cfg->gait_aware))
-    return fail(nullptr, MPC_ERR_UNSUPPORTED, "exact_discretization / foot_drift / gait_aware are built for horizon 10 only");
   MpcEngine* e = nullptr;
   int rc = create_common(0, device, &e);
   if (rc != MPC_OK) return rc;
@@ -807,7 +809,7 @@ int mpc_stream_reset(MpcEngine* e) {
   if (!e || e->kind != 0) return MPC_ERR_INVALID;
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->d_warm)
-    CUDA_TRY(e, cudaMemsetAsync(e->d_warm, 0, size_t(e->warm_capacity) * kWarmStride * sizeof(double), e->stream));
+    CUDA_TRY(e, cudaMemsetAsync(e->d_warm, 0, size_t(e->warm_capacity) * e->warm_stride() * sizeof(double), e->stream));
   return MPC_OK;
 }
 
@@ -818,7 +820,8 @@ int mpc_stream_reset_slots(MpcEngine* e, const int32_t* idx, int32_t k) {
   for (int i = 0; i < k; ++i) {
     if (idx[i] < 0) return fail(e, MPC_ERR_INVALID, "negative slot index");
     if (idx[i] >= e->warm_capacity) continue;  // a slot that never solved is not live
-    CUDA_TRY(e, cudaMemsetAsync(e->d_warm + size_t(idx[i]) * kWarmStride + kWarmLive, 0, sizeof(double), e->stream));
+    CUDA_TRY(e, cudaMemsetAsync(e->d_warm + size_t(idx[i]) * e->warm_stride() + e->warm_live_offset(), 0, sizeof(double),
+                                e->stream));
   }
   return MPC_OK;
 }
@@ -843,16 +846,18 @@ int mpc_engine_update_model(MpcEngine* e, const MpcConfig* cfg) {
 
 int mpc_solve_warm_async(MpcEngine* e) {
   if (!e || e->kind != 0) return MPC_ERR_INVALID;
-  if (e->H != kH) return fail(e, MPC_ERR_UNSUPPORTED, "warm-started streaming is built for horizon 10 only");
+  if (e->H != kH && !e->structured)
+    return fail(e, MPC_ERR_UNSUPPORTED, "warm-started long-horizon solves need the Riccati solver (structured_solver 0 or 1)");
   if (!e->built) return fail(e, MPC_ERR_STATE, "mpc_solve_warm before mpc_build_qp");
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->n > e->warm_capacity) {
     // growing the slot array keeps the live solvers of the slots that already exist
     double* grown = nullptr;
-    CUDA_TRY(e, cudaMalloc(&grown, size_t(e->n) * kWarmStride * sizeof(double)));
-    cudaError_t crc = cudaMemsetAsync(grown, 0, size_t(e->n) * kWarmStride * sizeof(double), e->stream);
+    const size_t ws = size_t(e->warm_stride());
+    CUDA_TRY(e, cudaMalloc(&grown, size_t(e->n) * ws * sizeof(double)));
+    cudaError_t crc = cudaMemsetAsync(grown, 0, size_t(e->n) * ws * sizeof(double), e->stream);
     if (crc == cudaSuccess && e->d_warm)
-      crc = cudaMemcpyAsync(grown, e->d_warm, size_t(e->warm_capacity) * kWarmStride * sizeof(double),
+      crc = cudaMemcpyAsync(grown, e->d_warm, size_t(e->warm_capacity) * ws * sizeof(double),
                             cudaMemcpyDeviceToDevice, e->stream);
     if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
     if (crc != cudaSuccess) {
@@ -1161,6 +1166,11 @@ int mpc_solve_qp(MpcEngine* e, const double* hessian, const double* gradient, co
                  const double* ub, double* solution, int32_t* status, int32_t* iters) {
   if (!e || e->kind != 0) return MPC_ERR_INVALID;
   if (!hessian || !gradient || !lb || !ub || !solution) return fail(e, MPC_ERR_INVALID, "NULL QP input");
+  // The device solvers do not evaluate OSQP's infeasibility certificates (the QPs of this path are feasible
+  // and strictly convex by construction); a caller-supplied QP with crossed bounds is refused here like
+  // osqp_setup / osqp_update_bounds refuse it, instead of burning max_iter iterations on it.
+  for (int i = 0; i < e->ncon(); ++i)
+    if (!(lb[i] <= ub[i])) return fail(e, MPC_ERR_INVALID, "mpc_solve_qp: lb[" + std::to_string(i) + "] > ub (or NaN)");
   CUDA_TRY(e, cudaSetDevice(e->device));
   const int Hh = e->H, nv = e->nvar(), nc = e->ncon();
   const size_t rs = (Hh == kH) ? size_t(kNP) : size_t(nv);

@@ -212,8 +212,12 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
                      const float* __restrict__ u_all, const double* __restrict__ model_all,
                      const MpcStateIn* __restrict__ states, MpcResult* __restrict__ results,
                      float* __restrict__ x_all, int num, int* __restrict__ counter,
+                     double* __restrict__ warm, int warm_stride,
                      const __grid_constant__ BuildParams bp, const __grid_constant__ SolveParams sp) {
   constexpr int n = 12 * H, m = 20 * H;
+  // warm-start slot of one robot (the solver the controller keeps alive, A1RobotControl.cpp:522-538):
+  // scaled x | previous unscaled q | scaled z | scaled y | rho | live -- the layout of admm_kernel.cuh
+  constexpr int kWX = 0, kWQ = n, kWZ = 2 * n, kWY = 2 * n + m, kWRho = 2 * n + 2 * m, kWLive = kWRho + 1;
   extern __shared__ __align__(16) unsigned char ric_smem_raw[];
   RicSmem<H>& sm = *reinterpret_cast<RicSmem<H>*>(ric_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -251,20 +255,25 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
     const double* Pg = P_all + size_t(p) * p_stride;
     const double* model = model_all + size_t(p) * (169 + H * 156);
 
+    // a live slot makes this an update + warm solve (osqp_update_P / _lin_cost / _bounds, then solve):
+    // the equilibration still sees the PREVIOUS gradient, x, z, y and rho carry over
+    double* const ws = warm ? warm + size_t(p) * warm_stride : nullptr;
+    const bool live = warm && ws[kWLive] != 0.0;
+    const double rho0 = live ? ws[kWRho] : sp.rho;
     // ---- load: A_d, bounds, gradient ----
     for (int i = tid; i < 169; i += kRicThreads) sm.A[i] = model[i];
     for (int i = tid; i < n; i += kRicThreads) {
       sm.Dv[i] = 1.0;
-      sm.x[i] = 0.0;
+      sm.x[i] = live ? ws[kWX + i] : 0.0;
     }
     for (int i = tid; i < m; i += kRicThreads) {
       sm.Ev[i] = 1.0;
-      sm.z[i] = 0.0;
-      sm.y[i] = 0.0;
+      sm.z[i] = live ? ws[kWZ + i] : 0.0;
+      sm.y[i] = live ? ws[kWY + i] : 0.0;
     }
     if (tid == 0) {
       sm.scal[0] = 1.0;
-      sm.scal[2] = sp.rho;
+      sm.scal[2] = rho0;
       sm.flags[0] = 0;
       sm.flags[1] = MPC_STATUS_UNSOLVED;
     }
@@ -362,7 +371,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
         sm.Px[r] = v;
         if (accumulate) {
           psum += v;
-          qmax = fmax(qmax, fabs(c_run * sm.Dv[r] * q_all[size_t(p) * n + r]));
+          qmax = fmax(qmax, fabs(c_run * sm.Dv[r] * (live ? ws[kWQ + r] : q_all[size_t(p) * n + r])));
         }
       }
     };
@@ -420,7 +429,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       int ctype = 0;
       if (lo < -MPC_INFTY * 1e-4 && hi > MPC_INFTY * 1e-4) ctype = -1;
       else if (hi - lo < 1e-4) ctype = 1;
-      const double rv = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * sp.rho : sp.rho;
+      const double rv = (ctype == -1) ? 1e-6 : (ctype == 1) ? 1e3 * rho0 : rho0;
       sm.rv[i] = rv;
       // the constraint type is re-derived from the bounds at every rho update (same test)
     }
@@ -428,7 +437,25 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
       const int k = idx / 156, e = idx - 156 * k, a = e % 12;
       sm.Bs[k][e] = model[169 + idx] * sm.Dv[12 * k + a];
     }
-    for (int j = tid; j < n; j += kRicThreads) sm.rhs[j] = -sm.qb[j];  // iteration 1: x = z = y = 0
+    __syncthreads();
+    // first rhs = sigma x - q + A'(rho z - y) (= -q on a cold start: x = z = y = 0)
+    for (int j = tid; j < n; j += kRicThreads) {
+      const int ls = j / 3, vc = j - 3 * ls;
+      const int r0 = 5 * ls;
+      double s_ = 0.0;
+      if (live) {
+        if (vc == 0) {
+          s_ = sm.cca[r0] * (sm.rv[r0] * sm.z[r0] - sm.y[r0]) + sm.cca[r0 + 1] * (sm.rv[r0 + 1] * sm.z[r0 + 1] - sm.y[r0 + 1]);
+        } else if (vc == 1) {
+          s_ = sm.cca[r0 + 2] * (sm.rv[r0 + 2] * sm.z[r0 + 2] - sm.y[r0 + 2]) +
+               sm.cca[r0 + 3] * (sm.rv[r0 + 3] * sm.z[r0 + 3] - sm.y[r0 + 3]);
+        } else {
+#pragma unroll
+          for (int rw = 0; rw < 5; ++rw) s_ = fma(sm.ccz[r0 + rw], sm.rv[r0 + rw] * sm.z[r0 + rw] - sm.y[r0 + rw], s_);
+        }
+      }
+      sm.rhs[j] = live ? (sigma * sm.x[j] - sm.qb[j] + s_) : -sm.qb[j];
+    }
     __syncthreads();
 
     int iter = 0, rho_updates = 0, status = MPC_STATUS_UNSOLVED;
@@ -436,7 +463,7 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
     int until_check = sp.check_termination > 0 ? sp.check_termination : 0x7fffffff;
     int until_adapt = (sp.adaptive_rho && sp.adaptive_rho_interval > 0) ? sp.adaptive_rho_interval : 0x7fffffff;
     bool need_factor = true;
-    double rho_cur = sp.rho, rinv_in = 1.0 / sp.rho, rinv_eq = 1.0 / (1e3 * sp.rho);
+    double rho_cur = rho0, rinv_in = 1.0 / rho0, rinv_eq = 1.0 / (1e3 * rho0);
     const double rinv_free = 1.0 / 1e-6;
     for (iter = 1; iter <= sp.max_iter; ++iter) {
       if (need_factor) {
@@ -880,6 +907,28 @@ riccati_solve_kernel(const double* __restrict__ P_all, size_t p_stride, int p_ro
     }
     if (iter > sp.max_iter) iter = sp.max_iter;
 
+    if (warm) {
+      // keep the solver alive for the next tick; a solve that ended with non-finite iterates leaves its
+      // slot dead (the robot's next tick is an initSolver), so one bad record cannot poison later ticks
+      bool own_ok = true;
+      for (int j = tid; j < n; j += kRicThreads) {
+        const double xv = sm.x[j];
+        own_ok = own_ok && isfinite(xv);
+        ws[kWX + j] = xv;
+        ws[kWQ + j] = q_all[size_t(p) * n + j];
+      }
+      for (int i = tid; i < m; i += kRicThreads) {
+        const double zv = sm.z[i], yv = sm.y[i];
+        own_ok = own_ok && isfinite(zv) && isfinite(yv);
+        ws[kWZ + i] = zv;
+        ws[kWY + i] = yv;
+      }
+      const int all_ok = __syncthreads_and(own_ok);
+      if (tid == 0) {
+        ws[kWRho] = sm.scal[2];
+        ws[kWLive] = (all_ok && isfinite(sm.scal[2])) ? 1.0 : 0.0;
+      }
+    }
     // ---- unscale, rotate the first step to the body frame, write ----
     if (x_all != nullptr)
       for (int j = tid; j < n; j += kRicThreads) x_all[size_t(p) * n + j] = (float)(sm.Dv[j] * sm.x[j]);

@@ -63,6 +63,12 @@ typedef enum MpcError {
  * A1RobotControl.cpp:431,540). */
 #define MPC_STATUS_SOLVED 1
 #define MPC_STATUS_MAX_ITER_REACHED (-2)
+/* -3 / -4 are OSQP's certificates of infeasibility.  The DEVICE solvers never produce them: every QP of
+ * this path is feasible (f = 0 satisfies all rows) and strictly convex (P >= 2 r I), so the certificates
+ * cannot fire (the oracle evaluates them and the tests assert that they never do); eps_prim_inf /
+ * eps_dual_inf are therefore accepted and unused on the device.  mpc_solve_qp, the one entry that takes
+ * caller bounds, refuses lb > ub with MPC_ERR_INVALID like osqp_setup does; a caller QP that is infeasible
+ * in a subtler way ends as MPC_STATUS_MAX_ITER_REACHED where OSQP would report -3 / -4. */
 #define MPC_STATUS_PRIMAL_INFEASIBLE (-3)
 #define MPC_STATUS_DUAL_INFEASIBLE (-4)
 #define MPC_STATUS_UNSOLVED (-10)

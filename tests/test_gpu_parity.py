@@ -295,6 +295,15 @@ def test_error_behaviour(pkg):
     with pytest.raises(pkg.MpcError) as ei:
         pkg.MpcEngine(cfg, 0)
     assert ei.value.code == pkg.abi.MPC_ERR_UNSUPPORTED
+    # caller QP with crossed bounds: refused like osqp_setup refuses it (the device evaluates no certificates)
+    e = pkg.MpcEngine(pkg.config_default(), 0)
+    n, m = 120, 200
+    lb, ub = np.zeros(m), np.ones(m)
+    lb[7] = 2.0
+    with pytest.raises(pkg.MpcError) as ei:
+        e.solve_qp(np.eye(n), np.zeros(n), lb, ub)
+    assert ei.value.code == pkg.abi.MPC_ERR_INVALID
+    e.close()
     cfg = pkg.config_default()
     cfg.osqp.adaptive_rho_interval = 0   # the wall-clock dependent library default is refused
     with pytest.raises(pkg.MpcError) as ei:
@@ -456,16 +465,36 @@ def test_warm_stream_golden(pkg, name):
     e.close()
 
 
-def test_warm_stream_unsupported_horizon(pkg):
+def test_warm_stream_long_horizon(pkg, ob):
+    """The persistent solver at H = 30 (Riccati-structured kernel): the same OSQP update semantics,
+    tick by tick against the oracle's MpcStream, across a trot swap."""
     cfg = pkg.config_default()
     cfg.horizon = 30
+    N, T = 48, 6
+    st = np.stack([pkg.generate_stream_states(1006, 0, N, 45 + t) for t in range(T)])
+    assert (st[2]["contacts"] != st[3]["contacts"]).any()
+    ref = ob.mpc_stream(cfg, st)
     e = pkg.MpcEngine(cfg, 0)
-    e.load_states(pkg.generate_states(1, 0, 2))
-    e.build_qp()
+    cold = e.compute_grf_batch(st[1]).copy()
+    for t in range(T):
+        res = e.stream_step(st[t])
+        assert_same_iterates(res, ref[t], max_flipped=0.0, what=f"H=30 warm tick {t}")
+    assert ref["iters"][1].mean() < 0.8 * cold["iters"].mean()      # a warm tick is cheaper
+    e.stream_reset()
+    again = e.stream_step(st[0])
+    assert np.array_equal(again["iters"], ref["iters"][0])
+    # the dense long-horizon workspace path has no warm start
+    cfg2 = pkg.config_default()
+    cfg2.horizon = 30
+    cfg2.structured_solver = 2
+    e2 = pkg.MpcEngine(cfg2, 0)
+    e2.load_states(st[0][:2])
+    e2.build_qp()
     with pytest.raises(pkg.MpcError) as ei:
-        e.solve_warm()
+        e2.solve_warm()
     assert ei.value.code == pkg.abi.MPC_ERR_UNSUPPORTED
     e.close()
+    e2.close()
 
 
 def _check_torques(ob, states, tin, res, tq, balance=False):
@@ -651,13 +680,36 @@ def test_horizon_extensions_parity(pkg, ob, flags):
     e.close()
 
 
-def test_horizon_extensions_unsupported_for_h30(pkg):
+@pytest.mark.parametrize("flags", [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)])
+def test_horizon_extensions_long_horizon(pkg, ob, flags):
+    """The same three flags at H = 30 (gen_build_kernel<30> + Riccati solver) against the oracle's restatement."""
     cfg = pkg.config_default()
     cfg.horizon = 30
-    cfg.exact_discretization = 1
-    with pytest.raises(pkg.MpcError) as ei:
-        pkg.MpcEngine(cfg, 0)
-    assert ei.value.code == pkg.abi.MPC_ERR_UNSUPPORTED
+    cfg.exact_discretization, cfg.foot_drift, cfg.gait_aware = flags
+    n = 64
+    st = pkg.generate_states(1004, 0, n)
+    gait = pkg.generate_gait_inputs(1004, 0, n, 0)
+    e = pkg.MpcEngine(cfg, 0)
+    e.load_states(st)
+    if cfg.gait_aware:
+        e.set_gait_inputs(gait)
+    e.build_qp()
+    worst = 0.0
+    for i in (0, 9, 63):
+        P, q, l, u = e.get_qp(i)
+        Po, qo, lo, uo = ob.mpc_build_qp_ext(cfg, st[i], gait[i])
+        worst = max(worst, np.abs(P - Po).max() / np.abs(Po).max(), np.abs(q - qo).max() / np.abs(qo).max())
+        assert np.array_equal(l, lo.astype(np.float32)) and np.array_equal(u, uo.astype(np.float32))
+    assert worst <= TOL_QP, worst
+    e.solve()
+    res = e.get_results()
+    ref = ob.mpc_compute_grf_ext(cfg, st, gait)
+    assert_same_iterates(res, ref, max_flipped=0.0, what=f"H=30 {flags}")
+    base_cfg = pkg.config_default()
+    base_cfg.horizon = 30
+    base = ob.mpc_compute_grf(base_cfg, st)
+    assert grf_rel(res["grf"], base["grf"]).max() > 1e-4
+    e.close()
 
 
 def test_run_to_run_determinism(pkg):
