@@ -289,22 +289,10 @@ int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l,
 int launch_wrench(MpcEngine* e, int n, double* warm, bool with_torque) {
   const MpcTorqueIn* tin = with_torque ? e->d_tin : nullptr;
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
-  // MPC_WRENCH_CTAS=5 selects the 96-register instantiation (five CTAs per SM), a tuning experiment
-  static const int ctas = [] {
-    const char* v = std::getenv("MPC_WRENCH_CTAS");
-    return (v && v[0] == '5') ? 5 : (v && v[0] == '3') ? 3 : kWrCtasPerSm;
-  }();
-  const int full = e->num_sms * ctas;
+  const int full = e->num_sms * kWrCtasPerSm;
   const int grid = n < full ? n : full;
-  if (ctas == 3)
-    wrench_solve_kernel<3><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
-        e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
-  else if (ctas == 5)
-    wrench_solve_kernel<5><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
-        e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
-  else
-    wrench_solve_kernel<kWrCtasPerSm><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
-        e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
+  wrench_solve_kernel<kWrCtasPerSm><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
+      e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
   ++e->launches;
   CUDA_TRY(e, cudaGetLastError());
   return MPC_OK;
@@ -370,8 +358,6 @@ int create_common(int kind, int device, MpcEngine** out) {
   opt_in((const void*)gen_build_kernel<30>, sizeof(GenBuildSmem<30>), "gen_build_kernel<30> shared memory");
   opt_in((const void*)gen_solve_kernel<30>, sizeof(GenSolveSmem<30>), "gen_solve_kernel<30> shared memory");
   opt_in((const void*)wrench_solve_kernel<kWrCtasPerSm>, sizeof(WrenchSmem), "wrench_solve_kernel shared memory");
-  opt_in((const void*)wrench_solve_kernel<5>, sizeof(WrenchSmem), "wrench_solve_kernel<5> shared memory");
-  opt_in((const void*)wrench_solve_kernel<3>, sizeof(WrenchSmem), "wrench_solve_kernel<3> shared memory");
   if (crc != cudaSuccess) {
     std::string msg = std::string("engine setup (") + what + "): " + cudaGetErrorString(crc);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
