@@ -240,6 +240,9 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # host-side barrier (gloo): a rank waiting in an NCCL barrier spins a kernel on its GPU, which would
+    # time-slice against rank 0's process when that one drives every GPU itself (fleet extra)
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -334,7 +337,8 @@ def run_ours(args):
     if world > 1:
         res_view = None
         if rank == 0:
-            gather_list = [torch.empty(BATCH * rsz, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            gather_dev = torch.empty(world * BATCH * rsz, dtype=torch.uint8, device="cuda")
+            gather_list = list(gather_dev.chunk(world))          # views: the gather lands contiguously
             gather_out = torch.empty(world * BATCH * rsz, dtype=torch.uint8).pin_memory()
 
     def e2e_step(s):
@@ -343,8 +347,7 @@ def run_ours(args):
             view = torch.as_tensor(DevBuf(eng.results_device_ptr(), BATCH * rsz), device="cuda")
             dist.gather(view, gather_list, dst=0)
             if rank == 0:
-                for r in range(world):
-                    gather_out[r * BATCH * rsz:(r + 1) * BATCH * rsz].copy_(gather_list[r], non_blocking=True)
+                gather_out.copy_(gather_dev, non_blocking=True)   # ONE device-to-host copy of all ranks' records
                 torch.cuda.current_stream().synchronize()
 
     lat = []
@@ -500,7 +503,11 @@ def run_ours(args):
     # ---------------- extra: every GPU of the box through ONE C-ABI call from ONE process (rank 0) ----------------
     def x_fleet():
         ndev = torch.cuda.device_count() if world == 1 else world
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=host_group)      # every GPU idle from here on
         if rank != 0:
+            dist.barrier(group=host_group)      # CPU wait while rank 0's process uses all the GPUs
             return None
         fl = pkg.MpcFleet(cfg, list(range(ndev)))
         n = BATCH * ndev
@@ -520,6 +527,8 @@ def run_ours(args):
              "ms_per_batch": 1e3 * dt / reps, "all_solved": bool((fo["status"] == 1).all()),
              "note": "host array in, ONE host array out; per-GPU cudaMemcpyAsync is the gather, no NCCL"}
         fl.close()
+        if world > 1:
+            dist.barrier(group=host_group)
         return r
     extra("fleet_c_abi", x_fleet)
 
