@@ -20,6 +20,7 @@
 #include "riccati_kernel.cuh"
 #include "torque_map.cuh"
 #include "wrench_kernel.cuh"
+#include "wrench_riccati_kernel.cuh"
 
 using namespace mpcb200;
 
@@ -289,6 +290,15 @@ int launch_solve(MpcEngine* e, const double* P, const double* q, const float* l,
 int launch_wrench(MpcEngine* e, int n, double* warm, bool with_torque) {
   const MpcTorqueIn* tin = with_torque ? e->d_tin : nullptr;
   CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
+  if (e->H != kH) {
+    const int full = e->num_sms * kWrcCtasPerSm;
+    const int grid = n < full ? n : full;
+    wrench_riccati_kernel<30><<<grid, kWrcThreads, sizeof(WrcSmem<30>), e->stream>>>(
+        e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, e->warm_stride(), tin, e->d_tout, e->bp, e->sp);
+    ++e->launches;
+    CUDA_TRY(e, cudaGetLastError());
+    return MPC_OK;
+  }
   const int full = e->num_sms * kWrCtasPerSm;
   const int grid = n < full ? n : full;
   wrench_solve_kernel<kWrCtasPerSm><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
@@ -356,6 +366,7 @@ int create_common(int kind, int device, MpcEngine** out) {
   opt_in((const void*)riccati_solve_kernel<kH>, sizeof(RicSmem<kH>), "riccati_solve_kernel<10> shared memory");
   opt_in((const void*)riccati_solve_kernel<30>, sizeof(RicSmem<30>), "riccati_solve_kernel<30> shared memory");
   opt_in((const void*)gen_build_kernel<30>, sizeof(GenBuildSmem<30>), "gen_build_kernel<30> shared memory");
+  opt_in((const void*)wrench_riccati_kernel<30>, sizeof(WrcSmem<30>), "wrench_riccati_kernel<30> shared memory");
   opt_in((const void*)gen_solve_kernel<30>, sizeof(GenSolveSmem<30>), "gen_solve_kernel<30> shared memory");
   opt_in((const void*)wrench_solve_kernel<kWrCtasPerSm>, sizeof(WrenchSmem), "wrench_solve_kernel shared memory");
   if (crc != cudaSuccess) {
@@ -452,12 +463,16 @@ int mpc_engine_create(const MpcConfig* cfg, int32_t device, MpcEngine** out) {
     }
   }
   fill_model(e, cfg);
-  if (cfg->structured_solver < 0 || cfg->structured_solver > 3 || (cfg->structured_solver == 3 && cfg->horizon != kH)) {
+  if (cfg->structured_solver < 0 || cfg->structured_solver > 3 ||
+      (cfg->structured_solver == 3 && cfg->horizon != kH && cfg->exact_discretization)) {
     mpc_engine_destroy(e);
-    return fail(nullptr, MPC_ERR_INVALID, "structured_solver must be 0..3 (3 = wrench-space, horizon 10 only)");
+    return fail(nullptr, MPC_ERR_INVALID,
+                "structured_solver must be 0..3 (3 = wrench-space; at horizon 30 not with exact_discretization)");
   }
-  e->structured = cfg->structured_solver == 1 || (cfg->structured_solver == 0 && cfg->horizon != kH);
-  e->wrench = cfg->horizon == kH && (cfg->structured_solver == 0 || cfg->structured_solver == 3);
+  // wrench-space engines (fused build + solve, nothing in HBM): H = 10 dense 60 x 60 core, H = 30 six-input Riccati
+  e->wrench = (cfg->structured_solver == 0 || cfg->structured_solver == 3) &&
+              (cfg->horizon == kH || !cfg->exact_discretization);
+  e->structured = cfg->structured_solver == 1 || (cfg->structured_solver == 0 && cfg->horizon != kH && !e->wrench);
   e->sp = make_solve_params(cfg->osqp, cfg->mu);
   *out = e;
   return MPC_OK;
@@ -832,8 +847,8 @@ int mpc_engine_update_model(MpcEngine* e, const MpcConfig* cfg) {
 
 int mpc_solve_warm_async(MpcEngine* e) {
   if (!e || e->kind != 0) return MPC_ERR_INVALID;
-  if (e->H != kH && !e->structured)
-    return fail(e, MPC_ERR_UNSUPPORTED, "warm-started long-horizon solves need the Riccati solver (structured_solver 0 or 1)");
+  if (e->H != kH && !e->structured && !e->wrench)
+    return fail(e, MPC_ERR_UNSUPPORTED, "warm-started long-horizon solves need a structured solver (structured_solver 0, 1 or 3)");
   if (!e->built) return fail(e, MPC_ERR_STATE, "mpc_solve_warm before mpc_build_qp");
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->n > e->warm_capacity) {
