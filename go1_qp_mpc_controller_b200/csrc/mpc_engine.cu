@@ -294,7 +294,8 @@ int launch_wrench(MpcEngine* e, int n, double* warm, bool with_torque) {
     const int full = e->num_sms * kWrcCtasPerSm;
     const int grid = n < full ? n : full;
     wrench_riccati_kernel<30><<<grid, kWrcThreads, sizeof(WrcSmem<30>), e->stream>>>(
-        e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, e->warm_stride(), tin, e->d_tout, e->bp, e->sp);
+        e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, e->warm_stride(), e->d_workspace, tin, e->d_tout,
+        e->bp, e->sp);
     ++e->launches;
     CUDA_TRY(e, cudaGetLastError());
     return MPC_OK;

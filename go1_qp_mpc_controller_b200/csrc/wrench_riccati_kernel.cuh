@@ -48,29 +48,29 @@ struct WrcSmem {
   static constexpr int n = 12 * H, m = 20 * H, nG = (H + 3) / 4;
   alignas(16) double Mt[H][6 * kMS];   // M~ = N^-1 G_ Delta^-1 (rows; first G_ Delta^-1 during a factorisation)
   alignas(16) double Fk[H][6 * kMS];   // F_k (rows; first G_ during a factorisation)
-  alignas(16) double Lk[H][36];        // Cholesky factor of N_k, row-major, zeros above the diagonal
   alignas(16) double Nk[H][36];
   alignas(16) double Zk[H][36];
-  double Li[H][6];                     // 1 / L_cc (0 for a zero pivot)
   alignas(16) double Phi[nG - 2][12 * kMS];  // Phi_1 .. Phi_(nG-2)
   alignas(16) double rhs[n];
-  alignas(16) double uv[6 * H];
-  alignas(16) double ev[6 * H];        // e, then h = N u - dlt
-  alignas(16) double pv[(H + 1) * 12];
-  alignas(16) double Xv[(H + 1) * 12];
-  alignas(16) double Pb[(nG + 1) * 12];  // group boundaries of the backward recursion (index = group)
-  alignas(16) double Xb[(nG + 1) * 12];  // ... of the forward recursion
+  // iteration view:      pv | Xv | Pb | Xb | uv | ev   (recursion vectors, group boundaries, u, e / h)
+  // factorisation view:  Lk [H][36] | Li [H][6]       (Cholesky factor of N_k and its inverse pivots)
+  static constexpr int oPv = 0, oXv = oPv + (H + 1) * 12, oPb = oXv + (H + 1) * 12, oXb = oPb + (nG + 1) * 12,
+                       oUv = oXb + (nG + 1) * 12, oEv = oUv + 6 * H, kItv = oEv + 6 * H;
+  static_assert(kItv >= 42 * H, "the factorisation view must fit");
+  alignas(16) double itv[kItv];
+  // per leg-step constants of the iteration: kap[5] | Delta^-1 00 01 02 11 12 22 | q_ x y z  (read-only in the loop)
+  alignas(16) double legc[4 * H][14];
+  // per leg-step iterates of the five rows, normalised: zh[5] | uh[5]  (registers would starve the recursions)
+  alignas(16) double zu[4 * H][10];
   alignas(16) double zero12[12];
   alignas(16) double Dp[n];
-  alignas(16) double cca[m];           // E_row D_own of every row (checks, warm slot)
-  alignas(16) double gam[6 * H];
   // Ruiz: column-norm halves [2][n] | build: Q e [H][14] | factorisation: Riccati scratch | check: D x, G D x, S G D x
   alignas(16) double scr[2 * n];
   alignas(16) double B6t[3][12];       // top rows of B6c (step 0)
   double dT[9];                        // foot_drift: top rows of step k are B6t - k dT (same for every leg)
   double red[kWrcWarps * 16];
   double scal[16];                     // 0:c 1:1/c 2:rho 4:pri_res
-  float be[H * H];                     // sum_{i >= max(k,l)} (i - k)(i - l)  (exact in fp32)
+  unsigned short be[H * H];            // sum_{i >= max(k,l)} (i - k)(i - l)  (< 2^16 for H <= 30)
   float st[48];
   int contacts[4 * H];
   int flags[8];                        // 0:done 1:status 2:refactor 3:problem index
@@ -143,11 +143,344 @@ __device__ __forceinline__ void wrc_block_sum_max(double& s, double& q, double* 
   }
 }
 
+
+// The iterates a leg lane carries through a stretch of ADMM iterations.
+struct WrcIter {
+  double x[3];
+};
+
+#ifdef WRC_PROF
+#define WRP(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); pc_[i] += t_ - *pm_; *pm_ = t_; } } while (0)
+#else
+#define WRP(i) do {} while (0)
+#endif
+
+// Shared-memory accesses of the iteration loop, by 32-bit shared address.  Volatile asm keeps them in program
+// order among themselves: every phase issues ALL its loads first (the compiler, left alone, re-derived the
+// addresses from %tid / %cluster_ctaid in every recursion step and interleaved loads with their uses, one exposed
+// 29-cycle latency each -- 430 cycles per step instead of ~90).  The loop uses nothing but these for shared
+// memory, so ordering against ordinary accesses is never in question.
+__device__ __forceinline__ double2 wrc_ld2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double wrc_ld(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void wrc_st(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t wrc_sa(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// `run` ADMM iterations.
+#ifndef WRC_ITER_ATTR
+#define WRC_ITER_ATTR __forceinline__
+#endif
+template <int H>
+__device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, double tzx, double tzy, double lo4,
+                                         double hi4, double cyaw, double syaw, double dt, double sigma, double alpha
+#ifdef WRC_PROF
+                                         , long long* pc_, long long* pm_
+#endif
+                                         ) {
+  using Smem = WrcSmem<H>;
+  constexpr int nG = Smem::nG;
+  constexpr uint32_t RS = kMS * 8;  // row stride of the 6 x 12 / 12 x 12 matrices in bytes
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int team = lane >> 3, t8 = lane & 7;
+  const int kraw = 4 * warp + team;
+  const bool on = kraw < H;
+  const int k = on ? kraw : H - 1;
+  const bool isleg = on && t8 < 4, isax = on && t8 < 6;
+  const int lg = t8 & 3;
+  const int c = t8 < 6 ? t8 : t8 - 6;
+  const int klast = (4 * warp + 3 < H - 1) ? 4 * warp + 3 : H - 1;
+  const bool glast = (k == klast);
+  // addresses
+  const uint32_t a_itv = wrc_sa(sm.itv);
+  const uint32_t a_pv = a_itv + 8 * Smem::oPv, a_Xv = a_itv + 8 * Smem::oXv, a_Pb = a_itv + 8 * Smem::oPb,
+                 a_Xb = a_itv + 8 * Smem::oXb;
+  const uint32_t a_uk = a_itv + 8 * (Smem::oUv + 6 * k), a_ek = a_itv + 8 * (Smem::oEv + 6 * k);
+  const uint32_t a_zero = wrc_sa(sm.zero12);
+  const uint32_t a_mt = wrc_sa(&sm.Mt[k][0]), a_fk = wrc_sa(&sm.Fk[k][0]);
+  const uint32_t a_nrow = wrc_sa(&sm.Nk[k][6 * c]), a_zrow = wrc_sa(&sm.Zk[k][6 * c]);
+  const uint32_t a_rhsk = wrc_sa(&sm.rhs[12 * k]), a_rhsj = a_rhsk + 24 * lg;
+  const uint32_t a_lc = wrc_sa(&sm.legc[4 * k + lg][0]);
+  const uint32_t a_phi = wrc_sa(&sm.Phi[0][0]);
+  // forward: reads X_k (group boundary for team 0), writes X_k+1; backward: reads p_k+1, writes p_k
+  const uint32_t xin = (team == 0) ? a_Xb + 96 * warp : a_Xv + 96 * k;
+  const uint32_t xout = glast ? a_Xb + 96 * (warp + 1) : a_Xv + 96 * (k + 1);
+  const uint32_t pin = glast ? a_Pb + 96 * (warp + 1) : a_pv + 96 * (k + 1);
+  const uint32_t pout = (team == 0) ? a_Pb + 96 * warp : a_pv + 96 * k;
+  const uint32_t xin1 = (team == 0) ? a_zero : xin;            // first sweep: zero boundaries
+  const uint32_t pin1 = glast ? a_zero : pin;
+  const uint32_t pin3 = (glast && warp == nG - 1) ? a_zero : pin;  // p_H = 0 is the last group's true boundary
+  // rotation coefficients of the lane's state pair (rows of Rt / Rt')
+  const double fa = (c == 0) ? cyaw : (c == 1) ? -syaw : 0.0, fb = (c == 0) ? syaw : (c == 1) ? cyaw : 0.0;
+  const double ba = (c == 0) ? cyaw : (c == 1) ? syaw : 0.0, bb = (c == 0) ? -syaw : (c == 1) ? cyaw : 0.0;
+  const double fo = (c < 2) ? 0.0 : 1.0;
+  const double oma = 1.0 - alpha;
+
+  const uint32_t a_zu = wrc_sa(&sm.zu[4 * k + lg][0]);
+  double x[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) x[i] = st.x[i];
+
+#pragma unroll 1
+  for (int q_ = 0; q_ < run; ++q_) {
+    // ---- u = M~ r (axis) ----
+    __syncwarp();
+    double uc;
+    {
+      double2 mv[6], rv[6];
+#pragma unroll
+      for (int h2 = 0; h2 < 6; ++h2) rv[h2] = wrc_ld2(a_rhsk + 16 * h2);
+#pragma unroll
+      for (int h2 = 0; h2 < 6; ++h2) mv[h2] = wrc_ld2(a_mt + RS * c + 16 * h2);
+      double s0 = mv[0].x * rv[0].x, s1 = mv[0].y * rv[0].y, s2 = mv[1].x * rv[1].x, s3 = mv[1].y * rv[1].y;
+#pragma unroll
+      for (int h2 = 2; h2 < 6; h2 += 2) {
+        s0 = fma(mv[h2].x, rv[h2].x, s0); s1 = fma(mv[h2].y, rv[h2].y, s1);
+        s2 = fma(mv[h2 + 1].x, rv[h2 + 1].x, s2); s3 = fma(mv[h2 + 1].y, rv[h2 + 1].y, s3);
+      }
+      uc = (s0 + s1) + (s2 + s3);
+      if (isax) wrc_st(a_uk + 8 * c, uc);
+    }
+    __syncwarp();
+    // (N u)_c and t = -F' u (the addend of the backward recursion); F columns c and 6 + c stay in registers
+    double fc[12], nuc, tpos, tvel;
+    {
+      const double2 u01 = wrc_ld2(a_uk), u23 = wrc_ld2(a_uk + 16), u45 = wrc_ld2(a_uk + 32);
+      const double2 n01 = wrc_ld2(a_nrow), n23 = wrc_ld2(a_nrow + 16), n45 = wrc_ld2(a_nrow + 32);
+#pragma unroll
+      for (int d = 0; d < 6; ++d) {
+        fc[d] = wrc_ld(a_fk + RS * d + 8 * c);
+        fc[6 + d] = wrc_ld(a_fk + RS * d + 8 * c + 48);
+      }
+      const double u6[6] = {u01.x, u01.y, u23.x, u23.y, u45.x, u45.y};
+      nuc = fma(n45.x, u45.x, fma(n23.x, u23.x, n01.x * u01.x)) + fma(n45.y, u45.y, fma(n23.y, u23.y, n01.y * u01.y));
+      double sp0 = fc[0] * u6[0], sp1 = fc[1] * u6[1], sv0 = fc[6] * u6[0], sv1 = fc[7] * u6[1];
+#pragma unroll
+      for (int d = 2; d < 6; d += 2) {
+        sp0 = fma(fc[d], u6[d], sp0); sp1 = fma(fc[d + 1], u6[d + 1], sp1);
+        sv0 = fma(fc[6 + d], u6[d], sv0); sv1 = fma(fc[7 + d], u6[d + 1], sv1);
+      }
+      tpos = -(sp0 + sp1); tvel = -(sv0 + sv1);
+    }
+    WRP(2);  // u, N u, t
+    // ---- backward recursion  p_k = Acl_k' p_k+1 + t_k ----
+    auto bstep = [&](uint32_t src, uint32_t dst, bool wr) {
+      const double2 v01 = wrc_ld2(src + 48), v23 = wrc_ld2(src + 64), v45 = wrc_ld2(src + 80), p01 = wrc_ld2(src);
+      const double own_pos = wrc_ld(src + 8 * c), own_vel = wrc_ld(src + 48 + 8 * c);
+      double s0 = fma(fc[0], v01.x, tpos), s1 = fc[1] * v01.y, s2 = fma(fc[6], v01.x, tvel), s3 = fc[7] * v01.y;
+      s0 = fma(fc[2], v23.x, s0); s1 = fma(fc[3], v23.y, s1);
+      s2 = fma(fc[8], v23.x, s2); s3 = fma(fc[9], v23.y, s3);
+      s0 = fma(fc[4], v45.x, s0); s1 = fma(fc[5], v45.y, s1);
+      s2 = fma(fc[10], v45.x, s2); s3 = fma(fc[11], v45.y, s3);
+      const double rot = fma(ba, p01.x, fma(bb, p01.y, fo * own_pos));
+      const double np_ = own_pos + (s0 + s1);
+      const double nv_ = fma(dt, rot, own_vel) + (s2 + s3);
+      if (wr) { wrc_st(dst + 8 * c, np_); wrc_st(dst + 48 + 8 * c, nv_); }
+    };
+#pragma unroll 1
+    for (int s_ = 3; s_ >= 0; --s_) {
+      if (team == s_) bstep(pin1, pout, isax);
+      __syncwarp();
+    }
+    WRP(8);  // backward sweep 1
+    __syncthreads();
+    if (warp == 0) {
+      const int i = lane < 12 ? lane : 0;
+#pragma unroll 1
+      for (int gj = nG - 2; gj >= 1; --gj) {
+        const uint32_t aph = a_phi + (12 * kMS * 8) * (gj - 1) + 8 * i, apb = a_Pb + 96 * (gj + 1);
+        double ph[12];
+        double2 v[6];
+#pragma unroll
+        for (int h2 = 0; h2 < 6; ++h2) v[h2] = wrc_ld2(apb + 16 * h2);
+        double s0 = wrc_ld(a_Pb + 96 * gj + 8 * i);
+#pragma unroll
+        for (int r = 0; r < 12; ++r) ph[r] = wrc_ld(aph + RS * r);
+        double s1 = ph[1] * v[0].y, s2 = ph[2] * v[1].x, s3 = ph[3] * v[1].y;
+        s0 = fma(ph[0], v[0].x, s0);
+#pragma unroll
+        for (int h2 = 2; h2 < 6; h2 += 2) {
+          s0 = fma(ph[2 * h2], v[h2].x, s0); s1 = fma(ph[2 * h2 + 1], v[h2].y, s1);
+          s2 = fma(ph[2 * h2 + 2], v[h2 + 1].x, s2); s3 = fma(ph[2 * h2 + 3], v[h2 + 1].y, s3);
+        }
+        if (lane < 12) wrc_st(a_Pb + 96 * gj + 8 * i, (s0 + s1) + (s2 + s3));
+        __syncwarp();
+      }
+    }
+    WRP(9);  // barrier + backward sweep 2
+    // (the F columns are re-read rather than kept across the boundary sweep: with them live, the sweep's own 24
+    // operands no longer fit and ptxas issues its loads one by one)
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      fc[d] = wrc_ld(a_fk + RS * d + 8 * c);
+      fc[6 + d] = wrc_ld(a_fk + RS * d + 8 * c + 48);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int s_ = 3; s_ >= 1; --s_) {
+      if (team == s_) bstep(pin3, pout, isax);
+      __syncwarp();
+    }
+    WRP(3);  // backward sweep 3
+    // ---- e = p_k+1,vel - u,  b = -Z e,  F row ----
+    double fr[12], bfw, dl = 0.0;
+    {
+      const double ec = wrc_ld(pin3 + 48 + 8 * c) - uc;
+      if (isax) wrc_st(a_ek + 8 * c, ec);
+      const double2 z01 = wrc_ld2(a_zrow), z23 = wrc_ld2(a_zrow + 16), z45 = wrc_ld2(a_zrow + 32);
+#pragma unroll
+      for (int h2 = 0; h2 < 6; ++h2) {
+        const double2 f = wrc_ld2(a_fk + RS * c + 16 * h2);
+        fr[2 * h2] = f.x; fr[2 * h2 + 1] = f.y;
+      }
+      __syncwarp();
+      const double2 e01 = wrc_ld2(a_ek), e23 = wrc_ld2(a_ek + 16), e45 = wrc_ld2(a_ek + 32);
+      const double s0 = fma(z45.x, e45.x, fma(z23.x, e23.x, z01.x * e01.x));
+      const double s1 = fma(z45.y, e45.y, fma(z23.y, e23.y, z01.y * e01.y));
+      bfw = -(s0 + s1);
+    }
+    WRP(4);  // e, b, F row
+    // ---- forward recursion  dlt_k = F_k X_k + b_k,  X_k+1 = A X_k + [0; dlt_k] ----
+    auto fstep = [&](uint32_t src, uint32_t dst, bool wr) {
+      double2 xv[6];
+#pragma unroll
+      for (int h2 = 0; h2 < 6; ++h2) xv[h2] = wrc_ld2(src + 16 * h2);
+      const double own_pos = wrc_ld(src + 8 * c), own_vel = wrc_ld(src + 48 + 8 * c);
+      double s0 = fma(fr[0], xv[0].x, bfw), s1 = fr[1] * xv[0].y, s2 = fr[2] * xv[1].x, s3 = fr[3] * xv[1].y;
+#pragma unroll
+      for (int h2 = 2; h2 < 6; h2 += 2) {
+        s0 = fma(fr[2 * h2], xv[h2].x, s0); s1 = fma(fr[2 * h2 + 1], xv[h2].y, s1);
+        s2 = fma(fr[2 * h2 + 2], xv[h2 + 1].x, s2); s3 = fma(fr[2 * h2 + 3], xv[h2 + 1].y, s3);
+      }
+      dl = (s0 + s1) + (s2 + s3);
+      const double rot = fma(fa, xv[3].x, fma(fb, xv[3].y, fo * own_vel));
+      if (wr) { wrc_st(dst + 8 * c, fma(dt, rot, own_pos)); wrc_st(dst + 48 + 8 * c, own_vel + dl); }
+    };
+#pragma unroll 1
+    for (int s_ = 0; s_ < 4; ++s_) {
+      if (team == s_) fstep(xin1, xout, isax);
+      __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int i = lane < 12 ? lane : 0;
+#pragma unroll 1
+      for (int gj = 1; gj <= nG - 2; ++gj) {
+        const uint32_t aph = a_phi + (12 * kMS * 8) * (gj - 1) + RS * i, axb = a_Xb + 96 * gj;
+        double2 v[6], f[6];
+#pragma unroll
+        for (int h2 = 0; h2 < 6; ++h2) v[h2] = wrc_ld2(axb + 16 * h2);
+        double s0 = wrc_ld(a_Xb + 96 * (gj + 1) + 8 * i);
+#pragma unroll
+        for (int h2 = 0; h2 < 6; ++h2) f[h2] = wrc_ld2(aph + 16 * h2);
+        double s1 = f[0].y * v[0].y, s2 = f[1].x * v[1].x, s3 = f[1].y * v[1].y;
+        s0 = fma(f[0].x, v[0].x, s0);
+#pragma unroll
+        for (int h2 = 2; h2 < 6; h2 += 2) {
+          s0 = fma(f[h2].x, v[h2].x, s0); s1 = fma(f[h2].y, v[h2].y, s1);
+          s2 = fma(f[h2 + 1].x, v[h2 + 1].x, s2); s3 = fma(f[h2 + 1].y, v[h2 + 1].y, s3);
+        }
+        if (lane < 12) wrc_st(a_Xb + 96 * (gj + 1) + 8 * i, (s0 + s1) + (s2 + s3));
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int h2 = 0; h2 < 6; ++h2) {
+      const double2 f = wrc_ld2(a_fk + RS * c + 16 * h2);
+      fr[2 * h2] = f.x; fr[2 * h2 + 1] = f.y;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int s_ = 0; s_ < 4; ++s_) {
+      if (team == s_) fstep(xin, xout, isax && !glast);
+      __syncwarp();
+    }
+    WRP(5);  // forward recursion
+    // ---- h = N u - dlt (axis);  x~ = a - M~' h, row updates, next rhs (leg) ----
+    if (isax) wrc_st(a_ek + 8 * c, nuc - dl);
+    {
+      // everything that does not wait for h first: the leg's constant block, its rhs, its three columns of M~
+      double2 l2[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) l2[i] = wrc_ld2(a_lc + 16 * i);  // kap0 kap1 | kap2 kap3 | kap4 di0 | di1 di2 | di3 di4 | di5 qx | qy qz
+      const double rh0 = wrc_ld(a_rhsj), rh1 = wrc_ld(a_rhsj + 8), rh2 = wrc_ld(a_rhsj + 16);
+      double z[5], u[5];
+      {
+        const double2 z01 = wrc_ld2(a_zu), z23 = wrc_ld2(a_zu + 16), z4u0 = wrc_ld2(a_zu + 32), u12 = wrc_ld2(a_zu + 48),
+                      u34 = wrc_ld2(a_zu + 64);
+        z[0] = z01.x; z[1] = z01.y; z[2] = z23.x; z[3] = z23.y; z[4] = z4u0.x;
+        u[0] = z4u0.y; u[1] = u12.x; u[2] = u12.y; u[3] = u34.x; u[4] = u34.y;
+      }
+      double mc[6][3];
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        mc[cc][0] = wrc_ld(a_mt + RS * cc + 24 * lg);
+        mc[cc][1] = wrc_ld(a_mt + RS * cc + 24 * lg + 8);
+        mc[cc][2] = wrc_ld(a_mt + RS * cc + 24 * lg + 16);
+      }
+      const double a0 = l2[2].y * rh0 + l2[3].x * rh1 + l2[3].y * rh2;   // a = Delta^-1 r
+      const double a1 = l2[3].x * rh0 + l2[4].x * rh1 + l2[4].y * rh2;
+      const double a2 = l2[3].y * rh0 + l2[4].y * rh1 + l2[5].x * rh2;
+      __syncwarp();
+      const double2 h01 = wrc_ld2(a_ek), h23 = wrc_ld2(a_ek + 16), h45 = wrc_ld2(a_ek + 32);
+      const double h6[6] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y};
+      double sx0 = mc[0][0] * h6[0], sx1 = mc[1][0] * h6[1], sy0 = mc[0][1] * h6[0], sy1 = mc[1][1] * h6[1],
+             sz0 = mc[0][2] * h6[0], sz1 = mc[1][2] * h6[1];
+#pragma unroll
+      for (int cc = 2; cc < 6; cc += 2) {
+        sx0 = fma(mc[cc][0], h6[cc], sx0); sx1 = fma(mc[cc + 1][0], h6[cc + 1], sx1);
+        sy0 = fma(mc[cc][1], h6[cc], sy0); sy1 = fma(mc[cc + 1][1], h6[cc + 1], sy1);
+        sz0 = fma(mc[cc][2], h6[cc], sz0); sz1 = fma(mc[cc + 1][2], h6[cc + 1], sz1);
+      }
+      const double xtx = a0 - (sx0 + sx1), xty = a1 - (sy0 + sy1), xtz = a2 - (sz0 + sz1);
+      x[0] = alpha * xtx + oma * x[0];
+      x[1] = alpha * xty + oma * x[1];
+      x[2] = alpha * xtz + oma * x[2];
+      const double zt[5] = {fma(tzx, xtz, xtx), fma(-tzx, xtz, xtx), fma(tzy, xtz, xty), fma(-tzy, xtz, xty), xtz};
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const double zr = alpha * zt[i] + oma * z[i];
+        double zn = zr + u[i];
+        if (i == 0 || i == 2) zn = (zn < 0.0) ? 0.0 : zn;
+        else if (i == 1 || i == 3) zn = (zn > 0.0) ? 0.0 : zn;
+        else { zn = (zn < lo4) ? lo4 : zn; zn = (zn > hi4) ? hi4 : zn; }
+        u[i] = u[i] + (zr - zn);
+        z[i] = zn;
+      }
+      // next rhs = sigma x - q + A_'(rho z - y)
+      const double e0 = l2[0].x * (z[0] - u[0]), e1 = l2[0].y * (z[1] - u[1]), e2 = l2[1].x * (z[2] - u[2]),
+                   e3 = l2[1].y * (z[3] - u[3]), e4 = l2[2].x * (z[4] - u[4]);
+      const double r0_ = sigma * x[0] - l2[5].y + (e0 + e1);
+      const double r1_ = sigma * x[1] - l2[6].x + (e2 + e3);
+      const double r2_ = sigma * x[2] - l2[6].y + (e4 + (tzx * (e0 - e1) + tzy * (e2 - e3)));
+      if (isleg) {
+        wrc_st(a_rhsj, r0_); wrc_st(a_rhsj + 8, r1_); wrc_st(a_rhsj + 16, r2_);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { wrc_st(a_zu + 8 * i, z[i]); wrc_st(a_zu + 40 + 8 * i, u[i]); }
+      }
+    }
+    WRP(6);  // x~, rows, rhs
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 3; ++i) st.x[i] = x[i];
+}
+
+
 template <int H>
 __global__ void __launch_bounds__(kWrcThreads, kWrcCtasPerSm)
 wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __restrict__ gait,
                       MpcResult* __restrict__ results, float* __restrict__ x_all, int num, int* __restrict__ counter,
-                      double* __restrict__ warm, int warm_stride, const MpcTorqueIn* __restrict__ tin,
+                      double* __restrict__ warm, int warm_stride, double* __restrict__ gscr,
+                      const MpcTorqueIn* __restrict__ tin,
                       MpcTorqueOut* __restrict__ tout, const __grid_constant__ BuildParams bp,
                       const __grid_constant__ SolveParams sp) {
   using Smem = WrcSmem<H>;
@@ -155,6 +488,14 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
   constexpr int kWX = 0, kWQ = n, kWZ = 2 * n, kWY = 2 * n + m, kWRho = 2 * n + 2 * m, kWLive = kWRho + 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  double* const s_pv = sm.itv + Smem::oPv;
+  double* const s_Xv = sm.itv + Smem::oXv;
+  double* const s_Pb = sm.itv + Smem::oPb;
+  double* const s_Xb = sm.itv + Smem::oXb;
+  double* const s_uv = sm.itv + Smem::oUv;
+  double* const s_ev = sm.itv + Smem::oEv;
+  double (*const s_Lk)[36] = reinterpret_cast<double (*)[36]>(sm.itv);
+  double (*const s_Li)[6] = reinterpret_cast<double (*)[6]>(sm.itv + 36 * H);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int team = lane >> 3, t8 = lane & 7;
   const int kraw = 4 * warp + team;
@@ -164,12 +505,11 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
   const int lg = t8 & 3;                                // leg (leg role)
   const int c = t8 < 6 ? t8 : t8 - 6;                   // component (axis role)
   const int j0 = 12 * k + 3 * lg, r0 = 5 * (4 * k + lg);  // first variable / first row of the leg-step
-  const int klast = (4 * warp + 3 < H - 1) ? 4 * warp + 3 : H - 1;  // last step of this warp's group
+
   const bool kWarm = warm != nullptr;
   const double mu = sp.mu, sigma = sp.sigma, alpha = sp.alpha;
   const double dt = bp.dt, inv_m = 1.0 / bp.mass;
   const double dt2 = dt * dt, dt4 = dt2 * dt2;
-  const double r2x = bp.Rd[3 * lg], r2y = bp.Rd[3 * lg + 1], r2z = bp.Rd[3 * lg + 2];
 
   // ---- once per CTA ----
   for (int i = tid; i < H * H; i += kWrcThreads) {
@@ -177,19 +517,28 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
     const int mxk = kk > ll ? kk : ll;
     int s = 0;
     for (int q = mxk; q < H; ++q) s += (q - kk) * (q - ll);
-    sm.be[i] = (float)s;
+    sm.be[i] = (unsigned short)s;
   }
-  if (tid < 12) {
-    sm.zero12[tid] = 0.0;
-    sm.Xb[tid] = 0.0;  // X_0 = 0: the true boundary of the first group
-  }
+  if (tid < 12) sm.zero12[tid] = 0.0;
 
+  // Profiling build only (-DWRC_PROF; scripts/prof_wrc.py): thread 0 accumulates clock64 per phase and prints
+  // the totals of the first two problems.  Compiled out otherwise.
+#undef WRP
+#ifdef WRC_PROF
+  long long pc_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pm_ = 0;
+#define WRP(i) do { if (tid == 0) { const long long t_ = clock64(); pc_[i] += t_ - pm_; pm_ = t_; } } while (0)
+#else
+#define WRP(i) do {} while (0)
+#endif
   for (;;) {
     __syncthreads();
     if (tid == 0) sm.flags[3] = atomicAdd(counter, 1);
     __syncthreads();
     const int p = sm.flags[3];
     if (p >= num) break;
+#ifdef WRC_PROF
+    if (tid == 0) pm_ = clock64();
+#endif
 
     // ---- K0: record load ----
     if (tid < 48) sm.st[tid] = reinterpret_cast<const float*>(states + p)[tid];
@@ -212,6 +561,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
     const double th00 = cyaw * cyaw * Q0 + syaw * syaw * Q1, th01 = cyaw * syaw * Q0 - syaw * cyaw * Q1,
                  th11 = syaw * syaw * Q0 + cyaw * cyaw * Q1, th22 = Q2;
     double (*Qe)[14] = reinterpret_cast<double (*)[14]>(sm.scr);
+    double* const gamv = sm.scr + 14 * H;  // gam (6H), next to Q e; both are dead once the gradient is formed
     if (tid < H) {
       // Q (A_d^(i+1) x0 - x_ref,i): A_d^m x0 = x0 + m dt A_c x0 + c2 g e_5 (A_c^2 x0 = g e_5, A_c^3 = 0)
       const int i = tid;
@@ -330,25 +680,38 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
         else { lin = e[6 + cc]; rot = e[cc]; }
         s += dt * lin + kp * rot;
       }
-      sm.gam[tid] = s;
+      gamv[tid] = s;
     }
     __syncthreads();
 
     // ---- per-leg constants of the build (leg role) ----
     const bool drift = bp.foot_drift != 0;
-    double top[3][3];  // top[i][q]: row i of B6c, column 3 lg + q, at this step
+    // top[i][q]: row i of B6c, column 3 lg + q, at this step (re-formed where it is needed: nine registers less
+    // across the iteration loop)
+    auto load_top = [&](double (&top)[3][3]) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int q = 0; q < 3; ++q) top[i][q] = fma(-(double)k, sm.dT[3 * i + q], sm.B6t[i][3 * lg + q]);
-    double q0v[3], pjj[3];
+        for (int q = 0; q < 3; ++q) top[i][q] = fma(-(double)k, sm.dT[3 * i + q], sm.B6t[i][3 * lg + q]);
+    };
+    // gradient (ConvexMpc.cpp:215-217): q_j = B6c[:, j] . gam_k
+    auto gradient = [&](const double (&top)[3][3], double (&q0v)[3]) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        q0v[q] = top[0][q] * gamv[6 * k] + top[1][q] * gamv[6 * k + 1] + top[2][q] * gamv[6 * k + 2] +
+                 inv_m * gamv[6 * k + 3 + q];
+    };
+    double qb[3], pjj[3], qsc[3];
     {
+      double top[3][3], q0v[3];
+      load_top(top);
+      gradient(top, q0v);
       const double a = (double)(H - k) * dt2, b = dt4 * (double)sm.be[H * k + k];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        // gradient (ConvexMpc.cpp:215-217): q_j = B6c[:, j] . gam_k
-        q0v[q] = top[0][q] * sm.gam[6 * k] + top[1][q] * sm.gam[6 * k + 1] + top[2][q] * sm.gam[6 * k + 2] +
-                 inv_m * sm.gam[6 * k + 3 + q];
+        qb[q] = q0v[q];  // scaled after the equilibration
+        qsc[q] = (live && isleg) ? ws[kWQ + j0 + q] : q0v[q];
+        if (kWarm && isleg) ws[kWQ + j0 + q] = q0v[q];  // the slot's q of the NEXT update (the old one was just read)
         // diagonal entry of P (the only one R2 touches): P_jj = B6c_j' S_kk B6c_j + 2 r_j
         const double u10 = bp.Qd[6] * top[0][q], u11 = bp.Qd[7] * top[1][q], u12 = bp.Qd[8] * top[2][q];
         const double u20 = th00 * top[0][q] + th01 * top[1][q], u21 = th01 * top[0][q] + th11 * top[1][q],
@@ -358,9 +721,6 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
                  (a * vb1 + b * vb2) + bp.Rd[3 * lg + q];
       }
     }
-    double qsc[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) qsc[q] = (live && isleg) ? ws[kWQ + j0 + q] : q0v[q];
     // bounds of row 4 (ConvexMpc.cpp:223-245); fp32 like the dense path's hand-over.  Rows 0, 2 are [0, inf),
     // rows 1, 3 (-inf, 0]: only their finite side can bind.
     double lo4, hi4;
@@ -437,73 +797,73 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
       }
     }
     const double cs = c_run;
+    WRP(0);  // load, build, Ruiz
     if (tid == 0) { sm.scal[0] = cs; sm.scal[1] = 1.0 / cs; }
-    double qb[3];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) qb[q] = cs * D[q] * q0v[q];
+    for (int q = 0; q < 3; ++q) qb[q] = cs * D[q] * qb[q];
     // constraint types (auxil.c set_rho_vec): -1 loose, 1 equality, 0 inequality
     auto ctype_of = [](double lo, double hi) {
       return (lo < -MPC_INFTY * 1e-4 && hi > MPC_INFTY * 1e-4) ? -1 : ((hi - lo < 1e-4) ? 1 : 0);
     };
     auto rho_of = [](int ct, double rho) { return (ct == -1) ? 1e-6 : (ct == 1) ? 1e3 * rho : rho; };
-    int ct[5];
-    ct[0] = ctype_of(0.0, (double)(float)MPC_INFTY * E[0]);
-    ct[1] = ctype_of(-(double)(float)MPC_INFTY * E[1], 0.0);
-    ct[2] = ctype_of(0.0, (double)(float)MPC_INFTY * E[2]);
-    ct[3] = ctype_of(-(double)(float)MPC_INFTY * E[3], 0.0);
-    ct[4] = ctype_of(lo4 * E[4], hi4 * E[4]);
+    // (two bits per row, value + 1; D, cca = E_row D_own and the rho vector are re-read / re-derived where they
+    // are needed instead of living in registers across the iteration loop)
+    int ctp;
+    {
+      const int c0 = ctype_of(0.0, (double)(float)MPC_INFTY * E[0]), c1 = ctype_of(-(double)(float)MPC_INFTY * E[1], 0.0);
+      const int c2 = ctype_of(0.0, (double)(float)MPC_INFTY * E[2]), c3 = ctype_of(-(double)(float)MPC_INFTY * E[3], 0.0);
+      const int c4 = ctype_of(lo4 * E[4], hi4 * E[4]);
+      ctp = (c0 + 1) | ((c1 + 1) << 2) | ((c2 + 1) << 4) | ((c3 + 1) << 6) | ((c4 + 1) << 8);
+    }
+    auto rho_row = [&](int i, double rho) { return rho_of(((ctp >> (2 * i)) & 3) - 1, rho); };
     // Rows in normalised form (wrench_kernel.cuh): row i = cca_i (x_own +- t x_fz), the kernel iterates on
     // zh = z / cca and uh = y / (rho cca);  kap = rho cca^2.
-    double cca[5], kap[5], rv[5];
-    cca[0] = E[0] * D[0]; cca[1] = E[1] * D[0]; cca[2] = E[2] * D[1]; cca[3] = E[3] * D[1]; cca[4] = E[4] * D[2];
+    double* const lc = sm.legc[4 * k + lg];
+    double kap[5];
     const double tzx = mu * D[2] / D[0], tzy = mu * D[2] / D[1];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      rv[i] = rho_of(ct[i], rho0);
-      kap[i] = rv[i] * cca[i] * cca[i];
-      if (isleg) sm.cca[r0 + i] = cca[i];
-    }
-    lo4 = lo4 * E[4] / cca[4];
-    hi4 = hi4 * E[4] / cca[4];
-
-    // iterates
-    double x[3] = {0.0, 0.0, 0.0}, z[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, u[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    if (live && isleg) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) x[q] = ws[kWX + j0 + q];
+    // iterates: x in registers, zh / uh of the five rows in shared memory (zu); cca = E_row D_own of the rows goes
+    // to the CTA's global scratch line (L2): only the residual checks, rho updates and the warm slot read it
+    double x[3] = {0.0, 0.0, 0.0};
+    double* const zu = sm.zu[4 * k + lg];
+    double* const gcca = gscr + size_t(blockIdx.x) * (20 * H) + r0;
+    {
+      const double cca[5] = {E[0] * D[0], E[1] * D[0], E[2] * D[1], E[3] * D[1], E[4] * D[2]};
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        z[i] = ws[kWZ + r0 + i] / cca[i];
-        u[i] = ws[kWY + r0 + i] / (rv[i] * cca[i]);
+        const double rvi = rho_row(i, rho0);
+        kap[i] = rvi * cca[i] * cca[i];
+        if (isleg) {
+          gcca[i] = cca[i];
+          zu[i] = live ? ws[kWZ + r0 + i] / cca[i] : 0.0;
+          zu[5 + i] = live ? ws[kWY + r0 + i] / (rvi * cca[i]) : 0.0;
+        }
+      }
+      lo4 = lo4 * E[4] / cca[4];
+      hi4 = hi4 * E[4] / cca[4];
+      if (live && isleg) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) x[q] = ws[kWX + j0 + q];
       }
     }
-    double di[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // Delta_leg^-1: 00 01 02 11 12 22
-    double rh[3];                                    // rhs of the leg's variables
+    double rho_cur = rho0;
+    if (isleg) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) lc[i] = kap[i];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) lc[11 + q] = qb[q];
+    }
 
-    // rhs = sigma x - q + A_'(rho z - y)
+    // rhs = sigma x - q + A_'(rho z - y)   (kap and q_ from the leg's constant block)
     auto publish_rhs = [&]() {
-      const double e0 = kap[0] * (z[0] - u[0]), e1 = kap[1] * (z[1] - u[1]), e2 = kap[2] * (z[2] - u[2]),
-                   e3 = kap[3] * (z[3] - u[3]), e4 = kap[4] * (z[4] - u[4]);
-      rh[0] = sigma * x[0] - qb[0] + (e0 + e1);
-      rh[1] = sigma * x[1] - qb[1] + (e2 + e3);
-      rh[2] = sigma * x[2] - qb[2] + (e4 + (tzx * (e0 - e1) + tzy * (e2 - e3)));
-      if (isleg) { sm.rhs[j0] = rh[0]; sm.rhs[j0 + 1] = rh[1]; sm.rhs[j0 + 2] = rh[2]; }
+      const double2* l2 = reinterpret_cast<const double2*>(lc);
+      const double2 k01 = l2[0], k23 = l2[1], k4_ = l2[2], dq = l2[5], q12 = l2[6];
+      const double e0 = k01.x * (zu[0] - zu[5]), e1 = k01.y * (zu[1] - zu[6]), e2 = k23.x * (zu[2] - zu[7]),
+                   e3 = k23.y * (zu[3] - zu[8]), e4 = k4_.x * (zu[4] - zu[9]);
+      const double r0_ = sigma * x[0] - dq.y + (e0 + e1);
+      const double r1_ = sigma * x[1] - q12.x + (e2 + e3);
+      const double r2_ = sigma * x[2] - q12.y + (e4 + (tzx * (e0 - e1) + tzy * (e2 - e3)));
+      if (isleg) { sm.rhs[j0] = r0_; sm.rhs[j0 + 1] = r1_; sm.rhs[j0 + 2] = r2_; }
     };
-
-    // per-lane constants of the recursions (axis role)
-    const double fa = (c == 0) ? cyaw : (c == 1) ? -syaw : 0.0, fb = (c == 0) ? syaw : (c == 1) ? cyaw : 0.0;
-    const double ba = (c == 0) ? cyaw : (c == 1) ? syaw : 0.0, bb = (c == 0) ? -syaw : (c == 1) ? cyaw : 0.0;
-    const double fo = (c < 2) ? 0.0 : 1.0;
-    const bool glast = (k == klast);
-    // forward: reads X_k (group boundary for team 0), writes X_k+1; backward: reads p_k+1, writes p_k
-    const double* const xin = (team == 0) ? &sm.Xb[12 * warp] : &sm.Xv[12 * k];
-    double* const xout = glast ? &sm.Xb[12 * (warp + 1)] : &sm.Xv[12 * (k + 1)];
-    const double* const pin = glast ? &sm.Pb[12 * (warp + 1)] : &sm.pv[12 * (k + 1)];
-    double* const pout = (team == 0) ? &sm.Pb[12 * warp] : &sm.pv[12 * k];
-    const double* const xin1 = (team == 0) ? sm.zero12 : xin;   // first sweep: zero boundaries
-    const double* const pin1 = glast ? sm.zero12 : pin;
-    const bool pb_zero = (warp == nG - 1);                      // p_H = 0 is this group's true boundary
-    const double* const pin3 = (glast && pb_zero) ? sm.zero12 : pin;
 
     int iter = 0, rho_updates = 0, status = MPC_STATUS_UNSOLVED;
     double pri_res_out = 0.0;
@@ -516,27 +876,38 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
         need_factor = false;
         // ================= K3b: factorisation =================
         // Delta_leg = diag(c D^2 r2 + sigma) + A_leg' rho A_leg  (3 x 3, zero xy entry), inverse by cofactors
+        const double D0 = sm.Dp[j0], D1 = sm.Dp[j0 + 1], D2 = sm.Dp[j0 + 2];
+        double di[6];
         {
+          const double kap[5] = {lc[0], lc[1], lc[2], lc[3], lc[4]};
+          const double r2x = bp.Rd[3 * lg], r2y = bp.Rd[3 * lg + 1], r2z = bp.Rd[3 * lg + 2];
           const double sa = kap[0] + kap[1], sb = kap[2] + kap[3];
-          const double dxx = cs * D[0] * D[0] * r2x + sigma + sa, dyy = cs * D[1] * D[1] * r2y + sigma + sb;
-          const double dzz = cs * D[2] * D[2] * r2z + sigma + kap[4] + tzx * tzx * sa + tzy * tzy * sb;
+          const double dxx = cs * D0 * D0 * r2x + sigma + sa, dyy = cs * D1 * D1 * r2y + sigma + sb;
+          const double dzz = cs * D2 * D2 * r2z + sigma + kap[4] + tzx * tzx * sa + tzy * tzy * sb;
           const double dxz = tzx * (kap[0] - kap[1]), dyz = tzy * (kap[2] - kap[3]);
           const double m00 = dyy * dzz - dyz * dyz, m11 = dxx * dzz - dxz * dxz, m22 = dxx * dyy;
           const double idet = 1.0 / (dxx * m00 - dxz * dxz * dyy);
           di[0] = m00 * idet; di[1] = dxz * dyz * idet; di[2] = -dyy * dxz * idet;
           di[3] = m11 * idet; di[4] = -dxx * dyz * idet; di[5] = m22 * idet;
+          if (isleg) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) lc[5 + i] = di[i];
+          }
         }
         // G_ (into Fk) and M1 = G_ Delta^-1 (into Mt): the leg's three columns.  G_ = dt B6c D: the step's
         // velocity increment per unit of (scaled) force
         if (isleg) {
           const double dm[3][3] = {{di[0], di[1], di[2]}, {di[1], di[3], di[4]}, {di[2], di[4], di[5]}};
+          const double Dq[3] = {D0, D1, D2};
+          double top[3][3];
+          load_top(top);
 #pragma unroll
           for (int cc = 0; cc < 6; ++cc) {
             double gq[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
               const double b6 = (cc < 3) ? top[cc < 3 ? cc : 0][q] : ((cc - 3 == q) ? inv_m : 0.0);
-              gq[q] = dt * D[q] * b6;
+              gq[q] = dt * Dq[q] * b6;
               sm.Fk[k][cc * kMS + 3 * lg + q] = gq[q];
             }
 #pragma unroll
@@ -581,7 +952,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
             const bool ok = d > 0.0;
             const double ld = ok ? sqrt(d) : 0.0, li = ok ? 1.0 / ld : 0.0;
             Lm[cc][cc] = ld;
-            sm.Li[k][cc] = li;
+            s_Li[k][cc] = li;
 #pragma unroll
             for (int a = cc + 1; a < 6; ++a) {
               double s = Lm[a][cc];
@@ -593,13 +964,13 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
 #pragma unroll
           for (int a = 0; a < 6; ++a)
 #pragma unroll
-            for (int b = 0; b < 6; ++b) sm.Lk[k][6 * a + b] = (b <= a) ? Lm[a][b] : 0.0;
+            for (int b = 0; b < 6; ++b) s_Lk[k][6 * a + b] = (b <= a) ? Lm[a][b] : 0.0;
         }
         __syncwarp();
         // M~ = L^-T L^-1 M1: the leg's three columns, forward then backward substitution
         if (isleg) {
-          const double* Lp = sm.Lk[k];
-          const double* li = sm.Li[k];
+          const double* Lp = s_Lk[k];
+          const double* li = s_Li[k];
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             double y6[6];
@@ -634,7 +1005,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
           __syncwarp();
 #pragma unroll 1
           for (int ks = H - 1; ks >= 0; --ks) {
-            const double* Lp = sm.Lk[ks];
+            const double* Lp = s_Lk[ks];
             // Y = Pi A:  columns 0-5 unchanged, column 6 + j gains dt (Pi[:, 0:6] Rt)[:, j]
             for (int e = lane; e < 144; e += 32) {
               const int i = e / 12, j = e - 12 * i;
@@ -782,196 +1153,24 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
 #pragma unroll
           for (int r = 0; r < 12; ++r) sm.Phi[gj - 1][r * kMS + col] = T[r];
         }
+        if (tid >= 128 && tid < 140) s_Xb[tid - 128] = 0.0;  // X_0 = 0: the true boundary of the first group
         publish_rhs();
         __syncthreads();
+        WRP(1);  // factorisation
       }
       int run = until_check < until_adapt ? until_check : until_adapt;
       run = run < sp.max_iter - iter ? run : sp.max_iter - iter;
-#pragma unroll 1
-      for (int q_ = 0; q_ < run; ++q_) {
-        // ---- u = M~ r (axis), a = Delta^-1 r (leg) ----
-        __syncwarp();
-        double uc = 0.0;
-        {
-          const double2* mp = reinterpret_cast<const double2*>(&sm.Mt[k][c * kMS]);
-          const double2* rp = reinterpret_cast<const double2*>(&sm.rhs[12 * k]);
-          double s0 = 0.0, s1 = 0.0;
+      {
+        WrcIter st_;
 #pragma unroll
-          for (int h2 = 0; h2 < 6; ++h2) {
-            const double2 mv = mp[h2], r = rp[h2];
-            s0 = fma(mv.x, r.x, s0);
-            s1 = fma(mv.y, r.y, s1);
-          }
-          uc = s0 + s1;
-          if (isax) sm.uv[6 * k + c] = uc;
-        }
-        const double a0 = di[0] * rh[0] + di[1] * rh[1] + di[2] * rh[2];
-        const double a1 = di[1] * rh[0] + di[3] * rh[1] + di[4] * rh[2];
-        const double a2 = di[2] * rh[0] + di[4] * rh[1] + di[5] * rh[2];
-        __syncwarp();
-        // (N u)_c and t = -F' u (the addend of the backward recursion); F columns c and 6 + c stay in registers
-        double u6[6], fc[12], nuc, tpos, tvel;
-        {
-          const double2* up = reinterpret_cast<const double2*>(&sm.uv[6 * k]);
-          const double2 v0 = up[0], v1 = up[1], v2 = up[2];
-          u6[0] = v0.x; u6[1] = v0.y; u6[2] = v1.x; u6[3] = v1.y; u6[4] = v2.x; u6[5] = v2.y;
-          const double* np = &sm.Nk[k][6 * c];
-          const double* fp = &sm.Fk[k][c];
-          double s = 0.0, sp_ = 0.0, sv = 0.0;
+        for (int i = 0; i < 3; ++i) st_.x[i] = x[i];
+#ifdef WRC_PROF
+        wrc_iterate<H>(sm, st_, run, tzx, tzy, lo4, hi4, cyaw, syaw, dt, sigma, alpha, pc_, &pm_);
+#else
+        wrc_iterate<H>(sm, st_, run, tzx, tzy, lo4, hi4, cyaw, syaw, dt, sigma, alpha);
+#endif
 #pragma unroll
-          for (int d = 0; d < 6; ++d) {
-            fc[d] = fp[d * kMS];
-            fc[6 + d] = fp[d * kMS + 6];
-            s = fma(np[d], u6[d], s);
-            sp_ = fma(fc[d], u6[d], sp_);
-            sv = fma(fc[6 + d], u6[d], sv);
-          }
-          nuc = s; tpos = -sp_; tvel = -sv;
-        }
-        // ---- backward recursion  p_k = Acl_k' p_k+1 + t_k ----
-        auto bstep = [&](const double* src, double* dst, bool wr) {
-          const double2* pp = reinterpret_cast<const double2*>(src);
-          const double2 p01 = pp[0], v01 = pp[3], v23 = pp[4], v45 = pp[5];
-          const double own_pos = src[c], own_vel = src[6 + c];
-          double s0 = tpos, s1 = 0.0, s2 = tvel, s3 = 0.0;
-          s0 = fma(fc[0], v01.x, s0); s1 = fma(fc[1], v01.y, s1);
-          s2 = fma(fc[6], v01.x, s2); s3 = fma(fc[7], v01.y, s3);
-          s0 = fma(fc[2], v23.x, s0); s1 = fma(fc[3], v23.y, s1);
-          s2 = fma(fc[8], v23.x, s2); s3 = fma(fc[9], v23.y, s3);
-          s0 = fma(fc[4], v45.x, s0); s1 = fma(fc[5], v45.y, s1);
-          s2 = fma(fc[10], v45.x, s2); s3 = fma(fc[11], v45.y, s3);
-          const double rot = fma(ba, p01.x, fma(bb, p01.y, fo * own_pos));
-          const double np_ = own_pos + (s0 + s1);
-          const double nv_ = fma(dt, rot, own_vel) + (s2 + s3);
-          if (wr) { dst[c] = np_; dst[6 + c] = nv_; }
-        };
-#pragma unroll
-        for (int s_ = 3; s_ >= 0; --s_) {
-          if (team == s_) bstep(pin1, pout, isax);
-          __syncwarp();
-        }
-        __syncthreads();
-        if (warp == 0) {
-          const int i = lane < 12 ? lane : 0;
-#pragma unroll 1
-          for (int gj = nG - 2; gj >= 1; --gj) {
-            const double2* pp = reinterpret_cast<const double2*>(&sm.Pb[12 * (gj + 1)]);
-            const double* ph = &sm.Phi[gj - 1][i];
-            double s0 = sm.Pb[12 * gj + i], s1 = 0.0;
-#pragma unroll
-            for (int h2 = 0; h2 < 6; ++h2) {
-              const double2 v = pp[h2];
-              s0 = fma(ph[(2 * h2) * kMS], v.x, s0);
-              s1 = fma(ph[(2 * h2 + 1) * kMS], v.y, s1);
-            }
-            if (lane < 12) sm.Pb[12 * gj + i] = s0 + s1;
-            __syncwarp();
-          }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int s_ = 3; s_ >= 1; --s_) {
-          if (team == s_) bstep(pin3, pout, isax);
-          __syncwarp();
-        }
-        // ---- e = p_k+1,vel - u,  b = -Z e ----
-        const double ec = pin3[6 + c] - uc;
-        if (isax) sm.ev[6 * k + c] = ec;
-        __syncwarp();
-        double bfw;
-        {
-          const double2* ep = reinterpret_cast<const double2*>(&sm.ev[6 * k]);
-          const double2 e01 = ep[0], e23 = ep[1], e45 = ep[2];
-          const double* zp = &sm.Zk[k][6 * c];
-          double s0 = zp[0] * e01.x, s1 = zp[1] * e01.y;
-          s0 = fma(zp[2], e23.x, s0); s1 = fma(zp[3], e23.y, s1);
-          s0 = fma(zp[4], e45.x, s0); s1 = fma(zp[5], e45.y, s1);
-          bfw = -(s0 + s1);
-        }
-        // ---- forward recursion  dlt_k = F_k X_k + b_k,  X_k+1 = A X_k + [0; dlt_k] ----
-        double fr[12], dl = 0.0;
-        {
-          const double2* fp = reinterpret_cast<const double2*>(&sm.Fk[k][c * kMS]);
-#pragma unroll
-          for (int h2 = 0; h2 < 6; ++h2) { const double2 v = fp[h2]; fr[2 * h2] = v.x; fr[2 * h2 + 1] = v.y; }
-        }
-        auto fstep = [&](const double* src, double* dst, bool wr) {
-          const double2* xp = reinterpret_cast<const double2*>(src);
-          const double own_pos = src[c], own_vel = src[6 + c];
-          double s0 = bfw, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-          double2 w01;
-#pragma unroll
-          for (int h2 = 0; h2 < 6; h2 += 2) {
-            const double2 va = xp[h2], vb = xp[h2 + 1];
-            s0 = fma(fr[2 * h2], va.x, s0); s1 = fma(fr[2 * h2 + 1], va.y, s1);
-            s2 = fma(fr[2 * h2 + 2], vb.x, s2); s3 = fma(fr[2 * h2 + 3], vb.y, s3);
-          }
-          w01 = xp[3];
-          dl = (s0 + s1) + (s2 + s3);
-          const double rot = fma(fa, w01.x, fma(fb, w01.y, fo * own_vel));
-          if (wr) { dst[c] = fma(dt, rot, own_pos); dst[6 + c] = own_vel + dl; }
-        };
-#pragma unroll
-        for (int s_ = 0; s_ < 4; ++s_) {
-          if (team == s_) fstep(xin1, xout, isax);
-          __syncwarp();
-        }
-        __syncthreads();
-        if (warp == 0) {
-          const int i = lane < 12 ? lane : 0;
-#pragma unroll 1
-          for (int gj = 1; gj <= nG - 2; ++gj) {
-            const double2* xp = reinterpret_cast<const double2*>(&sm.Xb[12 * gj]);
-            const double2* ph = reinterpret_cast<const double2*>(&sm.Phi[gj - 1][i * kMS]);
-            double s0 = sm.Xb[12 * (gj + 1) + i], s1 = 0.0;
-#pragma unroll
-            for (int h2 = 0; h2 < 6; ++h2) {
-              const double2 v = xp[h2], f = ph[h2];
-              s0 = fma(f.x, v.x, s0);
-              s1 = fma(f.y, v.y, s1);
-            }
-            if (lane < 12) sm.Xb[12 * (gj + 1) + i] = s0 + s1;
-            __syncwarp();
-          }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int s_ = 0; s_ < 4; ++s_) {
-          if (team == s_) fstep(xin, xout, isax && !glast);
-          __syncwarp();
-        }
-        // ---- h = N u - dlt (axis);  x~ = a - M~' h, row updates, next rhs (leg) ----
-        if (isax) sm.ev[6 * k + c] = nuc - dl;
-        __syncwarp();
-        {
-          const double2* hp = reinterpret_cast<const double2*>(&sm.ev[6 * k]);
-          const double2 h01 = hp[0], h23 = hp[1], h45 = hp[2];
-          const double h6[6] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y};
-          const double* mp = &sm.Mt[k][3 * lg];
-          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) {
-            s0 = fma(mp[cc * kMS], h6[cc], s0);
-            s1 = fma(mp[cc * kMS + 1], h6[cc], s1);
-            s2 = fma(mp[cc * kMS + 2], h6[cc], s2);
-          }
-          const double xtx = a0 - s0, xty = a1 - s1, xtz = a2 - s2;
-          x[0] = alpha * xtx + (1.0 - alpha) * x[0];
-          x[1] = alpha * xty + (1.0 - alpha) * x[1];
-          x[2] = alpha * xtz + (1.0 - alpha) * x[2];
-          const double zt[5] = {fma(tzx, xtz, xtx), fma(-tzx, xtz, xtx), fma(tzy, xtz, xty), fma(-tzy, xtz, xty), xtz};
-#pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const double zr = alpha * zt[i] + (1.0 - alpha) * z[i];
-            double zn = zr + u[i];
-            if (i == 0 || i == 2) zn = (zn < 0.0) ? 0.0 : zn;
-            else if (i == 1 || i == 3) zn = (zn > 0.0) ? 0.0 : zn;
-            else { zn = (zn < lo4) ? lo4 : zn; zn = (zn > hi4) ? hi4 : zn; }
-            u[i] = u[i] + (zr - zn);
-            z[i] = zn;
-          }
-          publish_rhs();
-        }
+        for (int i = 0; i < 3; ++i) x[i] = st_.x[i];
       }
       __syncwarp();
       iter += run;
@@ -988,6 +1187,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
       double* const xD = sm.scr;            // D x            (n)
       double* const vt = sm.scr + n;        // G D x          (6H)
       double* const vo = sm.scr + n + 6 * H;  // S G D x      (6H)
+      const double D[3] = {sm.Dp[j0], sm.Dp[j0 + 1], sm.Dp[j0 + 2]};
       if (isleg) { xD[j0] = D[0] * x[0]; xD[j0 + 1] = D[1] * x[1]; xD[j0 + 2] = D[2] * x[2]; }
       __syncwarp();
       if (isax) {
@@ -1026,6 +1226,10 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
 #pragma unroll
       for (int i = 0; i < 10; ++i) v[i] = 0.0;
       if (isleg) {
+        const double cca[5] = {gcca[0], gcca[1], gcca[2], gcca[3], gcca[4]};
+        const double z[5] = {zu[0], zu[1], zu[2], zu[3], zu[4]}, u[5] = {zu[5], zu[6], zu[7], zu[8], zu[9]};
+        double top[3][3];
+        load_top(top);
         const double Ah[5] = {fma(tzx, x[2], x[0]), fma(-tzx, x[2], x[0]), fma(tzy, x[2], x[1]), fma(-tzy, x[2], x[1]), x[2]};
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -1040,9 +1244,10 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
         }
         // P_ x = c D (R2 D x + G' w) ; A_' y
         const double* wv = &vo[6 * k];
-        const double f0 = kap[0] * u[0], f1 = kap[1] * u[1], f2 = kap[2] * u[2], f3 = kap[3] * u[3], f4 = kap[4] * u[4];
+        const double f0 = lc[0] * u[0], f1 = lc[1] * u[1], f2 = lc[2] * u[2], f3 = lc[3] * u[3], f4 = lc[4] * u[4];
+        const double qb[3] = {lc[11], lc[12], lc[13]};
         const double Aty[3] = {f0 + f1, f2 + f3, f4 + (tzx * (f0 - f1) + tzy * (f2 - f3))};
-        const double r2v[3] = {r2x, r2y, r2z};
+        const double r2v[3] = {bp.Rd[3 * lg], bp.Rd[3 * lg + 1], bp.Rd[3 * lg + 2]};
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
           const double gtw = top[0][q] * wv[0] + top[1][q] * wv[1] + top[2][q] * wv[2] + inv_m * wv[3 + q];
@@ -1100,6 +1305,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
         sm.flags[2] = refactor;
       }
       __syncthreads();
+      WRP(7);  // residual check
       if (sm.flags[0]) {
         status = sm.flags[1];
         pri_res_out = sm.scal[4];
@@ -1110,11 +1316,14 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
         const double rho = sm.scal[2];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-          const double rn = rho_of(ct[i], rho);
-          u[i] *= rv[i] / rn;   // y stays, uh = y / (rho cca) follows the new rho
-          rv[i] = rn;
-          kap[i] = rn * cca[i] * cca[i];
+          const double rn = rho_row(i, rho), ro = rho_row(i, rho_cur);
+          if (isleg) {
+            const double cc_ = gcca[i];
+            zu[5 + i] *= ro / rn;   // y stays, uh = y / (rho cca) follows the new rho
+            lc[i] = rn * cc_ * cc_;
+          }
         }
+        rho_cur = rho;
         need_factor = true;  // the factorisation ends by rebuilding the right-hand side with the new rho vector
       }
     }
@@ -1128,18 +1337,16 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
 #pragma unroll
       for (int q = 0; q < 3; ++q) fin = fin && isfinite(x[q]);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) fin = fin && isfinite(z[i]) && isfinite(u[i]);
+      for (int i = 0; i < 5; ++i) fin = fin && isfinite(zu[i]) && isfinite(zu[5 + i]);
       const int all_ok = __syncthreads_and(fin || !isleg);
       if (isleg) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          ws[kWX + j0 + q] = x[q];
-          ws[kWQ + j0 + q] = q0v[q];
-        }
+        for (int q = 0; q < 3; ++q) ws[kWX + j0 + q] = x[q];   // (q went into the slot when it was formed)
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-          ws[kWZ + r0 + i] = cca[i] * z[i];            // OSQP's scaled z, y
-          ws[kWY + r0 + i] = rv[i] * cca[i] * u[i];
+          const double cc_ = gcca[i];
+          ws[kWZ + r0 + i] = cc_ * zu[i];            // OSQP's scaled z, y
+          ws[kWY + r0 + i] = rho_row(i, rho_cur) * cc_ * zu[5 + i];
         }
       }
       if (tid == 0) {
@@ -1147,7 +1354,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
         ws[kWLive] = (all_ok && isfinite(sm.scal[2])) ? 1.0 : 0.0;
       }
     }
-    const double f0 = D[0] * x[0], f1 = D[1] * x[1], f2 = D[2] * x[2];
+    const double f0 = sm.Dp[j0] * x[0], f1 = sm.Dp[j0 + 1] * x[1], f2 = sm.Dp[j0 + 2] * x[2];
     if (x_all != nullptr && isleg) {
       x_all[size_t(p) * n + j0] = (float)f0;
       x_all[size_t(p) * n + j0 + 1] = (float)f1;
@@ -1187,6 +1394,11 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
         if (lane == 0) tout[p].nan_mask = (int32_t)(nanbits & 0xfff);
       }
     }
+#ifdef WRC_PROF
+    if (tid == 0 && p < 2)
+      printf("WRCPROF p %d iters %d: ruiz %lld factor %lld u %lld bwd1 %lld bwd2 %lld bwd3 %lld eb %lld fwd %lld xrow %lld check %lld\n", p, iter,
+             pc_[0], pc_[1], pc_[2], pc_[8], pc_[9], pc_[3], pc_[4], pc_[5], pc_[6], pc_[7]);
+#endif
     if (tid == 0) {
       results[p].status = status;
       results[p].iters = iter;
