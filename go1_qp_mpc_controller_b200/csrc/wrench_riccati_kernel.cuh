@@ -144,6 +144,17 @@ __device__ __forceinline__ void wrc_block_sum_max(double& s, double& q, double* 
 }
 
 
+// Horizon step of (warp, team).  Spread layout: a warp holds the steps at ONE position (warp / 2) of four groups
+// (group = 4 (warp % 2) + team, step = 4 group + position), so that a round of a recursion sweep -- position r of
+// every group -- is two warps working with all their teams, not eight warps working with one team each (the FP64
+// pipe takes two cycles per warp instruction whatever the number of active lanes; with eight lanes of 32 active
+// the sweeps of two co-resident CTAs were bound by it: 230 cycles per step against 150 alone).
+__device__ __forceinline__ int wrc_stage(int warp, int team, int& pos, int& grp) {
+  pos = warp >> 1;
+  grp = 4 * (warp & 1) + team;
+  return 4 * grp + pos;
+}
+
 // The iterates a leg lane carries through a stretch of ADMM iterations.
 struct WrcIter {
   double x[3];
@@ -191,13 +202,14 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
   constexpr uint32_t RS = kMS * 8;  // row stride of the 6 x 12 / 12 x 12 matrices in bytes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int team = lane >> 3, t8 = lane & 7;
-  const int kraw = 4 * warp + team;
+  int pos, grp;
+  const int kraw = wrc_stage(warp, team, pos, grp);
   const bool on = kraw < H;
   const int k = on ? kraw : H - 1;
   const bool isleg = on && t8 < 4, isax = on && t8 < 6;
   const int lg = t8 & 3;
   const int c = t8 < 6 ? t8 : t8 - 6;
-  const int klast = (4 * warp + 3 < H - 1) ? 4 * warp + 3 : H - 1;
+  const int klast = (4 * grp + 3 < H - 1) ? 4 * grp + 3 : H - 1;
   const bool glast = (k == klast);
   // addresses
   const uint32_t a_itv = wrc_sa(sm.itv);
@@ -211,13 +223,13 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
   const uint32_t a_lc = wrc_sa(&sm.legc[4 * k + lg][0]);
   const uint32_t a_phi = wrc_sa(&sm.Phi[0][0]);
   // forward: reads X_k (group boundary for team 0), writes X_k+1; backward: reads p_k+1, writes p_k
-  const uint32_t xin = (team == 0) ? a_Xb + 96 * warp : a_Xv + 96 * k;
-  const uint32_t xout = glast ? a_Xb + 96 * (warp + 1) : a_Xv + 96 * (k + 1);
-  const uint32_t pin = glast ? a_Pb + 96 * (warp + 1) : a_pv + 96 * (k + 1);
-  const uint32_t pout = (team == 0) ? a_Pb + 96 * warp : a_pv + 96 * k;
-  const uint32_t xin1 = (team == 0) ? a_zero : xin;            // first sweep: zero boundaries
+  const uint32_t xin = (pos == 0) ? a_Xb + 96 * grp : a_Xv + 96 * k;
+  const uint32_t xout = glast ? a_Xb + 96 * (grp + 1) : a_Xv + 96 * (k + 1);
+  const uint32_t pin = glast ? a_Pb + 96 * (grp + 1) : a_pv + 96 * (k + 1);
+  const uint32_t pout = (pos == 0) ? a_Pb + 96 * grp : a_pv + 96 * k;
+  const uint32_t xin1 = (pos == 0) ? a_zero : xin;             // first sweep: zero boundaries
   const uint32_t pin1 = glast ? a_zero : pin;
-  const uint32_t pin3 = (glast && warp == nG - 1) ? a_zero : pin;  // p_H = 0 is the last group's true boundary
+  const uint32_t pin3 = (glast && grp == nG - 1) ? a_zero : pin;   // p_H = 0 is the last group's true boundary
   // rotation coefficients of the lane's state pair (rows of Rt / Rt')
   const double fa = (c == 0) ? cyaw : (c == 1) ? -syaw : 0.0, fb = (c == 0) ? syaw : (c == 1) ? cyaw : 0.0;
   const double ba = (c == 0) ? cyaw : (c == 1) ? syaw : 0.0, bb = (c == 0) ? -syaw : (c == 1) ? cyaw : 0.0;
@@ -285,13 +297,13 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
       const double nv_ = fma(dt, rot, own_vel) + (s2 + s3);
       if (wr) { wrc_st(dst + 8 * c, np_); wrc_st(dst + 48 + 8 * c, nv_); }
     };
+    // a round = position r of every group (two warps, all teams); the block barrier hands over to position r - 1
 #pragma unroll 1
-    for (int s_ = 3; s_ >= 0; --s_) {
-      if (team == s_) bstep(pin1, pout, isax);
-      __syncwarp();
+    for (int r_ = 3; r_ >= 0; --r_) {
+      if (pos == r_) bstep(pin1, pout, isax);
+      __syncthreads();
     }
     WRP(8);  // backward sweep 1
-    __syncthreads();
     if (warp == 0) {
       const int i = lane < 12 ? lane : 0;
 #pragma unroll 1
@@ -325,9 +337,9 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
     }
     __syncthreads();
 #pragma unroll 1
-    for (int s_ = 3; s_ >= 1; --s_) {
-      if (team == s_) bstep(pin3, pout, isax);
-      __syncwarp();
+    for (int r_ = 3; r_ >= 1; --r_) {
+      if (pos == r_) bstep(pin3, pout, isax);
+      __syncthreads();
     }
     WRP(3);  // backward sweep 3
     // ---- e = p_k+1,vel - u,  b = -Z e,  F row ----
@@ -365,11 +377,10 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
       if (wr) { wrc_st(dst + 8 * c, fma(dt, rot, own_pos)); wrc_st(dst + 48 + 8 * c, own_vel + dl); }
     };
 #pragma unroll 1
-    for (int s_ = 0; s_ < 4; ++s_) {
-      if (team == s_) fstep(xin1, xout, isax);
-      __syncwarp();
+    for (int r_ = 0; r_ < 4; ++r_) {
+      if (pos == r_) fstep(xin1, xout, isax);
+      __syncthreads();
     }
-    __syncthreads();
     if (warp == 0) {
       const int i = lane < 12 ? lane : 0;
 #pragma unroll 1
@@ -399,10 +410,11 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
     }
     __syncthreads();
 #pragma unroll 1
-    for (int s_ = 0; s_ < 4; ++s_) {
-      if (team == s_) fstep(xin, xout, isax && !glast);
-      __syncwarp();
+    for (int r_ = 0; r_ < 3; ++r_) {
+      if (pos == r_) fstep(xin, xout, isax && !glast);
+      __syncthreads();
     }
+    if (pos == 3) fstep(xin, xout, false);
     WRP(5);  // forward recursion
     // ---- h = N u - dlt (axis);  x~ = a - M~' h, row updates, next rhs (leg) ----
     if (isax) wrc_st(a_ek + 8 * c, nuc - dl);
@@ -498,7 +510,8 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
   double (*const s_Li)[6] = reinterpret_cast<double (*)[6]>(sm.itv + 36 * H);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int team = lane >> 3, t8 = lane & 7;
-  const int kraw = 4 * warp + team;
+  int pos_, grp_;
+  const int kraw = wrc_stage(warp, team, pos_, grp_);
   const bool on = kraw < H;
   const int k = on ? kraw : H - 1;                      // idle teams shadow the last step (never write)
   const bool isleg = on && t8 < 4, isax = on && t8 < 6;
