@@ -155,6 +155,17 @@ __device__ __forceinline__ int wrc_stage(int warp, int team, int& pos, int& grp)
   return 4 * grp + pos;
 }
 
+// Shared-memory slot of a horizon step: position-major, so that the four teams of a warp (same position,
+// consecutive groups) sit in CONSECUTIVE slots.  Indexed by the step itself they were four slots apart -- a multiple
+// of 128 bytes for every per-step array -- and each of their loads hit the same banks four times over (ncu: 256 M
+// bank conflicts per launch of 592 problems, LSU data pipe 50 % busy).  H = 30: 8 + 8 + 7 + 7 slots.
+template <int H>
+__device__ __forceinline__ int wrc_slot(int k) {
+  constexpr int nG = (H + 3) / 4, full = H - 4 * (nG - 1);  // positions < full exist in the last group too
+  const int pos = k & 3, grp = k >> 2;
+  return (pos <= full ? nG * pos : nG * full + (nG - 1) * (pos - full)) + grp;
+}
+
 // The iterates a leg lane carries through a stretch of ADMM iterations.
 struct WrcIter {
   double x[3];
@@ -215,18 +226,20 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
   const uint32_t a_itv = wrc_sa(sm.itv);
   const uint32_t a_pv = a_itv + 8 * Smem::oPv, a_Xv = a_itv + 8 * Smem::oXv, a_Pb = a_itv + 8 * Smem::oPb,
                  a_Xb = a_itv + 8 * Smem::oXb;
-  const uint32_t a_uk = a_itv + 8 * (Smem::oUv + 6 * k), a_ek = a_itv + 8 * (Smem::oEv + 6 * k);
+  const int sl = wrc_slot<H>(k);
+  const uint32_t a_uk = a_itv + 8 * (Smem::oUv + 6 * sl), a_ek = a_itv + 8 * (Smem::oEv + 6 * sl);
   const uint32_t a_zero = wrc_sa(sm.zero12);
-  const uint32_t a_mt = wrc_sa(&sm.Mt[k][0]), a_fk = wrc_sa(&sm.Fk[k][0]);
-  const uint32_t a_nrow = wrc_sa(&sm.Nk[k][6 * c]), a_zrow = wrc_sa(&sm.Zk[k][6 * c]);
-  const uint32_t a_rhsk = wrc_sa(&sm.rhs[12 * k]), a_rhsj = a_rhsk + 24 * lg;
-  const uint32_t a_lc = wrc_sa(&sm.legc[4 * k + lg][0]);
+  const uint32_t a_mt = wrc_sa(&sm.Mt[sl][0]), a_fk = wrc_sa(&sm.Fk[sl][0]);
+  const uint32_t a_nrow = wrc_sa(&sm.Nk[sl][6 * c]), a_zrow = wrc_sa(&sm.Zk[sl][6 * c]);
+  const uint32_t a_rhsk = wrc_sa(&sm.rhs[12 * sl]), a_rhsj = a_rhsk + 24 * lg;
+  const uint32_t a_lc = wrc_sa(&sm.legc[4 * sl + lg][0]);
   const uint32_t a_phi = wrc_sa(&sm.Phi[0][0]);
   // forward: reads X_k (group boundary for team 0), writes X_k+1; backward: reads p_k+1, writes p_k
-  const uint32_t xin = (pos == 0) ? a_Xb + 96 * grp : a_Xv + 96 * k;
-  const uint32_t xout = glast ? a_Xb + 96 * (grp + 1) : a_Xv + 96 * (k + 1);
-  const uint32_t pin = glast ? a_Pb + 96 * (grp + 1) : a_pv + 96 * (k + 1);
-  const uint32_t pout = (pos == 0) ? a_Pb + 96 * grp : a_pv + 96 * k;
+  const int sln = wrc_slot<H>(glast ? k : k + 1);  // slot of the next step of the group
+  const uint32_t xin = (pos == 0) ? a_Xb + 96 * grp : a_Xv + 96 * sl;
+  const uint32_t xout = glast ? a_Xb + 96 * (grp + 1) : a_Xv + 96 * sln;
+  const uint32_t pin = glast ? a_Pb + 96 * (grp + 1) : a_pv + 96 * sln;
+  const uint32_t pout = (pos == 0) ? a_Pb + 96 * grp : a_pv + 96 * sl;
   const uint32_t xin1 = (pos == 0) ? a_zero : xin;             // first sweep: zero boundaries
   const uint32_t pin1 = glast ? a_zero : pin;
   const uint32_t pin3 = (glast && grp == nG - 1) ? a_zero : pin;   // p_H = 0 is the last group's true boundary
@@ -236,7 +249,7 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
   const double fo = (c < 2) ? 0.0 : 1.0;
   const double oma = 1.0 - alpha;
 
-  const uint32_t a_zu = wrc_sa(&sm.zu[4 * k + lg][0]);
+  const uint32_t a_zu = wrc_sa(&sm.zu[4 * sl + lg][0]);
   double x[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) x[i] = st.x[i];
@@ -518,6 +531,8 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
   const int lg = t8 & 3;                                // leg (leg role)
   const int c = t8 < 6 ? t8 : t8 - 6;                   // component (axis role)
   const int j0 = 12 * k + 3 * lg, r0 = 5 * (4 * k + lg);  // first variable / first row of the leg-step
+  const int sl = wrc_slot<H>(k);                           // shared-memory slot of the step's matrices and vectors
+  const int js = 12 * sl + 3 * lg;                         // the leg's entries of rhs
 
   const bool kWarm = warm != nullptr;
   const double mu = sp.mu, sigma = sp.sigma, alpha = sp.alpha;
@@ -831,13 +846,13 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
     auto rho_row = [&](int i, double rho) { return rho_of(((ctp >> (2 * i)) & 3) - 1, rho); };
     // Rows in normalised form (wrench_kernel.cuh): row i = cca_i (x_own +- t x_fz), the kernel iterates on
     // zh = z / cca and uh = y / (rho cca);  kap = rho cca^2.
-    double* const lc = sm.legc[4 * k + lg];
+    double* const lc = sm.legc[4 * sl + lg];
     double kap[5];
     const double tzx = mu * D[2] / D[0], tzy = mu * D[2] / D[1];
     // iterates: x in registers, zh / uh of the five rows in shared memory (zu); cca = E_row D_own of the rows goes
     // to the CTA's global scratch line (L2): only the residual checks, rho updates and the warm slot read it
     double x[3] = {0.0, 0.0, 0.0};
-    double* const zu = sm.zu[4 * k + lg];
+    double* const zu = sm.zu[4 * sl + lg];
     double* const gcca = gscr + size_t(blockIdx.x) * (20 * H) + r0;
     {
       const double cca[5] = {E[0] * D[0], E[1] * D[0], E[2] * D[1], E[3] * D[1], E[4] * D[2]};
@@ -875,7 +890,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
       const double r0_ = sigma * x[0] - dq.y + (e0 + e1);
       const double r1_ = sigma * x[1] - q12.x + (e2 + e3);
       const double r2_ = sigma * x[2] - q12.y + (e4 + (tzx * (e0 - e1) + tzy * (e2 - e3)));
-      if (isleg) { sm.rhs[j0] = r0_; sm.rhs[j0 + 1] = r1_; sm.rhs[j0 + 2] = r2_; }
+      if (isleg) { sm.rhs[js] = r0_; sm.rhs[js + 1] = r1_; sm.rhs[js + 2] = r2_; }
     };
 
     int iter = 0, rho_updates = 0, status = MPC_STATUS_UNSOLVED;
@@ -921,11 +936,11 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
             for (int q = 0; q < 3; ++q) {
               const double b6 = (cc < 3) ? top[cc < 3 ? cc : 0][q] : ((cc - 3 == q) ? inv_m : 0.0);
               gq[q] = dt * Dq[q] * b6;
-              sm.Fk[k][cc * kMS + 3 * lg + q] = gq[q];
+              sm.Fk[sl][cc * kMS + 3 * lg + q] = gq[q];
             }
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-              sm.Mt[k][cc * kMS + 3 * lg + q] = gq[0] * dm[0][q] + gq[1] * dm[1][q] + gq[2] * dm[2][q];
+              sm.Mt[sl][cc * kMS + 3 * lg + q] = gq[0] * dm[0][q] + gq[1] * dm[1][q] + gq[2] * dm[2][q];
           }
         }
         __syncwarp();
@@ -934,7 +949,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
           double mr[12];
 #pragma unroll
           for (int h2 = 0; h2 < 6; ++h2) {
-            const double2 v = *reinterpret_cast<const double2*>(&sm.Mt[k][c * kMS + 2 * h2]);
+            const double2 v = *reinterpret_cast<const double2*>(&sm.Mt[sl][c * kMS + 2 * h2]);
             mr[2 * h2] = v.x; mr[2 * h2 + 1] = v.y;
           }
 #pragma unroll
@@ -942,11 +957,11 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
             double s = 0.0;
 #pragma unroll
             for (int h2 = 0; h2 < 6; ++h2) {
-              const double2 v = *reinterpret_cast<const double2*>(&sm.Fk[k][d * kMS + 2 * h2]);
+              const double2 v = *reinterpret_cast<const double2*>(&sm.Fk[sl][d * kMS + 2 * h2]);
               s = fma(mr[2 * h2], v.x, s);
               s = fma(mr[2 * h2 + 1], v.y, s);
             }
-            sm.Nk[k][6 * c + d] = s;
+            sm.Nk[sl][6 * c + d] = s;
           }
         }
         __syncwarp();
@@ -956,7 +971,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
 #pragma unroll
           for (int a = 0; a < 6; ++a)
 #pragma unroll
-            for (int b = 0; b <= a; ++b) Lm[a][b] = sm.Nk[k][6 * a + b];
+            for (int b = 0; b <= a; ++b) Lm[a][b] = sm.Nk[sl][6 * a + b];
 #pragma unroll
           for (int cc = 0; cc < 6; ++cc) {
             double d = Lm[cc][cc];
@@ -989,7 +1004,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
             double y6[6];
 #pragma unroll
             for (int cc = 0; cc < 6; ++cc) {
-              double s = sm.Mt[k][cc * kMS + 3 * lg + q];
+              double s = sm.Mt[sl][cc * kMS + 3 * lg + q];
 #pragma unroll
               for (int b = 0; b < cc; ++b) s -= Lp[6 * cc + b] * y6[b];
               y6[cc] = s * li[cc];
@@ -1002,7 +1017,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
               y6[cc] = s * li[cc];
             }
 #pragma unroll
-            for (int cc = 0; cc < 6; ++cc) sm.Mt[k][cc * kMS + 3 * lg + q] = y6[cc];
+            for (int cc = 0; cc < 6; ++cc) sm.Mt[sl][cc * kMS + 3 * lg + q] = y6[cc];
           }
         }
         __syncthreads();
@@ -1019,6 +1034,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
 #pragma unroll 1
           for (int ks = H - 1; ks >= 0; --ks) {
             const double* Lp = s_Lk[ks];
+            const int ss = wrc_slot<H>(ks);
             // Y = Pi A:  columns 0-5 unchanged, column 6 + j gains dt (Pi[:, 0:6] Rt)[:, j]
             for (int e = lane; e < 144; e += 32) {
               const int i = e / 12, j = e - 12 * i;
@@ -1107,8 +1123,8 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
                 double s = 0.0;
 #pragma unroll
                 for (int q = 0; q < 6; ++q) s = fma(T2[6 * a + q], Lp[6 * b + q], s);
-                sm.Zk[ks][6 * a + b] = s;
-                sm.Zk[ks][6 * b + a] = s;
+                sm.Zk[ss][6 * a + b] = s;
+                sm.Zk[ss][6 * b + a] = s;
               }
             }
             __syncwarp();
@@ -1117,8 +1133,8 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
               const int a = e / 12, j = e - 12 * a;
               double s = 0.0;
 #pragma unroll
-              for (int q = 0; q < 6; ++q) s = fma(sm.Zk[ks][6 * a + q], Y[12 * (6 + q) + j], s);
-              sm.Fk[ks][a * kMS + j] = -s;
+              for (int q = 0; q < 6; ++q) s = fma(sm.Zk[ss][6 * a + q], Y[12 * (6 + q) + j], s);
+              sm.Fk[ss][a * kMS + j] = -s;
             }
             __syncwarp();
             // Pi <- cQ + G + U' F  (upper triangle, mirrored)
@@ -1129,7 +1145,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
               const int j = i + rem;
               double s = 0.5 * (G[12 * i + j] + G[12 * j + i]);
 #pragma unroll
-              for (int q = 0; q < 6; ++q) s = fma(Y[12 * (6 + q) + i], sm.Fk[ks][q * kMS + j], s);
+              for (int q = 0; q < 6; ++q) s = fma(Y[12 * (6 + q) + i], sm.Fk[ss][q * kMS + j], s);
               if (i == j) s += cs * bp.Qd[i];
               Pi[12 * i + j] = s;
               Pi[12 * j + i] = s;
@@ -1146,7 +1162,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
           for (int i = 0; i < 12; ++i) T[i] = (i == col) ? 1.0 : 0.0;
 #pragma unroll 1
           for (int s_ = 0; s_ < 4; ++s_) {
-            const double* Fp = sm.Fk[4 * gj + s_];
+            const double* Fp = sm.Fk[wrc_slot<H>(4 * gj + s_)];
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
               double acc = T[6 + a];
