@@ -316,7 +316,6 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
       if (pos == r_) bstep(pin1, pout, isax);
       __syncthreads();
     }
-    WRP(8);  // backward sweep 1
     if (warp == 0) {
       const int i = lane < 12 ? lane : 0;
 #pragma unroll 1
@@ -340,7 +339,6 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
         __syncwarp();
       }
     }
-    WRP(9);  // barrier + backward sweep 2
     // (the F columns are re-read rather than kept across the boundary sweep: with them live, the sweep's own 24
     // operands no longer fit and ptxas issues its loads one by one)
 #pragma unroll
@@ -1021,76 +1019,122 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
           }
         }
         __syncthreads();
-        // Riccati recursion on warp 0 (scratch in scr): Pi 144 | Y 144 | G 144 | T1 36 | Mm 36 | T2 36
+        WRP(8);  // factorisation: per-step part (Delta^-1, G_, N, Cholesky, M~)
+        // Riccati recursion on warp 0 (scratch in scr): Pi 144 | G 144 | U 72 | T1 36 | Mi 36.  Six short phases per
+        // step with fixed lane roles and unrolled index arithmetic:
+        //   A  rows of Y = Pi A in registers -> U = Y_v, G = A' Y (12 lanes), T1 = Pi_vv L (6 lanes)
+        //   B  Mm = I + L' T1, row per lane;  C  Mm^-1 by Gauss-Jordan through shuffles (pivots >= 1)
+        //   D  Z = L Mm^-1 L' (21 lanes, upper triangle mirrored);  E  F = -Z U (24 lanes);
+        //   F  Pi <- cQ + sym(G) + U' F (12 lanes, entries j >= i mirrored)
+        // (Spreading the phases over the whole CTA, one output per thread and a block barrier between phases, was
+        // measured too: 118 k solves/s against 122 k -- the other CTA of the SM fills the idle warps' slots anyway.)
         if (warp == 0) {
           double* const Pi = sm.scr;
-          double* const Y = sm.scr + 144;
-          double* const G = sm.scr + 288;
-          double* const T1 = sm.scr + 432;
-          double* const Mm = sm.scr + 468;
-          double* const T2 = sm.scr + 504;
+          double* const G = sm.scr + 144;
+          double* const U = sm.scr + 288;
+          double* const T1 = sm.scr + 360;
+          double* const Mi = sm.scr + 396;
           for (int i = lane; i < 144; i += 32) Pi[i] = (i / 12 == i % 12) ? cs * bp.Qd[i / 12] : 0.0;
           __syncwarp();
+          // (v R~)[b] of a 6-vector
+          auto colR = [&](const double (&v)[6], double (&o)[6]) {
+            o[0] = cyaw * v[0] - syaw * v[1];
+            o[1] = syaw * v[0] + cyaw * v[1];
+            o[2] = v[2]; o[3] = v[3]; o[4] = v[4]; o[5] = v[5];
+          };
+          // upper-triangle index of lane < 21 for phase D
+          int za = 0, zb = lane < 21 ? lane : 0;
+          while (zb >= 6 - za) { zb -= 6 - za; ++za; }
+          zb += za;
 #pragma unroll 1
           for (int ks = H - 1; ks >= 0; --ks) {
             const double* Lp = s_Lk[ks];
             const int ss = wrc_slot<H>(ks);
-            // Y = Pi A:  columns 0-5 unchanged, column 6 + j gains dt (Pi[:, 0:6] Rt)[:, j]
-            for (int e = lane; e < 144; e += 32) {
-              const int i = e / 12, j = e - 12 * i;
-              double v = Pi[e];
-              if (j >= 6) {
-                const int q = j - 6;
-                const double add = (q == 0) ? (cyaw * Pi[12 * i] - syaw * Pi[12 * i + 1])
-                                 : (q == 1) ? (syaw * Pi[12 * i] + cyaw * Pi[12 * i + 1])
-                                            : Pi[12 * i + q];
-                v = fma(dt, add, v);
-              }
-              Y[e] = v;
-            }
-            // T1 = Pi_vv L
-            for (int e = lane; e < 36; e += 32) {
-              const int a = e / 6, b = e - 6 * a;
-              double s = 0.0;
+            // ---- A ----
+            if (lane < 12) {
+              const int i = lane;
+              double yr[12];  // row i of Y = Pi A: columns 0-5 unchanged, columns 6-11 gain dt (Pi[i, 0:6] R~)
+              {
+                double pr[12], t6[6];
 #pragma unroll
-              for (int q = 0; q < 6; ++q) s = fma(Pi[12 * (6 + a) + 6 + q], Lp[6 * q + b], s);
-              T1[e] = s;
+                for (int h2 = 0; h2 < 6; ++h2) {
+                  const double2 v = *reinterpret_cast<const double2*>(&Pi[12 * i + 2 * h2]);
+                  pr[2 * h2] = v.x; pr[2 * h2 + 1] = v.y;
+                }
+                const double p6[6] = {pr[0], pr[1], pr[2], pr[3], pr[4], pr[5]};
+                colR(p6, t6);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { yr[j] = pr[j]; yr[6 + j] = fma(dt, t6[j], pr[6 + j]); }
+              }
+              if (i < 6) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) G[12 * i + j] = yr[j];          // G rows 0-5 = Y rows 0-5
+              } else {
+                // G row 6 + a = Y row 6 + a + dt (R~' Y[0:6, :])[a, :]; the pos rows of Y it needs are re-formed here
+                const int a6 = i - 6;
+                const int ra = a6 < 2 ? 0 : a6, rb = a6 < 2 ? 1 : a6;
+                const double ca = a6 == 0 ? cyaw : a6 == 1 ? syaw : 1.0, cb = a6 == 0 ? -syaw : a6 == 1 ? cyaw : 0.0;
+                double ya[12], yb[12];
+                {
+                  double pa[12], pb[12], ta[6], tb[6];
+#pragma unroll
+                  for (int h2 = 0; h2 < 6; ++h2) {
+                    const double2 v = *reinterpret_cast<const double2*>(&Pi[12 * ra + 2 * h2]);
+                    const double2 w = *reinterpret_cast<const double2*>(&Pi[12 * rb + 2 * h2]);
+                    pa[2 * h2] = v.x; pa[2 * h2 + 1] = v.y; pb[2 * h2] = w.x; pb[2 * h2 + 1] = w.y;
+                  }
+                  const double a6v[6] = {pa[0], pa[1], pa[2], pa[3], pa[4], pa[5]};
+                  const double b6v[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
+                  colR(a6v, ta);
+                  colR(b6v, tb);
+#pragma unroll
+                  for (int j = 0; j < 6; ++j) {
+                    ya[j] = pa[j]; ya[6 + j] = fma(dt, ta[j], pa[6 + j]);
+                    yb[j] = pb[j]; yb[6 + j] = fma(dt, tb[j], pb[6 + j]);
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                  U[12 * a6 + j] = yr[j];
+                  G[12 * i + j] = fma(dt, fma(ca, ya[j], cb * yb[j]), yr[j]);
+                }
+              }
+            } else if (lane < 18) {
+              // T1 = Pi_vv L, row a
+              const int a = lane - 12;
+              double pv6[6];
+#pragma unroll
+              for (int q = 0; q < 6; ++q) pv6[q] = Pi[12 * (6 + a) + 6 + q];
+#pragma unroll
+              for (int b = 0; b < 6; ++b) {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; ++q)
+                  if (q >= b) s = fma(pv6[q], Lp[6 * q + b], s);
+                T1[6 * a + b] = s;
+              }
             }
             __syncwarp();
-            // G = A' Y: rows 0-5 unchanged, row 6 + i gains dt (Rt' Y[0:6, :])[i, :]
-            for (int e = lane; e < 144; e += 32) {
-              const int i = e / 12, j = e - 12 * i;
-              double v = Y[e];
-              if (i >= 6) {
-                const int q = i - 6;
-                const double add = (q == 0) ? (cyaw * Y[j] - syaw * Y[12 + j])
-                                 : (q == 1) ? (syaw * Y[j] + cyaw * Y[12 + j])
-                                            : Y[12 * q + j];
-                v = fma(dt, add, v);
-              }
-              G[e] = v;
-            }
-            // Mm = I + L' T1
-            for (int e = lane; e < 36; e += 32) {
-              const int a = e / 6, b = e - 6 * a;
-              double s = (a == b) ? 1.0 : 0.0;
-#pragma unroll
-              for (int q = 0; q < 6; ++q) s = fma(Lp[6 * q + a], T1[6 * q + b], s);
-              Mm[e] = s;
-            }
-            __syncwarp();
-            // Mm^-1 by Gauss-Jordan, lane r < 6 holds row r, the pivot row travels by shuffle (pivots >= 1)
+            // ---- B, C ----
             {
               const int r = lane < 6 ? lane : 0;
               double row[6];
 #pragma unroll
-              for (int j = 0; j < 6; ++j) row[j] = Mm[6 * r + j];
+              for (int b = 0; b < 6; ++b) {
+                double s = (r == b) ? 1.0 : 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) s = fma(Lp[6 * q + r], T1[6 * q + b], s);   // L[q][r] = 0 for q < r
+                row[b] = s;
+              }
 #pragma unroll
               for (int pv_ = 0; pv_ < 6; ++pv_) {
                 double rowp[6];
 #pragma unroll
                 for (int j = 0; j < 6; ++j) rowp[j] = __shfl_sync(0xffffffffu, row[j], pv_);
-                const double d = 1.0 / rowp[pv_];
+                // reciprocal of the pivot (>= 1): fp32 seed, two Newton steps in fp64 (a third of a division's latency)
+                double d = (double)__frcp_rn((float)rowp[pv_]);
+                d = fma(d, fma(-rowp[pv_], d, 1.0), d);
+                d = fma(d, fma(-rowp[pv_], d, 1.0), d);
                 const bool piv = (lane == pv_);
                 const double f = row[pv_] * d;
 #pragma unroll
@@ -1100,60 +1144,67 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
                   row[j] = piv ? prw : upd;
                 }
               }
-              __syncwarp();
               if (lane < 6) {
 #pragma unroll
-                for (int j = 0; j < 6; ++j) Mm[6 * lane + j] = row[j];
+                for (int j = 0; j < 6; ++j) Mi[6 * lane + j] = row[j];
               }
             }
             __syncwarp();
-            // T2 = L Mm^-1
-            for (int e = lane; e < 36; e += 32) {
-              const int a = e / 6, b = e - 6 * a;
+            // ---- D: Z[za][zb] = sum_p L[za][p] (sum_q Mi[p][q] L[zb][q]) ----
+            if (lane < 21) {
+              double lb6[6], la6[6];
+#pragma unroll
+              for (int q = 0; q < 6; ++q) { lb6[q] = Lp[6 * zb + q]; la6[q] = Lp[6 * za + q]; }
               double s = 0.0;
 #pragma unroll
-              for (int q = 0; q < 6; ++q) s = fma(Lp[6 * a + q], Mm[6 * q + b], s);
-              T2[e] = s;
+              for (int p_ = 0; p_ < 6; ++p_) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) t = fma(Mi[6 * p_ + q], lb6[q], t);
+                s = fma(la6[p_], t, s);
+              }
+              sm.Zk[ss][6 * za + zb] = s;
+              sm.Zk[ss][6 * zb + za] = s;
             }
             __syncwarp();
-            // Z = T2 L'  (symmetric: the upper triangle is computed and mirrored)
-            for (int e = lane; e < 36; e += 32) {
-              const int a = e / 6, b = e - 6 * a;
-              if (a <= b) {
+            // ---- E: F = -Z U, lane (a, three columns) ----
+            if (lane < 24) {
+              const int a = lane % 6, j3 = 3 * (lane / 6);
+              double zr[6];
+#pragma unroll
+              for (int q = 0; q < 6; ++q) zr[q] = sm.Zk[ss][6 * a + q];
+#pragma unroll
+              for (int jj = 0; jj < 3; ++jj) {
                 double s = 0.0;
 #pragma unroll
-                for (int q = 0; q < 6; ++q) s = fma(T2[6 * a + q], Lp[6 * b + q], s);
-                sm.Zk[ss][6 * a + b] = s;
-                sm.Zk[ss][6 * b + a] = s;
+                for (int q = 0; q < 6; ++q) s = fma(zr[q], U[12 * q + j3 + jj], s);
+                sm.Fk[ss][a * kMS + j3 + jj] = -s;
               }
             }
             __syncwarp();
-            // F = -Z U,  U = Y[6:12, :]
-            for (int e = lane; e < 72; e += 32) {
-              const int a = e / 12, j = e - 12 * a;
-              double s = 0.0;
+            // ---- F: Pi <- cQ + sym(G) + U' F, entries j >= i of row i, mirrored ----
+            if (lane < 12) {
+              const int i = lane;
+              double ui[6];
 #pragma unroll
-              for (int q = 0; q < 6; ++q) s = fma(sm.Zk[ss][6 * a + q], Y[12 * (6 + q) + j], s);
-              sm.Fk[ss][a * kMS + j] = -s;
-            }
-            __syncwarp();
-            // Pi <- cQ + G + U' F  (upper triangle, mirrored)
-            for (int e = lane; e < 78; e += 32) {
-              // e -> (i, j), i <= j, row by row of the upper triangle
-              int i = 0, rem = e;
-              while (rem >= 12 - i) { rem -= 12 - i; ++i; }
-              const int j = i + rem;
-              double s = 0.5 * (G[12 * i + j] + G[12 * j + i]);
+              for (int q = 0; q < 6; ++q) ui[q] = U[12 * q + i];
 #pragma unroll
-              for (int q = 0; q < 6; ++q) s = fma(Y[12 * (6 + q) + i], sm.Fk[ss][q * kMS + j], s);
-              if (i == j) s += cs * bp.Qd[i];
-              Pi[12 * i + j] = s;
-              Pi[12 * j + i] = s;
+              for (int j = 0; j < 12; ++j) {
+                if (j >= i) {
+                  double s = 0.5 * (G[12 * i + j] + G[12 * j + i]);
+#pragma unroll
+                  for (int q = 0; q < 6; ++q) s = fma(ui[q], sm.Fk[ss][q * kMS + j], s);
+                  if (i == j) s += cs * bp.Qd[i];
+                  Pi[12 * i + j] = s;
+                  Pi[12 * j + i] = s;
+                }
+              }
             }
             __syncwarp();
           }
         }
         __syncthreads();
+        WRP(9);  // factorisation: Riccati recursion
         // group transitions Phi_j = Acl_(4j+3) ... Acl_4j, j = 1 .. nG-2: one thread per column
         if (tid < (nG - 2) * 12) {
           const int gj = 1 + tid / 12, col = tid % 12;
@@ -1425,8 +1476,8 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
     }
 #ifdef WRC_PROF
     if (tid == 0 && p < 2)
-      printf("WRCPROF p %d iters %d: ruiz %lld factor %lld u %lld bwd1 %lld bwd2 %lld bwd3 %lld eb %lld fwd %lld xrow %lld check %lld\n", p, iter,
-             pc_[0], pc_[1], pc_[2], pc_[8], pc_[9], pc_[3], pc_[4], pc_[5], pc_[6], pc_[7]);
+      printf("WRCPROF p %d iters %d: ruiz %lld factor: local %lld riccati %lld phi %lld | u %lld bwd %lld eb %lld fwd %lld xrow %lld check %lld\n", p, iter,
+             pc_[0], pc_[8], pc_[9], pc_[1], pc_[2], pc_[3], pc_[4], pc_[5], pc_[6], pc_[7]);
 #endif
     if (tid == 0) {
       results[p].status = status;

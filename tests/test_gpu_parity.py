@@ -795,6 +795,87 @@ def test_structured_solver_hardware_weights_and_extensions(pkg, ob):
     e.close()
 
 
+@pytest.mark.parametrize("which", ["gazebo", "hardware"])
+def test_long_horizon_wrench_engine(pkg, ob, which):
+    """H = 30 through wrench_riccati_kernel.cuh (structured_solver = 3, the default at H = 30): the fused build +
+    six-input Riccati ADMM.  Same gates as every other engine: oracle iteration counts on every state, GRF inside
+    the gate; and the three long-horizon engines (wrench, Riccati on the dense build, dense workspace) agree."""
+    cfg = pkg.config_default() if which == "gazebo" else pkg.config_hardware()
+    cfg.horizon = 30
+    cfg.structured_solver = 3
+    n = 160
+    st = pkg.generate_states(1004, 0, n)
+    e = pkg.MpcEngine(cfg, 0)
+    l0 = e.kernel_launches()
+    res = e.compute_grf_batch(st).copy()
+    assert e.kernel_launches() - l0 == 1                     # ONE kernel from the records to the results
+    ref = ob.mpc_compute_grf(cfg, st)
+    assert (res["status"] == 1).all()
+    assert_same_iterates(res, ref, max_flipped=0.0, what=f"H=30 wrench engine ({which})")
+    # the other long-horizon engines on the same states
+    for mode, m in ((1, n), (2, 16)):
+        c2 = pkg.config_default() if which == "gazebo" else pkg.config_hardware()
+        c2.horizon = 30
+        c2.structured_solver = mode
+        d = pkg.MpcEngine(c2, 0)
+        r2 = d.compute_grf_batch(st[:m])
+        assert np.array_equal(r2["iters"], res["iters"][:m])
+        assert np.abs(r2["grf"] - res["grf"][:m]).max() <= 1e-3
+        d.close()
+    # full primal solution: feasible, and the first step is what the result record holds
+    x = e.get_solution(5).astype(np.float64).reshape(30, 4, 3)
+    assert np.maximum(np.abs(x[..., :2]).max(-1) - cfg.mu * x[..., 2], 0).max() <= TOL_CONE * cfg.fz_max
+    R = st["rot_mat"][5].astype(np.float64).reshape(3, 3)
+    assert np.abs((x[0] @ R).ravel() - res["grf"][5]).max() <= 1e-3 * max(np.abs(res["grf"][5]).max(), 1.0)
+    # the fused torque map
+    tin = pkg.generate_torque_inputs(1004, 0, n)
+    e.load_states(st)
+    e.set_torque_inputs(tin)
+    e.build_qp()
+    e.solve()
+    _check_torques(ob, st, tin, e.get_results(), e.get_torques())
+    # a repeat is bit-identical; ragged sizes around the resident CTA count
+    assert e.compute_grf_batch(st).tobytes() == res.tobytes()
+    big = pkg.generate_states(1004, 0, 2 * 148 + 5)
+    rb = e.compute_grf_batch(big)
+    assert rb[:n].tobytes() == res.tobytes()
+    e.close()
+
+
+def test_long_horizon_wrench_engine_extensions_and_refusals(pkg, ob):
+    """foot_drift and gait_aware inside the H = 30 wrench kernel; exact_discretization is the Riccati engine's
+    (automatic under structured_solver = 0, refused under 3)."""
+    n = 96
+    st = pkg.generate_states(1002, 0, n)
+    gait = pkg.generate_gait_inputs(1002, 0, n, 0)
+    for flags in ((0, 1, 0), (0, 0, 1), (0, 1, 1)):
+        cfg = pkg.config_default()
+        cfg.horizon = 30
+        cfg.structured_solver = 3
+        cfg.exact_discretization, cfg.foot_drift, cfg.gait_aware = flags
+        e = pkg.MpcEngine(cfg, 0)
+        e.load_states(st)
+        if cfg.gait_aware:
+            e.set_gait_inputs(gait)
+        e.build_qp()
+        e.solve()
+        ref = ob.mpc_compute_grf_ext(cfg, st, gait)
+        assert_same_iterates(e.get_results(), ref, max_flipped=0.0, what=f"H=30 wrench engine, flags {flags}")
+        e.close()
+    cfg = pkg.config_default()
+    cfg.horizon = 30
+    cfg.exact_discretization = 1
+    cfg.structured_solver = 3
+    with pytest.raises(pkg.MpcError):
+        pkg.MpcEngine(cfg, 0)
+    cfg.structured_solver = 0                                 # auto: falls back to the Riccati engine
+    e = pkg.MpcEngine(cfg, 0)
+    res = e.compute_grf_batch(st[:32])
+    ref = ob.mpc_compute_grf_ext(cfg, st[:32], gait[:32])
+    assert_same_iterates(res, ref, max_flipped=0.0, what="H=30 auto with exact_discretization")
+    e.close()
+
+
 def test_long_horizon_dense_workspace_path(pkg, ob):
     """H = 30 through the dense K^-1-in-L2-workspace kernels (structured_solver = 2), kept as the
     independent second implementation of the long horizon."""
