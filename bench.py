@@ -425,24 +425,32 @@ def run_ours(args):
 
     # ---------------- extra: BASELINE configs[3], long horizon H = 30 (360 variables) ----------------
     def x_h30():
-        cfg30 = pkg.config_default()
-        cfg30.horizon = 30
-        eng30 = pkg.MpcEngine(cfg30, local_rank)
-        n30 = 8192 // world if world > 1 else 2048
+        n30 = max(8192 // world, 1024)
         st30 = pkg.generate_states(1004, rank * n30, n30)
-        eng30.compute_grf_batch(st30)  # full-size warm-up: the engine sizes its buffers on first use
-        barrier()
-        t0 = time.perf_counter()
-        reps30 = 3
-        for _ in range(reps30):
-            out30 = eng30.compute_grf_batch(st30)
-        torch.cuda.synchronize()
-        dt30 = max_over_ranks(time.perf_counter() - t0)
-        r = {"metric": "batched MPC QP solves/sec (H=30)", "value": world * n30 * reps30 / dt30,
-             "unit": "solves/s", "states_per_gpu": n30, "ms_per_batch": 1e3 * dt30 / reps30,
-             "mean_iters": float(out30["iters"].mean()), "all_solved": bool((out30["status"] == 1).all())}
-        eng30.close()
-        return r
+
+        def run30(solver, reps30):
+            cfg30 = pkg.config_default()
+            cfg30.horizon = 30
+            cfg30.structured_solver = solver
+            eng30 = pkg.MpcEngine(cfg30, local_rank)
+            eng30.compute_grf_batch(st30)  # full-size warm-up: the engine sizes its buffers on first use
+            l0 = eng30.kernel_launches()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps30):
+                out = eng30.compute_grf_batch(st30)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            launches = (eng30.kernel_launches() - l0) // reps30
+            eng30.close()
+            return world * n30 * reps30 / dt, 1e3 * dt / reps30, out, launches
+        v3, ms3, out30, l3 = run30(0, 3)      # default at H = 30: wrench_riccati_kernel (fused build + six-input Riccati ADMM)
+        v1, ms1, out1, l1 = run30(1, 1)       # round 1's engine: dense build + riccati_solve_kernel
+        return {"metric": "batched MPC QP solves/sec (H=30)", "value": v3, "unit": "solves/s", "states_per_gpu": n30,
+                "ms_per_batch": ms3, "kernel": "wrench_riccati_kernel<30>", "launches_per_batch": int(l3),
+                "mean_iters": float(out30["iters"].mean()), "all_solved": bool((out30["status"] == 1).all()),
+                "riccati_engine": {"value": v1, "ms_per_batch": ms1, "launches_per_batch": int(l1),
+                                   "same_iterations": bool(np.array_equal(out1["iters"], out30["iters"]))}}
     extra("long_horizon_h30", x_h30)
 
     # ---------------- extra: BASELINE configs[4], stance-balance QP, 1 M problems over 8 GPUs ----------------

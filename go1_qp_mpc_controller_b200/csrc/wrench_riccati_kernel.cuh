@@ -42,6 +42,10 @@ constexpr int kWrcThreads = 256;
 constexpr int kWrcWarps = kWrcThreads / 32;
 constexpr int kWrcCtasPerSm = 2;
 constexpr int kMS = 14;  // row stride of the 6 x 12 and 12 x 12 matrices (16-byte loads of six rows hit six bank groups)
+// Column of F_k in shared memory: (pos_c, vel_c) interleaved, so that the two columns a lane of the backward
+// recursion needs are ONE 16-byte load per row (they were two 8-byte loads 48 bytes apart, two-way bank conflicts
+// between the teams of a warp: half of the kernel's excess wavefronts)
+__host__ __device__ constexpr int wrc_fcol(int j) { return j < 6 ? 2 * j : 2 * (j - 6) + 1; }
 
 template <int H>
 struct WrcSmem {
@@ -282,8 +286,9 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
       const double2 n01 = wrc_ld2(a_nrow), n23 = wrc_ld2(a_nrow + 16), n45 = wrc_ld2(a_nrow + 32);
 #pragma unroll
       for (int d = 0; d < 6; ++d) {
-        fc[d] = wrc_ld(a_fk + RS * d + 8 * c);
-        fc[6 + d] = wrc_ld(a_fk + RS * d + 8 * c + 48);
+        const double2 f = wrc_ld2(a_fk + RS * d + 16 * c);   // F[d][c], F[d][6 + c]
+        fc[d] = f.x;
+        fc[6 + d] = f.y;
       }
       const double u6[6] = {u01.x, u01.y, u23.x, u23.y, u45.x, u45.y};
       nuc = fma(n45.x, u45.x, fma(n23.x, u23.x, n01.x * u01.x)) + fma(n45.y, u45.y, fma(n23.y, u23.y, n01.y * u01.y));
@@ -343,8 +348,9 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
     // operands no longer fit and ptxas issues its loads one by one)
 #pragma unroll
     for (int d = 0; d < 6; ++d) {
-      fc[d] = wrc_ld(a_fk + RS * d + 8 * c);
-      fc[6 + d] = wrc_ld(a_fk + RS * d + 8 * c + 48);
+      const double2 f = wrc_ld2(a_fk + RS * d + 16 * c);
+      fc[d] = f.x;
+      fc[6 + d] = f.y;
     }
     __syncthreads();
 #pragma unroll 1
@@ -361,8 +367,8 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
       const double2 z01 = wrc_ld2(a_zrow), z23 = wrc_ld2(a_zrow + 16), z45 = wrc_ld2(a_zrow + 32);
 #pragma unroll
       for (int h2 = 0; h2 < 6; ++h2) {
-        const double2 f = wrc_ld2(a_fk + RS * c + 16 * h2);
-        fr[2 * h2] = f.x; fr[2 * h2 + 1] = f.y;
+        const double2 f = wrc_ld2(a_fk + RS * c + 16 * h2);   // F[c][h2], F[c][6 + h2]
+        fr[h2] = f.x; fr[6 + h2] = f.y;
       }
       __syncwarp();
       const double2 e01 = wrc_ld2(a_ek), e23 = wrc_ld2(a_ek + 16), e45 = wrc_ld2(a_ek + 32);
@@ -417,7 +423,7 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
 #pragma unroll
     for (int h2 = 0; h2 < 6; ++h2) {
       const double2 f = wrc_ld2(a_fk + RS * c + 16 * h2);
-      fr[2 * h2] = f.x; fr[2 * h2 + 1] = f.y;
+      fr[h2] = f.x; fr[6 + h2] = f.y;
     }
     __syncthreads();
 #pragma unroll 1
@@ -1178,7 +1184,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
                 double s = 0.0;
 #pragma unroll
                 for (int q = 0; q < 6; ++q) s = fma(zr[q], U[12 * q + j3 + jj], s);
-                sm.Fk[ss][a * kMS + j3 + jj] = -s;
+                sm.Fk[ss][a * kMS + wrc_fcol(j3 + jj)] = -s;
               }
             }
             __syncwarp();
@@ -1193,7 +1199,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
                 if (j >= i) {
                   double s = 0.5 * (G[12 * i + j] + G[12 * j + i]);
 #pragma unroll
-                  for (int q = 0; q < 6; ++q) s = fma(ui[q], sm.Fk[ss][q * kMS + j], s);
+                  for (int q = 0; q < 6; ++q) s = fma(ui[q], sm.Fk[ss][q * kMS + wrc_fcol(j)], s);
                   if (i == j) s += cs * bp.Qd[i];
                   Pi[12 * i + j] = s;
                   Pi[12 * j + i] = s;
@@ -1218,7 +1224,7 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
             for (int a = 0; a < 6; ++a) {
               double acc = T[6 + a];
 #pragma unroll
-              for (int i = 0; i < 12; ++i) acc = fma(Fp[a * kMS + i], T[i], acc);
+              for (int i = 0; i < 12; ++i) acc = fma(Fp[a * kMS + wrc_fcol(i)], T[i], acc);
               Tn[a] = acc;
             }
             T[0] = fma(dt, cyaw * T[6] + syaw * T[7], T[0]);

@@ -237,13 +237,17 @@ typedef struct MpcConfig {
   int32_t gait_aware;           /* per-step contacts from the gait counters (mpc_set_gait_inputs)
                                    instead of today's contacts replicated (ConvexMpc.cpp:242-245) */
   int32_t structured_solver;    /* how K x = r is solved inside the ADMM (same iterates up to rounding):
-                                   0 automatic: wrench-space solver for H = 10 (wrench_kernel.cuh: build and
-                                     solve fused, 60 x 60 Woodbury core, no Hessian in memory), Riccati
-                                     recursion over the horizon (riccati_kernel.cuh) for H = 30;
-                                   1 Riccati recursion (cold solves; warm-started solves stay dense);
+                                   0 automatic: the fused wrench-space kernels, build and solve in one launch,
+                                     no Hessian in memory -- H = 10: 60 x 60 Woodbury core in registers
+                                     (wrench_kernel.cuh); H = 30: the core solved as a 12-state / 6-input
+                                     Riccati recursion (wrench_riccati_kernel.cuh); H = 30 with
+                                     exact_discretization: as 1;
+                                   1 Riccati recursion on the dense build (riccati_kernel.cuh; at H = 10 cold
+                                     solves only, warm-started solves stay dense);
                                    2 dense: qp_build_kernel + admm_solve_kernel, K^-1 (120 x 120) in registers
                                      (for H = 30: K^-1 in a per-CTA L2 workspace, 7x slower);
-                                   3 wrench-space, explicitly (horizon 10 only) */
+                                   3 wrench-space, explicitly (MPC_ERR_INVALID for H = 30 with
+                                     exact_discretization) */
 } MpcConfig;
 
 /* Gait scheduler state of one robot (A1CtrlStates.h:24-28,103; A1RobotControl.cpp:156-164),
