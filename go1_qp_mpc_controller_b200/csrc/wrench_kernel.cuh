@@ -92,38 +92,48 @@ __device__ __forceinline__ double wr_colnorm_t(const WrenchSmem& sm, int kj, int
   double mx = 0.0;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
-    double tp[3][6];
+    // alpha and beta are all that depends on the block row: entry = alpha A_i + beta B_i with
+    // A_i = top_i . u1 + [.] vb1, B_i = top_i . u2 + [.] vb2 formed once per half (without foot_drift)
+    double A0[6], B0[6];
     if (!kDrift) {
 #pragma unroll
-      for (int c3 = 0; c3 < 3; ++c3) {
-        const double2* t = reinterpret_cast<const double2*>(&sm.B6[0][c3][6 * half]);
-        const double2 q0 = t[0], q1 = t[1], q2 = t[2];
-        tp[c3][0] = q0.x; tp[c3][1] = q0.y; tp[c3][2] = q1.x; tp[c3][3] = q1.y; tp[c3][4] = q2.x; tp[c3][5] = q2.y;
+      for (int i = 0; i < 6; ++i) {
+        const double t0 = sm.B6[0][0][6 * half + i], t1 = sm.B6[0][1][6 * half + i], t2 = sm.B6[0][2][6 * half + i];
+        const bool same = (i % 3) == comp;   // (6 half + i) % 3 == i % 3
+        A0[i] = fma(t0, u1[0], fma(t1, u1[1], fma(t2, u1[2], same ? vb1 : 0.0)));
+        B0[i] = fma(t0, u2[0], fma(t1, u2[1], fma(t2, u2[2], same ? vb2 : 0.0)));
       }
     }
 #pragma unroll 2
     for (int k = 0; k < kH; ++k) {
       const double a = sm.al[kH * k + kj], b = sm.be[kH * k + kj];
-      const double v0 = fma(b, u2[0], a * u1[0]), v1 = fma(b, u2[1], a * u1[1]), v2 = fma(b, u2[2], a * u1[2]);
-      const double vbm = fma(b, vb2, a * vb1);
+      const double2* dk = reinterpret_cast<const double2*>(&sm.Dp[12 * k + 6 * half]);
+      const double2 d01 = dk[0], d23 = dk[1], d45 = dk[2];
+      const double dd[6] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y};
       if (kDrift) {
+        const double v0 = fma(b, u2[0], a * u1[0]), v1 = fma(b, u2[1], a * u1[1]), v2 = fma(b, u2[2], a * u1[2]);
+        const double vbm = fma(b, vb2, a * vb1);
+        double tp[3][6];
 #pragma unroll
         for (int c3 = 0; c3 < 3; ++c3) {
           const double2* t = reinterpret_cast<const double2*>(&sm.B6[k][c3][6 * half]);
           const double2 q0 = t[0], q1 = t[1], q2 = t[2];
           tp[c3][0] = q0.x; tp[c3][1] = q0.y; tp[c3][2] = q1.x; tp[c3][3] = q1.y; tp[c3][4] = q2.x; tp[c3][5] = q2.y;
         }
-      }
-      const double2* dk = reinterpret_cast<const double2*>(&sm.Dp[12 * k + 6 * half]);
-      const double2 d01 = dk[0], d23 = dk[1], d45 = dk[2];
-      const double dd[6] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y};
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        double e = ((i % 3) == comp) ? vbm : 0.0;   // (6 half + i) % 3 == i % 3
-        e = fma(tp[0][i], v0, e);
-        e = fma(tp[1][i], v1, e);
-        e = fma(tp[2][i], v2, e);
-        mx = max_bits(mx, fabs(e) * dd[i]);
+        for (int i = 0; i < 6; ++i) {
+          double e = ((i % 3) == comp) ? vbm : 0.0;
+          e = fma(tp[0][i], v0, e);
+          e = fma(tp[1][i], v1, e);
+          e = fma(tp[2][i], v2, e);
+          mx = max_bits(mx, fabs(e) * dd[i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const double e = fma(b, B0[i], a * A0[i]);
+          mx = max_bits(mx, fabs(e) * dd[i]);
+        }
       }
     }
   }
