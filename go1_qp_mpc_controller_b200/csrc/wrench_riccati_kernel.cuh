@@ -338,14 +338,15 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
         if (lane < 12) wrc_st(a_Pb + 96 * gj + 8 * i, (s0 + s1) + (s2 + s3));
         __syncwarp();
       }
-    }
-    // (the F columns are re-read rather than kept across the boundary sweep: with them live, the sweep's own 24
-    // operands no longer fit and ptxas issues its loads one by one)
+      // The warp that ran the boundary sweep re-reads its F columns: with them live across the sweep, the sweep's own
+      // 24 operands no longer fit and ptxas issues its loads one by one.  Only this warp pays (a load instruction
+      // costs the shared-memory pipe the same four cycles whatever its active lanes: scripts/micro/lds_bench.cu).
 #pragma unroll
-    for (int d = 0; d < 6; ++d) {
-      const double2 f = wrc_ld2(a_fk + RS * d + 16 * c);
-      fc[d] = f.x;
-      fc[6 + d] = f.y;
+      for (int d = 0; d < 6; ++d) {
+        const double2 f = wrc_ld2(a_fk + RS * d + 16 * c);
+        fc[d] = f.x;
+        fc[6 + d] = f.y;
+      }
     }
     __syncthreads();
 #pragma unroll 1
@@ -414,11 +415,11 @@ __device__ WRC_ITER_ATTR void wrc_iterate(WrcSmem<H>& sm, WrcIter& st, int run, 
         if (lane < 12) wrc_st(a_Xb + 96 * (gj + 1) + 8 * i, (s0 + s1) + (s2 + s3));
         __syncwarp();
       }
-    }
 #pragma unroll
-    for (int h2 = 0; h2 < 6; ++h2) {
-      const double2 f = wrc_ld2(a_fk + RS * c + 16 * h2);
-      fr[h2] = f.x; fr[6 + h2] = f.y;
+      for (int h2 = 0; h2 < 6; ++h2) {
+        const double2 f = wrc_ld2(a_fk + RS * c + 16 * h2);
+        fr[h2] = f.x; fr[6 + h2] = f.y;
+      }
     }
     __syncthreads();
 #pragma unroll 1
