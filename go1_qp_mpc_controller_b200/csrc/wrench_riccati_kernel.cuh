@@ -176,19 +176,19 @@ struct WrcIter {
 #define WRP(i) do {} while (0)
 #endif
 
-// Shared-memory accesses of the iteration loop, by 32-bit shared address.  Volatile asm keeps them in program
-// order among themselves: every phase issues ALL its loads first (the compiler, left alone, re-derived the
-// addresses from %tid / %cluster_ctaid in every recursion step and interleaved loads with their uses, one exposed
-// 29-cycle latency each -- 430 cycles per step instead of ~90).  The loop uses nothing but these for shared
-// memory, so ordering against ordinary accesses is never in question.
+// Shared-memory accesses of the iteration loop, by 32-bit shared address computed once per call.  The compiler, left
+// alone at the 128-register cap, re-derived the addresses from %tid / %cluster_ctaid in every recursion step.  Every asm
+// carries a "memory" clobber: without one NVVM merges identical `asm volatile` loads (seen in scripts/micro/
+// lds_bench.cu) and may move loads across the loop's stores; the loop uses nothing but these for shared memory, so
+// ordering against ordinary accesses is never in question.  (Same speed with and without the clobber: 135 k solves/s.)
 __device__ __forceinline__ double2 wrc_ld2(uint32_t a) {
   double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
   return v;
 }
 __device__ __forceinline__ double wrc_ld(uint32_t a) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
   return v;
 }
 __device__ __forceinline__ void wrc_st(uint32_t a, double v) {
