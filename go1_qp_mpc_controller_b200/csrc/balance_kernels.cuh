@@ -396,4 +396,466 @@ balance_qp_kernel(const BalanceStateIn* __restrict__ states, int num, int* __res
  }  // next problem
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Second layout of the same QP: FOUR LANES PER PROBLEM, eight problems per warp.  The constraint rows of the
+// balance QP are leg-local (row i: fz_i; rows 4+4i .. 7+4i: +-fx_i - mu fz_i, +-fy_i - mu fz_i), so a lane that
+// owns a leg -- its three variables, its five rows, three rows of P and of -K^-1 -- does everything but the
+// 12-term dot products and the norms inside itself; those take the other legs' values by width-4 shuffles.
+// The one-warp-per-problem kernel above issues 243 warp instructions per ADMM iteration for ONE problem (12
+// to 20 of 32 lanes busy, a 64-bit shuffle pair per exchanged value); this one ~135 for EIGHT.  The eight
+// problems of a warp run in lockstep on one iteration counter (checks and rho updates fall on the same
+// iterations for everybody, so a refactorisation is one pass with the groups that need it active); a group that
+// has converged waits for the slowest of its warp -- with iteration counts from 25 to a few thousand around a
+// mean of 230 that costs about half of the lane-time, and still leaves a factor ~5 over the warp kernel.
+// Arithmetic is the warp kernel's, operation for operation (same products, same summation order inside the dot
+// products, same sweep); only the cross-variable sums of the cost normalisation are ordered differently.
+constexpr int kBalLegThreads = 128;
+constexpr int kBalLegCtasPerSm = 2;
+constexpr int kBalLegPStride = 146;  // doubles per problem in shared memory (144 + 2: groups on different banks)
+
+__device__ __forceinline__ double bshfl4(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 4); }
+__device__ __forceinline__ double bmax4(double v) {
+  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 1, 4));
+  return fmax(v, __shfl_xor_sync(0xffffffffu, v, 2, 4));
+}
+
+__global__ void __launch_bounds__(kBalLegThreads, kBalLegCtasPerSm)
+balance_qp_leg_kernel(const BalanceStateIn* __restrict__ states, int num, int* __restrict__ counter,
+                      float* __restrict__ P_out, float* __restrict__ q_out, float* __restrict__ l_out,
+                      float* __restrict__ u_out, MpcResult* __restrict__ results,
+                      const __grid_constant__ BalanceParams bp) {
+  extern __shared__ __align__(16) double bal_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane >> 2, lg = lane & 3;                 // problem of the warp, leg
+  double* const Ps = bal_smem + (warp * 8 + grp) * kBalLegPStride;   // P of this group's problem, 12 x 12
+  const double mu = bp.mu;
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, 8);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= num) break;  // warp-uniform
+    const int p = base + grp;
+    const bool valid = p < num;
+    const float* st = reinterpret_cast<const float*>(states + (valid ? p : num - 1));
+
+    // ---- build: root_acc, M = inertia_inv (6x12), P, q (A1RobotControl.cpp:379-406) ----
+    double R[9], Rz[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { R[k] = (double)st[kBRot + k]; Rz[k] = (double)st[kBRotZ + k]; }
+    double acc[6];
+    {
+      double ee[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ee[k] = (double)st[kBEulerD + k] - (double)st[kBEuler + k];
+      if (ee[2] > 3.1415926 * 1.5) ee[2] = (double)st[kBEulerD + 2] - 3.1415926 * 2 - (double)st[kBEuler + 2];
+      else if (ee[2] < -3.1415926 * 1.5) ee[2] = (double)st[kBEulerD + 2] + 3.1415926 * 2 - (double)st[kBEuler + 2];
+      double Rtv[3], Rtw[3], tmp[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        Rtv[k] = R[k] * (double)st[kBLinVel] + R[3 + k] * (double)st[kBLinVel + 1] + R[6 + k] * (double)st[kBLinVel + 2];
+        Rtw[k] = R[k] * (double)st[kBAngVel] + R[3 + k] * (double)st[kBAngVel + 1] + R[6 + k] * (double)st[kBAngVel + 2];
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) tmp[k] = bp.kd_lin[k] * ((double)st[kBLinVelD + k] - Rtv[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        acc[k] = bp.kp_lin[k] * ((double)st[kBPosD + k] - (double)st[kBPos + k]) +
+                 (R[3 * k] * tmp[0] + R[3 * k + 1] * tmp[1] + R[3 * k + 2] * tmp[2]);
+        acc[3 + k] = bp.kp_ang[k] * ee[k] + bp.kd_ang[k] * ((double)st[kBAngVelD + k] - Rtw[k]);
+      }
+      acc[2] += bp.mass * 9.8;
+    }
+    // bottom halves of the leg's three columns of M: column cj of Rz' * skew(foot) (the top halves are e_cj)
+    double mb[3][3];  // mb[cj][k] = M[3 + k][3 lg + cj]
+    {
+      const double fx = st[kBFoot + 3 * lg], fy = st[kBFoot + 3 * lg + 1], fz = st[kBFoot + 3 * lg + 2];
+      const double sk[9] = {0.0, -fz, fy, fz, 0.0, -fx, -fy, fx, 0.0};
+#pragma unroll
+      for (int cj = 0; cj < 3; ++cj)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double s = 0.0;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) s += Rz[3 * t + k] * sk[3 * t + cj];  // (Rz')[k][t] = Rz[t][k]
+          mb[cj][k] = s;
+        }
+    }
+    // rows 3 lg .. 3 lg + 2 of P:  P[j][b] = sum_k (m_j[k] Q_k) m_b[k] + R [b == j], k in the warp kernel's order
+    double Prow[3][12], q0[3];
+#pragma unroll
+    for (int lb = 0; lb < 4; ++lb)
+#pragma unroll
+      for (int cb = 0; cb < 3; ++cb) {
+        const double o0 = bshfl4(mb[cb][0], lb), o1 = bshfl4(mb[cb][1], lb), o2 = bshfl4(mb[cb][2], lb);
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) {
+          double s = (lb == lg && cb == cj) ? bp.R : 0.0;
+          // k = 0..2: m_j[k] = [k == cj], m_b[k] = [k == cb]; k = 3..5: bottom halves
+          if (cj == cb) s += (1.0 * bp.Q[cj]) * 1.0;
+          s += (mb[cj][0] * bp.Q[3]) * o0;
+          s += (mb[cj][1] * bp.Q[4]) * o1;
+          s += (mb[cj][2] * bp.Q[5]) * o2;
+          Prow[cj][3 * lb + cb] = s;
+        }
+      }
+#pragma unroll
+    for (int cj = 0; cj < 3; ++cj) {
+      double s = 0.0;
+      s += 1.0 * bp.Q[cj] * acc[cj];
+      s += mb[cj][0] * bp.Q[3] * acc[3];
+      s += mb[cj][1] * bp.Q[4] * acc[4];
+      s += mb[cj][2] * bp.Q[5] * acc[5];
+      q0[cj] = -s;
+    }
+    // bounds (:409-413, :33-47): row 0 = fz of the leg, rows 1..4 = +fx, -fx, +fy, -fy - mu fz in (-inf, 0]
+    const double cf = (st[kBContacts + lg] != 0.0f) ? 1.0 : 0.0;
+    double lb0 = cf * bp.F_min, ub0 = cf * bp.F_max;
+    if (valid) {
+      if (P_out != nullptr) {
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj)
+#pragma unroll
+          for (int b = 0; b < 12; ++b) P_out[size_t(p) * 144 + (3 * lg + cj) * 12 + b] = (float)Prow[cj][b];
+      }
+      if (q_out != nullptr) {
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) q_out[size_t(p) * 12 + 3 * lg + cj] = (float)q0[cj];
+      }
+      if (l_out != nullptr) {
+        l_out[size_t(p) * 20 + lg] = (float)lb0;
+        u_out[size_t(p) * 20 + lg] = (float)ub0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          l_out[size_t(p) * 20 + 4 + 4 * lg + t] = (float)(-MPC_INFTY);
+          u_out[size_t(p) * 20 + 4 + 4 * lg + t] = 0.0f;
+        }
+      }
+    }
+    // P to shared memory for the factorisations and the residual checks
+    __syncwarp();
+#pragma unroll
+    for (int cj = 0; cj < 3; ++cj)
+#pragma unroll
+      for (int b = 0; b < 12; ++b) Ps[(3 * lg + cj) * 12 + b] = Prow[cj][b];
+    __syncwarp();
+
+    // ---- Ruiz equilibration: D of the leg's variables, E of its rows (row 0, then +fx, -fx, +fy, -fy) ----
+    double D[3] = {1.0, 1.0, 1.0}, E[5] = {1.0, 1.0, 1.0, 1.0, 1.0}, c = 1.0;
+    auto p_row_norms = [&](double (&nrm)[3]) {
+      nrm[0] = nrm[1] = nrm[2] = 0.0;
+#pragma unroll
+      for (int lb = 0; lb < 4; ++lb)
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+          const double db = bshfl4(D[cb], lb);
+#pragma unroll
+          for (int cj = 0; cj < 3; ++cj) nrm[cj] = fmax(nrm[cj], fabs(Prow[cj][3 * lb + cb]) * db);
+        }
+    };
+    if (bp.scaling > 0) {
+      double nP[3];
+      p_row_norms(nP);
+      for (int it = 0; it < bp.scaling; ++it) {
+        double nA[3];
+        nA[0] = fmax(E[1], E[2]) * D[0];
+        nA[1] = fmax(E[3], E[4]) * D[1];
+        {
+          double m = fabs(1.0) * E[0];
+#pragma unroll
+          for (int t = 1; t < 5; ++t) m = fmax(m, fabs(-mu) * E[t]);
+          nA[2] = m * D[2];
+        }
+        double Dt[3], Et[5];
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) Dt[cj] = rsqrt(blimit(fmax(nP[cj], nA[cj])));
+        Et[0] = rsqrt(blimit(E[0] * fmax(0.0 * D[0], 1.0 * D[2])));
+        Et[1] = rsqrt(blimit(E[1] * fmax(1.0 * D[0], fabs(-mu) * D[2])));
+        Et[2] = rsqrt(blimit(E[2] * fmax(1.0 * D[0], fabs(-mu) * D[2])));
+        Et[3] = rsqrt(blimit(E[3] * fmax(1.0 * D[1], fabs(-mu) * D[2])));
+        Et[4] = rsqrt(blimit(E[4] * fmax(1.0 * D[1], fabs(-mu) * D[2])));
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) D[cj] *= Dt[cj];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) E[t] *= Et[t];
+        double nr[3], nP2[3];
+        p_row_norms(nr);
+        double part = 0.0, qn = 0.0;
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) {
+          nP2[cj] = c * D[cj] * nr[cj];
+          part += nP2[cj];
+          qn = fmax(qn, fabs(c * D[cj] * q0[cj]));
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 2, 4);
+        qn = bmax4(qn);
+        const double mean = part / 12.0;
+        const double ct = 1.0 / blimit(fmax(mean, blimit(qn)));
+        c *= ct;
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) nP[cj] = nP2[cj] * ct;
+      }
+    }
+    const double cinv = 1.0 / c;
+    double qb[3];
+#pragma unroll
+    for (int cj = 0; cj < 3; ++cj) qb[cj] = c * D[cj] * q0[cj];
+    // scaled bounds, constraint types, rho of the rows
+    lb0 *= E[0];
+    ub0 *= E[0];
+    const int ct0 = (lb0 < -MPC_INFTY * 1e-4 && ub0 > MPC_INFTY * 1e-4) ? -1 : ((ub0 - lb0 < 1e-4) ? 1 : 0);
+    int ctp = ct0 + 1;
+    double lbr[5], ubr[5];
+    lbr[0] = lb0; ubr[0] = ub0;
+#pragma unroll
+    for (int t = 1; t < 5; ++t) {
+      lbr[t] = -MPC_INFTY * E[t];
+      ubr[t] = 0.0 * E[t];
+      const int ctt = (lbr[t] < -MPC_INFTY * 1e-4 && ubr[t] > MPC_INFTY * 1e-4) ? -1 : ((ubr[t] - lbr[t] < 1e-4) ? 1 : 0);
+      ctp |= (ctt + 1) << (2 * t);
+    }
+    auto rho_row = [&](int t, double rh) {
+      const int ctt = ((ctp >> (2 * t)) & 3) - 1;
+      return (ctt == -1) ? 1e-6 : (ctt == 1) ? 1e3 * rh : rh;
+    };
+    double rho = bp.rho;
+    double rv[5], rinv[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) { rv[t] = rho_row(t, rho); rinv[t] = 1.0 / rv[t]; }
+    // scaled constraint coefficients: row t = ca[t] x_lat(t) + cz[t] x_fz,  lat(1, 2) = fx, lat(3, 4) = fy
+    double ca[5], cz[5];
+    ca[0] = E[0] * 0.0 * D[0];
+    cz[0] = E[0] * 1.0 * D[2];
+    ca[1] = E[1] * 1.0 * D[0];  cz[1] = E[1] * (-mu) * D[2];
+    ca[2] = E[2] * (-1.0) * D[0]; cz[2] = E[2] * (-mu) * D[2];
+    ca[3] = E[3] * 1.0 * D[1];  cz[3] = E[3] * (-mu) * D[2];
+    ca[4] = E[4] * (-1.0) * D[1]; cz[4] = E[4] * (-mu) * D[2];
+
+    double a[3][12];  // rows 3 lg .. 3 lg + 2 of -K^-1
+    auto factor = [&]() {
+      // K = c D P D + sigma I + A' diag(rho) A
+#pragma unroll
+      for (int lb = 0; lb < 4; ++lb)
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+          const double db = bshfl4(D[cb], lb);
+#pragma unroll
+          for (int cj = 0; cj < 3; ++cj) {
+            double v = c * D[cj] * Ps[(3 * lg + cj) * 12 + 3 * lb + cb] * db;
+            if (lb == lg && cb == cj) v += bp.sigma;
+            a[cj][3 * lb + cb] = v;
+          }
+        }
+      // A' rho A on the leg's own 3 x 3 block, rows in the warp kernel's order (fx: rows 1, 2; fy: 3, 4; fz: 0, 1, 2, 3, 4)
+#pragma unroll
+      for (int lb = 0; lb < 4; ++lb) {
+        if (lb == lg) {
+          // variable fx
+          {
+            const double w1 = rv[1] * ca[1], w2 = rv[2] * ca[2];
+            a[0][3 * lb + 0] += w1 * ca[1]; a[0][3 * lb + 2] += w1 * cz[1];
+            a[0][3 * lb + 0] += w2 * ca[2]; a[0][3 * lb + 2] += w2 * cz[2];
+          }
+          {
+            const double w3 = rv[3] * ca[3], w4 = rv[4] * ca[4];
+            a[1][3 * lb + 1] += w3 * ca[3]; a[1][3 * lb + 2] += w3 * cz[3];
+            a[1][3 * lb + 1] += w4 * ca[4]; a[1][3 * lb + 2] += w4 * cz[4];
+          }
+          {
+            const double w0 = rv[0] * cz[0];
+            a[2][3 * lb + 2] += w0 * cz[0];
+            const double w1 = rv[1] * cz[1], w2 = rv[2] * cz[2], w3 = rv[3] * cz[3], w4 = rv[4] * cz[4];
+            a[2][3 * lb + 0] += w1 * ca[1]; a[2][3 * lb + 2] += w1 * cz[1];
+            a[2][3 * lb + 0] += w2 * ca[2]; a[2][3 * lb + 2] += w2 * cz[2];
+            a[2][3 * lb + 1] += w3 * ca[3]; a[2][3 * lb + 2] += w3 * cz[3];
+            a[2][3 * lb + 1] += w4 * ca[4]; a[2][3 * lb + 2] += w4 * cz[4];
+          }
+        }
+      }
+      // symmetric sweep, 12 pivots; pivot row k lives in lane k / 3 of the group
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        double v[12];
+#pragma unroll
+        for (int b = 0; b < 12; ++b) v[b] = bshfl4(a[k % 3][b], k / 3);
+        const double d = v[k];
+        const double dinv = 1.0 / d;
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) {
+          const bool pivot_row = (k / 3 == lg) && (k % 3 == cj);
+          // v[3 lg + cj] without a dynamic index
+          double vr = 0.0;
+#pragma unroll
+          for (int lb = 0; lb < 4; ++lb)
+            if (lb == lg) vr = v[3 * lb + cj];
+          const double w = -vr * dinv;
+#pragma unroll
+          for (int b = 0; b < 12; ++b) {
+            const double vb = (b == k) ? (d - 1.0) : v[b];
+            const double upd = fma(w, vb, a[cj][b]);
+            const double prw = (b == k) ? -dinv : a[cj][b] * dinv;
+            a[cj][b] = pivot_row ? prw : upd;
+          }
+        }
+      }
+    };
+    factor();
+
+    // ---- ADMM, the eight problems of the warp in lockstep ----
+    double x[3] = {0.0, 0.0, 0.0}, z[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, y[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    int iter = 0;
+    bool done = !valid;
+    int status_out = MPC_STATUS_UNSOLVED, iter_out = 0, rho_updates = 0, rho_out = 0;
+    double pri_out = 0.0, xo[3] = {0.0, 0.0, 0.0};
+    const int chk = bp.check_termination > 0 ? bp.check_termination : 0x7fffffff;
+    const int adp = (bp.adaptive_rho && bp.adaptive_rho_interval > 0) ? bp.adaptive_rho_interval : 0x7fffffff;
+    int until_check = chk, until_adapt = adp;
+    for (;;) {
+      int run = until_check < until_adapt ? until_check : until_adapt;
+      run = run < bp.max_iter - iter ? run : bp.max_iter - iter;
+#pragma unroll 1
+      for (int qq = 0; qq < run; ++qq) {
+        // rhs = sigma x - q + A'(rho z - y), rows in the warp kernel's order
+        double w[5];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) w[t] = rv[t] * z[t] - y[t];
+        double rhs[3];
+        rhs[0] = fma(ca[2], w[2], fma(ca[1], w[1], bp.sigma * x[0] - qb[0]));
+        rhs[1] = fma(ca[4], w[4], fma(ca[3], w[3], bp.sigma * x[1] - qb[1]));
+        rhs[2] = fma(cz[4], w[4], fma(cz[3], w[3], fma(cz[2], w[2], fma(cz[1], w[1], fma(cz[0], w[0], bp.sigma * x[2] - qb[2])))));
+        double e0[3] = {0.0, 0.0, 0.0}, e1[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int lb = 0; lb < 4; ++lb) {
+          const double r0 = bshfl4(rhs[0], lb), r1 = bshfl4(rhs[1], lb), r2 = bshfl4(rhs[2], lb);
+          // b = 3 lb, 3 lb + 1, 3 lb + 2 go to the even / odd accumulator by the parity of b
+#pragma unroll
+          for (int cj = 0; cj < 3; ++cj) {
+            if ((3 * lb) % 2 == 0) {
+              e0[cj] = fma(a[cj][3 * lb], r0, e0[cj]);
+              e1[cj] = fma(a[cj][3 * lb + 1], r1, e1[cj]);
+              e0[cj] = fma(a[cj][3 * lb + 2], r2, e0[cj]);
+            } else {
+              e1[cj] = fma(a[cj][3 * lb], r0, e1[cj]);
+              e0[cj] = fma(a[cj][3 * lb + 1], r1, e0[cj]);
+              e1[cj] = fma(a[cj][3 * lb + 2], r2, e1[cj]);
+            }
+          }
+        }
+        double xt[3];
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) {
+          xt[cj] = -(e0[cj] + e1[cj]);
+          x[cj] = bp.alpha * xt[cj] + (1.0 - bp.alpha) * x[cj];
+        }
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+          const double xl = (t == 0) ? xt[0] : (t < 3 ? xt[0] : xt[1]);
+          const double zt = ca[t] * xl + cz[t] * xt[2];
+          const double zr = bp.alpha * zt + (1.0 - bp.alpha) * z[t];
+          double zn = zr + rinv[t] * y[t];
+          zn = (zn < lbr[t]) ? lbr[t] : zn;
+          zn = (zn > ubr[t]) ? ubr[t] : zn;
+          y[t] += rv[t] * (zr - zn);
+          z[t] = zn;
+        }
+      }
+      iter += run;
+      until_check -= run;
+      until_adapt -= run;
+      const bool can_check = until_check == 0, can_adapt = until_adapt == 0;
+      if (can_check) until_check = chk;
+      if (can_adapt) until_adapt = adp;
+      const bool last = iter == bp.max_iter;
+      // residuals
+      double m0 = 0.0, m1 = 0.0, m2 = 0.0, m4 = 0.0, m6 = 0.0, m7 = 0.0, m8 = 0.0, m9 = 0.0;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        const double xl = (t < 3) ? x[0] : x[1];
+        const double Ax = ca[t] * xl + cz[t] * x[2];
+        const double rp = Ax - z[t];
+        const double Einv = 1.0 / E[t];
+        m0 = fmax(m0, fabs(rp));
+        m1 = fmax(m1, fabs(Einv * rp));
+        m2 = fmax(m2, fmax(fabs(Einv * z[t]), fabs(Einv * Ax)));
+        m4 = fmax(m4, fmax(fabs(z[t]), fabs(Ax)));
+      }
+      {
+        double Px[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int lb = 0; lb < 4; ++lb)
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+            const double xd = bshfl4(D[cb] * x[cb], lb);
+#pragma unroll
+            for (int cj = 0; cj < 3; ++cj) Px[cj] = fma(Ps[(3 * lg + cj) * 12 + 3 * lb + cb], xd, Px[cj]);
+          }
+        double Aty[3];
+        Aty[0] = fma(ca[2], y[2], fma(ca[1], y[1], 0.0));
+        Aty[1] = fma(ca[4], y[4], fma(ca[3], y[3], 0.0));
+        Aty[2] = fma(cz[4], y[4], fma(cz[3], y[3], fma(cz[2], y[2], fma(cz[1], y[1], fma(cz[0], y[0], 0.0)))));
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) {
+          const double px = Px[cj] * (c * D[cj]);
+          const double rd = px + qb[cj] + Aty[cj];
+          const double Dinv = 1.0 / D[cj];
+          m6 = fmax(m6, fabs(rd));
+          m7 = fmax(m7, fabs(Dinv * rd));
+          m8 = fmax(m8, fmax(fmax(fabs(Dinv * qb[cj]), fabs(Dinv * Aty[cj])), fabs(Dinv * px)));
+          m9 = fmax(m9, fmax(fmax(fabs(qb[cj]), fabs(Aty[cj])), fabs(px)));
+        }
+      }
+      m0 = bmax4(m0); m1 = bmax4(m1); m2 = bmax4(m2); m4 = bmax4(m4);
+      m6 = bmax4(m6); m7 = bmax4(m7); m8 = bmax4(m8); m9 = bmax4(m9);
+      const double pri = m1, dua = cinv * m7;
+      const double eps_pri = bp.eps_abs + bp.eps_rel * m2;
+      const double eps_dua = bp.eps_abs + bp.eps_rel * cinv * m8;
+      bool refactor = false;
+      if (!done) {
+        bool fin = false;
+        int stt = MPC_STATUS_UNSOLVED;
+        if ((can_check || last) && pri < eps_pri && dua < eps_dua) { fin = true; stt = MPC_STATUS_SOLVED; }
+        else if (last) { fin = true; stt = (pri < 10.0 * eps_pri && dua < 10.0 * eps_dua) ? 2 : MPC_STATUS_MAX_ITER_REACHED; }
+        if (fin) {
+          done = true;
+          status_out = stt; iter_out = iter; rho_out = rho_updates; pri_out = pri;
+#pragma unroll
+          for (int cj = 0; cj < 3; ++cj) xo[cj] = D[cj] * x[cj];
+        } else if (can_adapt) {
+          const double pn = m0 / (m4 + 1e-10);
+          const double dn = m6 / (m9 + 1e-10);
+          double rho_new = rho * sqrt(pn / (dn + 1e-10));
+          rho_new = fmin(fmax(rho_new, 1e-6), 1e6);
+          if (rho_new > rho * bp.adaptive_rho_tolerance || rho_new < rho / bp.adaptive_rho_tolerance) {
+            rho = rho_new;
+#pragma unroll
+            for (int t = 0; t < 5; ++t) { rv[t] = rho_row(t, rho); rinv[t] = 1.0 / rv[t]; }
+            ++rho_updates;
+            refactor = true;
+          }
+        }
+      }
+      if (__all_sync(0xffffffffu, done)) break;
+      // one pass of the factorisation; groups that do not need it recompute the factors they have (bit-identical)
+      if (__any_sync(0xffffffffu, refactor)) factor();
+    }
+
+    // ---- rotate the leg's force to the body frame (:439-444), write ----
+    if (valid) {
+      const bool bad = isnan(xo[0]) || isnan(xo[1]) || isnan(xo[2]);
+#pragma unroll
+      for (int cj = 0; cj < 3; ++cj) {
+        const double g = R[cj] * xo[0] + R[3 + cj] * xo[1] + R[6 + cj] * xo[2];
+        results[p].grf[3 * lg + cj] = bad ? 0.0f : (float)g;
+      }
+      if (lg == 0) {
+        results[p].status = status_out;
+        results[p].iters = iter_out;
+        results[p].rho_updates = rho_out;
+        results[p].pri_res = (float)pri_out;
+      }
+    }
+  }  // next eight problems
+}
+
 }  // namespace mpcb200

@@ -1241,12 +1241,23 @@ int balance_solve(MpcEngine* e) {
   if (!e || e->kind != 1) return MPC_ERR_INVALID;
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->n > 0) {
-    const int warps_per_cta = kBalanceThreads / 32;
-    const int need = (e->n + warps_per_cta - 1) / warps_per_cta, full = e->num_sms * kBalanceCtasPerSm;
-    const int grid = need < full ? need : full;
     CUDA_TRY(e, cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
-    balance_qp_kernel<<<grid, kBalanceThreads, 0, e->stream>>>(e->d_bstates, e->n, e->d_counter, e->d_Pb, e->d_qb,
-                                                               e->d_l, e->d_u, e->d_results, e->bal);
+    static const bool warp_kernel = [] { const char* v = std::getenv("MPC_BALANCE_KERNEL"); return v && v[0] == 'w'; }();
+    if (warp_kernel) {
+      // one warp per problem (round 1's layout, kept as the second implementation: MPC_BALANCE_KERNEL=warp)
+      const int warps_per_cta = kBalanceThreads / 32;
+      const int need = (e->n + warps_per_cta - 1) / warps_per_cta, full = e->num_sms * kBalanceCtasPerSm;
+      const int grid = need < full ? need : full;
+      balance_qp_kernel<<<grid, kBalanceThreads, 0, e->stream>>>(e->d_bstates, e->n, e->d_counter, e->d_Pb, e->d_qb,
+                                                                 e->d_l, e->d_u, e->d_results, e->bal);
+    } else {
+      // four lanes per problem, 32 problems per CTA
+      const int per_cta = kBalLegThreads / 4;
+      const int need = (e->n + per_cta - 1) / per_cta, full = e->num_sms * kBalLegCtasPerSm;
+      const int grid = need < full ? need : full;
+      balance_qp_leg_kernel<<<grid, kBalLegThreads, per_cta * kBalLegPStride * sizeof(double), e->stream>>>(
+          e->d_bstates, e->n, e->d_counter, e->d_Pb, e->d_qb, e->d_l, e->d_u, e->d_results, e->bal);
+    }
     ++e->launches;
     CUDA_TRY(e, cudaGetLastError());
     if (e->torque_on) {
