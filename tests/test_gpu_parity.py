@@ -946,6 +946,38 @@ def test_config4_full_size_h30(pkg, ob):
     e.close()
 
 
+def test_balance_kernels_agree(pkg, ob, tmp_path):
+    """The two layouts of the stance-balance QP -- four lanes per problem (default) and one warp per problem
+    (MPC_BALANCE_KERNEL=warp, read once per process, hence the second process) -- carry the same arithmetic:
+    identical iteration counts and rho updates, forces equal to fp32 rounding of the last bits."""
+    import subprocess
+    import sys
+    n = 4096
+    bcfg = pkg.balance_config_default()
+    st = pkg.generate_balance_states(1005, 77, n)
+    be = pkg.MpcEngine(bcfg, 0, balance=True)
+    res = be.compute_grf_batch(st).copy()
+    be.close()
+    out = tmp_path / "warp.npy"
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import go1_qp_mpc_controller_b200 as pkg;"
+        "e = pkg.MpcEngine(pkg.balance_config_default(), 0, balance=True);"
+        "np.save(%r, e.compute_grf_batch(pkg.generate_balance_states(1005, 77, %d))); e.close()"
+        % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(out), n))
+    env = dict(os.environ, MPC_BALANCE_KERNEL="warp")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+    ref = np.load(out)
+    assert np.array_equal(res["status"], ref["status"])
+    assert np.array_equal(res["iters"], ref["iters"]) and np.array_equal(res["rho_updates"], ref["rho_updates"])
+    assert grf_rel(res["grf"], ref["grf"].astype(np.float64)).max() <= 1e-5
+    # ragged sizes: not a multiple of the eight problems of a warp, fewer than one warp
+    be = pkg.MpcEngine(bcfg, 0, balance=True)
+    for m in (1, 7, 9, 33, 1001):
+        r = be.compute_grf_batch(st[:m])
+        assert r.tobytes() == res[:m].tobytes(), m
+    be.close()
+
+
 def test_config5_full_size_balance(pkg, ob):
     """BASELINE configs[4] at its full size: 1 000 000 stance-balance QPs (on one GPU here; bench.py times
     the per-GPU share).  Status / iteration histogram on all of them, the oracle on a 1/1024 sample."""
