@@ -478,6 +478,8 @@ def run_ours(args):
         r = {"metric": "stance-balance QP solves/sec (12 var / 20 con)", "value": world * nb * reps / dt,
              "unit": "solves/s", "problems_per_gpu": nb, "ms_per_batch": 1e3 * dt / reps, "mean_iters": it,
              "max_iters": int(ob_["iters"].max()), "all_solved": bool((ob_["status"] == 1).all()),
+             "kernel": "balance_qp_leg_kernel (four lanes per problem, eight problems per warp)",
+             "host_buffers": "page-locked",
              "roofline": {"bound": "fp64-fma", "achieved": nb * reps * fl / dt / 1e12, "unit": "TFLOP/s",
                           "algorithmic_flops_per_solve": fl, "note": "host to host, per GPU"}}
         be.close()
