@@ -444,13 +444,37 @@ def run_ours(args):
             launches = (eng30.kernel_launches() - l0) // reps30
             eng30.close()
             return world * n30 * reps30 / dt, 1e3 * dt / reps30, out, launches
+        def warm30():
+            # the controller's streaming use at the long horizon: one persistent warm-started solver per robot
+            cfg30 = pkg.config_default()
+            cfg30.horizon = 30
+            eng30 = pkg.MpcEngine(cfg30, local_rank)
+            nw, ticks = 2048, 8
+            sts = [pkg.generate_stream_states(SEED, rank * nw, nw, 40 + t) for t in range(ticks)]
+            o = np.zeros(nw, dtype=pkg.abi.RESULT_DTYPE)
+            eng30.stream_reset()
+            eng30.stream_step(sts[0], o)
+            eng30.stream_step(sts[1], o)
+            barrier()
+            t0 = time.perf_counter()
+            its = 0.0
+            for t in range(2, ticks):
+                eng30.stream_step(sts[t], o)
+                its += float(o["iters"].mean())
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            ok = bool((o["status"] == 1).all())
+            eng30.close()
+            return {"value": world * nw * (ticks - 2) / dt, "unit": "robot-ticks/s", "robots_per_gpu": nw,
+                    "ms_per_tick": 1e3 * dt / (ticks - 2), "mean_iters": its / (ticks - 2), "all_solved": ok}
         v3, ms3, out30, l3 = run30(0, 3)      # default at H = 30: wrench_riccati_kernel (fused build + six-input Riccati ADMM)
         v1, ms1, out1, l1 = run30(1, 1)       # round 1's engine: dense build + riccati_solve_kernel
         return {"metric": "batched MPC QP solves/sec (H=30)", "value": v3, "unit": "solves/s", "states_per_gpu": n30,
                 "ms_per_batch": ms3, "kernel": "wrench_riccati_kernel<30>", "launches_per_batch": int(l3),
                 "mean_iters": float(out30["iters"].mean()), "all_solved": bool((out30["status"] == 1).all()),
                 "riccati_engine": {"value": v1, "ms_per_batch": ms1, "launches_per_batch": int(l1),
-                                   "same_iterations": bool(np.array_equal(out1["iters"], out30["iters"]))}}
+                                   "same_iterations": bool(np.array_equal(out1["iters"], out30["iters"]))},
+                "stream_warm": warm30()}
     extra("long_horizon_h30", x_h30)
 
     # ---------------- extra: BASELINE configs[4], stance-balance QP, 1 M problems over 8 GPUs ----------------
