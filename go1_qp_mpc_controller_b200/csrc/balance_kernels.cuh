@@ -419,6 +419,15 @@ __device__ __forceinline__ double bmax4(double v) {
   v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 1, 4));
   return fmax(v, __shfl_xor_sync(0xffffffffu, v, 2, 4));
 }
+// max of NON-NEGATIVE doubles through their bit patterns: a NaN compares above everything, so a bad state record
+// reaches the termination test (and fails it) instead of being dropped by fmax and reported as solved
+__device__ __forceinline__ double bmaxn(double a, double b) {
+  return (__double_as_longlong(a) > __double_as_longlong(b)) ? a : b;
+}
+__device__ __forceinline__ double bmaxn4(double v) {
+  v = bmaxn(v, __shfl_xor_sync(0xffffffffu, v, 1, 4));
+  return bmaxn(v, __shfl_xor_sync(0xffffffffu, v, 2, 4));
+}
 
 __global__ void __launch_bounds__(kBalLegThreads, kBalLegCtasPerSm)
 balance_qp_leg_kernel(const BalanceStateIn* __restrict__ states, int num, int* __restrict__ counter,
@@ -775,10 +784,10 @@ balance_qp_leg_kernel(const BalanceStateIn* __restrict__ states, int num, int* _
         const double Ax = ca[t] * xl + cz[t] * x[2];
         const double rp = Ax - z[t];
         const double Einv = 1.0 / E[t];
-        m0 = fmax(m0, fabs(rp));
-        m1 = fmax(m1, fabs(Einv * rp));
-        m2 = fmax(m2, fmax(fabs(Einv * z[t]), fabs(Einv * Ax)));
-        m4 = fmax(m4, fmax(fabs(z[t]), fabs(Ax)));
+        m0 = bmaxn(m0, fabs(rp));
+        m1 = bmaxn(m1, fabs(Einv * rp));
+        m2 = bmaxn(m2, bmaxn(fabs(Einv * z[t]), fabs(Einv * Ax)));
+        m4 = bmaxn(m4, bmaxn(fabs(z[t]), fabs(Ax)));
       }
       {
         double Px[3] = {0.0, 0.0, 0.0};
@@ -799,14 +808,14 @@ balance_qp_leg_kernel(const BalanceStateIn* __restrict__ states, int num, int* _
           const double px = Px[cj] * (c * D[cj]);
           const double rd = px + qb[cj] + Aty[cj];
           const double Dinv = 1.0 / D[cj];
-          m6 = fmax(m6, fabs(rd));
-          m7 = fmax(m7, fabs(Dinv * rd));
-          m8 = fmax(m8, fmax(fmax(fabs(Dinv * qb[cj]), fabs(Dinv * Aty[cj])), fabs(Dinv * px)));
-          m9 = fmax(m9, fmax(fmax(fabs(qb[cj]), fabs(Aty[cj])), fabs(px)));
+          m6 = bmaxn(m6, fabs(rd));
+          m7 = bmaxn(m7, fabs(Dinv * rd));
+          m8 = bmaxn(m8, bmaxn(bmaxn(fabs(Dinv * qb[cj]), fabs(Dinv * Aty[cj])), fabs(Dinv * px)));
+          m9 = bmaxn(m9, bmaxn(bmaxn(fabs(qb[cj]), fabs(Aty[cj])), fabs(px)));
         }
       }
-      m0 = bmax4(m0); m1 = bmax4(m1); m2 = bmax4(m2); m4 = bmax4(m4);
-      m6 = bmax4(m6); m7 = bmax4(m7); m8 = bmax4(m8); m9 = bmax4(m9);
+      m0 = bmaxn4(m0); m1 = bmaxn4(m1); m2 = bmaxn4(m2); m4 = bmaxn4(m4);
+      m6 = bmaxn4(m6); m7 = bmaxn4(m7); m8 = bmaxn4(m8); m9 = bmaxn4(m9);
       const double pri = m1, dua = cinv * m7;
       const double eps_pri = bp.eps_abs + bp.eps_rel * m2;
       const double eps_dua = bp.eps_abs + bp.eps_rel * cinv * m8;

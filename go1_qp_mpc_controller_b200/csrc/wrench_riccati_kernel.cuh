@@ -1304,6 +1304,9 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
         vo[6 * k + c] = w;
       }
       __syncwarp();
+      // (maxima of non-negative values through their bit patterns: a NaN -- a bad state record -- compares above
+      // everything and reaches the test below, where it fails every comparison; fmax would drop it and report
+      // the problem solved at the first check)
       double v[10];
 #pragma unroll
       for (int i = 0; i < 10; ++i) v[i] = 0.0;
@@ -1317,12 +1320,12 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
         for (int i = 0; i < 5; ++i) {
           const double Dn = (i < 2) ? D[0] : (i < 4) ? D[1] : D[2];
           const double rp = Ah[i] - z[i];
-          v[0] = fmax(v[0], fabs(cca[i] * rp));   // scaled primal residual
-          v[1] = fmax(v[1], Dn * fabs(rp));       // unscaled: E^-1 cca = D
-          v[2] = fmax(v[2], fabs(Dn * z[i]));
-          v[3] = fmax(v[3], fabs(Dn * Ah[i]));
-          v[4] = fmax(v[4], fabs(cca[i] * z[i]));
-          v[5] = fmax(v[5], fabs(cca[i] * Ah[i]));
+          v[0] = max_bits(v[0], fabs(cca[i] * rp));   // scaled primal residual
+          v[1] = max_bits(v[1], Dn * fabs(rp));       // unscaled: E^-1 cca = D
+          v[2] = max_bits(v[2], fabs(Dn * z[i]));
+          v[3] = max_bits(v[3], fabs(Dn * Ah[i]));
+          v[4] = max_bits(v[4], fabs(cca[i] * z[i]));
+          v[5] = max_bits(v[5], fabs(cca[i] * Ah[i]));
         }
         // P_ x = c D (R2 D x + G' w) ; A_' y
         const double* wv = &vo[6 * k];
@@ -1336,16 +1339,16 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
           const double Px = cs * D[q] * (r2v[q] * (D[q] * x[q]) + gtw);
           const double Dinv = 1.0 / D[q];
           const double rd = Px + qb[q] + Aty[q];
-          v[6] = fmax(v[6], fabs(rd));
-          v[7] = fmax(v[7], fabs(Dinv * rd));
-          v[8] = fmax(v[8], fmax(fmax(fabs(Dinv * qb[q]), fabs(Dinv * Aty[q])), fabs(Dinv * Px)));
-          v[9] = fmax(v[9], fmax(fmax(fabs(qb[q]), fabs(Aty[q])), fabs(Px)));
+          v[6] = max_bits(v[6], fabs(rd));
+          v[7] = max_bits(v[7], fabs(Dinv * rd));
+          v[8] = max_bits(v[8], max_bits(max_bits(fabs(Dinv * qb[q]), fabs(Dinv * Aty[q])), fabs(Dinv * Px)));
+          v[9] = max_bits(v[9], max_bits(max_bits(fabs(qb[q]), fabs(Aty[q])), fabs(Px)));
         }
       }
 #pragma unroll
       for (int i = 0; i < 10; ++i) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[i] = fmax(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
+        for (int o = 16; o > 0; o >>= 1) v[i] = max_bits(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
       }
       if (lane == 0) {
 #pragma unroll
@@ -1358,11 +1361,11 @@ wrench_riccati_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __
         for (int i = 0; i < 10; ++i) {
           double t = sm.red[i];
 #pragma unroll
-          for (int w = 1; w < kWrcWarps; ++w) t = fmax(t, sm.red[w * 16 + i]);
+          for (int w = 1; w < kWrcWarps; ++w) t = max_bits(t, sm.red[w * 16 + i]);
           mres[i] = t;
         }
         const double pri = mres[1], dua = cinv * mres[7];
-        const double eps_pri = sp.eps_abs + sp.eps_rel * fmax(mres[2], mres[3]);
+        const double eps_pri = sp.eps_abs + sp.eps_rel * max_bits(mres[2], mres[3]);
         const double eps_dua = sp.eps_abs + sp.eps_rel * cinv * mres[8];
         sm.scal[4] = pri;
         int done = 0, refactor = 0;

@@ -976,6 +976,16 @@ def test_balance_kernels_agree(pkg, ob, tmp_path):
         r = be.compute_grf_batch(st[:m])
         assert r.tobytes() == res[:m].tobytes(), m
     be.close()
+    # a bad record (NaN) is reported unsolved with zero force (A1RobotControl.cpp:441-443) and its seven
+    # warp-mates do not notice
+    be = pkg.MpcEngine(bcfg, 0, balance=True)
+    bad = st[:64].copy()
+    bad["pos"][5] = np.nan
+    r = be.compute_grf_batch(bad)
+    assert r["status"][5] != 1 and (r["grf"][5] == 0).all()
+    ok = np.arange(64) != 5
+    assert r[ok].tobytes() == res[:64][ok].tobytes()
+    be.close()
 
 
 def test_config5_full_size_balance(pkg, ob):
@@ -1040,12 +1050,14 @@ def test_mirror_compute_grf_keeps_one_warm_solver(pkg, ob):
     assert ctl.last_iters >= 100                                   # cold again
 
 
-def test_warm_slot_fault_containment_and_slot_reset(pkg, ob):
+@pytest.mark.parametrize("H", [10, 30])
+def test_warm_slot_fault_containment_and_slot_reset(pkg, ob, H):
     """One bad record (NaN) poisons only its own robot slot, and only for that tick: the kernel leaves the
     slot dead, so the robot's next tick is an initSolver; every other robot keeps its warm solver.
-    mpc_stream_reset_slots forgets chosen robots only."""
+    mpc_stream_reset_slots forgets chosen robots only.  Both fused kernels (H = 10 and H = 30)."""
     cfg = pkg.config_hardware()
-    N = 96
+    cfg.horizon = H
+    N = 96 if H == 10 else 40
     st = [pkg.generate_stream_states(1006, 0, N, 44 + t) for t in range(4)]
     ref = ob.mpc_stream(cfg, np.stack(st))
     e = pkg.MpcEngine(cfg, 0)
