@@ -876,6 +876,30 @@ def test_long_horizon_wrench_engine_extensions_and_refusals(pkg, ob):
     e.close()
 
 
+@pytest.mark.parametrize("H", [10, 30])
+def test_solver_settings_sweep(pkg, ob, H):
+    """The fused kernels follow the oracle under every OSQP setting the ABI exposes, not only the defaults: no
+    equilibration, fixed rho, loose tolerance, iteration limits that end mid-way (status 2 / -2), no relaxation,
+    other check / adaptation intervals, other initial rho, fewer Ruiz passes."""
+    cases = [dict(scaling=0), dict(adaptive_rho=0), dict(eps_abs=1e-3, eps_rel=1e-3), dict(max_iter=60),
+             dict(max_iter=110), dict(alpha=1.0), dict(check_termination=10, adaptive_rho_interval=20), dict(rho=1.0),
+             dict(scaling=3)]
+    st = pkg.generate_states(1004, 0, 64)
+    seen = set()
+    for kw in cases:
+        cfg = pkg.config_hardware()
+        cfg.horizon = H
+        for k, v in kw.items():
+            setattr(cfg.osqp, k, v)
+        e = pkg.MpcEngine(cfg, 0)
+        r = e.compute_grf_batch(st)
+        e.close()
+        ref = ob.mpc_compute_grf(cfg, st)
+        assert_same_iterates(r, ref, max_flipped=0.0, what=f"H={H} {kw}")
+        seen |= set(r["status"].tolist())
+    assert {1, 2, -2} <= seen          # the iteration limits really ended solves mid-way
+
+
 def test_long_horizon_dense_workspace_path(pkg, ob):
     """H = 30 through the dense K^-1-in-L2-workspace kernels (structured_solver = 2), kept as the
     independent second implementation of the long horizon."""
