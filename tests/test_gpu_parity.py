@@ -900,6 +900,22 @@ def test_solver_settings_sweep(pkg, ob, H):
     assert {1, 2, -2} <= seen          # the iteration limits really ended solves mid-way
 
 
+@pytest.mark.parametrize("H", [10, 30])
+def test_degenerate_foot_geometry(pkg, ob, H):
+    """All four feet at ONE point: the wrench map B6c has rank 3, the 6 x 6 matrices N_k of the wrench-space
+    kernels are singular (zero Cholesky pivots).  The fused kernels still produce the oracle's iterates."""
+    cfg = pkg.config_default()
+    cfg.horizon = H
+    st = pkg.generate_states(1004, 0, 32)
+    fp = st["foot_pos_abs"].reshape(-1, 4, 3).copy()
+    fp[:, :, :] = fp[:, :1, :]
+    st["foot_pos_abs"] = fp.reshape(st["foot_pos_abs"].shape)
+    e = pkg.MpcEngine(cfg, 0)
+    r = e.compute_grf_batch(st)
+    e.close()
+    assert_same_iterates(r, ob.mpc_compute_grf(cfg, st), max_flipped=0.0, what=f"degenerate feet, H={H}")
+
+
 def test_long_horizon_dense_workspace_path(pkg, ob):
     """H = 30 through the dense K^-1-in-L2-workspace kernels (structured_solver = 2), kept as the
     independent second implementation of the long horizon."""
