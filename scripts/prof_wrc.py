@@ -1,4 +1,12 @@
-"""Batches of H = 30 states through the long-horizon wrench-space engine: the ncu / WRC_PROF target."""
+"""Batches of H = 30 states through the long-horizon wrench-space engine: the ncu / WRC_PROF target.
+
+Phase cycle counts (clock64 per phase, thread 0 of a CTA, printed for the first two problems) need a profiling build of
+the library -- the same nvcc line as __graft_entry__.build() plus -DWRC_PROF:
+    nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -DWRC_PROF \
+         -o go1_qp_mpc_controller_b200/libmpc_b200.so go1_qp_mpc_controller_b200/csrc/mpc_engine.cu \
+         go1_qp_mpc_controller_b200/csrc/host_config.cpp -ccbin /usr/bin/g++
+(rebuild with __graft_entry__.build() afterwards; each probe costs ~500 cycles, see
+profiles/experiments/r02_wrench_riccati_tuning.md)."""
 import os
 import sys
 
