@@ -21,6 +21,7 @@
 #include "torque_map.cuh"
 #include "wrench_kernel.cuh"
 #include "wrench_riccati_kernel.cuh"
+#include "wrench_tile_kernel.cuh"
 
 using namespace mpcb200;
 
@@ -302,6 +303,11 @@ int launch_wrench(MpcEngine* e, int n, double* warm, bool with_torque) {
   }
   const int full = e->num_sms * kWrCtasPerSm;
   const int grid = n < full ? n : full;
+  static const bool tile = [] { const char* v = std::getenv("MPC_WRENCH_TILE"); return v && v[0] == '1'; }();
+  if (tile)
+    wrench_tile_kernel<kWrCtasPerSm><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
+        e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
+  else
   wrench_solve_kernel<kWrCtasPerSm><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
       e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);
   ++e->launches;
@@ -370,6 +376,7 @@ int create_common(int kind, int device, MpcEngine** out) {
   opt_in((const void*)wrench_riccati_kernel<30>, sizeof(WrcSmem<30>), "wrench_riccati_kernel<30> shared memory");
   opt_in((const void*)gen_solve_kernel<30>, sizeof(GenSolveSmem<30>), "gen_solve_kernel<30> shared memory");
   opt_in((const void*)wrench_solve_kernel<kWrCtasPerSm>, sizeof(WrenchSmem), "wrench_solve_kernel shared memory");
+  opt_in((const void*)wrench_tile_kernel<kWrCtasPerSm>, sizeof(WrenchSmem), "wrench_tile_kernel shared memory");
   if (crc != cudaSuccess) {
     std::string msg = std::string("engine setup (") + what + "): " + cudaGetErrorString(crc);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);

@@ -1,158 +1,21 @@
-// K0..K5 fused, H = 10: the whole compute_grf MPC branch (A1RobotControl.cpp:446-561) for one robot
-// state per CTA -- state record in, body-frame GRF (+ joint torques) out -- with NO Hessian in
-// memory.  One CTA of 128 threads per problem, four CTAs per SM, problems pulled from an atomic
-// counter.  Same OSQP 0.6.x iteration as admm_kernel.cuh (Ruiz equilibration, per-row rho, alpha
-// relaxation, checks every 25, rho adaptation every 50); what changes is the linear algebra.
-//
-// Structure used (checked against the dense formulation in scripts/proto_wrench.py and by
-// tests/test_gpu_parity.py: identical iteration counts, GRF within 1e-12 of the dense path's):
-//   B_d = Gam B6c with B6c = [I_w^-1 [r_leg]x ; I/m] (6 x 12) and Gam = dt J (13 x 6), so every input
-//   acts through the net wrench w_k = B6c u_k of its step:  B_qp = calA G,  G = blockdiag_k(B6c_k),
-//       P = B_qp' Q B_qp + R = G' S G + R2,    S = calA' Q calA  (60 x 60),   q = G' gam.
-//   A_c is nilpotent with two non-zeros per column of A_d^m Gam (ConvexMpc.cpp:110-130), which gives
-//       S_kl = alpha_kl D1 + beta_kl D2,  alpha_kl = (H - max(k,l)) dt^2,
-//       beta_kl = dt^4 sum_{i >= max(k,l)} kap_(i-k) kap_(i-l)   (kap_m = m; m + 1/2 when exact_discretization),
-//       D1 = diag(Q_6..Q_11),  D2 = blockdiag(Rz diag(Q_0..2) Rz', diag(Q_3..5)):
-//   two 10 x 10 tables and a 3 x 3 matrix stand for the Hessian.  With the scaling D, E, c of OSQP
-//       K = c D P D + sigma I + A_' rho A_ = G_' C G_ + Delta,   G_ = G D,  C = c S,
-//       Delta = c D R2 D + sigma I + A_' rho A_   block diagonal, 3 x 3 per leg-step,
-//   and with N_k = G_k Delta^-1 G_k' = L_k L_k' (6 x 6 Cholesky per step), G^ = L^-1 G_, M^ = G^ Delta^-1:
-//       K^-1 r = a - M^' Y' G^ a,   a = Delta^-1 r,   Y' = I - (I + L' C L)^-1          (Woodbury)
-//   -- per ADMM iteration one 60 x 60 mat-vec (Y' in registers, 30 doubles per thread) between two
-//   block-diagonal 6 x 12 products, per factorisation a 60 x 60 symmetric sweep of a matrix whose
-//   eigenvalues are >= 1 (no inverse of N or C is ever formed; a singular N_k -- collinear feet --
-//   zeroes a column of L_k and the formula stays valid).  0.40 of the dense path's flops per
-//   iteration, 1/8 per factorisation, 35 KB of shared memory instead of 222 KB.
-//
-// Thread roles (warp w, lane < 30 active, j = 30 w + lane):
-//   variable role   j = variable (leg-step g = j / 3, component j % 3, horizon step k = j / 12); owns
-//                   x_j and the constraint rows of "its" coefficient: fx -> rows 5g, 5g+1 (fx +- mu fz),
-//                   fy -> rows 5g+2, 5g+3, fz -> row 5g+4.  z, y of those rows live in its registers;
-//                   the three lanes of a leg-step exchange by shuffles.
-//   wrench role     j = 2 r + h: half h of row r of Y' (30 doubles), of G^ (6) and of the sweep.
+// Variant of wrench_kernel.cuh with a 2-D register tiling of the 60 x 60 core: thread (rp, q) of the tile role
+// holds rows 2 rp, 2 rp + 1 x columns 16 q .. 16 q + 15 of the swept matrix / of Y' (the matrix padded to 64 columns)
+// instead of half a row.  The mat-vec omega = Y' tau then needs 16 entries of tau per thread instead of 30, and a
+// sweep step 2 x 16 entries of the pivot rows instead of 2 x 30 -- the shared-memory pipe, charged per load
+// instruction by width, is the kernel's bound (profiles/r02_wrench_v1_ncu_summary.txt, scripts/micro/lds_bench.cu).
+// The four partial sums of a row meet by two shuffles.  Everything else is wrench_kernel.cuh's, line for line.
 #pragma once
 
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include "admm_kernel.cuh"
+#include "wrench_kernel.cuh"
 
 namespace mpcb200 {
-
-constexpr int kWrThreads = 128;
-constexpr int kWrWarps = kWrThreads / 32;
-#ifndef WR_CTAS_PER_SM
-#define WR_CTAS_PER_SM 4
-#endif
-constexpr int kWrCtasPerSm = WR_CTAS_PER_SM;  // resident CTAs per SM (128 registers at 4, 168 at 3)
-constexpr int kW6 = 6 * kH;  // wrench dimension
-
-struct WrenchSmem {
-  alignas(16) double B6[kH][6][12];   // B6c per step (identical unless foot_drift)
-  alignas(16) double Mr[kN][6];       // M^ by rows: slot 2r+h holds row r, columns 12 (r/6) + 6h .. +5
-  alignas(16) double Mh[kN][6];       // M^ by columns: slot j holds column j (first M1 = G_ Delta^-1 during a factorisation)
-  alignas(16) double L[kH][36];       // N_k, then its Cholesky factor (row-major, zeros above the diagonal)
-  double Linvd[kH][6];                // 1 / L_cc (0 for a zero pivot)
-  double al[kH * kH], be[kH * kH];    // alpha_kl, beta_kl
-  double Th[4];                       // Theta = Rz diag(Q0..2) Rz': 00, 01, 11, 22
-  double Qe[kH][14];                  // Q (A^(i+1) x0 - x_ref,i)
-  alignas(16) double gam[kW6 + 4];
-  alignas(16) double va[kWrThreads];  // rhs of the linear system   (variable order)
-  alignas(16) double vt[kW6 + 12];    // tau = G^ a = M^ rhs       (wrench order; the tile variant pads its four blocks to 18)
-  alignas(16) double vo[kW6 + 4];     // omega = Y' tau
-  alignas(16) double xD[kWrThreads];  // D x for the residual check
-  alignas(16) double Dp[kWrThreads];  // D
-  alignas(16) double prow[2][2][kW6 + 12];  // published pivot rows of the sweep (two per block), double buffered
-  double loA[kWrThreads], hiA[kWrThreads];  // normalised bounds of row A (row B is (-inf, 0] or absent)
-  double red[kWrWarps * 16];
-  double scal[16];                    // 0:c 1:1/c 2:rho 4:pri_res 6:rho 7:1000 rho 8:1/rho 9:1/(1000 rho)
-  float st[48];
-  int contacts[4 * kH];
-  int flags[8];                       // 0:done 1:status 2:refactor 3:problem index
-};
-
-// the three lanes lb, lb+1, lb+2 of a leg-step
-struct Leg3 { double a, b, c; };
-__device__ __forceinline__ Leg3 leg3(double v, int lb) {
-  Leg3 r;
-  r.a = shfl(v, lb);
-  r.b = shfl(v, lb + 1);
-  r.c = shfl(v, lb + 2);
-  return r;
-}
-__device__ __forceinline__ double max_bits(double a, double b) {  // max of non-negative doubles on the integer ALU
-  return (__double_as_longlong(a) > __double_as_longlong(b)) ? a : b;
-}
-
-// max_i |(G' S G)_ij| D_i over all 120 rows i, for column j of horizon step kj, component comp:
-// (G' S G)_ij = top_i . v + [comp_i == comp] vbm,  v = alpha u1 + beta u2 (3-vector), per block row k.
-// Without foot_drift every step has the same B6c: the top rows of two legs (18 doubles) are loaded once
-// and the block rows are walked twice (legs 0-1, then 2-3) -- a quarter of the shared-memory loads of the
-// generic form (hoisting all 36 at once spills).  Same products, same maxima.
-template <bool kDrift>
-__device__ __forceinline__ double wr_colnorm_t(const WrenchSmem& sm, int kj, int comp, const double (&u1)[3],
-                                               const double (&u2)[3], double vb1, double vb2) {
-  double mx = 0.0;
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    // alpha and beta are all that depends on the block row: entry = alpha A_i + beta B_i with
-    // A_i = top_i . u1 + [.] vb1, B_i = top_i . u2 + [.] vb2 formed once per half (without foot_drift)
-    double A0[6], B0[6];
-    if (!kDrift) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double t0 = sm.B6[0][0][6 * half + i], t1 = sm.B6[0][1][6 * half + i], t2 = sm.B6[0][2][6 * half + i];
-        const bool same = (i % 3) == comp;   // (6 half + i) % 3 == i % 3
-        A0[i] = fma(t0, u1[0], fma(t1, u1[1], fma(t2, u1[2], same ? vb1 : 0.0)));
-        B0[i] = fma(t0, u2[0], fma(t1, u2[1], fma(t2, u2[2], same ? vb2 : 0.0)));
-      }
-    }
-#pragma unroll 2
-    for (int k = 0; k < kH; ++k) {
-      const double a = sm.al[kH * k + kj], b = sm.be[kH * k + kj];
-      const double2* dk = reinterpret_cast<const double2*>(&sm.Dp[12 * k + 6 * half]);
-      const double2 d01 = dk[0], d23 = dk[1], d45 = dk[2];
-      const double dd[6] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y};
-      if (kDrift) {
-        const double v0 = fma(b, u2[0], a * u1[0]), v1 = fma(b, u2[1], a * u1[1]), v2 = fma(b, u2[2], a * u1[2]);
-        const double vbm = fma(b, vb2, a * vb1);
-        double tp[3][6];
-#pragma unroll
-        for (int c3 = 0; c3 < 3; ++c3) {
-          const double2* t = reinterpret_cast<const double2*>(&sm.B6[k][c3][6 * half]);
-          const double2 q0 = t[0], q1 = t[1], q2 = t[2];
-          tp[c3][0] = q0.x; tp[c3][1] = q0.y; tp[c3][2] = q1.x; tp[c3][3] = q1.y; tp[c3][4] = q2.x; tp[c3][5] = q2.y;
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          double e = ((i % 3) == comp) ? vbm : 0.0;
-          e = fma(tp[0][i], v0, e);
-          e = fma(tp[1][i], v1, e);
-          e = fma(tp[2][i], v2, e);
-          mx = max_bits(mx, fabs(e) * dd[i]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const double e = fma(b, B0[i], a * A0[i]);
-          mx = max_bits(mx, fabs(e) * dd[i]);
-        }
-      }
-    }
-  }
-  return mx;
-}
-__device__ __forceinline__ double wr_colnorm(const WrenchSmem& sm, bool drift, int kj, int comp, const double (&u1)[3],
-                                             const double (&u2)[3], double vb1, double vb2) {
-  return drift ? wr_colnorm_t<true>(sm, kj, comp, u1, u2, vb1, vb2) : wr_colnorm_t<false>(sm, kj, comp, u1, u2, vb1, vb2);
-}
 
 // `warm` == nullptr: cold solves.  ONE instantiation serves both, so a fresh warm slot takes the cold
 // path instruction for instruction (bit-identical results: the all-four-stance states amplify even a
 // different FMA contraction of two template instances into the last float32 bits).
 template <int kCtas>
 __global__ void __launch_bounds__(kWrThreads, kCtas)
-wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __restrict__ gait,
+wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __restrict__ gait,
                     MpcResult* __restrict__ results, float* __restrict__ x_all, int num, int* __restrict__ counter,
                     double* __restrict__ warm, const MpcTorqueIn* __restrict__ tin, MpcTorqueOut* __restrict__ tout,
                     const __grid_constant__ BuildParams bp, const __grid_constant__ SolveParams sp) {
@@ -192,7 +55,16 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
     sm.be[tid] = (dt * dt) * (dt * dt) * s;
   }
 
-  double y[30];  // wrench role: half a row of the swept matrix / of Y'
+  // tile role: tid = 4 rp + q holds rows 2 rp, 2 rp + 1 x columns 16 q .. 16 q + 15 (columns 60 .. 63 are padding)
+  const bool tact = tid < 2 * kW6;            // 120 tile threads
+  const int trp = tact ? (tid >> 2) : 0, tq = tid & 3;
+  const int tr0 = 2 * trp;                    // first row of the tile
+  double y0[16], y1[16];
+  // Column blocks sit 18 doubles apart in shared memory (16 would put the four blocks of a row pair on the same banks:
+  // measured 651 M bank conflicts per launch); entry r of a 60-vector is at r + 2 (r / 16).
+  constexpr int kTS = 18;
+  auto tpad = [](int r_) { return r_ + 2 * (r_ >> 4); };
+  if (tid < 4) sm.vt[kTS * 3 + 12 + tid] = 0.0;   // padding entries of tau (the padding columns of Y' are zero, 0 * NaN is not)
 
   for (;;) {
     __syncthreads();
@@ -577,31 +449,36 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
             }
           }
         }
-        // I + W, W = L' C L, half a row per thread: W[r][6l + c] = sum_{c~ >= c} t[c~] L_l[c~][c],
+        // I + W, W = L' C L, the tile's 2 x 16 entries: W[r][6l + c] = sum_{c~ >= c} t[c~] L_l[c~][c],
         // t[c~] = c (alpha_kr,l p1[c~] + beta_kr,l p2[c~]),  p1 = D1 lam, p2 = D2 lam, lam = L_kr[:, rr]
+        __syncthreads();   // (the tile role reads L of steps other warps factored)
         {
-          const double* Lk = sm.L[kr];
-          double lam[6], p1[6], p2[6];
 #pragma unroll
-          for (int q = 0; q < 6; ++q) lam[q] = Lk[6 * q + rr];
-          p1[0] = bp.Qd[6] * lam[0]; p1[1] = bp.Qd[7] * lam[1]; p1[2] = bp.Qd[8] * lam[2];
-          p1[3] = bp.Qd[9] * lam[3]; p1[4] = bp.Qd[10] * lam[4]; p1[5] = bp.Qd[11] * lam[5];
-          p2[0] = th00 * lam[0] + th01 * lam[1]; p2[1] = th01 * lam[0] + th11 * lam[1]; p2[2] = th22 * lam[2];
-          p2[3] = bp.Qd[3] * lam[3]; p2[4] = bp.Qd[4] * lam[4]; p2[5] = bp.Qd[5] * lam[5];
+          for (int rw = 0; rw < 2; ++rw) {
+            const int rt = tr0 + rw, krt = rt / 6, rrt = rt - 6 * krt;
+            const double* Lk = sm.L[krt];
+            double lam[6], p1[6], p2[6];
 #pragma unroll
-          for (int bl = 0; bl < 5; ++bl) {
-            const int l = 5 * h + bl;
-            const double ca = c * sm.al[kH * kr + l], cb = c * sm.be[kH * kr + l];
-            double t[6];
+            for (int q = 0; q < 6; ++q) lam[q] = Lk[6 * q + rrt];
+            p1[0] = bp.Qd[6] * lam[0]; p1[1] = bp.Qd[7] * lam[1]; p1[2] = bp.Qd[8] * lam[2];
+            p1[3] = bp.Qd[9] * lam[3]; p1[4] = bp.Qd[10] * lam[4]; p1[5] = bp.Qd[11] * lam[5];
+            p2[0] = th00 * lam[0] + th01 * lam[1]; p2[1] = th01 * lam[0] + th11 * lam[1]; p2[2] = th22 * lam[2];
+            p2[3] = bp.Qd[3] * lam[3]; p2[4] = bp.Qd[4] * lam[4]; p2[5] = bp.Qd[5] * lam[5];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) t[q] = ca * p1[q] + cb * p2[q];
-            const double* Ll = sm.L[l];
+            for (int c16 = 0; c16 < 16; ++c16) {
+              const int col = 16 * tq + c16;
+              const bool real = col < kW6;
+              const int l = real ? col / 6 : 0, cc = real ? col - 6 * l : 0;
+              const double ca = c * sm.al[kH * krt + l], cb = c * sm.be[kH * krt + l];
+              const double* Ll = sm.L[l];
+              double sacc = (col == rt) ? 1.0 : 0.0;
 #pragma unroll
-            for (int cc = 0; cc < 6; ++cc) {
-              double s = (6 * l + cc == r) ? 1.0 : 0.0;
-#pragma unroll
-              for (int q = cc; q < 6; ++q) s = fma(t[q], Ll[6 * q + cc], s);
-              y[6 * bl + cc] = s;
+              for (int q = 0; q < 6; ++q) {
+                const double t = ca * p1[q] + cb * p2[q];
+                if (q >= cc) sacc = fma(t, Ll[6 * q + cc], sacc);
+              }
+              const double v = real ? sacc : 0.0;
+              if (rw == 0) y0[c16] = v; else y1[c16] = v;
             }
           }
         }
@@ -613,55 +490,71 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
         // the uniform update cancels catastrophically when the pivots are large -- after rho has adapted
         // to its 1e-6 floor they reach 1e6 and ten digits were lost there, enough to push all-four-stance
         // states past the GRF gate (profiles/experiments/r02_wrench_sweep_cancellation.md).
-        // Pivot indices are static (loop over halves, unrolled inside): no dynamic register index.
-        if (active && r < 2) {
+        // Pivot indices are static (loop over column blocks, unrolled inside): no dynamic register index.
+        // The pivot rows 2 pb, 2 pb + 1 are the tile rows of the four threads with rp == pb.
+        if (tact && trp == 0) {
 #pragma unroll
-          for (int cc = 0; cc < 30; ++cc) sm.prow[0][r][30 * h + cc] = y[cc];
+          for (int cc = 0; cc < 16; ++cc) { sm.prow[0][0][kTS * tq + cc] = y0[cc]; sm.prow[0][1][kTS * tq + cc] = y1[cc]; }
         }
         __syncthreads();
 #pragma unroll 1
-        for (int ph = 0; ph < 2; ++ph) {
+        for (int qs = 0; qs < 4; ++qs) {
 #pragma unroll
-          for (int pc = 0; pc < 30; pc += 2) {
-            const int pv = 30 * ph + pc;
-            const int buf = ((pc >> 1) + ph) & 1;  // block index 15 ph + pc / 2, parity
-            const double* r1 = sm.prow[buf][0];
-            const double* r2 = sm.prow[buf][1];
-            const double d1 = r1[pv], e12 = r1[pv + 1], d2 = r2[pv + 1];
-            const double idet = 1.0 / (d1 * d2 - e12 * e12);
-            const double m11 = d2 * idet, m12 = -e12 * idet, m22 = d1 * idet;
-            const double a1 = r1[rpin], a2 = r2[rpin];  // A_rp, A_r,p+1 by symmetry
-            const bool isrow1 = (r == pv), isrow2 = (r == pv + 1);
-            const bool isrow = isrow1 || isrow2;
-            const double g1 = isrow ? (isrow1 ? m11 : m12) : -(a1 * m11 + a2 * m12);
-            const double g2 = isrow ? (isrow1 ? m12 : m22) : -(a1 * m12 + a2 * m22);
-            const double2* v1p = reinterpret_cast<const double2*>(r1 + offTau);
-            const double2* v2p = reinterpret_cast<const double2*>(r2 + offTau);
-            if (isrow) {
+          for (int lc = 0; lc < 16; lc += 2) {
+            const int pv = 16 * qs + lc;
+            if (pv < kW6) {   // (uniform: the padding columns are never pivots)
+              const int pb = pv >> 1;
+              const int buf = pb & 1;
+              const double* r1 = sm.prow[buf][0];
+              const double* r2 = sm.prow[buf][1];
+              const int pvp = kTS * qs + lc;   // padded position of column pv
+              const double2 dA = *reinterpret_cast<const double2*>(r1 + pvp), dB = *reinterpret_cast<const double2*>(r2 + pvp);
+              const double d1 = dA.x, e12 = dA.y, d2 = dB.y;
+              const double idet = 1.0 / (d1 * d2 - e12 * e12);
+              const double m11 = d2 * idet, m12 = -e12 * idet, m22 = d1 * idet;
+              // A_r,p and A_r,p+1 of the tile's two rows, by symmetry from the pivot rows
+              const double2 aA = *reinterpret_cast<const double2*>(r1 + tpad(tr0)), aB = *reinterpret_cast<const double2*>(r2 + tpad(tr0));
+              const bool isrow = (trp == pb);
+              const double g10 = isrow ? m11 : -(aA.x * m11 + aB.x * m12);   // row tr0
+              const double g20 = isrow ? m12 : -(aA.x * m12 + aB.x * m22);
+              const double g11 = isrow ? m12 : -(aA.y * m11 + aB.y * m12);   // row tr0 + 1
+              const double g21 = isrow ? m22 : -(aA.y * m12 + aB.y * m22);
+              const double2* v1p = reinterpret_cast<const double2*>(r1 + kTS * tq);
+              const double2* v2p = reinterpret_cast<const double2*>(r2 + kTS * tq);
+              if (isrow) {
 #pragma unroll
-              for (int hh = 0; hh < 15; ++hh) {
-                const double2 v1 = v1p[hh], v2 = v2p[hh];
-                y[2 * hh] = fma(g2, v2.x, g1 * v1.x);
-                y[2 * hh + 1] = fma(g2, v2.y, g1 * v1.y);
+                for (int hh = 0; hh < 8; ++hh) {
+                  const double2 v1 = v1p[hh], v2 = v2p[hh];
+                  y0[2 * hh] = fma(g20, v2.x, g10 * v1.x);
+                  y0[2 * hh + 1] = fma(g20, v2.y, g10 * v1.y);
+                  y1[2 * hh] = fma(g21, v2.x, g11 * v1.x);
+                  y1[2 * hh + 1] = fma(g21, v2.y, g11 * v1.y);
+                }
+              } else {
+#pragma unroll
+                for (int hh = 0; hh < 8; ++hh) {
+                  const double2 v1 = v1p[hh], v2 = v2p[hh];
+                  y0[2 * hh] = fma(g20, v2.x, fma(g10, v1.x, y0[2 * hh]));
+                  y0[2 * hh + 1] = fma(g20, v2.y, fma(g10, v1.y, y0[2 * hh + 1]));
+                  y1[2 * hh] = fma(g21, v2.x, fma(g11, v1.x, y1[2 * hh]));
+                  y1[2 * hh + 1] = fma(g21, v2.y, fma(g11, v1.y, y1[2 * hh + 1]));
+                }
               }
-            } else {
-#pragma unroll
-              for (int hh = 0; hh < 15; ++hh) {
-                const double2 v1 = v1p[hh], v2 = v2p[hh];
-                y[2 * hh] = fma(g2, v2.x, fma(g1, v1.x, y[2 * hh]));
-                y[2 * hh + 1] = fma(g2, v2.y, fma(g1, v1.y, y[2 * hh + 1]));
+              if (tq == qs) {
+                // block columns written explicitly (see above); pivot rows: A_SS <- -M, diagonal stored plus one
+                y0[lc] = isrow ? (1.0 - m11) : -g10;
+                y0[lc + 1] = isrow ? -m12 : -g20;
+                y1[lc] = isrow ? -m12 : -g11;
+                y1[lc + 1] = isrow ? (1.0 - m22) : -g21;
               }
-            }
-            if (h == ph) {
-              y[pc] = isrow1 ? (1.0 - m11) : isrow2 ? -m12 : -g1;
-              y[pc + 1] = isrow1 ? -m12 : isrow2 ? (1.0 - m22) : -g2;
-            }
-            if (pv + 2 < kW6 && active && (r == pv + 2 || r == pv + 3)) {
-              double* nx = sm.prow[buf ^ 1][r - (pv + 2)];
+              if (pv + 2 < kW6 && tact && trp == pb + 1) {
+                double* n0 = sm.prow[buf ^ 1][0];
+                double* n1 = sm.prow[buf ^ 1][1];
 #pragma unroll
-              for (int cc = 0; cc < 30; ++cc) nx[30 * h + cc] = y[cc];
+                for (int cc = 0; cc < 16; ++cc) { n0[kTS * tq + cc] = y0[cc]; n1[kTS * tq + cc] = y1[cc]; }
+              }
+              __syncthreads();
             }
-            __syncthreads();
           }
         }
         rhs_own = publish_rhs();
@@ -685,24 +578,26 @@ wrench_solve_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __re
           s = fma(g2.x, a2.x, s); s2 = fma(g2.y, a2.y, s2);
           s += s2;
           s += shfl_xor(s, 1);
-          if (active && h == 0) sm.vt[rpin] = s;
+          if (active && h == 0) sm.vt[tpad(rpin)] = s;
           a_own = delta_inv(rhs_own);  // not needed before x~: overlaps the barrier
         }
         __syncthreads();
-        // omega = Y' tau
+        // omega = Y' tau: the tile's 2 x 16 products, the four column blocks of a row pair meet by two shuffles
         {
-          const double2* tp = reinterpret_cast<const double2*>(&sm.vt[offTau]);
-          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          const double2* tp = reinterpret_cast<const double2*>(&sm.vt[kTS * tq]);
+          double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
 #pragma unroll
-          for (int hh = 0; hh < 15; hh += 3) {
-            const double2 t0 = tp[hh], t1 = tp[hh + 1], t2 = tp[hh + 2];
-            s0 = fma(y[2 * hh], t0.x, s0); s0 = fma(y[2 * hh + 1], t0.y, s0);
-            s1 = fma(y[2 * hh + 2], t1.x, s1); s1 = fma(y[2 * hh + 3], t1.y, s1);
-            s2 = fma(y[2 * hh + 4], t2.x, s2); s2 = fma(y[2 * hh + 5], t2.y, s2);
+          for (int hh = 0; hh < 8; hh += 2) {
+            const double2 t0 = tp[hh], t1 = tp[hh + 1];
+            s0 = fma(y0[2 * hh], t0.x, s0); s0 = fma(y0[2 * hh + 1], t0.y, s0);
+            s1 = fma(y0[2 * hh + 2], t1.x, s1); s1 = fma(y0[2 * hh + 3], t1.y, s1);
+            u0 = fma(y1[2 * hh], t0.x, u0); u0 = fma(y1[2 * hh + 1], t0.y, u0);
+            u1 = fma(y1[2 * hh + 2], t1.x, u1); u1 = fma(y1[2 * hh + 3], t1.y, u1);
           }
-          double s = (s0 + s1) + s2;
-          s += shfl_xor(s, 1);
-          if (active && h == 0) sm.vo[rpin] = s;
+          double sa = s0 + s1, sb = u0 + u1;
+          sa += shfl_xor(sa, 1); sb += shfl_xor(sb, 1);
+          sa += shfl_xor(sa, 2); sb += shfl_xor(sb, 2);
+          if (tact && tq == 0) *reinterpret_cast<double2*>(&sm.vo[tr0]) = make_double2(sa, sb);
         }
         __syncthreads();
         // x~ = a - M^' omega ; x, z, y updates of the owned rows ; next rhs
