@@ -303,7 +303,8 @@ int launch_wrench(MpcEngine* e, int n, double* warm, bool with_torque) {
   }
   const int full = e->num_sms * kWrCtasPerSm;
   const int grid = n < full ? n : full;
-  static const bool tile = [] { const char* v = std::getenv("MPC_WRENCH_TILE"); return v && v[0] == '1'; }();
+  // the 2-D tiled core is the default; MPC_WRENCH_TILE=0 (read once per process) selects the half-row kernel
+  static const bool tile = [] { const char* v = std::getenv("MPC_WRENCH_TILE"); return !(v && v[0] == '0'); }();
   if (tile)
     wrench_tile_kernel<kWrCtasPerSm><<<grid, kWrThreads, sizeof(WrenchSmem), e->stream>>>(
         e->d_states, e->d_gait, e->d_results, e->d_x, n, e->d_counter, warm, tin, e->d_tout, e->bp, e->sp);

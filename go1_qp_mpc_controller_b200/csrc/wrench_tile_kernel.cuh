@@ -35,7 +35,6 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
   const bool kWarm = warm != nullptr;
   // element offsets used in every iteration
   const int offRowIn = 12 * kr + 6 * h;  // first rhs entry of this thread's half row
-  const int offTau = 30 * h;
   const int offOm = 6 * k;
   const int jpin = j, rpin = r;
   const double mu = sp.mu, sigma = sp.sigma, alpha = sp.alpha;

@@ -986,6 +986,36 @@ def test_config4_full_size_h30(pkg, ob):
     e.close()
 
 
+def test_wrench_kernels_agree(pkg, ob, tmp_path):
+    """The two register layouts of the H = 10 wrench-space kernel -- 2 x 16 tiles (default) and half rows
+    (MPC_WRENCH_TILE=0, read once per process, hence the second process) -- produce the same iteration counts and
+    rho updates on every state, cold and warm-started, and forces equal far inside the gate."""
+    import subprocess
+    import sys
+    n = 2048
+    cfg = pkg.config_default()
+    st = pkg.generate_states(1002, 300, n)
+    w = [pkg.generate_stream_states(1006, 0, 256, 44 + t) for t in range(3)]
+    e = pkg.MpcEngine(cfg, 0)
+    res = e.compute_grf_batch(st).copy()
+    warm = [e.stream_step(s).copy() for s in w]
+    e.close()
+    out = tmp_path / "half.npz"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import go1_qp_mpc_controller_b200 as pkg;"
+        "e = pkg.MpcEngine(pkg.config_default(), 0);"
+        "r = e.compute_grf_batch(pkg.generate_states(1002, 300, %d)).copy();"
+        "w = [e.stream_step(pkg.generate_stream_states(1006, 0, 256, 44 + t)).copy() for t in range(3)];"
+        "np.savez(%r, r=r, w0=w[0], w1=w[1], w2=w[2]); e.close()" % (root, n, str(out)))
+    subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, MPC_WRENCH_TILE="0"), timeout=600)
+    ref = np.load(out)
+    for a, b in [(res, ref["r"]), (warm[0], ref["w0"]), (warm[1], ref["w1"]), (warm[2], ref["w2"])]:
+        assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iters"], b["iters"])
+        assert np.array_equal(a["rho_updates"], b["rho_updates"])
+        assert grf_rel(a["grf"], b["grf"].astype(np.float64)).max() <= 1e-4
+
+
 def test_balance_kernels_agree(pkg, ob, tmp_path):
     """The two layouts of the stance-balance QP -- four lanes per problem (default) and one warp per problem
     (MPC_BALANCE_KERNEL=warp, read once per process, hence the second process) -- carry the same arithmetic:
