@@ -14,7 +14,7 @@ collective, one final gather).  One JSON line on rank 0:
   e2e        the same metric through the reference-facing C ABI call with HOST buffers
              (mpc_compute_grf_batch: H2D + fused build/solve + D2H inside the timed region; at N > 1
              also the gather of every rank's results into one host array on rank 0, every step)
-  roofline   the one kernel of the step (wrench_solve_kernel): algorithmic flops / CUDA-event
+  roofline   the one kernel of the step (wrench_tile_kernel): algorithmic flops / CUDA-event
              duration against this GPU's FP64 FMA rate measured in the same run
   cpu_baseline  the oracle (CPU port of the reference path) timed on the host cores
 
@@ -44,11 +44,12 @@ F_ITER = 33.0e3
 # FP64 FMA peak: measured live by mpc_measure_fp64_peak in every run; this constant (round 1,
 # scripts/fp64_bench.cu, profiles/r01_fp64_peak.txt) is only the fallback if the probe fails
 FP64_PEAK_TFLOPS = 34.1
-# dram__bytes_read.sum + dram__bytes_write.sum of wrench_solve_kernel per solve, from the committed
-# ncu --set full capture (profiles/r02_wrench_v1_ncu_summary.txt: 958.7 KB read + 695.0 KB written by
-# one launch of 4096 solves): the 192 B record in, the 64 B result and the 480 B primal solution out.
-# (Round 1's two-kernel path moved 126 KB per solve through HBM for the padded f64 Hessian.)
-NCU_DRAM_BYTES_PER_SOLVE = (958.72e3 + 695.04e3) / 4096
+# dram__bytes_read.sum + dram__bytes_write.sum of wrench_tile_kernel per solve, from the committed
+# ncu --set full capture (profiles/r02_wrench_tile_ncu_summary.txt: 1.010 MB read + 7.820 MB written by
+# one launch of 4096 solves): the 192 B record in, the 64 B result and the 480 B primal solution out, plus
+# the write-back of the kernel's local-memory (spill) lines.  (The half-row kernel: 959 KB + 695 KB,
+# profiles/r02_wrench_v1_ncu_summary.txt; round 1's two-kernel path moved 126 KB per solve for the f64 Hessian.)
+NCU_DRAM_BYTES_PER_SOLVE = (1009.92e3 + 7820.288e3) / 4096
 
 
 def measured_hbm_peak_gbs():
@@ -620,15 +621,15 @@ def run_ours(args):
                                 "result buffer to rank 0, then one D2H copy into one pinned host array, every step",
                                 "verified": gather_ok})},
             "gpu_launches": int(launches),
-            "kernels": {"wrench_solve_kernel_ms": solve_ms, "launches_per_step": launches / max(1, args.steps)},
+            "kernels": {"wrench_tile_kernel_ms": solve_ms, "launches_per_step": launches / max(1, args.steps)},
             "roofline": {"bound": "fp64-fma (compute/latency; neither hbm nor tensor, SURVEY.md 8d)",
-                         "kernel": "wrench_solve_kernel", "achieved": achieved, "peak": peak,
+                         "kernel": "wrench_tile_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": ("mpc_measure_fp64_peak on this GPU in this run (register-only DFMA kernel, all SMs)"
                                          if fp64_peak else "profiles/r01_fp64_peak.txt (live probe failed)"),
                          "peak_clocks": (peak_clocks if fp64_peak else None),
                          "traffic": traffic,
-                         "traffic_source": "ncu --set full, profiles/r02_wrench_v1_ncu_summary.txt (dram read + write of one "
+                         "traffic_source": "ncu --set full, profiles/r02_wrench_tile_ncu_summary.txt (dram read + write of one "
                                            "4096-solve launch), scaled to this launch's solves",
                          "hbm": {"achieved": traffic / (solve_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": traffic / (solve_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
