@@ -58,11 +58,11 @@ struct WrenchSmem {
   double Qe[kH][14];                  // Q (A^(i+1) x0 - x_ref,i)
   alignas(16) double gam[kW6 + 4];
   alignas(16) double va[kWrThreads];  // rhs of the linear system   (variable order)
-  alignas(16) double vt[kW6 + 12];    // tau = G^ a = M^ rhs       (wrench order; the tile variant pads its four blocks to 18)
+  alignas(16) double vt[kW6 + 20];    // tau = G^ a = M^ rhs       (wrench order; the tile variant pads its eight blocks to 10)
   alignas(16) double vo[kW6 + 4];     // omega = Y' tau
   alignas(16) double xD[kWrThreads];  // D x for the residual check
   alignas(16) double Dp[kWrThreads];  // D
-  alignas(16) double prow[2][2][kW6 + 12];  // published pivot rows of the sweep (two per block), double buffered
+  alignas(16) double prow[2][2][kW6 + 20];  // published pivot rows of the sweep (two per block), double buffered
   double loA[kWrThreads], hiA[kWrThreads];  // normalised bounds of row A (row B is (-inf, 0] or absent)
   double red[kWrWarps * 16];
   double scal[16];                    // 0:c 1:1/c 2:rho 4:pri_res 6:rho 7:1000 rho 8:1/rho 9:1/(1000 rho)

@@ -1,9 +1,10 @@
-// Variant of wrench_kernel.cuh with a 2-D register tiling of the 60 x 60 core: thread (rp, q) of the tile role
-// holds rows 2 rp, 2 rp + 1 x columns 16 q .. 16 q + 15 of the swept matrix / of Y' (the matrix padded to 64 columns)
-// instead of half a row.  The mat-vec omega = Y' tau then needs 16 entries of tau per thread instead of 30, and a
-// sweep step 2 x 16 entries of the pivot rows instead of 2 x 30 -- the shared-memory pipe, charged per load
+// Variant of wrench_kernel.cuh with a 2-D register tiling of the 60 x 60 core: thread (rq, q) of the tile role
+// holds rows 4 rq .. 4 rq + 3 x columns 8 q .. 8 q + 7 of the swept matrix / of Y' (the matrix padded to 64 columns)
+// instead of half a row.  The mat-vec omega = Y' tau then needs 8 entries of tau per thread instead of 30, and a
+// sweep step 2 x 8 entries of the pivot rows instead of 2 x 30 -- the shared-memory pipe, charged per load
 // instruction by width, is the kernel's bound (profiles/r02_wrench_v1_ncu_summary.txt, scripts/micro/lds_bench.cu).
-// The four partial sums of a row meet by two shuffles.  Everything else is wrench_kernel.cuh's, line for line.
+// The eight partial sums of a row quad meet by a transposed reduction (four shuffles for four rows).  Everything
+// else is wrench_kernel.cuh's, line for line.
 #pragma once
 
 #include "wrench_kernel.cuh"
@@ -54,16 +55,17 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
     sm.be[tid] = (dt * dt) * (dt * dt) * s;
   }
 
-  // tile role: tid = 4 rp + q holds rows 2 rp, 2 rp + 1 x columns 16 q .. 16 q + 15 (columns 60 .. 63 are padding)
+  // tile role: tid = 8 rq + q holds rows 4 rq .. 4 rq + 3 x columns 8 q .. 8 q + 7 (columns 60 .. 63 are padding)
   const bool tact = tid < 2 * kW6;            // 120 tile threads
-  const int trp = tact ? (tid >> 2) : 0, tq = tid & 3;
-  const int tr0 = 2 * trp;                    // first row of the tile
-  double y0[16], y1[16];
-  // Column blocks sit 18 doubles apart in shared memory (16 would put the four blocks of a row pair on the same banks:
-  // measured 651 M bank conflicts per launch); entry r of a 60-vector is at r + 2 (r / 16).
-  constexpr int kTS = 18;
-  auto tpad = [](int r_) { return r_ + 2 * (r_ >> 4); };
-  if (tid < 4) sm.vt[kTS * 3 + 12 + tid] = 0.0;   // padding entries of tau (the padding columns of Y' are zero, 0 * NaN is not)
+  const int trp = tact ? (tid >> 3) : 0, tq = tid & 7;
+  const int tr0 = 4 * trp;                    // first row of the tile
+  double y[4][8];
+  // Column blocks sit 10 doubles apart in shared memory (8 apart, the blocks 0, 2, 4, 6 of a quarter-warp's 16-byte loads
+  // share banks; 10 x 8 = 80 bytes walks all eight 16-byte slots of a 128-byte line); entry r of a 60-vector is at
+  // r + 2 (r / 8).
+  constexpr int kTS = 10;
+  auto tpad = [](int r_) { return r_ + 2 * (r_ >> 3); };
+  if (tid < 4) sm.vt[kTS * 7 + 4 + tid] = 0.0;   // padding entries of tau (the padding columns of Y' are zero, 0 * NaN is not)
 
   for (;;) {
     __syncthreads();
@@ -448,12 +450,12 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
             }
           }
         }
-        // I + W, W = L' C L, the tile's 2 x 16 entries: W[r][6l + c] = sum_{c~ >= c} t[c~] L_l[c~][c],
+        // I + W, W = L' C L, the tile's 4 x 8 entries: W[r][6l + c] = sum_{c~ >= c} t[c~] L_l[c~][c],
         // t[c~] = c (alpha_kr,l p1[c~] + beta_kr,l p2[c~]),  p1 = D1 lam, p2 = D2 lam, lam = L_kr[:, rr]
         __syncthreads();   // (the tile role reads L of steps other warps factored)
         {
 #pragma unroll
-          for (int rw = 0; rw < 2; ++rw) {
+          for (int rw = 0; rw < 4; ++rw) {
             const int rt = tr0 + rw, krt = rt / 6, rrt = rt - 6 * krt;
             const double* Lk = sm.L[krt];
             double lam[6], p1[6], p2[6];
@@ -464,8 +466,8 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
             p2[0] = th00 * lam[0] + th01 * lam[1]; p2[1] = th01 * lam[0] + th11 * lam[1]; p2[2] = th22 * lam[2];
             p2[3] = bp.Qd[3] * lam[3]; p2[4] = bp.Qd[4] * lam[4]; p2[5] = bp.Qd[5] * lam[5];
 #pragma unroll
-            for (int c16 = 0; c16 < 16; ++c16) {
-              const int col = 16 * tq + c16;
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const int col = 8 * tq + c8;
               const bool real = col < kW6;
               const int l = real ? col / 6 : 0, cc = real ? col - 6 * l : 0;
               const double ca = c * sm.al[kH * krt + l], cb = c * sm.be[kH * krt + l];
@@ -476,8 +478,7 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
                 const double t = ca * p1[q] + cb * p2[q];
                 if (q >= cc) sacc = fma(t, Ll[6 * q + cc], sacc);
               }
-              const double v = real ? sacc : 0.0;
-              if (rw == 0) y0[c16] = v; else y1[c16] = v;
+              y[rw][c8] = real ? sacc : 0.0;
             }
           }
         }
@@ -490,19 +491,20 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
         // to its 1e-6 floor they reach 1e6 and ten digits were lost there, enough to push all-four-stance
         // states past the GRF gate (profiles/experiments/r02_wrench_sweep_cancellation.md).
         // Pivot indices are static (loop over column blocks, unrolled inside): no dynamic register index.
-        // The pivot rows 2 pb, 2 pb + 1 are the tile rows of the four threads with rp == pb.
+        // The pivot rows 2 pb, 2 pb + 1 are the rows 2 s, 2 s + 1 (s = pb & 1, static) of the eight tiles with rq == pb / 2.
         if (tact && trp == 0) {
 #pragma unroll
-          for (int cc = 0; cc < 16; ++cc) { sm.prow[0][0][kTS * tq + cc] = y0[cc]; sm.prow[0][1][kTS * tq + cc] = y1[cc]; }
+          for (int cc = 0; cc < 8; ++cc) { sm.prow[0][0][kTS * tq + cc] = y[0][cc]; sm.prow[0][1][kTS * tq + cc] = y[1][cc]; }
         }
         __syncthreads();
 #pragma unroll 1
-        for (int qs = 0; qs < 4; ++qs) {
+        for (int qs = 0; qs < 8; ++qs) {
 #pragma unroll
-          for (int lc = 0; lc < 16; lc += 2) {
-            const int pv = 16 * qs + lc;
+          for (int lc = 0; lc < 8; lc += 2) {
+            const int pv = 8 * qs + lc;
             if (pv < kW6) {   // (uniform: the padding columns are never pivots)
               const int pb = pv >> 1;
+              const int sp_ = (lc >> 1) & 1;           // pb & 1: which row pair of the tile holds the pivot rows
               const int buf = pb & 1;
               const double* r1 = sm.prow[buf][0];
               const double* r2 = sm.prow[buf][1];
@@ -511,46 +513,67 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
               const double d1 = dA.x, e12 = dA.y, d2 = dB.y;
               const double idet = 1.0 / (d1 * d2 - e12 * e12);
               const double m11 = d2 * idet, m12 = -e12 * idet, m22 = d1 * idet;
-              // A_r,p and A_r,p+1 of the tile's two rows, by symmetry from the pivot rows
-              const double2 aA = *reinterpret_cast<const double2*>(r1 + tpad(tr0)), aB = *reinterpret_cast<const double2*>(r2 + tpad(tr0));
-              const bool isrow = (trp == pb);
-              const double g10 = isrow ? m11 : -(aA.x * m11 + aB.x * m12);   // row tr0
-              const double g20 = isrow ? m12 : -(aA.x * m12 + aB.x * m22);
-              const double g11 = isrow ? m12 : -(aA.y * m11 + aB.y * m12);   // row tr0 + 1
-              const double g21 = isrow ? m22 : -(aA.y * m12 + aB.y * m22);
+              // A_r,p and A_r,p+1 of the tile's four rows, by symmetry from the pivot rows
+              const double2* aAp = reinterpret_cast<const double2*>(r1 + tpad(tr0));
+              const double2* aBp = reinterpret_cast<const double2*>(r2 + tpad(tr0));
+              const double2 aA0 = aAp[0], aA1 = aAp[1], aB0 = aBp[0], aB1 = aBp[1];
+              const double a1[4] = {aA0.x, aA0.y, aA1.x, aA1.y}, a2[4] = {aB0.x, aB0.y, aB1.x, aB1.y};
+              const bool inblk = (trp == (pb >> 1));
+              double g1[4], g2[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const bool prow_i = inblk && ((i >> 1) == sp_);
+                const double p1v = (i & 1) ? m12 : m11, p2v = (i & 1) ? m22 : m12;
+                g1[i] = prow_i ? p1v : -(a1[i] * m11 + a2[i] * m12);
+                g2[i] = prow_i ? p2v : -(a1[i] * m12 + a2[i] * m22);
+              }
               const double2* v1p = reinterpret_cast<const double2*>(r1 + kTS * tq);
               const double2* v2p = reinterpret_cast<const double2*>(r2 + kTS * tq);
-              if (isrow) {
+              if (inblk) {
 #pragma unroll
-                for (int hh = 0; hh < 8; ++hh) {
+                for (int hh = 0; hh < 4; ++hh) {
                   const double2 v1 = v1p[hh], v2 = v2p[hh];
-                  y0[2 * hh] = fma(g20, v2.x, g10 * v1.x);
-                  y0[2 * hh + 1] = fma(g20, v2.y, g10 * v1.y);
-                  y1[2 * hh] = fma(g21, v2.x, g11 * v1.x);
-                  y1[2 * hh + 1] = fma(g21, v2.y, g11 * v1.y);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    if ((i >> 1) == sp_) {
+                      y[i][2 * hh] = fma(g2[i], v2.x, g1[i] * v1.x);
+                      y[i][2 * hh + 1] = fma(g2[i], v2.y, g1[i] * v1.y);
+                    } else {
+                      y[i][2 * hh] = fma(g2[i], v2.x, fma(g1[i], v1.x, y[i][2 * hh]));
+                      y[i][2 * hh + 1] = fma(g2[i], v2.y, fma(g1[i], v1.y, y[i][2 * hh + 1]));
+                    }
+                  }
                 }
               } else {
 #pragma unroll
-                for (int hh = 0; hh < 8; ++hh) {
+                for (int hh = 0; hh < 4; ++hh) {
                   const double2 v1 = v1p[hh], v2 = v2p[hh];
-                  y0[2 * hh] = fma(g20, v2.x, fma(g10, v1.x, y0[2 * hh]));
-                  y0[2 * hh + 1] = fma(g20, v2.y, fma(g10, v1.y, y0[2 * hh + 1]));
-                  y1[2 * hh] = fma(g21, v2.x, fma(g11, v1.x, y1[2 * hh]));
-                  y1[2 * hh + 1] = fma(g21, v2.y, fma(g11, v1.y, y1[2 * hh + 1]));
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    y[i][2 * hh] = fma(g2[i], v2.x, fma(g1[i], v1.x, y[i][2 * hh]));
+                    y[i][2 * hh + 1] = fma(g2[i], v2.y, fma(g1[i], v1.y, y[i][2 * hh + 1]));
+                  }
                 }
               }
               if (tq == qs) {
                 // block columns written explicitly (see above); pivot rows: A_SS <- -M, diagonal stored plus one
-                y0[lc] = isrow ? (1.0 - m11) : -g10;
-                y0[lc + 1] = isrow ? -m12 : -g20;
-                y1[lc] = isrow ? -m12 : -g11;
-                y1[lc + 1] = isrow ? (1.0 - m22) : -g21;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const bool prow_i = inblk && ((i >> 1) == sp_);
+                  const double pa = (i & 1) ? -m12 : (1.0 - m11), pb2 = (i & 1) ? (1.0 - m22) : -m12;
+                  y[i][lc] = prow_i ? pa : -g1[i];
+                  y[i][lc + 1] = prow_i ? pb2 : -g2[i];
+                }
               }
-              if (pv + 2 < kW6 && tact && trp == pb + 1) {
+              if (pv + 2 < kW6 && tact && trp == ((pb + 1) >> 1)) {
                 double* n0 = sm.prow[buf ^ 1][0];
                 double* n1 = sm.prow[buf ^ 1][1];
+                const int sn = sp_ ^ 1;             // (pb + 1) & 1
 #pragma unroll
-                for (int cc = 0; cc < 16; ++cc) { n0[kTS * tq + cc] = y0[cc]; n1[kTS * tq + cc] = y1[cc]; }
+                for (int cc = 0; cc < 8; ++cc) {
+                  n0[kTS * tq + cc] = sn ? y[2][cc] : y[0][cc];
+                  n1[kTS * tq + cc] = sn ? y[3][cc] : y[1][cc];
+                }
               }
               __syncthreads();
             }
@@ -581,22 +604,26 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
           a_own = delta_inv(rhs_own);  // not needed before x~: overlaps the barrier
         }
         __syncthreads();
-        // omega = Y' tau: the tile's 2 x 16 products, the four column blocks of a row pair meet by two shuffles
+        // omega = Y' tau: the tile's 4 x 8 products; the eight column blocks of a row quad meet by a transposed
+        // reduction (each stage halves the rows a lane carries): lane q ends with row 2 (q & 1) + ((q >> 1) & 1)
         {
           const double2* tp = reinterpret_cast<const double2*>(&sm.vt[kTS * tq]);
-          double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
+          const double2 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
+          double acc[4];
 #pragma unroll
-          for (int hh = 0; hh < 8; hh += 2) {
-            const double2 t0 = tp[hh], t1 = tp[hh + 1];
-            s0 = fma(y0[2 * hh], t0.x, s0); s0 = fma(y0[2 * hh + 1], t0.y, s0);
-            s1 = fma(y0[2 * hh + 2], t1.x, s1); s1 = fma(y0[2 * hh + 3], t1.y, s1);
-            u0 = fma(y1[2 * hh], t0.x, u0); u0 = fma(y1[2 * hh + 1], t0.y, u0);
-            u1 = fma(y1[2 * hh + 2], t1.x, u1); u1 = fma(y1[2 * hh + 3], t1.y, u1);
+          for (int i = 0; i < 4; ++i) {
+            double sA = y[i][0] * t0.x, sB = y[i][4] * t2.x;
+            sA = fma(y[i][1], t0.y, sA); sB = fma(y[i][5], t2.y, sB);
+            sA = fma(y[i][2], t1.x, sA); sB = fma(y[i][6], t3.x, sB);
+            sA = fma(y[i][3], t1.y, sA); sB = fma(y[i][7], t3.y, sB);
+            acc[i] = sA + sB;
           }
-          double sa = s0 + s1, sb = u0 + u1;
-          sa += shfl_xor(sa, 1); sb += shfl_xor(sb, 1);
-          sa += shfl_xor(sa, 2); sb += shfl_xor(sb, 2);
-          if (tact && tq == 0) *reinterpret_cast<double2*>(&sm.vo[tr0]) = make_double2(sa, sb);
+          const bool b0 = tq & 1, b1 = tq & 2;
+          const double ra = (b0 ? acc[2] : acc[0]) + shfl_xor(b0 ? acc[0] : acc[2], 1);
+          const double rb = (b0 ? acc[3] : acc[1]) + shfl_xor(b0 ? acc[1] : acc[3], 1);
+          double v = (b1 ? rb : ra) + shfl_xor(b1 ? ra : rb, 2);
+          v += shfl_xor(v, 4);
+          if (tact && tq < 4) sm.vo[tr0 + 2 * (tq & 1) + (tq >> 1)] = v;
         }
         __syncthreads();
         // x~ = a - M^' omega ; x, z, y updates of the owned rows ; next rhs
