@@ -51,7 +51,7 @@ struct WrenchSmem {
   alignas(16) double B6[kH][6][12];   // B6c per step (identical unless foot_drift)
   alignas(16) double Mr[kN][6];       // M^ by rows: slot 2r+h holds row r, columns 12 (r/6) + 6h .. +5
   alignas(16) double Mh[kN][6];       // M^ by columns: slot j holds column j (first M1 = G_ Delta^-1 during a factorisation)
-  alignas(16) double L[kH][36];       // N_k, then its Cholesky factor (row-major, zeros above the diagonal)
+  alignas(16) double L[kH][37];       // N_k, then its Cholesky factor (row-major 6 x 6, zeros above the diagonal; 37: the tile build reads eight steps at once)
   double Linvd[kH][6];                // 1 / L_cc (0 for a zero pivot)
   double al[kH * kH], be[kH * kH];    // alpha_kl, beta_kl
   double Th[4];                       // Theta = Rz diag(Q0..2) Rz': 00, 01, 11, 22

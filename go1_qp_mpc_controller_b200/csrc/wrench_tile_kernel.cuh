@@ -293,7 +293,8 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
     }
     const double c = c_run;
     if (tid == 0) { sm.scal[0] = c; sm.scal[1] = 1.0 / c; }
-    const double qb = c * D * q0;
+    double qb = c * D * q0;
+    asm volatile("" : "+d"(qb));   // opaque: otherwise the loop re-forms c D q0 from three spilled values every iteration
     lbA *= EA; ubA *= EA; lbB *= EB; ubB *= EB;
     // constraint types of the owned rows (auxil.c set_rho_vec): -1 loose, 1 equality, 0 inequality
     auto ctype_of = [](double lo, double hi) {
