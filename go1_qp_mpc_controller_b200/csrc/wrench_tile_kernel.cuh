@@ -601,7 +601,8 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
           s = fma(g2.x, a2.x, s); s2 = fma(g2.y, a2.y, s2);
           s += s2;
           s += shfl_xor(s, 1);
-          if (active && h == 0) sm.vt[tpad(rpin)] = s;
+          // (active lanes: j = tid - 2 warp, so r = j / 2 = tid / 2 - warp: cheap to re-form, the loop has no register for it)
+          if (active && h == 0) sm.vt[tpad((tid >> 1) - warp)] = s;
           a_own = delta_inv(rhs_own);  // not needed before x~: overlaps the barrier
         }
         __syncthreads();
@@ -624,7 +625,7 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
           const double rb = (b0 ? acc[3] : acc[1]) + shfl_xor(b0 ? acc[1] : acc[3], 1);
           double v = (b1 ? rb : ra) + shfl_xor(b1 ? ra : rb, 2);
           v += shfl_xor(v, 4);
-          if (tact && tq < 4) sm.vo[tr0 + 2 * (tq & 1) + (tq >> 1)] = v;
+          if (tact && tq < 4) sm.vo[(tid >> 1) + 2 * (tid & 1)] = v;   // = tr0 + 2 (q & 1) + (q >> 1) for q < 4
         }
         __syncthreads();
         // x~ = a - M^' omega ; x, z, y updates of the owned rows ; next rhs
