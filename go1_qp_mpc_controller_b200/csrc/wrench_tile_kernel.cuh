@@ -26,10 +26,14 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
   const int lane = tid & 31, warp = tid >> 5;
   const bool active = lane < 30;
   const int j = 30 * warp + (active ? lane : 0);  // idle lanes shadow lane 0 (never write)
-  const int g = j / 3, comp = j - 3 * g;          // leg-step, component (0 fx, 1 fy, 2 fz)
+  // first lane of the leg-step, 3 (lane / 3) (30 warp is a multiple of 3; lane * 11 >> 5 = lane / 3 below 32), and the
+  // component (0 fx, 1 fy, 2 fz): written so that the loop re-forms them in three instructions instead of
+  // re-reading a spilled j / 3
+  const int lb = active ? 3 * ((lane * 11) >> 5) : 0;
+  const int comp = active ? lane - lb : 0;
+  const int g = j / 3;                            // leg-step
   const int k = j / 12, jj = j - 12 * k;          // horizon step, index inside the step
   const int leg = jj / 3;
-  const int lb = active ? lane - comp : 0;        // first lane of the leg-step
   const int r = j >> 1, h = j & 1;                // wrench role: row, half
   const int kr = k, rr = r - 6 * k;               // r / 6 = j / 12: the row's step is the variable's step
   const bool zlane = comp == 2;
