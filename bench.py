@@ -45,11 +45,11 @@ F_ITER = 33.0e3
 # scripts/fp64_bench.cu, profiles/r01_fp64_peak.txt) is only the fallback if the probe fails
 FP64_PEAK_TFLOPS = 34.1
 # dram__bytes_read.sum + dram__bytes_write.sum of wrench_tile_kernel per solve, from the committed
-# ncu --set full capture (profiles/r02_wrench_tile_ncu_summary.txt: 1.010 MB read + 7.820 MB written by
+# ncu --set full capture (profiles/r02_wrench_tile_ncu_summary.txt: 0.920 MB read + 1.487 MB written by
 # one launch of 4096 solves): the 192 B record in, the 64 B result and the 480 B primal solution out, plus
-# the write-back of the kernel's local-memory (spill) lines.  (The half-row kernel: 959 KB + 695 KB,
-# profiles/r02_wrench_v1_ncu_summary.txt; round 1's two-kernel path moved 126 KB per solve for the f64 Hessian.)
-NCU_DRAM_BYTES_PER_SOLVE = (1009.92e3 + 7820.288e3) / 4096
+# whatever of the kernel's local-memory (spill) lines L2 wrote back -- between 0.7 and 7.8 MB per launch across
+# the round's captures.  (Round 1's two-kernel path moved 126 KB per solve for the f64 Hessian.)
+NCU_DRAM_BYTES_PER_SOLVE = (919.552e3 + 1486.848e3) / 4096
 
 
 def measured_hbm_peak_gbs():
