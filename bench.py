@@ -343,13 +343,23 @@ def run_ours(args):
             gather_out = torch.empty(world * BATCH * rsz, dtype=torch.uint8).pin_memory()
 
     def e2e_step(s):
-        eng.compute_grf_batch(pin_np[s * BATCH:(s + 1) * BATCH], out_np)
-        if world > 1:
+        if world == 1:
+            eng.compute_grf_batch(pin_np[s * BATCH:(s + 1) * BATCH], out_np)
+            return
+        # N > 1: everything of a step is ordered on the engine's stream and the host waits ONCE -- H2D of the host
+        # states (mpc_load_states), the solve, the NCCL gather straight from the engine's device result buffer, and the
+        # device-to-host copy: all ranks' records into one pinned array on rank 0, the own records elsewhere
+        with torch.cuda.stream(stream):
+            eng.load_states(pin_np[s * BATCH:(s + 1) * BATCH])
+            eng.build_qp(sync=False)
+            eng.solve(sync=False)
             view = torch.as_tensor(DevBuf(eng.results_device_ptr(), BATCH * rsz), device="cuda")
             dist.gather(view, gather_list, dst=0)
             if rank == 0:
-                gather_out.copy_(gather_dev, non_blocking=True)   # ONE device-to-host copy of all ranks' records
-                torch.cuda.current_stream().synchronize()
+                gather_out.copy_(gather_dev, non_blocking=True)
+            else:
+                pinned_out.copy_(view, non_blocking=True)
+        stream.synchronize()
 
     lat = []
     for s in range(args.warmup):
@@ -364,11 +374,13 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t_start)
     barrier()
     e2e_value = world * BATCH * args.steps / e2e_s
-    last_out = out_np.copy()  # results of the last timed batch: the CPU baseline checks parity on these
     gather_ok = None
     if world > 1 and rank == 0:
         full = gather_out.numpy().view(pkg.abi.RESULT_DTYPE)
-        gather_ok = bool(np.array_equal(full[:BATCH]["grf"], last_out["grf"]) and (full["status"] == 1).all())
+        out_np[:] = full[:BATCH]              # rank 0's own shard is the first chunk of the gathered array
+        own = eng.get_results()               # the same records read back from the engine: the gather moved them intact
+        gather_ok = bool(np.array_equal(full[:BATCH]["grf"], own["grf"]) and (full["status"] == 1).all())
+    last_out = out_np.copy()  # results of the last timed batch: the CPU baseline checks parity on these
 
     extras = {}
 
@@ -613,12 +625,13 @@ def run_ours(args):
                              "per solve), so there is nothing for the L2 to retain between steps",
                        "parallelism": f"shard{world}"},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": BATCH * rec,
-                    "d2h_bytes_per_step": BATCH * rsz * (1 + (world if world > 1 else 0)),
+                    "d2h_bytes_per_step": BATCH * rsz * world,   # rank 0 (N > 1: all ranks' records in one copy)
                     "p50_batch_ms": 1e3 * float(np.percentile(lat, 50)),
                     "p99_batch_ms": 1e3 * float(np.percentile(lat, 99)),
                     "gather": (None if world == 1 else
                                {"inside_timed_region": True, "how": "NCCL gather of the 64 B records from every engine's device "
-                                "result buffer to rank 0, then one D2H copy into one pinned host array, every step",
+                                "result buffer to rank 0, then one D2H copy into one pinned host array, every step; "
+                                "stream-ordered behind the solve, one host wait per step",
                                 "verified": gather_ok})},
             "gpu_launches": int(launches),
             "kernels": {"wrench_tile_kernel_ms": solve_ms, "launches_per_step": launches / max(1, args.steps)},

@@ -239,7 +239,7 @@ typedef struct MpcConfig {
   int32_t structured_solver;    /* how K x = r is solved inside the ADMM (same iterates up to rounding):
                                    0 automatic: the fused wrench-space kernels, build and solve in one launch,
                                      no Hessian in memory -- H = 10: 60 x 60 Woodbury core in registers
-                                     (wrench_tile_kernel.cuh, 2 x 16 tiles; wrench_kernel.cuh, half rows, with
+                                     (wrench_tile_kernel.cuh, 4 x 8 tiles; wrench_kernel.cuh, half rows, with
                                      MPC_WRENCH_TILE=0 in the environment); H = 30: the core solved as a 12-state / 6-input
                                      Riccati recursion (wrench_riccati_kernel.cuh); H = 30 with
                                      exact_discretization: as 1;

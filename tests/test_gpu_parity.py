@@ -987,7 +987,7 @@ def test_config4_full_size_h30(pkg, ob):
 
 
 def test_wrench_kernels_agree(pkg, ob, tmp_path):
-    """The two register layouts of the H = 10 wrench-space kernel -- 2 x 16 tiles (default) and half rows
+    """The two register layouts of the H = 10 wrench-space kernel -- 4 x 8 tiles (default) and half rows
     (MPC_WRENCH_TILE=0, read once per process, hence the second process) -- produce the same iteration counts and
     rho updates on every state, cold and warm-started, and forces equal far inside the gate."""
     import subprocess
