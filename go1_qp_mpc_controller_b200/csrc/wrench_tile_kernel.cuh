@@ -41,7 +41,7 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
   // element offsets used in every iteration
   const int offRowIn = 12 * kr + 6 * h;  // first rhs entry of this thread's half row
   const int offOm = 6 * k;
-  const int jpin = j, rpin = r;
+  const int jpin = j;
   const double mu = sp.mu, sigma = sp.sigma, alpha = sp.alpha;
   const double dt = bp.dt, inv_m = 1.0 / bp.mass;
   const double r2 = bp.Rd[jj];                    // 2 r_weights of this variable (ConvexMpc.cpp:41)
