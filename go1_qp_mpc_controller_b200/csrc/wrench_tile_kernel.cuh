@@ -615,15 +615,15 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
         {
           const double2* tp = reinterpret_cast<const double2*>(&sm.vt[kTS * tq]);
           const double2 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
+          // one accumulator per row, the four rows interleaved: four independent chains keep the FP64 pipe fed
+          const double tv[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
           double acc[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            double sA = y[i][0] * t0.x, sB = y[i][4] * t2.x;
-            sA = fma(y[i][1], t0.y, sA); sB = fma(y[i][5], t2.y, sB);
-            sA = fma(y[i][2], t1.x, sA); sB = fma(y[i][6], t3.x, sB);
-            sA = fma(y[i][3], t1.y, sA); sB = fma(y[i][7], t3.y, sB);
-            acc[i] = sA + sB;
-          }
+          for (int i = 0; i < 4; ++i) acc[i] = y[i][0] * tv[0];
+#pragma unroll
+          for (int cc = 1; cc < 8; ++cc)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fma(y[i][cc], tv[cc], acc[i]);
           const bool b0 = tq & 1, b1 = tq & 2;
           const double ra = (b0 ? acc[2] : acc[0]) + shfl_xor(b0 ? acc[0] : acc[2], 1);
           const double rb = (b0 ? acc[3] : acc[1]) + shfl_xor(b0 ? acc[1] : acc[3], 1);
