@@ -92,7 +92,7 @@ __device__ __forceinline__ double max_bits(double a, double b) {  // max of non-
 template <bool kDrift>
 __device__ __forceinline__ double wr_colnorm_t(const WrenchSmem& sm, int kj, int comp, const double (&u1)[3],
                                                const double (&u2)[3], double vb1, double vb2) {
-  double mx = 0.0;
+  double mx = 0.0, mx1 = 0.0;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     // alpha and beta are all that depends on the block row: entry = alpha A_i + beta B_i with
@@ -135,12 +135,13 @@ __device__ __forceinline__ double wr_colnorm_t(const WrenchSmem& sm, int kj, int
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           const double e = fma(b, B0[i], a * A0[i]);
-          mx = max_bits(mx, fabs(e) * dd[i]);
+          if (i & 1) mx1 = max_bits(mx1, fabs(e) * dd[i]);   // two accumulators: the compare-select chain is the latency here
+          else mx = max_bits(mx, fabs(e) * dd[i]);
         }
       }
     }
   }
-  return mx;
+  return max_bits(mx, mx1);
 }
 __device__ __forceinline__ double wr_colnorm(const WrenchSmem& sm, bool drift, int kj, int comp, const double (&u1)[3],
                                              const double (&u2)[3], double vb1, double vb2) {
