@@ -63,6 +63,7 @@ struct WrenchSmem {
   alignas(16) double xD[kWrThreads];  // D x for the residual check
   alignas(16) double Dp[kWrThreads];  // D
   alignas(16) double prow[2][2][kW6 + 20];  // published pivot rows of the sweep (two per block), double buffered
+  alignas(16) double pm[2][4];        // tile variant: inverse of the published 2 x 2 pivot block (m11, m12, m22), double buffered
   double loA[kWrThreads], hiA[kWrThreads];  // normalised bounds of row A (row B is (-inf, 0] or absent)
   double red[kWrWarps * 16];
   double scal[16];                    // 0:c 1:1/c 2:rho 4:pri_res 6:rho 7:1000 rho 8:1/rho 9:1/(1000 rho)

@@ -500,6 +500,10 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
         if (tact && trp == 0) {
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) { sm.prow[0][0][kTS * tq + cc] = y[0][cc]; sm.prow[0][1][kTS * tq + cc] = y[1][cc]; }
+          if (tq == 0) {   // the thread that holds a pivot block inverts it for everybody
+            const double idet = 1.0 / (y[0][0] * y[1][1] - y[0][1] * y[0][1]);
+            sm.pm[0][0] = y[1][1] * idet; sm.pm[0][1] = -y[0][1] * idet; sm.pm[0][2] = y[0][0] * idet;
+          }
         }
         __syncthreads();
 #pragma unroll 1
@@ -513,11 +517,8 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
               const int buf = pb & 1;
               const double* r1 = sm.prow[buf][0];
               const double* r2 = sm.prow[buf][1];
-              const int pvp = kTS * qs + lc;   // padded position of column pv
-              const double2 dA = *reinterpret_cast<const double2*>(r1 + pvp), dB = *reinterpret_cast<const double2*>(r2 + pvp);
-              const double d1 = dA.x, e12 = dA.y, d2 = dB.y;
-              const double idet = 1.0 / (d1 * d2 - e12 * e12);
-              const double m11 = d2 * idet, m12 = -e12 * idet, m22 = d1 * idet;
+              const double2 m1112 = *reinterpret_cast<const double2*>(sm.pm[buf]);
+              const double m11 = m1112.x, m12 = m1112.y, m22 = sm.pm[buf][2];   // M = A_SS^-1, from the block's owner
               // A_r,p and A_r,p+1 of the tile's four rows, by symmetry from the pivot rows
               const double2* aAp = reinterpret_cast<const double2*>(r1 + tpad(tr0));
               const double2* aBp = reinterpret_cast<const double2*>(r2 + tpad(tr0));
@@ -578,6 +579,13 @@ wrench_tile_kernel(const MpcStateIn* __restrict__ states, const MpcGaitIn* __res
                 for (int cc = 0; cc < 8; ++cc) {
                   n0[kTS * tq + cc] = sn ? y[2][cc] : y[0][cc];
                   n1[kTS * tq + cc] = sn ? y[3][cc] : y[1][cc];
+                }
+                if (tq == ((pv + 2) >> 3)) {   // this thread holds the next pivot block: columns lcn, lcn + 1 of its tile
+                  const int lcn = (lc + 2) & 7;
+                  const double d1 = sn ? y[2][lcn] : y[0][lcn], e12 = sn ? y[2][lcn + 1] : y[0][lcn + 1];
+                  const double d2 = sn ? y[3][lcn + 1] : y[1][lcn + 1];
+                  const double idet = 1.0 / (d1 * d2 - e12 * e12);
+                  sm.pm[buf ^ 1][0] = d2 * idet; sm.pm[buf ^ 1][1] = -e12 * idet; sm.pm[buf ^ 1][2] = d1 * idet;
                 }
               }
               __syncthreads();
